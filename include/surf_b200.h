@@ -1,0 +1,187 @@
+/*
+ * surf_b200.h - C ABI of libsurf_b200.so: the B200 (sm_100a) implementation of DiffRend's
+ * ray-cast render path.
+ *
+ * Every entry point replaces (part of) one reference interface; the citations are into the
+ * reference tree (fmannan/surf_renderer):
+ *
+ *   surf_forward / surf_render_host      <- diffrend/torch/renderer.py:136-355  render(scene, **params)
+ *        ray generation                  <- diffrend/torch/utils.py:439-478     generate_rays
+ *        intersections + z-buffer        <- diffrend/torch/utils.py:238-366,481-512 ; renderer.py:170-202
+ *        shading + tonemap               <- renderer.py:82-125 fragment_shader ; :318-340 ; utils.py:430-432
+ *        shadow rays (opt.shadow)        <- renderer.py:291-314
+ *   surf_backward / surf_render_backward_host
+ *                                        <- torch autograd through the same graph (loss.backward(),
+ *                                           e.g. diffrend/torch/test_optimization.py:100-125)
+ *
+ * The reference has no FFI for this path (it is a Python function); the Python binding a
+ * maintainer would add is ctypes - see INTEGRATION.md and surf_renderer_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C, POD structs, raw pointers + sizes, no torch / C++ types.
+ *   - "device" entry points take DEVICE pointers and a CUDA stream (as void*); they are asynchronous
+ *     and stream-ordered, hold no device memory and no global state (thread-local error string only).
+ *   - "host" entry points take HOST pointers with the same structs; a SurfContext owns the staging
+ *     buffers, the device workspace and a stream.  They return after the results are in host memory.
+ *   - all entry points return 0 on success or a negative SurfStatus; surf_last_error() describes it.
+ *   - all float data is IEEE fp32; index outputs are int64 like torch's LongTensor.
+ *   - row strides are given in floats so that the reference's homogeneous [M,4] arrays and plain
+ *     [M,3] arrays are both accepted without a copy (the reference slices [:, :3], utils.py:245,288).
+ */
+#ifndef SURF_B200_H_
+#define SURF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURF_ABI_VERSION 1
+#define SURF_MAX_SETS 8
+
+typedef enum SurfStatus {
+    SURF_OK = 0,
+    SURF_ERR_BAD_ARG = -1,
+    SURF_ERR_UNSUPPORTED = -2,
+    SURF_ERR_CUDA = -3,
+    SURF_ERR_WORKSPACE = -4
+} SurfStatus;
+
+/* primitive kinds; the order of SurfScene.sets is the insertion order of scene['objects']
+ * (utils.py:486) and defines the global primitive index reported in `nearest`. */
+typedef enum SurfPrimKind { SURF_DISK = 0, SURF_PLANE = 1, SURF_SPHERE = 2, SURF_TRIANGLE = 3 } SurfPrimKind;
+
+typedef struct SurfPrimSet {
+    int32_t kind;            /* SurfPrimKind */
+    int32_t count;           /* M_k */
+    const float* pos;        /* disk/plane/sphere: [M_k, pos_stride]; triangle: face [M_k, 3, pos_stride] */
+    int32_t pos_stride;      /* 3 or 4 */
+    const float* normal;     /* disk/plane/triangle: [M_k, normal_stride] (un-normalised ok); sphere: NULL */
+    int32_t normal_stride;   /* 3 or 4 */
+    const float* radius;     /* disk/sphere: [M_k]; else NULL */
+    const int32_t* material_idx; /* [M_k] */
+} SurfPrimSet;
+
+typedef struct SurfScene {
+    int32_t n_sets;
+    SurfPrimSet sets[SURF_MAX_SETS];
+    int32_t n_lights;
+    const float* light_pos;      /* [L, light_pos_stride] */
+    int32_t light_pos_stride;    /* 3 or 4 */
+    const int32_t* light_color_idx; /* [L] rows of `colors` */
+    const float* light_attenuation; /* [L,3] (kc, kl, kq) */
+    const float* ambient;        /* [3] */
+    int32_t n_colors;
+    const float* colors;         /* [C,3] */
+    int32_t n_materials;
+    const float* albedo;         /* [K,3] */
+    const float* coeffs;         /* [K,3] (kd, ks, shininess) */
+    const float* gamma;          /* [1] tonemap gamma, or NULL for no tonemap (renderer.py:339) */
+} SurfScene;
+
+typedef struct SurfCamera {
+    int32_t proj;            /* 0 perspective, 1 orthographic (utils.py:462-469) */
+    int32_t width, height;   /* viewport[2]-viewport[0], viewport[3]-viewport[1] */
+    double fovy;             /* radians */
+    double focal_length;
+    const float* eye;        /* [3] (first three of the reference's 4-vector) */
+    const float* at;         /* [3] */
+    const float* up;         /* [3] */
+    float near_clip, far_clip;
+} SurfCamera;
+
+typedef struct SurfOptions {
+    int32_t double_sided;    /* renderer.py:107-112 */
+    int32_t use_quartic;     /* renderer.py:90 */
+    int32_t shadow;          /* renderer.py:291-314 */
+    int32_t pixel_begin;     /* render flat pixels [pixel_begin, pixel_end) of the H*W row-major grid;     */
+    int32_t pixel_end;       /* 0,0 = whole frame.  Output arrays are sized for the range (row bands / GPU) */
+    int32_t forced_nearest;  /* backward only: 1 = trust `nearest`/`hit` given by the caller (parity harness) */
+    int32_t pixels_per_thread; /* 0 = library default; tuning knob for the intersection kernel (2,4,8)      */
+    int32_t chunk_prims;     /* 0 = library default; primitives staged per TMA bulk copy (multiple of 32)   */
+    int32_t math_mode;       /* 0 = default (packed f32x2 FFMA2 filter), 1 = scalar FFMA filter              */
+} SurfOptions;
+
+/* outputs for n = pixel_end - pixel_begin pixels (row-major).  Any pointer may be NULL to skip it. */
+typedef struct SurfOutputs {
+    float* image;            /* [n,3] */
+    float* depth;            /* [n]   miss = far+1 (renderer.py:180) */
+    float* normal;           /* [n,3] */
+    float* pos;              /* [n,3] */
+    int64_t* nearest;        /* [n]   miss = 0 (argmin of an all-(far+1) column) */
+    float* ray_dir;          /* perspective: [3,n]; orthographic: [3,1] */
+} SurfOutputs;
+
+/* incoming gradients of the outputs (NULL = zero) */
+typedef struct SurfOutGrads {
+    const float* image;      /* [n,3] */
+    const float* depth;      /* [n]   */
+    const float* normal;     /* [n,3] */
+    const float* pos;        /* [n,3] */
+} SurfOutGrads;
+
+/* gradient accumulators, same layout/strides as the inputs they belong to; caller zero-initialises,
+ * the library adds.  NULL = not wanted.  (Disk radius has no gradient in the reference: SURVEY A.5.) */
+typedef struct SurfPrimSetGrads {
+    float* pos;              /* disk/plane/sphere centre; triangle: face (only vertex 0 receives gradient) */
+    float* normal;
+    float* radius;           /* sphere only */
+} SurfPrimSetGrads;
+
+typedef struct SurfSceneGrads {
+    SurfPrimSetGrads sets[SURF_MAX_SETS];
+    float* light_pos;        /* [L, light_pos_stride] */
+    float* light_attenuation;/* [L,3] */
+    float* ambient;          /* [3] */
+    float* colors;           /* [C,3] */
+    float* albedo;           /* [K,3] */
+    float* coeffs;           /* [K,3] */
+    float* gamma;            /* [1] */
+} SurfSceneGrads;
+
+int surf_abi_version(void);
+const char* surf_last_error(void);
+
+/* bytes of device scratch surf_forward / surf_backward need for this problem size */
+size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels);
+
+/* ---- device-pointer API (what the torch autograd.Function calls) ---- */
+int surf_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                 void* workspace, size_t workspace_bytes, const SurfOutputs* out, void* cuda_stream);
+
+/* `nearest` [n] int64 and `depth` [n] are the forward outputs (hit <=> depth <= far). */
+int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                  void* workspace, size_t workspace_bytes,
+                  const int64_t* nearest, const float* depth,
+                  const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads, void* cuda_stream);
+
+/* ---- host-pointer API (self-contained: H2D, kernels, D2H) ---- */
+typedef struct SurfContext SurfContext;
+SurfContext* surf_context_create(int32_t device);
+void surf_context_destroy(SurfContext* ctx);
+int surf_render_host(SurfContext* ctx, const SurfScene* scene, const SurfCamera* camera,
+                     const SurfOptions* options, const SurfOutputs* out);
+/* forward + backward in one call: renders, copies outputs out (if non-NULL), then back-propagates the
+ * host `out_grads` and copies the scene gradients back.  If `target_image` is non-NULL the image
+ * gradient is instead d/d(image) of mean((image-target)^2) and *loss receives that loss (the
+ * inverse-rendering step of test_optimization.py:100-125). */
+int surf_render_backward_host(SurfContext* ctx, const SurfScene* scene, const SurfCamera* camera,
+                              const SurfOptions* options, const SurfOutputs* out,
+                              const SurfOutGrads* out_grads, const float* target_image, float* loss,
+                              const SurfSceneGrads* scene_grads);
+/* bytes moved by the last host call */
+int surf_context_last_transfer(const SurfContext* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- measurement helpers ---- */
+/* FP32 FMA-pipe microbenchmark on the current device: lane-instructions/s for scalar FFMA (mode 0)
+ * and packed FFMA2 (mode 1, counted as two lane-FMAs per lane).  Returns <0 on error. */
+double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream);
+/* number of kernels the last device/host call on this thread launched */
+int surf_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURF_B200_H_ */

@@ -1,0 +1,201 @@
+"""Scene dict (the reference's schema, SURVEY A.1 / renderer.py:136-355) -> flat tensors + C structs.
+
+The render path reads: scene['camera'], ['lights'], ['colors'], ['materials'], ['objects'] (dict, in
+insertion order - utils.py:486) and optionally ['tonemap'].  Values may be tensors, numpy arrays, lists
+or python numbers (torch/render.py:88-107 make_torch_var produces tensors; the demos mix all of them).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+
+PRIM_FIELDS = {'disk': ('pos', 'normal', 'radius'), 'plane': ('pos', 'normal'),
+               'sphere': ('pos', 'radius'), 'triangle': ('face', 'normal')}
+
+
+def _as_float_tensor(v, device):
+    if isinstance(v, torch.Tensor):
+        t = v
+        if t.dtype != torch.float32:
+            t = t.float()
+        if t.device != device:
+            t = t.to(device)
+    else:
+        t = torch.tensor(np.asarray(v, dtype=np.float64), dtype=torch.float32, device=device)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _as_int_tensor(v, device):
+    """index arrays may arrive as long or float tensors, lists or numpy arrays (renderer.py:128,284)."""
+    if isinstance(v, torch.Tensor):
+        t = v.detach()
+    else:
+        t = torch.tensor(np.asarray(v))
+    t = t.long().to(torch.int32)          # .long() truncation first, like the reference's material_idx.long()
+    if t.device != device:
+        t = t.to(device)
+    return t.contiguous()
+
+
+def _scalar(v):
+    if isinstance(v, torch.Tensor):
+        return float(v.detach().cpu().reshape(-1)[0])
+    return float(np.asarray(v).reshape(-1)[0])
+
+
+class Marshalled:
+    """Flat, C-ready view of one scene dict on one device."""
+
+    def __init__(self, scene, device):
+        device = torch.device(device)
+        self.device = device
+        cam = scene['camera']
+        if 'proj_type' not in cam:
+            raise KeyError('proj_type')
+        proj = cam['proj_type']
+        if proj in ('persp', 'perspective'):
+            self.proj = 0
+        elif proj in ('ortho', 'orthographic'):
+            self.proj = 1
+        else:
+            raise ValueError('Invalid projection type')        # utils.py:470 falls through; Renderer:70 raises
+        vp = cam['viewport']
+        vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
+        self.width, self.height = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+        self.fovy, self.focal = _scalar(cam['fovy']), _scalar(cam['focal_length'])
+        self.near, self.far = _scalar(cam['near']), _scalar(cam['far'])
+        # camera vectors are constants of the render (the reference cannot differentiate them: utils.py:476)
+        self.cam_vecs = {k: _as_float_tensor(cam[k], device).detach().reshape(-1)[:3].contiguous()
+                         for k in ('eye', 'at', 'up')}
+
+        self.names, self.floats = [], []      # differentiable float inputs, canonical order
+        self.ints = {}
+        self.sets = []                        # (kind, count, pos_stride, normal_stride)
+
+        def add(name, v):
+            self.names.append(name)
+            self.floats.append(_as_float_tensor(v, device))
+            return len(self.floats) - 1
+
+        objects = scene['objects']
+        if len(objects) == 0 or len(objects) > _abi.SURF_MAX_SETS:
+            raise ValueError('scene needs between 1 and %d primitive sets' % _abi.SURF_MAX_SETS)
+        for kind, prim in objects.items():
+            if kind not in _abi.KIND:
+                raise KeyError(kind)                       # utils.py:488 intersection_fn[obj_type]
+            slots = {}
+            for f in PRIM_FIELDS[kind]:
+                slots[f] = add('objects/%s/%s' % (kind, f), prim[f])
+            geo = self.floats[slots['face' if kind == 'triangle' else 'pos']]
+            count, pstride = int(geo.shape[0]), int(geo.shape[-1])
+            nstride = int(self.floats[slots['normal']].shape[-1]) if 'normal' in slots else 0
+            self.ints['objects/%s/material_idx' % kind] = _as_int_tensor(prim['material_idx'], device)
+            self.sets.append((kind, count, pstride, nstride, slots))
+
+        lights = scene['lights']
+        self.i_light_pos = add('lights/pos', lights['pos'])
+        self.i_atten = add('lights/attenuation', lights['attenuation'])
+        self.i_ambient = add('lights/ambient', lights['ambient'])
+        self.ints['lights/color_idx'] = _as_int_tensor(lights['color_idx'], device)
+        self.i_colors = add('colors', scene['colors'])
+        self.i_albedo = add('materials/albedo', scene['materials']['albedo'])
+        self.i_coeffs = add('materials/coeffs', scene['materials']['coeffs'])
+        self.i_gamma = None
+        if 'tonemap' in scene:
+            tm = scene['tonemap']
+            if tm['type'] != 'gamma':
+                raise ValueError('only the gamma tonemap exists (utils.py:430-432)')
+            self.i_gamma = add('tonemap/gamma', tm['gamma'] if isinstance(tm['gamma'], torch.Tensor)
+                               else [float(tm['gamma'])])
+        self.total_prims = sum(s[1] for s in self.sets)
+        self.n_pixels = self.width * self.height
+        self._validate()
+
+    def _validate(self):
+        # the demos replace albedo with a 1-row table but keep SCENE_BASIC's 6-row coeffs
+        # (full_diff_renderer_demo.py:63): rows are only ever gathered by material_idx, so use the smaller table
+        n_mat = min(int(self.floats[self.i_albedo].shape[0]), int(self.floats[self.i_coeffs].shape[0]))
+        n_col = int(self.floats[self.i_colors].shape[0])
+        for (kind, count, _, _, _) in self.sets:
+            mi = self.ints['objects/%s/material_idx' % kind]
+            if mi.numel() != count:
+                raise ValueError('%s: material_idx has %d entries for %d primitives' % (kind, mi.numel(), count))
+        # index range checks on the host would force a sync for device tensors; do them only for CPU data
+        if self.device.type == 'cpu':
+            for (kind, _, _, _, _) in self.sets:
+                mi = self.ints['objects/%s/material_idx' % kind]
+                if mi.numel() and (int(mi.min()) < 0 or int(mi.max()) >= n_mat):
+                    raise IndexError('material_idx out of range')
+            ci = self.ints['lights/color_idx']
+            if int(ci.min()) < 0 or int(ci.max()) >= n_col:
+                raise IndexError('color_idx out of range')
+
+    # ------------------------------------------------------------------
+    def c_scene(self, floats=None):
+        """SurfScene over `floats` (defaults to the marshalled tensors; the autograd Function passes its args)."""
+        fl = self.floats if floats is None else floats
+        sc = _abi.SurfScene()
+        sc.n_sets = len(self.sets)
+        for k, (kind, count, pstride, nstride, slots) in enumerate(self.sets):
+            ps = sc.sets[k]
+            ps.kind, ps.count = _abi.KIND[kind], count
+            ps.pos = fl[slots['face' if kind == 'triangle' else 'pos']].data_ptr()
+            ps.pos_stride = pstride
+            if 'normal' in slots:
+                ps.normal = fl[slots['normal']].data_ptr()
+                ps.normal_stride = nstride
+            if 'radius' in slots:
+                ps.radius = fl[slots['radius']].data_ptr()
+            ps.material_idx = self.ints['objects/%s/material_idx' % kind].data_ptr()
+        lp = fl[self.i_light_pos]
+        sc.n_lights, sc.light_pos, sc.light_pos_stride = int(lp.shape[0]), lp.data_ptr(), int(lp.shape[-1])
+        sc.light_color_idx = self.ints['lights/color_idx'].data_ptr()
+        sc.light_attenuation = fl[self.i_atten].data_ptr()
+        sc.ambient = fl[self.i_ambient].data_ptr()
+        sc.n_colors, sc.colors = int(fl[self.i_colors].shape[0]), fl[self.i_colors].data_ptr()
+        sc.n_materials = min(int(fl[self.i_albedo].shape[0]), int(fl[self.i_coeffs].shape[0]))
+        sc.albedo, sc.coeffs = fl[self.i_albedo].data_ptr(), fl[self.i_coeffs].data_ptr()
+        sc.gamma = fl[self.i_gamma].data_ptr() if self.i_gamma is not None else None
+        return sc
+
+    def c_camera(self):
+        cam = _abi.SurfCamera()
+        cam.proj, cam.width, cam.height = self.proj, self.width, self.height
+        cam.fovy, cam.focal_length = self.fovy, self.focal
+        cam.eye, cam.at, cam.up = (self.cam_vecs[k].data_ptr() for k in ('eye', 'at', 'up'))
+        cam.near_clip, cam.far_clip = self.near, self.far
+        return cam
+
+    def c_grads(self, grads):
+        """SurfSceneGrads over a list of gradient tensors aligned with self.floats (None = not wanted)."""
+        sg = _abi.SurfSceneGrads()
+
+        def ptr(i):
+            return grads[i].data_ptr() if (i is not None and grads[i] is not None) else None
+
+        for k, (kind, count, pstride, nstride, slots) in enumerate(self.sets):
+            g = sg.sets[k]
+            g.pos = ptr(slots.get('face' if kind == 'triangle' else 'pos'))
+            g.normal = ptr(slots.get('normal'))
+            g.radius = ptr(slots.get('radius')) if kind == 'sphere' else None
+        sg.light_pos, sg.light_attenuation, sg.ambient = ptr(self.i_light_pos), ptr(self.i_atten), ptr(self.i_ambient)
+        sg.colors, sg.albedo, sg.coeffs, sg.gamma = ptr(self.i_colors), ptr(self.i_albedo), ptr(self.i_coeffs), ptr(self.i_gamma)
+        return sg
+
+
+def make_options(params, pixel_range=None, forced_nearest=False):
+    opt = _abi.SurfOptions()
+    opt.double_sided = int(bool(params.get('double_sided', False)))
+    opt.use_quartic = int(bool(params.get('use_quartic', False)))
+    opt.shadow = int(bool(params.get('shadow', False)))
+    if pixel_range is not None:
+        opt.pixel_begin, opt.pixel_end = int(pixel_range[0]), int(pixel_range[1])
+    opt.forced_nearest = int(forced_nearest)
+    opt.pixels_per_thread = int(params.get('_pixels_per_thread', 0))
+    opt.chunk_prims = int(params.get('_chunk_prims', 0))
+    opt.math_mode = int(params.get('_math_mode', 0))
+    return opt

@@ -1,0 +1,63 @@
+"""ctypes driver for the CPU emulation of the kernel math (tests/emul/surf_emul.cpp) - test infrastructure."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from surf_renderer_b200 import _abi                      # noqa: E402
+from surf_renderer_b200.marshal import Marshalled, make_options   # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        sys.path.insert(0, os.path.join(HERE, 'emul'))
+        import build as emul_build
+        _lib = C.CDLL(emul_build.build())
+        _lib.emul_forward.restype = C.c_longlong
+        _lib.emul_forward.argtypes = [C.POINTER(_abi.SurfScene), C.POINTER(_abi.SurfCamera), C.POINTER(_abi.SurfOptions),
+                                      C.POINTER(_abi.SurfOutputs), C.c_void_p]
+        _lib.emul_backward.restype = C.c_int
+        _lib.emul_backward.argtypes = [C.POINTER(_abi.SurfScene), C.POINTER(_abi.SurfCamera), C.POINTER(_abi.SurfOptions),
+                                       C.c_void_p, C.c_void_p, C.POINTER(_abi.SurfOutGrads), C.POINTER(_abi.SurfSceneGrads)]
+        _lib.emul_last_error.restype = C.c_char_p
+    return _lib
+
+
+def forward(scene, **params):
+    m = Marshalled(scene, 'cpu')
+    n = m.n_pixels
+    out = {'image': torch.empty(n, 3), 'depth': torch.empty(n), 'normal': torch.empty(n, 3), 'pos': torch.empty(n, 3),
+           'nearest': torch.empty(n, dtype=torch.int64),
+           'ray_dir': torch.empty(3, n if m.proj == 0 else 1)}
+    co = _abi.SurfOutputs(*[out[k].data_ptr() for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir')])
+    sc, cam, opt = m.c_scene(), m.c_camera(), make_options(params)
+    misses = lib().emul_forward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(co), None)
+    if misses < 0:
+        raise RuntimeError(lib().emul_last_error().decode())
+    H, W = m.height, m.width
+    res = {'image': out['image'].view(H, W, 3), 'depth': out['depth'].view(H, W), 'normal': out['normal'].view(H, W, 3),
+           'pos': out['pos'].view(H, W, 3), 'nearest': out['nearest'].view(H, W), 'ray_dir': out['ray_dir']}
+    return res, int(misses), m
+
+
+def backward(m, params, nearest, depth, gouts):
+    grads = [torch.zeros_like(t) for t in m.floats]
+    sg = m.c_grads(grads)
+    og = _abi.SurfOutGrads(*[(gouts[k].contiguous().data_ptr() if gouts.get(k) is not None else None)
+                             for k in ('image', 'depth', 'normal', 'pos')])
+    keep = [gouts[k].contiguous() for k in gouts if gouts[k] is not None]   # noqa: F841
+    og = _abi.SurfOutGrads(*[(t.data_ptr() if t is not None else None) for t in
+                             [gouts.get(k) for k in ('image', 'depth', 'normal', 'pos')]])
+    sc, cam, opt = m.c_scene(), m.c_camera(), make_options(params)
+    rc = lib().emul_backward(C.byref(sc), C.byref(cam), C.byref(opt), nearest.contiguous().data_ptr(),
+                             depth.contiguous().data_ptr(), C.byref(og), C.byref(sg))
+    if rc != 0:
+        raise RuntimeError(lib().emul_last_error().decode())
+    return dict(zip(m.names, grads))
