@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the render hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Workload (config.workload = "config_e"): BASELINE.json configs[4], the configuration the north-star target is
+quoted on - the inverse-rendering step of 100 000 synthetic disk splats at 1024x1024.
+One step = render (forward) -> mean((image-target)^2) -> backward to splat positions, normals, albedo and light
+positions -> Adam step.  `value` = ray-primitive tests per second of the whole job = H*W*M per step / step time
+with inputs resident in HBM; `e2e` = the same through the C-ABI host-pointer call (pinned HOST buffers in,
+gradients + loss back in host memory, H2D/D2H inside the timed region).  N>1: the frame is sharded into row
+bands, one per GPU (strong scaling of one frame), image bands all-gathered, packed gradients all-reduced (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions)
+N_SM, FP32_LANES = 148, 128
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='surf', choices=['surf', 'reference'])
+    ap.add_argument('--splats', type=int, default=100_000)
+    ap.add_argument('--size', type=int, default=1024)
+    ap.add_argument('--ppt', type=int, default=0, help='pixels per thread of the intersection kernel (0 = default)')
+    ap.add_argument('--chunk', type=int, default=0)
+    ap.add_argument('--math', type=int, default=0, help='0 = packed FFMA2 filter, 1 = scalar FFMA filter')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'sm_max_mhz': 1965.0}, 'fallback'
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (op-for-op restatement of the reference's torch path) on host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_step(scene, target_scene, subset, threads):
+    """One bounded sample of the workload on the CPU: fwd + loss + bwd over `subset` pixels of the frame."""
+    import scene_io
+    from oracle import torch_oracle
+    torch.set_num_threads(threads)
+    sc = scene_io.clone_scene(scene, requires_grad=False)
+    leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
+    for t in leaves:
+        t.requires_grad_(True)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        tgt = torch_oracle.render(target_scene, pixel_subset=subset, tile_size=512)['image']
+    t_target = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = torch_oracle.render(sc, pixel_subset=subset, tile_size=512)
+    loss = ((res['image'] - tgt) ** 2).mean()
+    t_fwd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loss.backward()
+    t_bwd = time.perf_counter() - t0
+    return t_fwd, t_bwd, t_target
+
+
+def cpu_sample(scene, n_pix_sample, seed=123):
+    vp = scene['camera']['viewport']
+    n = (vp[2] - vp[0]) * (vp[3] - vp[1])
+    g = torch.Generator().manual_seed(seed)
+    return torch.randperm(n, generator=g)[:n_pix_sample].sort().values
+
+
+def run_cpu_baseline(scene, target_scene, budget_s, threads, steps=1, warmup=0):
+    m = int(scene['objects']['disk']['pos'].shape[0])
+    # calibrate on 128 pixels, then size the sample for the time budget
+    sub = cpu_sample(scene, 128)
+    tf, tb, _ = cpu_reference_step(scene, target_scene, sub, threads)
+    per_pix = (tf + tb) / 128
+    vp = scene['camera']['viewport']
+    n_total = (vp[2] - vp[0]) * (vp[3] - vp[1])
+    n_pix = int(max(128, min(8192, n_total, budget_s / max(per_pix, 1e-9) / max(1, steps + warmup))))
+    sub = cpu_sample(scene, n_pix)
+    n_pix = int(sub.numel())
+    times = []
+    for i in range(warmup + steps):
+        tf, tb, _ = cpu_reference_step(scene, target_scene, sub, threads)
+        if i >= warmup:
+            times.append((tf, tb))
+    tf = float(np.mean([t[0] for t in times])); tb = float(np.mean([t[1] for t in times]))
+    tests = float(m) * n_pix
+    return {'value': tests / (tf + tb), 'unit': 'tests/s', 'cores': threads, 'kind': 'port',
+            'sample': '%d random pixels of the %dx%d frame x %d splats, fwd+bwd (fwd %.2fs, bwd %.2fs), torch-CPU '
+                      'op-for-op port of the reference, tile_size=512' % (n_pix, scene['camera']['viewport'][2],
+                                                                          scene['camera']['viewport'][3], m, tf, tb),
+            'fwd_tests_per_s': tests / tf, 'ms_per_sample_step': 1e3 * (tf + tb)}, n_pix, tf + tb
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    from surf_renderer_b200 import scenes as synth
+    scene = synth.config_e(m=args.splats, width=args.size, height=args.size)
+    target_scene = synth.config_e_target_scene(scene)
+    M, H, W = args.splats, args.size, args.size
+    tests_per_step = float(M) * H * W
+    config = {'workload': 'config_e', 'splats': M, 'width': W, 'height': H, 'lights': 3,
+              'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam',
+              'sharding': 'row-bands x%d' % max(1, args.gpus), 'l2': 'flushed between timed steps (256 MiB write)'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        cb, n_pix, step_s = run_cpu_baseline(scene, target_scene, budget_s=150.0, threads=threads,
+                                             steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+        line = {'impl': 'reference', 'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)',
+                'value': cb['value'], 'unit': 'tests/s', 'n_gpus': 0, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': 1e3 * step_s, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'config': config, 'cpu_baseline': cb,
+                'frames_per_s_extrapolated': cb['value'] / tests_per_step,
+                'e2e': {'value': cb['value'], 'unit': 'tests/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    import scene_io
+    import surf_renderer_b200
+    from surf_renderer_b200 import _abi, dist as sdist
+    from surf_renderer_b200._lib import check, lib
+    from surf_renderer_b200.marshal import Marshalled, make_options
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    peaks, peak_src = measured_peaks()
+    params = {'_pixels_per_thread': args.ppt, '_chunk_prims': args.chunk, '_math_mode': args.math}
+
+    sc = scene_io.clone_scene(scene, device=dev)
+    leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
+    for t in leaves:
+        t.requires_grad_(True)
+    opt = torch.optim.Adam(leaves, lr=1e-4)
+    with torch.no_grad():
+        tgt = surf_renderer_b200.render(scene_io.clone_scene(target_scene, device=dev), **params)['image']
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lib().surf_set_kernel_timing(1)
+    launches = []
+    k_ms = {0: [], 1: [], 2: []}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        if world > 1:
+            res = sdist.render_bands(sc, gather=('image',), **params)
+        else:
+            res = surf_renderer_b200.render(sc, **params)
+        n_launch = lib().surf_last_launch_count()
+        loss = ((res['image'] - tgt) ** 2).mean()
+        loss.backward()
+        n_launch += lib().surf_last_launch_count()
+        if world > 1:
+            sdist.allreduce_gradients(leaves)
+        opt.step()
+        return loss, n_launch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                      # L2 flush, outside the timed events
+        barrier()
+        ev[i][0].record()
+        loss, n_launch = step()
+        ev[i][1].record()
+        launches.append(n_launch)
+        for k in k_ms:
+            k_ms[k].append(lib().surf_last_kernel_ms(k))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = tests_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_intersect), timed live with CUDA events inside the library
+    isect_ms = float(np.mean([x for x in k_ms[0] if x > 0])) if any(x > 0 for x in k_ms[0]) else None
+    f_clk = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
+    peak_lane = N_SM * FP32_LANES * f_clk                    # lane-instr/s
+    roofline = None
+    if isect_ms:
+        tests_launch = tests_per_step / world
+        ach_lane = tests_launch * FMA_INSTR_PER_DISK_TEST / (isect_ms * 1e-3)
+        fma_meas = max(lib().surf_fma_peak(0, 8192, None), lib().surf_fma_peak(1, 8192, None))
+        roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
+                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane, 'traffic': None,
+                    'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no fp32 entry)' % peak_src,
+                    'peak_measured': fma_meas * 2 / 1e12, 'frac_of_measured': ach_lane / fma_meas if fma_meas > 0 else None,
+                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
+                    'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
+                    'shade_ms': float(np.mean(k_ms[1])), 'backward_ms': float(np.mean(k_ms[2]))}
+
+    # ---- e2e: C-ABI host-pointer call, pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hs = scene_io.clone_scene(scene)
+        m = Marshalled(hs, 'cpu')
+        m.floats = [t.pin_memory() for t in m.floats]
+        m.ints = {k: v.pin_memory() for k, v in m.ints.items()}
+        m.cam_vecs = {k: v.pin_memory() for k, v in m.cam_vecs.items()}
+        n_total = H * W
+        p0, p1 = sdist.band_range(n_total, rank, world)
+        target_host = tgt.detach().reshape(-1, 3)[p0:p1].cpu().pin_memory()
+        grads = [torch.zeros_like(t).pin_memory() for t in m.floats]
+        csc, ccam = m.c_scene(), m.c_camera()
+        copt = make_options(params, (p0, p1))
+        csg = m.c_grads(grads)
+        ctx = lib().surf_context_create(local_rank)
+        loss_c = C.c_float()
+
+        def e2e_step():
+            check(lib().surf_render_backward_host(ctx, C.byref(csc), C.byref(ccam), C.byref(copt), None, None,
+                                                  target_host.data_ptr(), C.byref(loss_c), C.byref(csg)))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d, d2h = C.c_uint64(), C.c_uint64()
+        lib().surf_context_last_transfer(ctx, C.byref(h2d), C.byref(d2h))
+        lib().surf_context_destroy(ctx)
+        e2e = {'value': tests_per_step / dt, 'unit': 'tests/s', 'h2d_bytes_per_step': int(h2d.value) * world,
+               'd2h_bytes_per_step': int(d2h.value) * world, 'ms_per_step': dt * 1e3, 'frames_per_s': 1.0 / dt,
+               'api': 'surf_render_backward_host (C ABI, pinned host buffers)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_baseline, _, _ = run_cpu_baseline(scene, target_scene, budget_s=20.0, threads=os.cpu_count() or 1)
+
+    line = {'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)', 'value': value, 'unit': 'tests/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss),
+            'gpu_launches': int(sum(launches)), 'gpu_launches_per_step': int(launches[-1]) if launches else 0,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
+            'wall_s_timed_region': wall}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

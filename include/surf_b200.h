@@ -98,7 +98,8 @@ typedef struct SurfOptions {
     int32_t shadow;          /* renderer.py:291-314 */
     int32_t pixel_begin;     /* render flat pixels [pixel_begin, pixel_end) of the H*W row-major grid;     */
     int32_t pixel_end;       /* 0,0 = whole frame.  Output arrays are sized for the range (row bands / GPU) */
-    int32_t forced_nearest;  /* backward only: 1 = trust `nearest`/`hit` given by the caller (parity harness) */
+    int32_t forced_nearest;  /* backward only: 2 = `workspace` still holds this frame's forward state (camera,
+                                rays, shadow visibility), skip recomputing it; 0/1 = recompute               */
     int32_t pixels_per_thread; /* 0 = library default; tuning knob for the intersection kernel (2,4,8)      */
     int32_t chunk_prims;     /* 0 = library default; primitives staged per TMA bulk copy (multiple of 32)   */
     int32_t math_mode;       /* 0 = default (packed f32x2 FFMA2 filter), 1 = scalar FFMA filter              */
@@ -144,8 +145,9 @@ typedef struct SurfSceneGrads {
 int surf_abi_version(void);
 const char* surf_last_error(void);
 
-/* bytes of device scratch surf_forward / surf_backward need for this problem size */
-size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels);
+/* bytes of device scratch surf_forward / surf_backward need for this problem size
+ * (n_lights and shadow only matter when options.shadow is set: + 4*L*n bytes of visibility) */
+size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow);
 
 /* ---- device-pointer API (what the torch autograd.Function calls) ---- */
 int surf_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
@@ -180,6 +182,11 @@ int surf_context_last_transfer(const SurfContext* ctx, uint64_t* h2d_bytes, uint
 double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream);
 /* number of kernels the last device/host call on this thread launched */
 int surf_last_launch_count(void);
+/* per-kernel device timing with CUDA events recorded on the launching stream (off by default).
+ * which: 0 = intersection (k_intersect), 1 = shading (k_shade), 2 = backward (k_backward).
+ * surf_last_kernel_ms synchronises on that kernel's end event; returns <0 when nothing was recorded. */
+void surf_set_kernel_timing(int32_t enabled);
+double surf_last_kernel_ms(int32_t which);
 
 #ifdef __cplusplus
 }

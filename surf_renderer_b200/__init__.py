@@ -1,0 +1,9 @@
+"""surf_renderer_b200 - B200 (sm_100a) implementation of DiffRend's ray-cast render path.
+
+    from surf_renderer_b200 import render      # instead of: from diffrend.torch.renderer import render
+
+See DESIGN.md for the path and its boundary, INTEGRATION.md for the reference-side binding.
+"""
+from .renderer import get_param_value, render, render_flat   # noqa: F401
+
+__all__ = ['render', 'render_flat', 'get_param_value']

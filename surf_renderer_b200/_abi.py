@@ -65,7 +65,7 @@ class SurfSceneGrads(C.Structure):
 SYMBOLS = {
     'surf_abi_version': (C.c_int, []),
     'surf_last_error': (C.c_char_p, []),
-    'surf_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'surf_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'surf_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
     'surf_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
@@ -82,6 +82,8 @@ SYMBOLS = {
     'surf_context_last_transfer': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     'surf_fma_peak': (C.c_double, [C.c_int32, C.c_int32, C.c_void_p]),
     'surf_last_launch_count': (C.c_int, []),
+    'surf_set_kernel_timing': (None, [C.c_int32]),
+    'surf_last_kernel_ms': (C.c_double, [C.c_int32]),
 }
 
 

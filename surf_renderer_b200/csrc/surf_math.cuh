@@ -433,9 +433,11 @@ SURF_HD void composite(const float lit[3], bool hit, const float* gamma, float o
 // ---------------------------------------------------------------------------------------------------
 // backward (derived from the reference graph).  `Sink` receives the additive gradient
 // contributions; the kernel's sink reduces + atomically adds, the emulation's sink adds into doubles.
-//   sink.prim(set, local, slot, v)   slot 0..2 = pos / v0 / centre, 3..5 = normal, 6 = radius (sphere)
 //   sink.albedo(m, c, v) .coeff(m, c, v) .light_pos(l, c, v) .atten(l, c, v) .color(row, c, v)
 //   sink.ambient(c, v) .gamma(v)
+//   sink.end_light(l, colour_row)     called once per light by every pixel (warp-uniform point)
+//   sink.end_pixel(set, local, idx, m, g7)   g7[0..2] = d/d(pos | v0 | centre), [3..5] = d/d(normal),
+//                                            [6] = d/d(radius) (sphere); called once by every pixel
 // ---------------------------------------------------------------------------------------------------
 struct PixelGrads {           // incoming output gradients at one pixel
     float image[3]; float depth; float pos[3]; float normal[3];
@@ -443,134 +445,138 @@ struct PixelGrads {           // incoming output gradients at one pixel
 
 template <class Sink>
 SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int idx, bool hit,
-                            float near_clip, float far_clip, ShadeFlags fl, const float* visibility,
-                            const PixelGrads& g, Sink& sink) {
-    (void)near_clip; (void)far_clip;
+                            ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink) {
+    // Control flow is kept uniform across pixels (no early exits around sink calls): the device sink
+    // reduces across the warp inside end_light()/end_pixel(), so every lane must reach them.  Inactive
+    // pixels compute on (finite-or-not) garbage and contribute selected zeros.
     Fragment f = fragment_at(sc, idx, o, d);
     const SetView& sv = sc.sets[f.set];
     Vec3 P = f.P, n = f.n;
     Vec3 gP = v3(g.pos[0], g.pos[1], g.pos[2]);
     Vec3 gn = v3(g.normal[0], g.normal[1], g.normal[2]);
 
-    if (hit) {
-        const int m = f.mat;
-        const float* A = sc.albedo + 3 * m;
-        const float kd = sc.coeffs[3 * m + 0], ks = sc.coeffs[3 * m + 1], sh = sc.coeffs[3 * m + 2];
-        // forward recompute of the composite to get dLoss/dI
-        float lit[3];
-        shade_pixel(sc, eye, P, n, m, fl, visibility, lit);
-        float gI[3];
-        bool any = false;
+    const int m = f.mat;
+    const float* A = sc.albedo + 3 * m;
+    const float kd = sc.coeffs[3 * m + 0], ks = sc.coeffs[3 * m + 1], sh = sc.coeffs[3 * m + 2];
+    // forward recompute of the composite to get dLoss/dI (renderer.py:330-340 backwards)
+    float lit[3] = {0.f, 0.f, 0.f};
+    if (hit) shade_pixel(sc, eye, P, n, m, fl, visibility, lit);
+    float gI[3];
+    bool active = false;
+    float g_gamma = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        float Ic = lit[c];
+        gI[c] = 0.f;
+        if (hit && Ic > 0.f) {
+            if (sc.gamma) {
+                float gm = sc.gamma[0];
+                gI[c] = g.image[c] * gm * powf(Ic, gm - 1.f);
+                if (g.image[c] != 0.f) g_gamma += g.image[c] * powf(Ic, gm) * logf(Ic);
+            } else {
+                gI[c] = g.image[c];
+            }
+        }
+        active |= (gI[c] != 0.f);
+    }
+    sink.gamma(g_gamma);
+
+    float sv_len;
+    Vec3 Vv = vsub(eye, P);
+    Vec3 V = unit_eps(Vv, &sv_len);
+    float sg = 1.f;
+    if (fl.double_sided) {
+        float dp = dot_seq(V, n);
+        sg = dp > 0.f ? 1.f : (dp < 0.f ? -1.f : 0.f);
+    }
+    Vec3 gV = v3(0.f, 0.f, 0.f);
+    for (int l = 0; l < sc.n_lights; ++l) {
+        Vec3 lp = ld3(sc.light_pos + (size_t)l * sc.light_pos_stride);
+        Vec3 Lv = vsub(lp, P);
+        float dl = xsqrt(sq3_seq(Lv));
+        bool dl_nz = fabsf(dl) > 0.f;
+        float ddiv = dl_nz ? dl : 1.f;
+        Vec3 L = v3(Lv.x / ddiv, Lv.y / ddiv, Lv.z / ddiv);
+        float d2 = dl * dl;
+        float pw = fl.use_quartic ? d2 * d2 : d2;
+        const float* at = sc.light_atten + 3 * l;
+        float den = at[0] + dl * at[1] + pw * at[2];
+        bool den_nz = fabsf(den) > 0.f;
+        float att = 1.f / (den_nz ? den : 1.f);
+        float Draw = att * fdot(n, L);
+        Vec3 inc = vneg(L);
+        float s = fdot(inc, n);
+        Vec3 R = faxpy(-2.f * s, n, inc);
+        float Sraw = fdot(V, R);
+        float Dsg = sg * Draw, Ssg = sg * Sraw;
+        float Dp = Dsg > 0.f ? Dsg : 0.f;
+        float Sp = Ssg > 0.f ? Ssg : 0.f;
+        float spec = powf(Sp, sh);
+        float scal = kd * Dp + ks * spec;
+        const int crow = sc.light_color_idx[l];
+        const float* col = sc.colors + 3 * crow;
+        float vis = visibility ? visibility[l] : 1.f;
+        float g_scal = 0.f;
         for (int c = 0; c < 3; ++c) {
-            float Ic = lit[c];
-            gI[c] = 0.f;
-            if (Ic > 0.f) {
-                if (sc.gamma) {
-                    float gm = sc.gamma[0];
-                    float outc = powf(Ic, gm);
-                    gI[c] = g.image[c] * gm * powf(Ic, gm - 1.f);
-                    if (g.image[c] != 0.f) sink.gamma(g.image[c] * outc * logf(Ic));
-                } else {
-                    gI[c] = g.image[c];
-                }
-            }
-            any |= (gI[c] != 0.f);
+            float tint = col[c] * A[c] * vis;
+            g_scal += gI[c] * tint;
+            float g_tint = gI[c] * scal * vis;
+            sink.color(crow, c, active ? g_tint * A[c] : 0.f);
+            sink.albedo(m, c, active ? g_tint * col[c] + gI[c] * sc.ambient[c] : 0.f);
+            sink.ambient(c, active ? gI[c] * A[c] : 0.f);
         }
-        if (any) {
-            float sv_len;
-            Vec3 Vv = vsub(eye, P);
-            Vec3 V = unit_eps(Vv, &sv_len);
-            float sg = 1.f;
-            if (fl.double_sided) {
-                float dp = dot_seq(V, n);
-                sg = dp > 0.f ? 1.f : (dp < 0.f ? -1.f : 0.f);
-            }
-            Vec3 gV = v3(0.f, 0.f, 0.f);
-            for (int l = 0; l < sc.n_lights; ++l) {
-                Vec3 lp = ld3(sc.light_pos + (size_t)l * sc.light_pos_stride);
-                Vec3 Lv = vsub(lp, P);
-                float dl = xsqrt(sq3_seq(Lv));
-                bool dl_nz = fabsf(dl) > 0.f;
-                float ddiv = dl_nz ? dl : 1.f;
-                Vec3 L = v3(Lv.x / ddiv, Lv.y / ddiv, Lv.z / ddiv);
-                float d2 = dl * dl;
-                float pw = fl.use_quartic ? d2 * d2 : d2;
-                const float* at = sc.light_atten + 3 * l;
-                float den = at[0] + dl * at[1] + pw * at[2];
-                bool den_nz = fabsf(den) > 0.f;
-                float att = 1.f / (den_nz ? den : 1.f);
-                float Draw = att * fdot(n, L);
-                Vec3 inc = vneg(L);
-                float s = fdot(inc, n);
-                Vec3 R = faxpy(-2.f * s, n, inc);
-                float Sraw = fdot(V, R);
-                float Dsg = sg * Draw, Ssg = sg * Sraw;
-                float Dp = Dsg > 0.f ? Dsg : 0.f;
-                float Sp = Ssg > 0.f ? Ssg : 0.f;
-                float spec = powf(Sp, sh);
-                float scal = kd * Dp + ks * spec;
-                const int crow = sc.light_color_idx[l];
-                const float* col = sc.colors + 3 * crow;
-                float vis = visibility ? visibility[l] : 1.f;
-                float g_scal = 0.f;
-                for (int c = 0; c < 3; ++c) {
-                    float tint = col[c] * A[c] * vis;
-                    g_scal += gI[c] * tint;
-                    float g_tint = gI[c] * scal * vis;
-                    sink.color(crow, c, g_tint * A[c]);
-                    sink.albedo(m, c, g_tint * col[c] + gI[c] * sc.ambient[c]);
-                    sink.ambient(c, gI[c] * A[c]);
-                }
-                sink.coeff(m, 0, g_scal * Dp);
-                sink.coeff(m, 1, g_scal * spec);
-                float g_spec = g_scal * ks;
-                float g_Sp = 0.f;
-                if (Sp > 0.f) {
-                    sink.coeff(m, 2, g_spec * spec * logf(Sp));
-                    if (sh != 0.f) g_Sp = g_spec * sh * powf(Sp, sh - 1.f);
-                }
-                float g_D = (Dsg > 0.f) ? g_scal * kd * sg : 0.f;
-                float g_S = (Ssg > 0.f) ? g_Sp * sg : 0.f;
-                // D = n . (att L)
-                gn = faxpy(g_D * att, L, gn);
-                Vec3 gL = vscale(g_D * att, n);
-                float g_att = g_D * fdot(n, L);
-                // S = V . R ;  R = (-2 s) n + inc ; s = inc . n ; inc = -L
-                gV = faxpy(g_S, R, gV);
-                Vec3 gR = vscale(g_S, V);
-                float g_s = -2.f * fdot(gR, n);
-                gn = faxpy(-2.f * s, gR, gn);
-                Vec3 g_inc = faxpy(g_s, n, gR);
-                gn = faxpy(g_s, inc, gn);
-                gL = v3(gL.x - g_inc.x, gL.y - g_inc.y, gL.z - g_inc.z);
-                // att = 1/den
-                float g_den = den_nz ? -g_att * att * att : 0.f;
-                sink.atten(l, 0, g_den);
-                sink.atten(l, 1, g_den * dl);
-                sink.atten(l, 2, g_den * pw);
-                float dpw = fl.use_quartic ? 4.f * d2 * dl : 2.f * dl;
-                float g_dl = g_den * (at[1] + at[2] * dpw);
-                // L = Lv / dl ; dl = |Lv|
-                Vec3 gLv;
-                if (dl_nz) {
-                    float gl_dot = fdot(gL, L);
-                    gLv = v3((gL.x - gl_dot * L.x) / dl + g_dl * L.x, (gL.y - gl_dot * L.y) / dl + g_dl * L.y,
-                             (gL.z - gl_dot * L.z) / dl + g_dl * L.z);
-                } else {
-                    gLv = gL;
-                }
-                sink.light_pos(l, 0, gLv.x); sink.light_pos(l, 1, gLv.y); sink.light_pos(l, 2, gLv.z);
-                gP = v3(gP.x - gLv.x, gP.y - gLv.y, gP.z - gLv.z);
-            }
-            // V = Vv / sv_len
-            float gv_dot = fdot(gV, V);
-            Vec3 gVv = v3((gV.x - gv_dot * V.x) / sv_len, (gV.y - gv_dot * V.y) / sv_len,
-                          (gV.z - gv_dot * V.z) / sv_len);
-            gP = v3(gP.x - gVv.x, gP.y - gVv.y, gP.z - gVv.z);
+        sink.coeff(m, 0, active ? g_scal * Dp : 0.f);
+        sink.coeff(m, 1, active ? g_scal * spec : 0.f);
+        float g_spec = g_scal * ks;
+        float g_Sp = 0.f, g_sh = 0.f;
+        if (Sp > 0.f) {
+            g_sh = g_spec * spec * logf(Sp);
+            if (sh != 0.f) g_Sp = g_spec * sh * powf(Sp, sh - 1.f);
         }
+        sink.coeff(m, 2, active ? g_sh : 0.f);
+        float g_D = (active && Dsg > 0.f) ? g_scal * kd * sg : 0.f;
+        float g_S = (active && Ssg > 0.f) ? g_Sp * sg : 0.f;
+        // D = n . (att L)
+        Vec3 gL = vscale(g_D * att, n);
+        float g_att = g_D * fdot(n, L);
+        // S = V . R ;  R = (-2 s) n + inc ; s = inc . n ; inc = -L
+        Vec3 gR = vscale(g_S, V);
+        float g_s = -2.f * fdot(gR, n);
+        Vec3 g_inc = faxpy(g_s, n, gR);
+        gL = v3(gL.x - g_inc.x, gL.y - g_inc.y, gL.z - g_inc.z);
+        // att = 1/den
+        float g_den = den_nz ? -g_att * att * att : 0.f;
+        float dpw = fl.use_quartic ? 4.f * d2 * dl : 2.f * dl;
+        float g_dl = g_den * (at[1] + at[2] * dpw);
+        // L = Lv / dl ; dl = |Lv|
+        Vec3 gLv = gL;
+        if (dl_nz) {
+            float gl_dot = fdot(gL, L);
+            gLv = v3((gL.x - gl_dot * L.x) / dl + g_dl * L.x, (gL.y - gl_dot * L.y) / dl + g_dl * L.y,
+                     (gL.z - gl_dot * L.z) / dl + g_dl * L.z);
+        }
+        if (active) {
+            gn = faxpy(g_D * att, L, gn);
+            gV = faxpy(g_S, R, gV);
+            gn = faxpy(-2.f * s, gR, gn);
+            gn = faxpy(g_s, inc, gn);
+            gP = v3(gP.x - gLv.x, gP.y - gLv.y, gP.z - gLv.z);
+        }
+        sink.atten(l, 0, active ? g_den : 0.f);
+        sink.atten(l, 1, active ? g_den * dl : 0.f);
+        sink.atten(l, 2, active ? g_den * pw : 0.f);
+        sink.light_pos(l, 0, active ? gLv.x : 0.f);
+        sink.light_pos(l, 1, active ? gLv.y : 0.f);
+        sink.light_pos(l, 2, active ? gLv.z : 0.f);
+        sink.end_light(l, crow);
+    }
+    if (active) {   // V = Vv / sv_len
+        float gv_dot = fdot(gV, V);
+        gP = v3(gP.x - (gV.x - gv_dot * V.x) / sv_len, gP.y - (gV.y - gv_dot * V.y) / sv_len,
+                gP.z - (gV.z - gv_dot * V.z) / sv_len);
     }
 
     const float g_depth = hit ? g.depth : 0.f;
+    float out7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (f.kind == KIND_SPHERE) {
         Vec3 c = ld3(sv.pos + (size_t)f.local * sv.pos_stride);
         float r = sv.radius[f.local];
@@ -590,8 +596,7 @@ SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int i
                 gr = gt * r / Gd;
             }
         }
-        sink.prim(f.set, f.local, 0, gc.x); sink.prim(f.set, f.local, 1, gc.y); sink.prim(f.set, f.local, 2, gc.z);
-        sink.prim(f.set, f.local, 6, gr);
+        out7[0] = gc.x; out7[1] = gc.y; out7[2] = gc.z; out7[6] = gr;
     } else {
         size_t prow = (sv.kind == KIND_TRIANGLE) ? (size_t)f.local * 3 * sv.pos_stride
                                                  : (size_t)f.local * sv.pos_stride;
@@ -606,11 +611,12 @@ SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int i
         gn = faxpy(gb, d, gn);
         Vec3 gp = vscale(ga, pc.n);
         float gdot = fdot(gn, pc.n);
-        Vec3 gnr = v3((gn.x - gdot * pc.n.x) / pc.len, (gn.y - gdot * pc.n.y) / pc.len,
-                      (gn.z - gdot * pc.n.z) / pc.len);
-        sink.prim(f.set, f.local, 0, gp.x); sink.prim(f.set, f.local, 1, gp.y); sink.prim(f.set, f.local, 2, gp.z);
-        sink.prim(f.set, f.local, 3, gnr.x); sink.prim(f.set, f.local, 4, gnr.y); sink.prim(f.set, f.local, 5, gnr.z);
+        out7[0] = gp.x; out7[1] = gp.y; out7[2] = gp.z;
+        out7[3] = (gn.x - gdot * pc.n.x) / pc.len;
+        out7[4] = (gn.y - gdot * pc.n.y) / pc.len;
+        out7[5] = (gn.z - gdot * pc.n.z) / pc.len;
     }
+    sink.end_pixel(f.set, f.local, idx, m, out7);
 }
 
 // ---------------------------------------------------------------------------------------------------

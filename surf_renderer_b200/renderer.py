@@ -1,0 +1,143 @@
+"""Drop-in for ``diffrend.torch.renderer.render`` (reference: diffrend/torch/renderer.py:136-355).
+
+Same call: ``render(scene: dict, **params) -> dict`` with the reference's scene-dict schema and
+kwargs (looked up like ``get_param_value``, diffrend/utils/utils.py:4-10).  Returned keys: ``image [H,W,3]``,
+``depth [H,W]``, ``normal [H,W,3]``, ``pos [H,W,3]``, ``nearest [H,W] int64``, ``ray_dir`` and ``ray_dist``
+(always ``None``: in the reference it is a last-tile artefact no caller reads).  ``image/depth/normal/pos`` are
+autograd-connected to every float tensor of the scene except the camera (not differentiable in the reference
+either, utils.py:476).  All compute runs in libsurf_b200.so on the current CUDA device and stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from ._lib import check, lib
+from .marshal import Marshalled, make_options
+
+
+def get_param_value(key, dict_var, default_val, required=False):
+    """diffrend/utils/utils.py:4-10."""
+    if key in dict_var:
+        return dict_var[key]
+    elif required:
+        raise ValueError('Missing required key {}'.format(key))
+    return default_val
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _RenderFn(torch.autograd.Function):
+    """forward: surf_forward; backward: surf_backward (recompute-the-winner analytic gradients)."""
+
+    @staticmethod
+    def forward(ctx, m, params, pixel_range, *floats):
+        dev = floats[0].device
+        n_total = m.n_pixels
+        p0, p1 = pixel_range if pixel_range is not None else (0, n_total)
+        n = p1 - p0
+        opt = make_options(params, (p0, p1))
+        shadow = int(opt.shadow)
+        n_lights = int(floats[m.i_light_pos].shape[0])
+        ws_bytes = lib().surf_workspace_bytes(m.total_prims, n, n_lights, shadow)
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        image = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        normal = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        pos = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        nearest = torch.empty(n, dtype=torch.int64, device=dev)
+        ray_dir = torch.empty(3, n if m.proj == 0 else 1, dtype=torch.float32, device=dev)
+        out = _abi.SurfOutputs(image.data_ptr(), depth.data_ptr(), normal.data_ptr(), pos.data_ptr(),
+                               nearest.data_ptr(), ray_dir.data_ptr())
+        sc, cam = m.c_scene(floats), m.c_camera()
+        with torch.cuda.device(dev):
+            check(lib().surf_forward(C.byref(sc), C.byref(cam), C.byref(opt), workspace.data_ptr(), ws_bytes,
+                                     C.byref(out), _stream_ptr()))
+        ctx.m, ctx.params, ctx.range = m, params, (p0, p1)
+        ctx.workspace = workspace
+        ctx.save_for_backward(nearest, depth, *floats)
+        ctx.mark_non_differentiable(nearest, ray_dir)
+        return image, depth, normal, pos, nearest, ray_dir
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_normal, g_pos, _g_nearest, _g_ray):
+        saved = ctx.saved_tensors
+        nearest, depth, floats = saved[0], saved[1], saved[2:]
+        m = ctx.m
+        dev = depth.device
+        opt = make_options(ctx.params, ctx.range)
+        opt.forced_nearest = 2          # ctx.workspace still holds this frame's camera state and rays
+        grads = [torch.zeros_like(t) if ctx.needs_input_grad[3 + i] else None for i, t in enumerate(floats)]
+
+        def c(t):
+            return None if t is None else t.contiguous()
+
+        g_image, g_depth, g_normal, g_pos = c(g_image), c(g_depth), c(g_normal), c(g_pos)
+        og = _abi.SurfOutGrads(*[(t.data_ptr() if t is not None else None)
+                                 for t in (g_image, g_depth, g_normal, g_pos)])
+        sg = m.c_grads(grads)
+        sc, cam = m.c_scene(floats), m.c_camera()
+        ws = ctx.workspace
+        with torch.cuda.device(dev):
+            check(lib().surf_backward(C.byref(sc), C.byref(cam), C.byref(opt), ws.data_ptr(), ws.numel(),
+                                      nearest.data_ptr(), depth.data_ptr(), C.byref(og), C.byref(sg),
+                                      _stream_ptr()))
+        return (None, None, None) + tuple(grads)
+
+
+def _resolve_device(scene):
+    """The scene's device, like the reference where every tensor lives on the device chosen at import
+    (diffrend/torch/utils.py:7-15).  CPU scenes are moved to the current CUDA device."""
+    def find(v):
+        if isinstance(v, torch.Tensor) and v.is_cuda:
+            return v.device
+        if isinstance(v, dict):
+            for x in v.values():
+                d = find(x)
+                if d is not None:
+                    return d
+        return None
+    dev = find(scene)
+    if dev is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('surf_renderer_b200.render needs a CUDA device (B200); there is no CPU path')
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
+def render_flat(scene, pixel_range=None, **params):
+    """render() on a contiguous flat pixel range [p0, p1) of the row-major grid (row bands for multi-GPU).
+    Returns flat tensors (image [n,3], depth [n], normal [n,3], pos [n,3], nearest [n], ray_dir) and (H, W)."""
+    if get_param_value('vis_stat', params, False):
+        raise RuntimeError('Removed Support for vis_stat')                      # renderer.py:233-234
+    if get_param_value('norm_depth_image_only', params, False):
+        raise NotImplementedError('norm_depth_image_only is broken in the reference under the default '
+                                  'tiling (renderer.py:245-260 reads untiled temporaries)')
+    dev = _resolve_device(scene)
+    m = Marshalled(scene, dev)
+    outs = _RenderFn.apply(m, dict(params), pixel_range, *m.floats)
+    return outs, (m.height, m.width)
+
+
+def render(scene, **params):
+    """Render.  Reference: diffrend/torch/renderer.py:136 ``render(scene, **params)``.
+
+    params honoured: double_sided, use_quartic, shadow.  Accepted and semantically no-ops here: tiled, tile_size
+    (the pixel tiling only bounded the reference's [M,N] temporaries), backface_culling (the reference only
+    labels the scene, renderer.py:152-159 - output unchanged).  vis_stat raises RuntimeError like the
+    reference; norm_depth_image_only raises NotImplementedError.
+    """
+    (image, depth, normal, pos, nearest, ray_dir), (H, W) = render_flat(scene, None, **params)
+    return {
+        'image': image.view(H, W, 3),
+        'depth': depth.view(H, W),
+        'normal': normal.view(H, W, 3),
+        'pos': pos.view(H, W, 3),
+        'ray_dist': None,
+        'nearest': nearest.view(H, W),
+        'ray_dir': ray_dir,
+    }

@@ -64,7 +64,10 @@ struct HostSink {
         g_color.assign(s.n_colors * 3, 0); g_amb.assign(3, 0);
     }
     // the interface backward_pixel() writes to
-    void prim(int set, int local, int slot, float v) { g_prim[set][(size_t)local * 7 + slot] += v; }
+    void end_light(int, int) {}
+    void end_pixel(int set, int local, int, int, const float* g7) {
+        for (int k = 0; k < 7; ++k) g_prim[set][(size_t)local * 7 + k] += g7[k];
+    }
     void albedo(int m, int c, float v) { g_albedo[m * 3 + c] += v; }
     void coeff(int m, int c, float v) { g_coeff[m * 3 + c] += v; }
     void light_pos(int l, int c, float v) { g_lpos[l * 3 + c] += v; }
@@ -176,7 +179,7 @@ int emul_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptio
         }
         g.depth = og->depth ? og->depth[k] : 0.f;
         const bool hit = depth[k] <= cs.far_clip && depth[k] >= cs.near_clip;
-        backward_pixel(sc, eye, o, d, (int)nearest[k], hit, cs.near_clip, cs.far_clip, fl, nullptr, g, sink);
+        backward_pixel(sc, eye, o, d, (int)nearest[k], hit, fl, nullptr, g, sink);
     }
     for (int s = 0; s < sc.n_sets; ++s) {
         const SetView& sv = sc.sets[s];

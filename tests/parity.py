@@ -1,0 +1,93 @@
+"""Parity comparison helpers (tests only): candidate render output vs oracle/golden output.
+
+Bar (BASELINE.json north_star): nearest index bit-exact except at documented epsilon-ties (oracle/margin64.py,
+SURVEY A.7); image / depth / pos / normal within 1e-4 relative / 1e-5 absolute on non-tie pixels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import margin64
+
+RTOL = 1e-4
+ATOL = 1e-5
+MAX_TIE_FRACTION = 5e-3     # of hit pixels
+
+
+def _to_np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def ray_for_pixel(scene, ref_ray_dir, flat_index, oracle_origin=None):
+    """float64 ray of a flat pixel from the oracle's fp32 rays."""
+    rd = _to_np(ref_ray_dir).astype(np.float64)
+    if rd.shape[1] > 1:
+        d = rd[:, flat_index]
+        o = _to_np(scene['camera']['eye']).astype(np.float64)[:3]
+    else:
+        d = rd[:, 0]
+        o = _to_np(oracle_origin).astype(np.float64)[flat_index]
+    return o, d
+
+
+def compare_forward(cand, ref, scene, ortho_origins=None, rtol=RTOL, atol=ATOL, check_ray=True):
+    """Returns a report dict; raises AssertionError on a parity violation."""
+    near, far = float(scene['camera']['near']), float(scene['camera']['far'])
+    c_near = _to_np(cand['nearest']).reshape(-1)
+    r_near = _to_np(ref['nearest']).reshape(-1)
+    c_depth = _to_np(cand['depth']).reshape(-1)
+    r_depth = _to_np(ref['depth']).reshape(-1)
+    c_hit, r_hit = c_depth <= far, r_depth <= far
+    mism = np.nonzero((c_near != r_near) | (c_hit != r_hit))[0]
+    ties = {}
+    for k in mism:
+        o, d = ray_for_pixel(scene, ref['ray_dir'], int(k), ortho_origins)
+        ok, why = margin64.is_excused(scene, o, d, int(r_near[k]), bool(r_hit[k]), int(c_near[k]), bool(c_hit[k]), near, far)
+        assert ok, ('pixel %d: nearest ref=%d(hit=%s, depth=%r) cand=%d(hit=%s, depth=%r) is not an epsilon-tie'
+                    % (k, r_near[k], r_hit[k], r_depth[k], c_near[k], c_hit[k], c_depth[k]))
+        ties[why] = ties.get(why, 0) + 1
+    n_hit = max(1, int(r_hit.sum()))
+    assert len(mism) <= max(2, MAX_TIE_FRACTION * n_hit), 'too many tie pixels: %d of %d hit pixels' % (len(mism), n_hit)
+    good = np.ones(c_near.shape[0], dtype=bool)
+    good[mism] = False
+    worst = {}
+    for key, width, hit_only in (('depth', 1, False), ('image', 3, False), ('pos', 3, True), ('normal', 3, True)):
+        a = _to_np(cand[key]).reshape(-1, width).astype(np.float64)
+        b = _to_np(ref[key]).reshape(-1, width).astype(np.float64)
+        sel = good & r_hit if hit_only else good
+        if key in ('pos', 'normal') and not hit_only:
+            sel = good
+        a, b = a[sel], b[sel]
+        finite = np.isfinite(b).all(axis=1)
+        a, b = a[finite], b[finite]
+        err = np.abs(a - b) - (atol + rtol * np.abs(b))
+        worst[key] = float(np.abs(a - b).max()) if a.size else 0.0
+        assert not (err > 0).any(), '%s: max abs diff %.3g exceeds %g + %g*|ref| at %d values' % (
+            key, np.abs(a - b).max(), atol, rtol, int((err > 0).sum()))
+    # miss pixels report primitive 0's plane hit / normal: looser, they are far-away garbage by design
+    if check_ray and 'ray_dir' in cand and cand['ray_dir'] is not None:
+        a, b = _to_np(cand['ray_dir']).astype(np.float64), _to_np(ref['ray_dir']).astype(np.float64)
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert np.abs(a - b).max() <= 5e-7, 'ray_dir differs by %.3g' % np.abs(a - b).max()
+    return {'mismatch_pixels': int(len(mism)), 'ties': ties, 'hit_pixels': int(r_hit.sum()), 'worst': worst,
+            'good_mask': good}
+
+
+def compare_grads(cand, ref, rtol=1e-4, atol_scale=1e-5, skip=()):
+    """cand/ref: {leaf name: array}.  Tolerance: 1e-4 relative to the element, plus 1e-5 of the leaf's max |grad|
+    (float atomics reorder the sum, so tiny elements carry the noise of the large ones)."""
+    worst = {}
+    for k, exp in ref.items():
+        if k in skip:
+            continue
+        got = _to_np(cand[k]).astype(np.float64)
+        exp = _to_np(exp).astype(np.float64)
+        assert got.shape == exp.shape, (k, got.shape, exp.shape)
+        scale = float(np.nanmax(np.abs(exp))) if exp.size else 0.0
+        err = np.abs(got - exp)
+        bound = atol_scale * max(scale, 1e-30) + rtol * np.abs(exp)
+        bad = err > bound
+        worst[k] = float(err.max() / max(scale, 1e-30)) if exp.size else 0.0
+        assert not bad.any(), '%s: %d elements off, worst %.3g (max |ref| %.3g)' % (k, int(bad.sum()), err.max(), scale)
+    return worst
