@@ -102,7 +102,8 @@ typedef struct SurfOptions {
                                 rays, shadow visibility), skip recomputing it; 0/1 = recompute               */
     int32_t pixels_per_thread; /* 0 = library default; tuning knob for the intersection kernel (2,4,8)      */
     int32_t chunk_prims;     /* 0 = library default; primitives staged per TMA bulk copy (multiple of 32)   */
-    int32_t math_mode;       /* 0 = default (packed f32x2 FFMA2 filter), 1 = scalar FFMA filter              */
+    int32_t math_mode;       /* disk filter: 0 = default (packed FFMA2, grouped branch), 1 = scalar FFMA,
+                                2 = packed FFMA2 with one branch per primitive                                */
 } SurfOptions;
 
 /* outputs for n = pixel_end - pixel_begin pixels (row-major).  Any pointer may be NULL to skip it. */

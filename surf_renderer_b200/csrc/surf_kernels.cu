@@ -30,10 +30,10 @@
 namespace surf {
 
 // ---------------------------------------------------------------------------------------------------
-// error handling / launch accounting (thread-local; the library keeps no other global state)
+// error handling (thread-local string) / launch accounting and optional timers (process-wide counters)
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string g_error;
-static thread_local int g_launches = 0;
+static int g_launches = 0;   // process-wide: autograd runs backward on its own thread
 
 // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
 struct KernelTimers {
@@ -42,7 +42,7 @@ struct KernelTimers {
     bool have[3] = {false, false, false};
     bool created = false;
 };
-static thread_local KernelTimers g_timers;
+static KernelTimers g_timers;   // process-wide (see g_launches)
 static void timer_mark(int which, int edge, cudaStream_t st) {
     if (!g_timers.enabled) return;
     if (!g_timers.created) {
@@ -83,6 +83,7 @@ struct Workspace {
     float* rays;                 // [3, n] SoA unit directions (perspective)
     unsigned long long* zbuf;    // [n] packed (depth key << 32 | primitive index)
     double* acc;                 // backward scalar accumulators
+    double* prim_acc;            // backward per-primitive accumulators [total_prims, 7]
     float* vis;                  // [L, n] shadow visibility
     size_t bytes;
 };
@@ -103,6 +104,7 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->rays = (float*)(p + off); off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
     ws->acc = (double*)(p + off); off += align_up((size_t)kMaxAccSlots * 8, 256);
+    ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
     ws->vis = (float*)(p + off);
     if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
     ws->bytes = off;
@@ -286,32 +288,73 @@ __device__ __forceinline__ void narrow(const IsectParams& prm, const SetView& sv
     }
 }
 
-template <int P, bool PACKED>
+// filter margin e = |(o-c) + t d|^2 - (r+slack)^2 of one disk for pixel pair q (two pixels per instruction)
+template <int P>
+__device__ __forceinline__ unsigned long long disk_margin2(const float4& A, const float4& B, const PixelRegs<P>& r, int q) {
+    const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z);
+    unsigned long long b2 = fma2(nz, r.dz[q], fma2(ny, r.dy[q], mul2(nx, r.dx[q])));
+    float b0, b1;
+    unpack2(b2, b0, b1);
+    unsigned long long t2 = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
+    unsigned long long rx = fma2(t2, r.dx[q], pack2(B.x, B.x));
+    unsigned long long ry = fma2(t2, r.dy[q], pack2(B.y, B.y));
+    unsigned long long rz = fma2(t2, r.dz[q], pack2(B.z, B.z));
+    return fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, pack2(B.w, B.w))));
+}
+
+// exact narrow phase of one pixel against one disk
+template <int P>
+__device__ __forceinline__ void narrow_one(const SetView& sv, int local, const float4& A, Vec3 eye, float near_clip,
+                                           float far_clip, PixelRegs<P>& r, int p) {
+    float t;
+    Vec3 d = ray_of<P>(r, p);
+    bool hit = exact_hit(sv, local, v3(A.x, A.y, A.z), A.w, eye, d, near_clip, far_clip, &t);
+    if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
+}
+
+// MODE 0: packed FFMA2 filter, G disks per branch (no per-primitive control dependency, ILP across disks)
+// MODE 1: scalar FFMA filter, one branch per disk          MODE 2: packed FFMA2 filter, one branch per disk
+template <int P, int MODE>
 __device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
                                             int local0, int count, Vec3 eye, float near_clip, float far_clip,
                                             PixelRegs<P>& r) {
-#pragma unroll 2
-    for (int i = 0; i < count; ++i) {
+    int i = 0;
+    if (MODE == 0) {
+        constexpr int G = (P >= 8) ? 2 : 4;
+        for (; i + G <= count; i += G) {
+            float e[G][P];
+            float m = INFINITY;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 A = s[2 * (i + g)];
+                const float4 B = s[2 * (i + g) + 1];
+#pragma unroll
+                for (int q = 0; q < P / 2; ++q) {
+                    unpack2(disk_margin2<P>(A, B, r, q), e[g][2 * q], e[g][2 * q + 1]);
+                    m = fminf(m, fminf(e[g][2 * q], e[g][2 * q + 1]));     // NaN-ignoring min: NaN margins are misses
+                }
+            }
+            if (m <= 0.f) {       // rare: some (disk, pixel) of this group passed the conservative filter
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float4 A = s[2 * (i + g)];
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        if (e[g][p] <= 0.f) narrow_one<P>(sv, local0 + i + g, A, eye, near_clip, far_clip, r, p);
+                }
+            }
+        }
+    }
+    for (; i < count; ++i) {
         const float4 A = s[2 * i];       // n.x n.y n.z numer      (LDS.128, warp-broadcast)
-        const float4 B = s[2 * i + 1];   // oc.x oc.y oc.z r2c
+        const float4 B = s[2 * i + 1];   // oc.x oc.y oc.z -(r+slack)^2
         bool any = false;
-        if (PACKED) {
-            const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z);
-            const unsigned long long nm = pack2(A.w, A.w);
-            const unsigned long long ox = pack2(B.x, B.x), oy = pack2(B.y, B.y), oz = pack2(B.z, B.z);
+        if (MODE != 1) {
 #pragma unroll
             for (int q = 0; q < P / 2; ++q) {
-                unsigned long long b2 = fma2(nz, r.dz[q], fma2(ny, r.dy[q], mul2(nx, r.dx[q])));
-                float b0, b1;
-                unpack2(b2, b0, b1);
-                unsigned long long t2 = mul2(nm, pack2(rcp_approx(b0), rcp_approx(b1)));
-                unsigned long long rx = fma2(t2, r.dx[q], ox);
-                unsigned long long ry = fma2(t2, r.dy[q], oy);
-                unsigned long long rz = fma2(t2, r.dz[q], oz);
-                unsigned long long d2 = fma2(rz, rz, fma2(ry, ry, mul2(rx, rx)));
                 float e0, e1;
-                unpack2(d2, e0, e1);
-                any |= (e0 <= B.w) | (e1 <= B.w);
+                unpack2(disk_margin2<P>(A, B, r, q), e0, e1);
+                any |= (e0 <= 0.f) | (e1 <= 0.f);
             }
         } else {
 #pragma unroll
@@ -320,8 +363,7 @@ __device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetVie
                 float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
                 float t = A.w * rcp_approx(b);
                 float rx = fmaf(t, d.x, B.x), ry = fmaf(t, d.y, B.y), rz = fmaf(t, d.z, B.z);
-                float d2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
-                any |= d2 <= B.w;
+                any |= fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, B.w))) <= 0.f;
             }
         }
         if (any) narrow<P>(prm, sv, local0 + i, A, eye, near_clip, far_clip, r);
@@ -373,7 +415,7 @@ __device__ __forceinline__ void chunk_triangles(const IsectParams& prm, const Se
     }
 }
 
-template <int P, bool PACKED>
+template <int P, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant__ IsectParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
@@ -458,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant
         const SetView& sv = prm.sc.sets[set];
         mbar_wait(&full_bar[stage], parity);
         const float4* s = stage_buf + (size_t)stage * prm.stage_f4;
-        if (sv.kind == KIND_DISK) chunk_disks<P, PACKED>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+        if (sv.kind == KIND_DISK) chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         else if (sv.kind == KIND_TRIANGLE) chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         else chunk_planes<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
@@ -625,6 +667,7 @@ struct BackwardParams {
     GradPtrs gp;
     SlotMap sm;
     double* acc;
+    double* prim_acc;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -711,23 +754,14 @@ struct DeviceSink {
             }
         }
         if (lane == leader) {
-            const SetView& sv = p.sc.sets[set];
-            float* gpos = p.gp.prim_pos[set];
-            if (gpos) {
-                const size_t row = sv.kind == KIND_TRIANGLE ? (size_t)local * 3 * sv.pos_stride : (size_t)local * sv.pos_stride;
+            // double accumulation: per-pixel contributions of a grazing primitive cancel heavily, and a
+            // sequential fp32 atomic sum would carry ~1e-4 relative noise (the reference sums pairwise)
+            double* dst = p.prim_acc + (size_t)idx * 7;
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (v[c] != 0.f) atomicAdd(gpos + row + c, v[c]);
-            }
-            float* gnr = p.gp.prim_normal[set];
-            if (gnr && sv.kind != KIND_SPHERE) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (v[3 + c] != 0.f) atomicAdd(gnr + (size_t)local * sv.normal_stride + c, v[3 + c]);
-            }
-            float* grd = p.gp.prim_radius[set];
-            if (grd && sv.kind == KIND_SPHERE && v[6] != 0.f) atomicAdd(grd + local, v[6]);
+            for (int c = 0; c < 7; ++c)
+                if (v[c] != 0.f) atomicAdd(dst + c, (double)v[c]);
         }
+        (void)set; (void)local;
     }
 };
 
@@ -765,9 +799,28 @@ __global__ void __launch_bounds__(128) k_backward(const __grid_constant__ Backwa
 
 struct FinalizeParams {
     GradPtrs gp; SlotMap sm; const double* acc; int K, L, Cn, light_pos_stride;
+    SceneView sc; const double* prim_acc;
 };
-__global__ void k_backward_finalize(const __grid_constant__ FinalizeParams p) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant__ FinalizeParams p) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < p.sc.total) {      // per-primitive accumulators -> fp32 leaves (caller's strides)
+        const int s = find_set(p.sc, j);
+        const SetView& sv = p.sc.sets[s];
+        const int local = j - sv.first;
+        const double* a = p.prim_acc + (size_t)j * 7;
+        float* gpos = p.gp.prim_pos[s];
+        if (gpos) {
+            const size_t row = sv.kind == KIND_TRIANGLE ? (size_t)local * 3 * sv.pos_stride : (size_t)local * sv.pos_stride;
+            for (int c = 0; c < 3; ++c) gpos[row + c] += (float)a[c];
+        }
+        float* gnr = p.gp.prim_normal[s];
+        if (gnr && sv.kind != KIND_SPHERE)
+            for (int c = 0; c < 3; ++c) gnr[(size_t)local * sv.normal_stride + c] += (float)a[3 + c];
+        float* grd = p.gp.prim_radius[s];
+        if (grd && sv.kind == KIND_SPHERE) grd[local] += (float)a[6];
+        return;
+    }
+    j -= p.sc.total;
     if (j >= p.sm.total) return;
     const float v = (float)p.acc[j];
     if (j < p.sm.coeffs) { if (p.gp.albedo) p.gp.albedo[j - p.sm.albedo] += v; }
@@ -879,9 +932,9 @@ static int make_frame(const SurfScene* scene, const SurfCamera* camera, const Su
     return SURF_OK;
 }
 
-template <int P, bool PACKED>
+template <int P, int MODE>
 static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaStream_t st) {
-    auto kern = k_intersect<P, PACKED>;
+    auto kern = k_intersect<P, MODE>;
     SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timer_mark(0, 0, st);
     kern<<<grid, kThreads, smem, st>>>(prm);
@@ -932,10 +985,19 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     const long long items = (long long)prm.n_tiles * nchunks;
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    const bool packed = opt->math_mode == 0;
-    if (P == 2) return packed ? launch_intersect<2, true>(prm, grid, smem, st) : launch_intersect<2, false>(prm, grid, smem, st);
-    if (P == 4) return packed ? launch_intersect<4, true>(prm, grid, smem, st) : launch_intersect<4, false>(prm, grid, smem, st);
-    return packed ? launch_intersect<8, true>(prm, grid, smem, st) : launch_intersect<8, false>(prm, grid, smem, st);
+    const int mode = opt->math_mode;
+    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0, 1 or 2");
+#define SURF_DISPATCH(PP)                                                      \
+    if (P == PP) {                                                             \
+        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
+        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
+        return launch_intersect<PP, 2>(prm, grid, smem, st);                   \
+    }
+    SURF_DISPATCH(2)
+    SURF_DISPATCH(4)
+    SURF_DISPATCH(8)
+#undef SURF_DISPATCH
+    return fail(SURF_ERR_BAD_ARG, "unsupported pixels_per_thread");
 }
 
 static int run_common_prologue(const Frame& f, float* ray_out, cudaStream_t st, bool need_rays_and_zbuf) {
@@ -996,11 +1058,12 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
         if (f.shadow) return fail(SURF_ERR_UNSUPPORTED, "shadow backward needs the forward workspace (visibility)");
     }
     SURF_CUDA(cudaMemsetAsync(f.ws.acc, 0, sizeof(double) * kMaxAccSlots, st));
+    SURF_CUDA(cudaMemsetAsync(f.ws.prim_acc, 0, sizeof(double) * 7 * (size_t)f.sc.total, st));
     BackwardParams bp;
     bp.sc = f.sc; bp.cam = f.ws.cam; bp.rays = f.ws.rays; bp.vis = f.shadow ? f.ws.vis : nullptr;
     bp.nearest = (const long long*)nearest; bp.depth = depth;
     bp.g_image = og->image; bp.g_depth = og->depth; bp.g_normal = og->normal; bp.g_pos = og->pos;
-    bp.pix0 = f.pix0; bp.n = f.n; bp.fl = f.fl; bp.sm = sm; bp.acc = f.ws.acc;
+    bp.pix0 = f.pix0; bp.n = f.n; bp.fl = f.fl; bp.sm = sm; bp.acc = f.ws.acc; bp.prim_acc = f.ws.prim_acc;
     for (int s = 0; s < kMaxSets; ++s) {
         bp.gp.prim_pos[s] = sg->sets[s].pos; bp.gp.prim_normal[s] = sg->sets[s].normal; bp.gp.prim_radius[s] = sg->sets[s].radius;
     }
@@ -1010,8 +1073,9 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     k_backward<<<(f.n + 127) / 128, 128, 0, st>>>(bp);
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_backward");
-    FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride};
-    k_backward_finalize<<<(sm.total + 127) / 128, 128, 0, st>>>(fp);
+    FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
+                      f.sc, f.ws.prim_acc};
+    k_backward_finalize<<<(f.sc.total + sm.total + 127) / 128, 128, 0, st>>>(fp);
     SURF_LAUNCHED("k_backward_finalize");
     return SURF_OK;
 }

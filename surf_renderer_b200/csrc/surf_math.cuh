@@ -195,14 +195,15 @@ SURF_HD float f_round_up(double v) {     // smallest-ish float >= v
 }
 SURF_HD double dlen(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
 
-// DISK: A = (n, numer)  B = (o-c, (r+slack)^2).  Filter: |(o-c) + t d|^2 <= B.w with t ~ numer * rcp(n.d)
+// DISK: A = (n, numer)  B = (o-c, -(r+slack)^2).  Filter: |(o-c) + t d|^2 + B.w <= 0 with t ~ numer * rcp(n.d)
+// (the negated radius rides as the addend of the first FMA of the squared distance)
 SURF_HD void prep_disk(Vec3 p, Vec3 nraw, float r, Vec3 o, F4* A, F4* B) {
     PlaneConst pc = plane_const(p, nraw);
     *A = f4(pc.n.x, pc.n.y, pc.n.z, plane_numer(pc, o));
     double ocx = (double)o.x - p.x, ocy = (double)o.y - p.y, ocz = (double)o.z - p.z;
     double scale = dlen(o.x, o.y, o.z) + dlen(p.x, p.y, p.z) + dlen(ocx, ocy, ocz) + fabs((double)r);
     double rs = fabs((double)r) + 2e-6 * scale;
-    *B = f4((float)ocx, (float)ocy, (float)ocz, f_round_up(rs * rs * (1.0 + 1e-6)));
+    *B = f4((float)ocx, (float)ocy, (float)ocz, -f_round_up(rs * rs * (1.0 + 1e-6)));
 }
 SURF_HD void prep_plane(Vec3 p, Vec3 nraw, Vec3 o, F4* A) {
     PlaneConst pc = plane_const(p, nraw);
@@ -264,8 +265,8 @@ SURF_HD bool disk_filter(const F4& A, const F4& B, Vec3 d) {
     float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
     float t = A.w * approx_rcp(b);
     float rx = fmaf(t, d.x, B.x), ry = fmaf(t, d.y, B.y), rz = fmaf(t, d.z, B.z);
-    float d2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
-    return d2 <= B.w;
+    float e = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, B.w)));
+    return e <= 0.f;
 }
 SURF_HD bool sphere_filter(const F4& S, Vec3 d) {
     float hb = fmaf(S.z, d.z, fmaf(S.y, d.y, S.x * d.x));

@@ -1,0 +1,137 @@
+"""CPU tests of the boundary: the C-ABI shared library loads and exports every symbol include/surf_b200.h declares
+(no compute calls), the ctypes mirror matches the header, and the host-side scene marshalling / error behaviour
+mirrors the reference's render() (diffrend/torch/renderer.py:136-355)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import scene_io
+from surf_renderer_b200 import _abi, scenes as synth
+from surf_renderer_b200.marshal import Marshalled, make_options
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'surf_b200.h')
+
+
+def _header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return set(re.findall(r'\b(surf_[a-z_0-9]+)\s*\(', text))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from surf_renderer_b200 import build
+    so = build.build()
+    assert os.path.exists(so)
+    handle = C.CDLL(so)
+    declared = _header_functions()
+    assert declared == set(_abi.SYMBOLS), (declared ^ set(_abi.SYMBOLS))
+    for name in declared:
+        assert hasattr(handle, name), name
+    _abi.bind(handle)
+    assert handle.surf_abi_version() == _abi.SURF_ABI_VERSION           # host-only call, no GPU needed
+    assert handle.surf_workspace_bytes(1000, 4096, 3, 0) > 4096 * 20
+    assert handle.surf_workspace_bytes(1000, 4096, 3, 1) >= handle.surf_workspace_bytes(1000, 4096, 3, 0) + 4096 * 12
+
+
+def test_library_is_sm100a_with_tma_and_packed_fma():
+    """The shipped cubin is sm_100a and the hot kernel contains TMA bulk copies, mbarrier waits and FFMA2."""
+    import shutil
+    import subprocess
+    from surf_renderer_b200 import build
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', build.build()], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    for mnemonic in ('UBLKCP', 'SYNCS.PHASECHK', 'FFMA2', 'MUFU.RCP'):
+        assert mnemonic in sass, mnemonic
+
+
+def test_struct_layouts_match_c():
+    """ctypes mirrors must have the C compiler's layout: check sizes against a tiny C program."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu", sizeof(SurfPrimSet), sizeof(SurfScene), sizeof(SurfCamera), sizeof(SurfOptions), sizeof(SurfOutputs), sizeof(SurfOutGrads), sizeof(SurfSceneGrads));return 0;}\n' % HEADER
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, 'a.c')
+        open(c, 'w').write(src)
+        exe = os.path.join(d, 'a.out')
+        subprocess.check_call(['gcc', '-std=c99', c, '-o', exe])        # the header is plain C
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    mine = [C.sizeof(t) for t in (_abi.SurfPrimSet, _abi.SurfScene, _abi.SurfCamera, _abi.SurfOptions,
+                                  _abi.SurfOutputs, _abi.SurfOutGrads, _abi.SurfSceneGrads)]
+    assert sizes == mine
+
+
+def test_marshal_accepts_reference_style_inputs():
+    scene = synth.random_mixed_scene(5, homogeneous=True)
+    scene['camera']['viewport'] = torch.tensor([0, 0, 48, 40])          # make_torch_var turns lists into int64 tensors
+    scene['objects']['disk']['material_idx'] = scene['objects']['disk']['material_idx'].float()   # may arrive as float
+    scene['lights']['color_idx'] = scene['lights']['color_idx'].tolist()
+    scene['colors'] = scene['colors'].numpy()
+    scene['tonemap']['gamma'] = 0.8
+    m = Marshalled(scene, 'cpu')
+    assert (m.width, m.height) == (48, 40)
+    assert [s[0] for s in m.sets] == list(scene['objects'].keys())
+    assert m.sets[0][2] == 4 and m.sets[0][3] == 4                      # homogeneous strides kept, no copy
+    sc = m.c_scene()
+    assert sc.n_sets == 4 and sc.sets[0].kind == _abi.KIND['disk'] and sc.sets[0].pos_stride == 4
+    assert m.ints['objects/disk/material_idx'].dtype == torch.int32
+    assert sc.gamma is not None
+    cam = m.c_camera()
+    assert cam.proj == 0 and abs(cam.fovy - scene['camera']['fovy']) < 1e-12
+
+
+def test_marshal_errors_mirror_reference():
+    scene = synth.scene_basic(16, 12)
+    bad = scene_io.clone_scene(scene); bad['camera']['proj_type'] = 'fisheye'
+    with pytest.raises(ValueError):
+        Marshalled(bad, 'cpu')
+    bad = scene_io.clone_scene(scene); del bad['lights']['ambient']
+    with pytest.raises(KeyError):
+        Marshalled(bad, 'cpu')                                          # renderer.py:274 requires it
+    bad = scene_io.clone_scene(scene); del bad['materials']['coeffs']
+    with pytest.raises(KeyError):
+        Marshalled(bad, 'cpu')                                          # renderer.py:277
+    bad = scene_io.clone_scene(scene); bad['objects'] = {'torus': bad['objects']['disk']}
+    with pytest.raises(KeyError):
+        Marshalled(bad, 'cpu')                                          # utils.py:488
+    bad = scene_io.clone_scene(scene); bad['objects']['disk']['material_idx'] = torch.tensor([0, 1, 99])
+    with pytest.raises(IndexError):
+        Marshalled(bad, 'cpu')
+
+
+def test_render_kwargs_behaviour_without_gpu():
+    import surf_renderer_b200
+    scene = synth.scene_basic(16, 12)
+    with pytest.raises(RuntimeError):
+        surf_renderer_b200.render(scene, vis_stat=True)                 # renderer.py:233-234
+    with pytest.raises(NotImplementedError):
+        surf_renderer_b200.render(scene, norm_depth_image_only=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU path'):
+            surf_renderer_b200.render(scene)                            # fails loudly, never falls back
+    assert surf_renderer_b200.get_param_value('a', {'a': 3}, 5) == 3
+    assert surf_renderer_b200.get_param_value('b', {'a': 3}, 5) == 5
+    with pytest.raises(ValueError):
+        surf_renderer_b200.get_param_value('b', {}, None, required=True)
+
+
+def test_options_mapping():
+    opt = make_options({'double_sided': True, 'use_quartic': 1, 'shadow': False, 'tile_size': 17}, (10, 20))
+    assert (opt.double_sided, opt.use_quartic, opt.shadow, opt.pixel_begin, opt.pixel_end) == (1, 1, 0, 10, 20)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the package (or bench's non-baseline path) may import it."""
+    pkg = os.path.join(ROOT, 'surf_renderer_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text and 'torch_oracle' not in text, f
