@@ -41,7 +41,8 @@ def _f32(x):
     """utils.py:19-22 ``tch_var_f`` without the device switch (oracle is CPU)."""
     if isinstance(x, torch.Tensor):
         return x
-    return torch.tensor(np.asarray(x, dtype=np.float64), dtype=torch.float32)
+    # fp32 in normal use; tests may switch the default dtype to float64 for a high-precision variant
+    return torch.tensor(np.asarray(x, dtype=np.float64), dtype=torch.get_default_dtype())
 
 
 def blend(cond, a, b):
@@ -200,8 +201,18 @@ def hit_triangle(origin, direction, prim, want_normals=True):
     return pts, blend(inside, t, MISS_SENTINEL), normals_full
 
 
+SAFE_SPHERE = False   # tests only: NaN-free variant for gradient checks (see hit_sphere)
+
+
 def hit_sphere(origin, direction, prim, want_normals=True):
-    """utils.py:238-278 (always returns normals)."""
+    """utils.py:238-278 (always returns normals).
+
+    With SAFE_SPHERE (oracle-only switch, never set by the reference semantics tests) the arithmetic blends
+    are replaced by selects and sqrt never sees a masked zero, so autograd yields finite sphere gradients
+    (the reference's are NaN), and a sphere entirely behind the ray origin is a miss instead of
+    the reference's data-dependent phantom hit."""
+    if SAFE_SPHERE:
+        return _hit_sphere_safe(origin, direction, prim)
     c = prim['pos'][:, :3]
     oc = origin[None, ...] - c[:, None, :]
     r = prim['radius']
@@ -220,6 +231,27 @@ def hit_sphere(origin, direction, prim, want_normals=True):
     t2 = blend(real * (t2 >= 0), t2, big)
     t, _ = torch.min(torch.stack((t1, t2), dim=2), dim=2)
     t = blend(real, t, MISS_SENTINEL)
+    pts = along_ray(origin, direction, t)
+    normals = unit(pts - c[:, None, :])
+    return pts, t, normals
+
+
+def _hit_sphere_safe(origin, direction, prim):
+    c = prim['pos'][:, :3]
+    oc = origin[None, ...] - c[:, None, :]
+    r = prim['radius']
+    qa = torch.sum(direction ** 2, dim=0)
+    qb = 2 * torch.sum(oc * direction.permute(1, 0)[None, ...], dim=-1)
+    qc = (torch.sum(oc ** 2, dim=-1) - r[:, None] ** 2)
+    disc = qb ** 2 - 4 * qa * qc
+    real = disc >= 0
+    root = torch.sqrt(torch.where(real, disc, torch.ones_like(disc)))
+    inv = 1. / (2 * qa)
+    t1 = (-qb - root) * inv
+    t2 = (-qb + root) * inv
+    inf = torch.full_like(t1, float('inf'))
+    t = torch.minimum(torch.where(real & (t1 >= 0), t1, inf), torch.where(real & (t2 >= 0), t2, inf))
+    t = torch.where(torch.isfinite(t), t, torch.full_like(t, float(MISS_SENTINEL)))
     pts = along_ray(origin, direction, t)
     normals = unit(pts - c[:, None, :])
     return pts, t, normals

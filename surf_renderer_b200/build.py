@@ -14,7 +14,7 @@ DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('surf_math.cuh', 'surf_view.h'
     [os.path.join(PKG, '..', 'include', 'surf_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '--expt-relaxed-constexpr', '-shared', '-Xcompiler', '-fPIC,-ffp-contract=off']
+              '--expt-relaxed-constexpr', '-fmad=false', '-shared', '-Xcompiler', '-fPIC,-ffp-contract=off']
 
 
 def nvcc_path():

@@ -616,25 +616,7 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowPa
     const unsigned long long key = p.zbuf[k];
     const int self = key == kMissKey ? 0 : (int)(key & 0xFFFFFFFFull);
     Fragment f = fragment_at(p.sc, self, o, d);
-    Vec3 Lv = vsub(ld3(p.sc.light_pos + (size_t)l * p.sc.light_pos_stride), f.P);
-    // norm_p(., 2): pow(sum(x^2 + 0), 1/2)
-    float dist = xsqrt(sq3_seq(Lv));
-    Vec3 L = v3(xdiv(Lv.x, dist), xdiv(Lv.y, dist), xdiv(Lv.z, dist));
-    Vec3 so = vadd(f.P, vscale(0.1f, L));
-    float best_t = kMissSentinel;
-    int best = 0;
-    for (int s = 0; s < p.sc.n_sets; ++s) {
-        const SetView& sv = p.sc.sets[s];
-        for (int i = 0; i < sv.count; ++i) {
-            Vec3 nn; float numer, t;
-            plane_consts_for_origin(sv, i, so, &nn, &numer);
-            // geometric hit without the camera range; the shadow range is the open interval (0, dist)
-            bool hit = exact_hit(sv, i, nn, numer, so, L, -INFINITY, INFINITY, &t);
-            if (hit && t > 0.f && t < dist && t < best_t) { best_t = t; best = sv.first + i; }
-        }
-    }
-    const bool visible = (best_t == kMissSentinel) || (best == self);
-    p.vis[(size_t)l * p.n + k] = visible ? 1.f : 0.f;
+    p.vis[(size_t)l * p.n + k] = shadow_visibility(p.sc, f.P, self, l);
 }
 
 // ---------------------------------------------------------------------------------------------------

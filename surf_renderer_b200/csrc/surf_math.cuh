@@ -380,32 +380,48 @@ struct ShadeFlags { int double_sided, use_quartic; };
 
 SURF_HD float pow_like_torch(float base, float e) { return powf(base, e); }
 
+// everything the fragment shader derives for one light at one fragment, in the reference's op order; shared by
+// the forward shader and the backward so that the relu gates (D > 0, S > 0) are the same bits in both.
+struct LightEval {
+    Vec3 L, R, inc;          // unit light direction, reflected direction, incident (-L)
+    float dl, ddiv, d2, pw, den, att, s, D, S;   // D, S: raw (before sign flip / relu)
+    bool dl_nz, den_nz;
+};
+SURF_HD LightEval eval_light(const SceneView& sc, int l, Vec3 P, Vec3 n, Vec3 V, ShadeFlags fl) {
+    LightEval e;
+    Vec3 Lv = vsub(ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), P);
+    e.dl = xsqrt(sq3_seq(Lv));
+    e.dl_nz = fabsf(e.dl) > 0.f;
+    e.ddiv = e.dl_nz ? e.dl : 1.f;
+    e.L = v3(xdiv(Lv.x, e.ddiv), xdiv(Lv.y, e.ddiv), xdiv(Lv.z, e.ddiv));
+    e.d2 = xmul(e.dl, e.dl);
+    e.pw = fl.use_quartic ? xmul(e.d2, e.d2) : e.d2;
+    const float* at = sc.light_atten + 3 * l;
+    e.den = xadd(xadd(at[0], xmul(e.dl, at[1])), xmul(e.pw, at[2]));
+    e.den_nz = fabsf(e.den) > 0.f;
+    e.att = xdiv(1.f, e.den_nz ? e.den : 1.f);
+    e.D = dot_seq(n, vscale(e.att, e.L));
+    e.inc = vneg(e.L);
+    e.s = dot_seq(e.inc, n);
+    e.R = vadd(vscale(xmul(-2.f, e.s), n), e.inc);
+    e.S = dot_seq(V, e.R);
+    return e;
+}
+SURF_HD float facing_sign(Vec3 V, Vec3 n) {
+    float dp = dot_seq(V, n);
+    return dp > 0.f ? 1.f : (dp < 0.f ? -1.f : (dp == 0.f ? 0.f : dp));
+}
+
 SURF_HD void shade_pixel(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int mat, ShadeFlags fl,
                          const float* visibility /* [L] or null */, float rgb[3]) {
     const float* A = sc.albedo + 3 * mat;
     const float kd = sc.coeffs[3 * mat + 0], ks = sc.coeffs[3 * mat + 1], sh = sc.coeffs[3 * mat + 2];
     Vec3 V = unit_eps(vsub(eye, P), nullptr);
-    float sg = 1.f;
-    if (fl.double_sided) {
-        float dp = dot_seq(V, n);
-        sg = dp > 0.f ? 1.f : (dp < 0.f ? -1.f : (dp == 0.f ? 0.f : dp));
-    }
+    const float sg = fl.double_sided ? facing_sign(V, n) : 1.f;
     float acc[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < sc.n_lights; ++l) {
-        Vec3 Lv = vsub(ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), P);
-        float dl = xsqrt(sq3_seq(Lv));
-        float ddiv = fabsf(dl) > 0.f ? dl : 1.f;
-        Vec3 L = v3(xdiv(Lv.x, ddiv), xdiv(Lv.y, ddiv), xdiv(Lv.z, ddiv));
-        float d2 = xmul(dl, dl);
-        float pw = fl.use_quartic ? xmul(d2, d2) : d2;
-        const float* at = sc.light_atten + 3 * l;
-        float den = xadd(xadd(at[0], xmul(dl, at[1])), xmul(pw, at[2]));
-        float att = xdiv(1.f, fabsf(den) > 0.f ? den : 1.f);
-        float D = dot_seq(n, vscale(att, L));
-        Vec3 inc = vneg(L);
-        float s = dot_seq(inc, n);
-        Vec3 R = vadd(vscale(xmul(-2.f, s), n), inc);
-        float S = dot_seq(V, R);
+        LightEval e = eval_light(sc, l, P, n, V, fl);
+        float D = e.D, S = e.S;
         if (fl.double_sided) { D = xmul(sg, D); S = xmul(sg, S); }
         D = D > 0.f ? D : 0.f;
         S = S > 0.f ? S : 0.f;
@@ -484,31 +500,18 @@ SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int i
     float sv_len;
     Vec3 Vv = vsub(eye, P);
     Vec3 V = unit_eps(Vv, &sv_len);
-    float sg = 1.f;
-    if (fl.double_sided) {
-        float dp = dot_seq(V, n);
-        sg = dp > 0.f ? 1.f : (dp < 0.f ? -1.f : 0.f);
-    }
+    float sg = fl.double_sided ? facing_sign(V, n) : 1.f;
+    if (!(sg == sg)) sg = 0.f;
     Vec3 gV = v3(0.f, 0.f, 0.f);
     for (int l = 0; l < sc.n_lights; ++l) {
-        Vec3 lp = ld3(sc.light_pos + (size_t)l * sc.light_pos_stride);
-        Vec3 Lv = vsub(lp, P);
-        float dl = xsqrt(sq3_seq(Lv));
-        bool dl_nz = fabsf(dl) > 0.f;
-        float ddiv = dl_nz ? dl : 1.f;
-        Vec3 L = v3(Lv.x / ddiv, Lv.y / ddiv, Lv.z / ddiv);
-        float d2 = dl * dl;
-        float pw = fl.use_quartic ? d2 * d2 : d2;
+        const LightEval ev = eval_light(sc, l, P, n, V, fl);
+        const Vec3 L = ev.L, inc = ev.inc, R = ev.R;
+        const float dl = ev.dl, d2 = ev.d2, pw = ev.pw, att = ev.att, s = ev.s;
+        const bool dl_nz = ev.dl_nz, den_nz = ev.den_nz;
         const float* at = sc.light_atten + 3 * l;
-        float den = at[0] + dl * at[1] + pw * at[2];
-        bool den_nz = fabsf(den) > 0.f;
-        float att = 1.f / (den_nz ? den : 1.f);
-        float Draw = att * fdot(n, L);
-        Vec3 inc = vneg(L);
-        float s = fdot(inc, n);
-        Vec3 R = faxpy(-2.f * s, n, inc);
-        float Sraw = fdot(V, R);
-        float Dsg = sg * Draw, Ssg = sg * Sraw;
+        // gate values are the forward's bits (xmul like shade_pixel) so relu' agrees with the forward relu
+        const float Dsg = fl.double_sided ? xmul(sg, ev.D) : ev.D;
+        const float Ssg = fl.double_sided ? xmul(sg, ev.S) : ev.S;
         float Dp = Dsg > 0.f ? Dsg : 0.f;
         float Sp = Ssg > 0.f ? Ssg : 0.f;
         float spec = powf(Sp, sh);
@@ -670,6 +673,29 @@ SURF_HD PixelOut resolve_pixel(const SceneView& sc, const CamState& cs, Vec3 o, 
     if (hit) shade_pixel(sc, v3(cs.eye[0], cs.eye[1], cs.eye[2]), f.P, f.n, f.mat, fl, visibility, lit);
     composite(lit, hit, sc.gamma, po.image);
     return po;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shadow rays (renderer.py:291-314): from frag_pos + 0.1 L toward light l against every primitive; visible
+// iff nothing is hit strictly inside (0, |L|), or the nearest such hit is the fragment's own primitive.
+// ---------------------------------------------------------------------------------------------------
+SURF_HD float shadow_visibility(const SceneView& sc, Vec3 P, int self_idx, int l) {
+    Vec3 Lv = vsub(ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), P);
+    float dist = xsqrt(sq3_seq(Lv));                                       // norm_p(., 2)
+    Vec3 L = v3(xdiv(Lv.x, dist), xdiv(Lv.y, dist), xdiv(Lv.z, dist));
+    Vec3 so = vadd(P, vscale(0.1f, L));
+    float best_t = kMissSentinel;
+    int best = 0;
+    for (int s = 0; s < sc.n_sets; ++s) {
+        const SetView& sv = sc.sets[s];
+        for (int i = 0; i < sv.count; ++i) {
+            Vec3 nn; float numer, t;
+            plane_consts_for_origin(sv, i, so, &nn, &numer);
+            bool hit = exact_hit(sv, i, nn, numer, so, L, -INFINITY, INFINITY, &t);
+            if (hit && t > 0.f && t < dist && t < best_t) { best_t = t; best = sv.first + i; }
+        }
+    }
+    return ((best_t == kMissSentinel) || (best == self_idx)) ? 1.f : 0.f;
 }
 
 // order-preserving float -> uint32 map for the packed z-buffer key (t_key << 32 | primitive index);

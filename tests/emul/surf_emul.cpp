@@ -138,7 +138,15 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
                                           : (((unsigned long long)float_order_key(best_t)) << 32) | (unsigned)best;
         const int k = pix - p0;
         if (keys_out) keys_out[k] = key;
-        PixelOut po = resolve_pixel(sc, cs, o, d, key, fl, nullptr);
+        float vis[16];
+        const float* visp = nullptr;
+        if (opt->shadow) {
+            const int self = best < 0 ? 0 : best;
+            Fragment fr = fragment_at(sc, self, o, d);
+            for (int l = 0; l < sc.n_lights && l < 16; ++l) vis[l] = shadow_visibility(sc, fr.P, self, l);
+            visp = vis;
+        }
+        PixelOut po = resolve_pixel(sc, cs, o, d, key, fl, visp);
         if (out->image) memcpy(out->image + 3 * (size_t)k, po.image, 12);
         if (out->depth) out->depth[k] = po.depth;
         if (out->normal) memcpy(out->normal + 3 * (size_t)k, po.normal, 12);
@@ -179,7 +187,14 @@ int emul_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptio
         }
         g.depth = og->depth ? og->depth[k] : 0.f;
         const bool hit = depth[k] <= cs.far_clip && depth[k] >= cs.near_clip;
-        backward_pixel(sc, eye, o, d, (int)nearest[k], hit, fl, nullptr, g, sink);
+        float vis[16];
+        const float* visp = nullptr;
+        if (opt->shadow) {
+            Fragment fr = fragment_at(sc, (int)nearest[k], o, d);
+            for (int l = 0; l < sc.n_lights && l < 16; ++l) vis[l] = shadow_visibility(sc, fr.P, (int)nearest[k], l);
+            visp = vis;
+        }
+        backward_pixel(sc, eye, o, d, (int)nearest[k], hit, fl, visp, g, sink);
     }
     for (int s = 0; s < sc.n_sets; ++s) {
         const SetView& sv = sc.sets[s];

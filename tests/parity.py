@@ -74,6 +74,34 @@ def compare_forward(cand, ref, scene, ortho_origins=None, rtol=RTOL, atol=ATOL, 
             'good_mask': good}
 
 
+def kink_mask(scene, ref, params=None, eps=2e-5):
+    """[N] bool: pixels sitting on a relu / sign kink of the shader (renderer.py:104-115): |n.L|, |V.R| or |V.n|
+    is rounding noise, so relu'(.) is decided by the last bit and the gradient is not defined there.  (SCENE_BASIC
+    has light 6 exactly in the plane of disk 2, so every pixel of that disk is such a tie.)  Such pixels are
+    dropped from the loss on both sides, like nearest-index ties."""
+    params = params or {}
+    P = _to_np(ref['pos']).reshape(-1, 3).astype(np.float64)
+    n = _to_np(ref['normal']).reshape(-1, 3).astype(np.float64)
+    eye = _to_np(scene['camera']['eye']).astype(np.float64)[:3]
+    V = eye[None, :] - P
+    V /= np.maximum(np.linalg.norm(V, axis=1, keepdims=True), 1e-300)
+    lp = _to_np(scene['lights']['pos']).astype(np.float64)[:, :3]
+    ks_any = bool((_to_np(scene['materials']['coeffs'])[:, 1] != 0).any())
+    bad = np.zeros(P.shape[0], dtype=bool)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        if params.get('double_sided', False):
+            bad |= np.abs(np.sum(V * n, axis=1)) <= eps
+        for l in range(lp.shape[0]):
+            L = lp[l][None, :] - P
+            L /= np.maximum(np.linalg.norm(L, axis=1, keepdims=True), 1e-300)
+            nl = np.sum(n * L, axis=1)
+            bad |= np.abs(nl) <= eps
+            if ks_any:
+                R = 2 * nl[:, None] * n - L
+                bad |= np.abs(np.sum(V * R, axis=1)) <= eps
+    return bad
+
+
 def compare_grads(cand, ref, rtol=1e-4, atol_scale=1e-5, skip=()):
     """cand/ref: {leaf name: array}.  Tolerance: 1e-4 relative to the element, plus 1e-5 of the leaf's max |grad|
     (float atomics reorder the sum, so tiny elements carry the noise of the large ones)."""
