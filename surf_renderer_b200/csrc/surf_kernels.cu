@@ -79,7 +79,8 @@ static int cuda_fail(cudaError_t e, const char* where) {
 // ---------------------------------------------------------------------------------------------------
 struct Workspace {
     CamState* cam;
-    float4* packed;              // filter records, per set, 128-byte aligned
+    float4* packed;              // plane-filter records, per set, 128-byte aligned (math_mode 1..3)
+    float4* circ;                // level-1 screen-circle records, one float4 per primitive in global order
     float* rays;                 // [3, n] SoA unit directions (perspective)
     unsigned long long* zbuf;    // [n] packed (depth key << 32 | primitive index)
     double* acc;                 // backward scalar accumulators
@@ -101,6 +102,7 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     size_t off = 0;
     ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
     ws->packed = (float4*)(p + off); off += align_up(packed_bytes_bound(total_prims), 256);
+    ws->circ = (float4*)(p + off); off += align_up((size_t)total_prims * 16 + 256, 256);
     ws->rays = (float*)(p + off); off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
     ws->acc = (double*)(p + off); off += align_up((size_t)kMaxAccSlots * 8, 256);
@@ -221,6 +223,15 @@ __global__ void __launch_bounds__(256) k_raygen(const CamState* __restrict__ cs,
     } else if (k == 0 && ray_out) {
         ray_out[0] = cs->odir[0]; ray_out[1] = cs->odir[1]; ray_out[2] = cs->odir[2];
     }
+}
+
+__global__ void __launch_bounds__(256) k_prep_screen(const __grid_constant__ SceneView sc, const CamState* __restrict__ cs,
+                                                     float4* __restrict__ circ) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= sc.total) return;
+    const int s = find_set(sc, g);
+    const F4 r = prep_screen(*cs, sc.sets[s], g - sc.sets[s].first);
+    circ[g] = make_float4(r.x, r.y, r.z, r.w);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -504,6 +515,199 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant
         else if (sv.kind == KIND_TRIANGLE) chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         else chunk_planes<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+    }
+    flush();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_intersect_screen: default intersection kernel (perspective).  Level 1 tests EVERY (pixel, primitive) pair
+// in registers against the primitive's screen-space bounding circle: per pixel pair one FADD2 + one FFMA2
+// (packed f32x2) + one FMNMX3, i.e. 2.25 FMA-pipe lane-instructions per test at P = 8 (the y-term is shared by
+// the P pixels of a thread, which sit in one image row).  The rare flagged pairs run the exact reference-order
+// test.  Same persistent-CTA / TMA-ring / atomicMin z-buffer structure as k_intersect.
+//   thread -> P consecutive columns of one row; warp -> 4P x 8 pixels; CTA -> 8P x 32 pixels.
+// ---------------------------------------------------------------------------------------------------
+struct ScreenParams {
+    SceneView sc;
+    const CamState* cam;
+    const float4* circ;              // [total] level-1 records
+    const float* rays;               // [3, n]
+    unsigned long long* zbuf;        // [n]
+    int pix0, n_pix, W, row0;
+    int tiles_x, n_tiles, n_chunks, chunk, total;
+};
+
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// exact test of one (pixel, primitive) pair; returns true and *t on a valid hit.  Out of line: rare path.
+__device__ __noinline__ bool exact_pair(const ScreenParams& prm, int idx, int k, float* t_out) {
+    const int set = find_set(prm.sc, idx);
+    const SetView& sv = prm.sc.sets[set];
+    const int local = idx - sv.first;
+    const Vec3 o = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
+    const Vec3 d = v3(prm.rays[k], prm.rays[(size_t)prm.n_pix + k], prm.rays[2 * (size_t)prm.n_pix + k]);
+    Vec3 nn;
+    float numer;
+    plane_consts_for_origin(sv, local, o, &nn, &numer);
+    return exact_hit(sv, local, nn, numer, o, d, prm.cam->near_clip, prm.cam->far_clip, t_out);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen(const __grid_constant__ ScreenParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+
+    const int tid = threadIdx.x;
+    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
+    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    if (lo >= hi) return;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int item, int stage) {
+        const int c = item % prm.n_chunks;
+        const int first = c * prm.chunk;
+        const int count = min(prm.chunk, prm.total - first);
+        const uint32_t bytes = (uint32_t)count * 16u;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(stage_buf + (size_t)stage * prm.chunk, prm.circ + first, bytes, &full_bar[stage]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
+
+    // thread geometry inside the CTA tile
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tcol = (warp & 1) * 4 * P + (lane & 3) * P;     // first column of this thread inside the tile
+    const int trow = (warp >> 1) * 8 + (lane >> 2);
+    constexpr int TW = 8 * P, TH = 32;
+
+    unsigned long long x2[P / 2];       // image-plane x of the thread's pixels, packed pairs
+    float y = 0.f;
+    float best_t[P];
+    int best_i[P];
+    int kbase = 0;                      // output index of the thread's first pixel
+    unsigned valid = 0;                 // bit p: pixel p is inside the frame and the launch's pixel range
+    int cur_tile = -1;
+
+    auto flush = [&]() {
+        if (cur_tile < 0) return;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            if (best_i[p] >= 0) {
+                unsigned long long key = ((unsigned long long)float_order_key(best_t[p]) << 32) | (unsigned)best_i[p];
+                atomicMin(prm.zbuf + kbase + p, key);
+            }
+    };
+
+    for (int it = lo; it < hi; ++it) {
+        const int kk = it - lo;
+        const int stage = kk % kStages;
+        const uint32_t parity = (uint32_t)((kk / kStages) & 1);
+        __syncthreads();
+        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (kk + kStages - 1) % kStages);
+
+        const int tile = it / prm.n_chunks;
+        if (tile != cur_tile) {
+            flush();
+            cur_tile = tile;
+            const int ty = tile / prm.tiles_x, tx = tile - ty * prm.tiles_x;
+            const int row = prm.row0 + ty * TH + trow;
+            const int col0 = tx * TW + tcol;
+            kbase = row * prm.W + col0 - prm.pix0;
+            valid = 0;
+            float xs[P];
+            float yy = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int col = col0 + p;
+                const int k = kbase + p;
+                const bool ok = col < prm.W && row < prm.cam->H && k >= 0 && k < prm.n_pix;
+                float xv = 3.0e18f;                   // far outside any circle: never flagged
+                if (ok) {
+                    pixel_xy(*prm.cam, row * prm.W + col, &xv, &yy);
+                    valid |= 1u << p;
+                }
+                xs[p] = xv;
+                best_t[p] = INFINITY;
+                best_i[p] = -1;
+            }
+            y = valid ? yy : 3.0e18f;
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) x2[q] = pack2(xs[2 * q], xs[2 * q + 1]);
+        }
+
+        const int first = (it % prm.n_chunks) * prm.chunk;
+        const int count = min(prm.chunk, prm.total - first);
+        mbar_wait(&full_bar[stage], parity);
+        const float4* __restrict__ s = stage_buf + (size_t)stage * prm.chunk;
+
+        constexpr int G = 4;
+        int i = 0;
+        for (; i + G <= count; i += G) {
+            float m = INFINITY;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 C = s[i + g];                  // -u, -v, -rho^2, 0   (LDS.128, warp broadcast)
+                const float dy = y + C.y;
+                const float sy = fmaf(dy, dy, C.z);
+                const unsigned long long mu = pack2(C.x, C.x), sy2 = pack2(sy, sy);
+#pragma unroll
+                for (int q = 0; q < P / 2; ++q) {
+                    const unsigned long long dx = add2(x2[q], mu);
+                    float e0, e1;
+                    unpack2(fma2(dx, dx, sy2), e0, e1);
+                    m = fminf(m, fminf(e0, e1));
+                }
+            }
+            if (m <= 0.f) {          // rare: some pair of this group lies inside its screen circle
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const float4 C = s[i + g];
+                    const float dy = y + C.y;
+                    const float sy = fmaf(dy, dy, C.z);
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        float lo_, hi_;
+                        unpack2(x2[p >> 1], lo_, hi_);
+                        const float dx = ((p & 1) ? hi_ : lo_) + C.x;
+                        if (fmaf(dx, dx, sy) <= 0.f) {
+                            float t;
+                            if (exact_pair(prm, first + i + g, kbase + p, &t) && t < best_t[p]) {
+                                best_t[p] = t;
+                                best_i[p] = first + i + g;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        for (; i < count; ++i) {     // chunk tail
+            const float4 C = s[i];
+            const float dy = y + C.y;
+            const float sy = fmaf(dy, dy, C.z);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float lo_, hi_;
+                unpack2(x2[p >> 1], lo_, hi_);
+                const float dx = ((p & 1) ? hi_ : lo_) + C.x;
+                if (fmaf(dx, dx, sy) <= 0.f) {
+                    float t;
+                    if (exact_pair(prm, first + i, kbase + p, &t) && t < best_t[p]) {
+                        best_t[p] = t;
+                        best_i[p] = first + i;
+                    }
+                }
+            }
+        }
     }
     flush();
 }
@@ -925,12 +1129,51 @@ static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaS
     return SURF_OK;
 }
 
+template <int P>
+static int launch_screen(const ScreenParams& prm, int grid, size_t smem, cudaStream_t st) {
+    auto kern = k_intersect_screen<P>;
+    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timer_mark(0, 0, st);
+    kern<<<grid, kThreads, smem, st>>>(prm);
+    timer_mark(0, 1, st);
+    SURF_LAUNCHED("k_intersect_screen");
+    return SURF_OK;
+}
+
+static int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStream_t st) {
+    ScreenParams prm;
+    prm.sc = f.sc; prm.cam = f.ws.cam; prm.circ = f.ws.circ; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
+    prm.pix0 = f.pix0; prm.n_pix = f.n; prm.W = f.cam.W; prm.total = f.sc.total;
+    int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
+    if (P != 4 && P != 8 && P != 16) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 4, 8 or 16 for math_mode 0");
+    const int row0 = f.pix0 / f.cam.W, row1 = (f.pix0 + f.n - 1) / f.cam.W;
+    prm.row0 = row0;
+    prm.tiles_x = (f.cam.W + 8 * P - 1) / (8 * P);
+    const int tiles_y = (row1 - row0 + 1 + 31) / 32;
+    prm.n_tiles = prm.tiles_x * tiles_y;
+    const int occ = P <= 8 ? 3 : 2;
+    const int grid_max = sm_count() * occ;
+    int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
+    if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
+    if (!opt->chunk_prims)
+        while (chunk > 64 && (long long)((f.sc.total + chunk - 1) / chunk) * prm.n_tiles < 4LL * grid_max) chunk /= 2;
+    prm.chunk = chunk;
+    prm.n_chunks = (f.sc.total + chunk - 1) / chunk;
+    const long long items = (long long)prm.n_tiles * prm.n_chunks;
+    const int grid = (int)std::min<long long>(items, grid_max);
+    const size_t smem = (size_t)kStages * chunk * sizeof(float4);
+    if (P == 4) return launch_screen<4>(prm, grid, smem, st);
+    if (P == 8) return launch_screen<8>(prm, grid, smem, st);
+    return launch_screen<16>(prm, grid, smem, st);
+}
+
 static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st) {
     if (f.cam.proj != 0) {
         k_intersect_generic<<<(f.n + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.pix0, f.n, f.ws.zbuf);
         SURF_LAUNCHED("k_intersect_generic");
         return SURF_OK;
     }
+    if (opt->math_mode == 0) return run_intersect_screen(f, opt, st);
     IsectParams prm;
     prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.n_pix = f.n;
@@ -968,11 +1211,11 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
     const int mode = opt->math_mode;
-    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0, 1 or 2");
+    if (mode < 1 || mode > 3) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..3");
 #define SURF_DISPATCH(PP)                                                      \
     if (P == PP) {                                                             \
-        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
-        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
+        if (mode == 1) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
+        if (mode == 2) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
         return launch_intersect<PP, 2>(prm, grid, smem, st);                   \
     }
     SURF_DISPATCH(2)
@@ -999,7 +1242,10 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
     int rc = make_frame(scene, camera, opt, workspace, workspace_bytes, &f);
     if (rc) return rc;
     if ((rc = run_common_prologue(f, out->ray_dir, st, true))) return rc;
-    if (f.cam.proj == 0) {
+    if (f.cam.proj == 0 && opt->math_mode == 0) {
+        k_prep_screen<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.circ);
+        SURF_LAUNCHED("k_prep_screen");
+    } else if (f.cam.proj == 0) {
         k_prep<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.packed);
         SURF_LAUNCHED("k_prep");
     }

@@ -249,6 +249,57 @@ SURF_HD void prep_triangle(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, Vec3 o, F4* A, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// level-1 screen-space record (perspective camera): a circle on the image plane z = -focal that contains the
+// projection of the primitive's bounding sphere.  Any exact hit point P of the primitive lies inside that
+// sphere, and the pixel's image-plane point is the projection of P, so a pixel outside the circle cannot hit.
+//   record = (-u, -v, -rho^2, 0):   flagged  <=>  (x_p - u)^2 + (y_p - v)^2 - rho^2 <= 0
+// rho = f R sqrt(1 + k^2) / (zc - R),  k = |c_xy| / zc  bounds |proj(c + delta) - proj(c)| over |delta| <= R.
+// Primitives that reach the camera plane (zc - R <= 0) and planes are always flagged (-rho^2 = -inf).
+// ---------------------------------------------------------------------------------------------------
+SURF_HD F4 screen_circle(const CamState& cs, double cx, double cy, double cz, double R) {
+    // camera coordinates: q = R^T (c - eye); columns of cs.R are the camera axes
+    const double ex = cx - (double)cs.eye[0], ey = cy - (double)cs.eye[1], ez = cz - (double)cs.eye[2];
+    const double qx = cs.R[0] * ex + cs.R[3] * ey + cs.R[6] * ez;
+    const double qy = cs.R[1] * ex + cs.R[4] * ey + cs.R[7] * ez;
+    const double qz = cs.R[2] * ex + cs.R[5] * ey + cs.R[8] * ez;
+    const double f = -(double)cs.neg_focal;
+    const double dist = dlen(ex, ey, ez);
+    const double scale = dlen(cs.eye[0], cs.eye[1], cs.eye[2]) + dlen(cx, cy, cz) + dist + R;
+    const double Rs = R + 4e-6 * scale;                     // fp32 noise of the exact path's hit point
+    const double zc = -qz;
+    if (!(zc - Rs > 1e-4 * (Rs + dist)) || !(f > 0.0)) return f4(0.f, 0.f, -INFINITY, 0.f);
+    const double u = f * qx / zc, v = f * qy / zc;
+    const double k2 = (qx * qx + qy * qy) / (zc * zc);
+    double rho = f * Rs * sqrt(1.0 + k2) / (zc - Rs);
+    rho = rho * (1.0 + 1e-4) + 2e-6 * ((double)fabsf(cs.sx) + (double)fabsf(cs.sy) + fabs(u) + fabs(v) + f);
+    return f4((float)(-u), (float)(-v), -f_round_up(rho * rho * (1.0 + 1e-6)), 0.f);
+}
+
+SURF_HD F4 prep_screen(const CamState& cs, const SetView& sv, int i) {
+    if (sv.kind == KIND_PLANE) return f4(0.f, 0.f, -INFINITY, 0.f);
+    if (sv.kind == KIND_TRIANGLE) {
+        const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
+        const double gx = ((double)f[0] + f[sv.pos_stride] + f[2 * sv.pos_stride]) / 3.0;
+        const double gy = ((double)f[1] + f[sv.pos_stride + 1] + f[2 * sv.pos_stride + 1]) / 3.0;
+        const double gz = ((double)f[2] + f[sv.pos_stride + 2] + f[2 * sv.pos_stride + 2]) / 3.0;
+        double R = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const float* v = f + k * sv.pos_stride;
+            const double d = dlen(v[0] - gx, v[1] - gy, v[2] - gz);
+            R = d > R ? d : R;
+        }
+        return screen_circle(cs, gx, gy, gz, R);
+    }
+    const float* c = sv.pos + (size_t)i * sv.pos_stride;
+    return screen_circle(cs, c[0], c[1], c[2], fabs((double)sv.radius[i]));
+}
+// scalar form of the level-1 test for pixel image-plane coordinates (x, y)
+SURF_HD bool screen_filter(const F4& C, float x, float y) {
+    const float dx = x + C.x, dy = y + C.y;
+    return fmaf(dx, dx, fmaf(dy, dy, C.z)) <= 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // coarse (conservative) filters - scalar forms; the intersection kernel has packed f32x2 versions of the
 // disk filter.  `rcp` is an approximate reciprocal on the device (MUFU.RCP), 1/x on the host.
 // ---------------------------------------------------------------------------------------------------

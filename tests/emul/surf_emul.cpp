@@ -112,9 +112,17 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
     const Vec3 eye = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
     if (cs.proj == 0) pack_all(sc, eye, &pk);
     long long filter_misses = 0;
+    std::vector<F4> circ;
+    if (cs.proj == 0) {
+        circ.resize(sc.total);
+        for (int s = 0; s < sc.n_sets; ++s)
+            for (int i = 0; i < sc.sets[s].count; ++i) circ[sc.sets[s].first + i] = prep_screen(cs, sc.sets[s], i);
+    }
     for (int pix = p0; pix < p1; ++pix) {
         Vec3 o, d;
         pixel_ray(cs, pix, &o, &d);
+        float px = 0.f, py = 0.f;
+        pixel_xy(cs, pix, &px, &py);
         float best_t = INFINITY;
         int best = -1;
         for (int s = 0; s < sc.n_sets; ++s) {
@@ -123,7 +131,7 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
                 Vec3 n; float numer; bool pass = true;
                 if (cs.proj == 0) {
                     const F4* r = &pk.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)];
-                    pass = filter_pass(sv, r, d);
+                    pass = filter_pass(sv, r, d) && screen_filter(circ[sv.first + i], px, py);
                     n = v3(r[0].x, r[0].y, r[0].z); numer = r[0].w;
                 } else {
                     plane_consts_for_origin(sv, i, o, &n, &numer);
