@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--ppt', type=int, default=0, help='pixels per thread of the intersection kernel (0 = default)')
     ap.add_argument('--chunk', type=int, default=0)
-    ap.add_argument('--math', type=int, default=0, help='0 = packed FFMA2 filter, 1 = scalar FFMA filter')
+    ap.add_argument('--math', type=int, default=0, help='intersection kernel: 0 = default ray-plane FFMA2 filter (10 instr/test), 3 = screen-space fast mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -281,6 +281,28 @@ def main():
                     'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
                     'shade_ms': float(np.mean(k_ms[1])), 'backward_ms': float(np.mean(k_ms[2]))}
 
+    # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
+    fast = None
+    if args.math == 0:
+        params_fast = dict(params, _math_mode=3, _pixels_per_thread=0)
+        params_keep = dict(params)
+        params.clear(); params.update(params_fast)
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_fast = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_fast):
+            step()
+        e1.record()
+        barrier()
+        ms_fast = e0.elapsed_time(e1) / n_fast
+        fast = {'math_mode': 3, 'ms_per_step': ms_fast, 'tests_per_s': tests_per_step / (ms_fast * 1e-3),
+                'frames_per_s': 1e3 / ms_fast, 'intersect_kernel_ms': lib().surf_last_kernel_ms(0),
+                'note': 'per-pair screen-space bounding-circle level-1 test (2.25 FMA-pipe lane-instr/test); bit-identical outputs'}
+        params.clear(); params.update(params_keep)
+
     # ---- e2e: C-ABI host-pointer call, pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -336,7 +358,7 @@ def main():
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss),
             'gpu_launches': int(sum(launches)), 'gpu_launches_per_step': int(launches[-1]) if launches else 0,
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'fast_mode': fast,
             'wall_s_timed_region': wall}
     print(json.dumps(line))
     if world > 1:

@@ -100,12 +100,13 @@ typedef struct SurfOptions {
     int32_t pixel_end;       /* 0,0 = whole frame.  Output arrays are sized for the range (row bands / GPU) */
     int32_t forced_nearest;  /* backward only: 2 = `workspace` still holds this frame's forward state (camera,
                                 rays, shadow visibility), skip recomputing it; 0/1 = recompute               */
-    int32_t pixels_per_thread; /* 0 = library default; tuning knob (mode 0: 4,8,16; modes 1-3: 2,4,8)        */
+    int32_t pixels_per_thread; /* 0 = library default; tuning knob (modes 0-2: 2,4,8; mode 3: 4,8,16)        */
     int32_t chunk_prims;     /* 0 = library default; primitives staged per TMA bulk copy (multiple of 32)   */
-    int32_t math_mode;       /* intersection kernel: 0 = default (level-1 screen-circle test per pair, packed
-                                FFMA2); 1 = ray-plane disk filter, packed FFMA2, grouped branch (10 FMA-pipe
-                                instr/test, the SURVEY 8d formulation); 2 = same, scalar FFMA; 3 = same, packed,
-                                one branch per primitive.  All modes give bit-identical results.               */
+    int32_t math_mode;       /* intersection kernel.  0 = default: ray-plane disk filter, packed FFMA2, grouped
+                                branch - 10 FMA-pipe lane-instr per ray-disk test, the SURVEY 8(d) formulation;
+                                1 = same, scalar FFMA; 2 = same, packed, one branch per primitive;
+                                3 = fast: per-pair screen-space bounding-circle test (2.25 lane-instr per test).
+                                All modes run the same exact narrow phase and give bit-identical results.      */
 } SurfOptions;
 
 /* outputs for n = pixel_end - pixel_begin pixels (row-major).  Any pointer may be NULL to skip it. */

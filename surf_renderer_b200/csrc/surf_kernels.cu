@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_intersect_screen: default intersection kernel (perspective).  Level 1 tests EVERY (pixel, primitive) pair
+// k_intersect_screen: opt-in fast intersection kernel (math_mode 3, perspective).  Level 1 tests EVERY (pixel, primitive) pair
 // in registers against the primitive's screen-space bounding circle: per pixel pair one FADD2 + one FFMA2
 // (packed f32x2) + one FMNMX3, i.e. 2.25 FMA-pipe lane-instructions per test at P = 8 (the y-term is shared by
 // the P pixels of a thread, which sit in one image row).  The rare flagged pairs run the exact reference-order
@@ -1145,7 +1145,7 @@ static int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStre
     prm.sc = f.sc; prm.cam = f.ws.cam; prm.circ = f.ws.circ; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.pix0 = f.pix0; prm.n_pix = f.n; prm.W = f.cam.W; prm.total = f.sc.total;
     int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
-    if (P != 4 && P != 8 && P != 16) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 4, 8 or 16 for math_mode 0");
+    if (P != 4 && P != 8 && P != 16) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 4, 8 or 16 for math_mode 3");
     const int row0 = f.pix0 / f.cam.W, row1 = (f.pix0 + f.n - 1) / f.cam.W;
     prm.row0 = row0;
     prm.tiles_x = (f.cam.W + 8 * P - 1) / (8 * P);
@@ -1173,11 +1173,11 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
         SURF_LAUNCHED("k_intersect_generic");
         return SURF_OK;
     }
-    if (opt->math_mode == 0) return run_intersect_screen(f, opt, st);
+    if (opt->math_mode == 3) return run_intersect_screen(f, opt, st);
     IsectParams prm;
     prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.n_pix = f.n;
-    int P = opt->pixels_per_thread ? opt->pixels_per_thread : 4;
+    int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
     if (P != 2 && P != 4 && P != 8) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 2, 4 or 8");
     const int tile = kThreads * P;
     prm.n_tiles = (f.n + tile - 1) / tile;
@@ -1211,11 +1211,11 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
     const int mode = opt->math_mode;
-    if (mode < 1 || mode > 3) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..3");
+    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..3");
 #define SURF_DISPATCH(PP)                                                      \
     if (P == PP) {                                                             \
-        if (mode == 1) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
-        if (mode == 2) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
+        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
+        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
         return launch_intersect<PP, 2>(prm, grid, smem, st);                   \
     }
     SURF_DISPATCH(2)
@@ -1242,7 +1242,7 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
     int rc = make_frame(scene, camera, opt, workspace, workspace_bytes, &f);
     if (rc) return rc;
     if ((rc = run_common_prologue(f, out->ray_dir, st, true))) return rc;
-    if (f.cam.proj == 0 && opt->math_mode == 0) {
+    if (f.cam.proj == 0 && opt->math_mode == 3) {
         k_prep_screen<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.circ);
         SURF_LAUNCHED("k_prep_screen");
     } else if (f.cam.proj == 0) {
