@@ -250,3 +250,83 @@ def test_fma_peak_microbenchmark_runs():
     packed = lib().surf_fma_peak(1, 4096, None)
     print('fma lane-instr/s scalar %.3e packed %.3e' % (scalar, packed))
     assert scalar > 1e12 and packed > 1e12
+
+
+@pytest.mark.parametrize('seed', [31, 32])
+def test_shadow_rays_match_oracle_restatement(seed):
+    """shadow=True (renderer.py:291-314).  The reference's own shadow branch only runs on CUDA (:311), so the oracle's
+    device-agnostic restatement is the checker (parity-unpinned for this row)."""
+    from surf_renderer_b200 import scenes as synth
+    scene = synth.random_mixed_scene(seed, width=36, height=28, n_disk=10, n_sphere=0, n_tri=6, n_plane=1)
+    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    res = _render(sc, shadow=True)
+    osc = scene_io.clone_scene(scene, requires_grad=True)
+    ref = torch_oracle.render(osc, shadow=True)
+    rep = parity.compare_forward(_cpu(res), _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), scene, atol=2e-5)
+    plain = _render(scene_io.clone_scene(scene, device='cuda'))
+    assert not torch.equal(plain['image'], res['image'].detach())
+    H, W = ref['depth'].shape
+    w = scene_io.loss_weights((H, W), seed)
+    kink = parity.kink_mask(scene, _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), {})
+    good = torch.tensor(rep['good_mask'] & ~kink).view(H, W)
+    for k in w:
+        w[k] = w[k] * (good[..., None] if w[k].dim() == 3 else good)
+    far = scene['camera']['far']
+    oloss = scene_io.weighted_loss(ref, w, far)
+    oleaves = scene_io.grad_leaves(osc)
+    names = [k for k, v in oleaves.items() if v.requires_grad]
+    og = torch.autograd.grad(oloss, [oleaves[k] for k in names], allow_unused=True)
+    ref_g = {k: g.numpy() for k, g in zip(names, og) if g is not None}
+    loss = scene_io.weighted_loss(res, w, far)
+    leaves = scene_io.grad_leaves(sc)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in ref_g], allow_unused=True)
+    cand = {k: (g.detach().cpu() if g is not None else torch.zeros_like(leaves[k]).cpu()) for k, g in zip(ref_g, gs)}
+    parity.compare_grads(cand, ref_g)
+
+
+def test_sphere_gradients_are_finite_and_match_float64_autograd():
+    """The reference yields NaN sphere gradients; ours are the analytic ones, checked against float64
+    autograd of the oracle's NaN-free sphere variant."""
+    from test_emul_extras import _to64, sphere_scene
+    scene = sphere_scene()
+    torch_oracle.SAFE_SPHERE = True
+    torch.set_default_dtype(torch.float64)
+    try:
+        sc64 = scene_io.clone_scene(_to64(scene), requires_grad=True)
+        ref = torch_oracle.render(sc64)
+        H, W = ref['depth'].shape
+        w = {k: v.double() for k, v in scene_io.loss_weights((H, W), 77).items()}
+        far = scene['camera']['far']
+        loss64 = scene_io.weighted_loss(ref, w, far)
+        leaves64 = scene_io.grad_leaves(sc64)
+        names = [k for k, v in leaves64.items() if v.requires_grad]
+        gs = torch.autograd.grad(loss64, [leaves64[k] for k in names], allow_unused=True)
+        ref_g = {k: g.detach().numpy() for k, g in zip(names, gs) if g is not None}
+    finally:
+        torch.set_default_dtype(torch.float32)
+        torch_oracle.SAFE_SPHERE = False
+    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    res = _render(sc)
+    assert np.array_equal(res['nearest'].cpu().numpy(), ref['nearest'].numpy())
+    w32 = {k: v.float() for k, v in w.items()}
+    loss = scene_io.weighted_loss(res, w32, far)
+    leaves = scene_io.grad_leaves(sc)
+    g = torch.autograd.grad(loss, [leaves[k] for k in ref_g], allow_unused=True)
+    cand = {k: x.detach().cpu() for k, x in zip(ref_g, g)}
+    assert torch.isfinite(cand['objects/sphere/pos']).all() and torch.isfinite(cand['objects/sphere/radius']).all()
+    parity.compare_grads(cand, ref_g, rtol=2e-4, atol_scale=2e-5, skip=('objects/sphere/pos', 'objects/sphere/radius'))
+    parity.compare_grads(cand, {k: ref_g[k] for k in ('objects/sphere/pos', 'objects/sphere/radius')}, rtol=1e-3, atol_scale=2e-4)
+
+
+def test_batch_of_scenes_config_d_shape():
+    """BASELINE configs[3] shape (64 scenes x 5K splats at 128x128, double sided): a few scenes of the batch against the
+    oracle at sampled pixels; every scene renders and back-propagates."""
+    from surf_renderer_b200 import scenes as synth
+    for idx in (0, 17, 63):
+        scene = synth.config_d_scene(idx)
+        rep = _oracle_subset_check(scene, {'double_sided': True}, 3000, idx)
+        assert rep['hit_pixels'] > 50
+    sc = scene_io.clone_scene(synth.config_d_scene(5), device='cuda', requires_grad=True)
+    res = _render(sc, double_sided=True)
+    res['image'].sum().backward()
+    assert torch.isfinite(sc['objects']['disk']['pos'].grad).all()
