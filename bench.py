@@ -63,17 +63,62 @@ def measured_peaks():
 # clocks sampling during the timed region
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region.  NVML in-process (cheap calls from a
+    thread); falls back to an `nvidia-smi -lms 200` child when pynvml is unavailable."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.proc, self.rows = None, []
+        self.mode = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = self.handle
+        bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(',')[self.index])
+                except Exception:
+                    phys = self.index
+            self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.mode = 'nvml'
+            self._thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = 'nvidia-smi'
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -83,9 +128,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.mode == 'nvml':
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            return {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                    'reasons': sorted(self.reasons), 'samples': len(self.samples), 'source': 'nvml'}
         if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable']}
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -98,7 +148,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -172,7 +222,8 @@ def main():
     tests_per_step = float(M) * H * W
     config = {'workload': 'config_e', 'splats': M, 'width': W, 'height': H, 'lights': 3,
               'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam',
-              'sharding': 'row-bands x%d' % max(1, args.gpus), 'l2': 'flushed between timed steps (256 MiB write)'}
+              'sharding': 'row-bands x%d' % max(1, args.gpus),
+              'l2': 'flushed between timed steps (256 MiB fill enqueued on the stream, inside the timed region)'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -214,7 +265,6 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     lib().surf_set_kernel_timing(1)
     launches = []
-    k_ms = {0: [], 1: [], 2: []}
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -242,20 +292,19 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lib().surf_set_kernel_timing(1)                   # reset the library's per-kernel event ring
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     t_wall0 = time.perf_counter()
+    ev0.record()
     for i in range(args.steps):
-        flush.fill_(i & 0xff)                      # L2 flush, outside the timed events
-        barrier()
-        ev[i][0].record()
+        flush.fill_(i & 0xff)                      # L2 flush between steps (stream-ordered, inside the timed region)
         loss, n_launch = step()
-        ev[i][1].record()
         launches.append(n_launch)
-        for k in k_ms:
-            k_ms[k].append(lib().surf_last_kernel_ms(k))
+    ev1.record()
     barrier()
     wall = time.perf_counter() - t_wall0
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,9 +312,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = tests_per_step / (ms_per_step * 1e-3)
+    n_timed = C.c_int32()
+    k_mean = {k: lib().surf_mean_kernel_ms(k, C.byref(n_timed)) for k in (0, 1, 2)}
 
     # ---- roofline of the dominant kernel (k_intersect), timed live with CUDA events inside the library
-    isect_ms = float(np.mean([x for x in k_ms[0] if x > 0])) if any(x > 0 for x in k_ms[0]) else None
+    isect_ms = k_mean[0] if k_mean[0] > 0 else None
     f_clk = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
     peak_lane = N_SM * FP32_LANES * f_clk                    # lane-instr/s
     roofline = None
@@ -279,7 +330,7 @@ def main():
                     'peak_measured': fma_meas * 2 / 1e12, 'frac_of_measured': ach_lane / fma_meas if fma_meas > 0 else None,
                     'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
                     'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
-                    'shade_ms': float(np.mean(k_ms[1])), 'backward_ms': float(np.mean(k_ms[2]))}
+                    'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
 
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
     fast = None

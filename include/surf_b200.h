@@ -189,8 +189,11 @@ int surf_last_launch_count(void);
 /* per-kernel device timing with CUDA events recorded on the launching stream (off by default).
  * which: 0 = intersection (k_intersect), 1 = shading (k_shade), 2 = backward (k_backward).
  * surf_last_kernel_ms synchronises on that kernel's end event; returns <0 when nothing was recorded. */
-void surf_set_kernel_timing(int32_t enabled);
+void surf_set_kernel_timing(int32_t enabled);          /* (re-)enabling resets the recorded launches */
 double surf_last_kernel_ms(int32_t which);
+/* mean duration over the launches recorded since timing was enabled (ring of the last 256); the events are
+ * recorded asynchronously, only this call synchronises.  *launches receives how many were averaged. */
+double surf_mean_kernel_ms(int32_t which, int32_t* launches);
 
 #ifdef __cplusplus
 }

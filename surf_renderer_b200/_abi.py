@@ -84,6 +84,7 @@ SYMBOLS = {
     'surf_last_launch_count': (C.c_int, []),
     'surf_set_kernel_timing': (None, [C.c_int32]),
     'surf_last_kernel_ms': (C.c_double, [C.c_int32]),
+    'surf_mean_kernel_ms': (C.c_double, [C.c_int32, C.POINTER(C.c_int32)]),
 }
 
 

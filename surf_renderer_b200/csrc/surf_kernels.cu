@@ -35,23 +35,34 @@ namespace surf {
 static thread_local std::string g_error;
 static int g_launches = 0;   // process-wide: autograd runs backward on its own thread
 
-// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
+// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg): a ring of
+// event pairs per kernel kind so that a whole timed region can be averaged without synchronising inside it
+constexpr int kTimerRing = 256;
 struct KernelTimers {
     bool enabled = false;
-    cudaEvent_t ev[3][2] = {};
-    bool have[3] = {false, false, false};
     bool created = false;
+    cudaEvent_t ev[3][kTimerRing][2] = {};
+    long long count[3] = {0, 0, 0};     // launches recorded since timing was (re-)enabled
 };
 static KernelTimers g_timers;   // process-wide (see g_launches)
 static void timer_mark(int which, int edge, cudaStream_t st) {
     if (!g_timers.enabled) return;
     if (!g_timers.created) {
         for (int k = 0; k < 3; ++k)
-            for (int e = 0; e < 2; ++e) cudaEventCreate(&g_timers.ev[k][e]);
+            for (int r = 0; r < kTimerRing; ++r)
+                for (int e = 0; e < 2; ++e) cudaEventCreate(&g_timers.ev[k][r][e]);
         g_timers.created = true;
     }
-    cudaEventRecord(g_timers.ev[which][edge], st);
-    if (edge == 1) g_timers.have[which] = true;
+    const int slot = (int)(g_timers.count[which] % kTimerRing);
+    cudaEventRecord(g_timers.ev[which][slot][edge], st);
+    if (edge == 1) ++g_timers.count[which];
+}
+static double timer_ms(int which, long long index) {
+    const int slot = (int)(index % kTimerRing);
+    if (cudaEventSynchronize(g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_timers.ev[which][slot][0], g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 static int fail(int code, const std::string& msg) {
@@ -1327,13 +1338,27 @@ extern "C" {
 int surf_abi_version(void) { return SURF_ABI_VERSION; }
 const char* surf_last_error(void) { return g_error.c_str(); }
 int surf_last_launch_count(void) { return g_launches; }
-void surf_set_kernel_timing(int32_t enabled) { g_timers.enabled = enabled != 0; }
+void surf_set_kernel_timing(int32_t enabled) {
+    g_timers.enabled = enabled != 0;
+    for (int k = 0; k < 3; ++k) g_timers.count[k] = 0;
+}
 double surf_last_kernel_ms(int32_t which) {
-    if (which < 0 || which > 2 || !g_timers.created || !g_timers.have[which]) return -1.0;
-    if (cudaEventSynchronize(g_timers.ev[which][1]) != cudaSuccess) return -1.0;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_timers.ev[which][0], g_timers.ev[which][1]) != cudaSuccess) return -1.0;
-    return (double)ms;
+    if (which < 0 || which > 2 || !g_timers.created || g_timers.count[which] == 0) return -1.0;
+    return timer_ms(which, g_timers.count[which] - 1);
+}
+double surf_mean_kernel_ms(int32_t which, int32_t* launches) {
+    if (launches) *launches = 0;
+    if (which < 0 || which > 2 || !g_timers.created || g_timers.count[which] == 0) return -1.0;
+    const long long n = g_timers.count[which];
+    const long long first = n > kTimerRing ? n - kTimerRing : 0;
+    double sum = 0.0;
+    int used = 0;
+    for (long long i = first; i < n; ++i) {
+        const double ms = timer_ms(which, i);
+        if (ms >= 0.0) { sum += ms; ++used; }
+    }
+    if (launches) *launches = used;
+    return used ? sum / used : -1.0;
 }
 
 size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow) {
