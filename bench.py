@@ -259,7 +259,7 @@ def main():
     leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
     for t in leaves:
         t.requires_grad_(True)
-    opt = torch.optim.Adam(leaves, lr=1e-4)
+    opt = torch.optim.Adam(leaves, lr=1e-4, fused=True)
     with torch.no_grad():
         tgt = surf_renderer_b200.render(scene_io.clone_scene(target_scene, device=dev), **params)['image']
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -372,9 +372,19 @@ def main():
         ctx = lib().surf_context_create(local_rank)
         loss_c = C.c_float()
 
+        want = [i for i, nme in enumerate(m.names) if nme in ('objects/disk/pos', 'objects/disk/normal',
+                                                                'materials/albedo', 'lights/pos')]
+        flat_host = torch.empty(sum(grads[i].numel() for i in want)).pin_memory()
+
         def e2e_step():
             check(lib().surf_render_backward_host(ctx, C.byref(csc), C.byref(ccam), C.byref(copt), None, None,
                                                   target_host.data_ptr(), C.byref(loss_c), C.byref(csg)))
+            if world > 1:      # sum the per-band partial gradients across ranks (packed buffer, one all-reduce)
+                torch.cat([grads[i].reshape(-1) for i in want], out=flat_host)
+                flat_dev = flat_host.to(dev, non_blocking=True)
+                dist.all_reduce(flat_dev, op=dist.ReduceOp.SUM)
+                flat_host.copy_(flat_dev, non_blocking=True)
+                torch.cuda.synchronize()
         for _ in range(2):
             e2e_step()
         barrier()

@@ -1197,15 +1197,26 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
     const int grid_max = sm_count() * 2;
     if (!opt->chunk_prims) {
-        while (chunk > 64) {
+        // pick the largest chunk whose item count splits over the persistent grid with <= 1.5% quantisation loss
+        // (items are dealt as equal contiguous ranges: the slowest CTA runs ceil(items / grid) of them)
+        auto items_for = [&](int ch) {
             long long items = 0;
             for (int s = 0; s < f.sc.n_sets; ++s) {
-                const int ppc = (chunk * 2) / rec_f4(f.sc.sets[s].kind);
+                const int ppc = (ch * 2) / rec_f4(f.sc.sets[s].kind);
                 items += (f.sc.sets[s].count + ppc - 1) / ppc;
             }
-            if (items * prm.n_tiles >= 4LL * grid_max) break;
-            chunk /= 2;
+            return items * prm.n_tiles;
+        };
+        int best = 64;
+        double best_loss = 1e30;
+        for (int ch = 1024; ch >= 64; ch /= 2) {
+            const long long items = items_for(ch);
+            const long long per = (items + grid_max - 1) / grid_max;
+            const double loss = (double)per * grid_max / (double)items - 1.0;
+            if (loss <= 0.015) { best = ch; best_loss = loss; break; }
+            if (loss < best_loss) { best = ch; best_loss = loss; }
         }
+        chunk = best;
     }
     prm.stage_f4 = chunk * 2;
     int nchunks = 0;

@@ -35,6 +35,10 @@ class _GatherBands(torch.autograd.Function):
         world = len(sizes)
         if world == 1:
             return band.clone()
+        if min(sizes) == max(sizes):          # equal bands: gather straight into the full-frame tensor
+            out = band.new_empty((sum(sizes),) + tuple(band.shape[1:]))
+            dist.all_gather_into_tensor(out, band.contiguous(), group=group)
+            return out
         mx = max(sizes)
         pad = band
         if band.shape[0] < mx:
