@@ -331,6 +331,17 @@ def main():
                     'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
                     'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
                     'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
+        # the two HBM-side kernels (north star: achieved GB/s against the measured copy bandwidth)
+        n_loc = H * W / world
+        hbm = float(peaks.get('hbm_gbs', 6650.0))
+        shade_bytes = n_loc * (12 + 8 + 48)            # rays + z-buffer key read; image/depth/normal/pos/nearest written
+        bwd_bytes = n_loc * (12 + 8 + 4 + 12)          # rays, nearest, depth, d(image) read (+ ~28 B per hit pixel of atomics)
+        roofline['hbm_kernels'] = {
+            'peak_gbs': hbm, 'peak_source': peak_src + ' MEASURED_PEAKS.json hbm_gbs',
+            'k_shade': {'ms': k_mean[1], 'algorithmic_bytes': shade_bytes, 'achieved_gbs': shade_bytes / (k_mean[1] * 1e-3) / 1e9,
+                        'frac': shade_bytes / (k_mean[1] * 1e-3) / 1e9 / hbm} if k_mean[1] > 0 else None,
+            'k_backward': {'ms': k_mean[2], 'algorithmic_bytes': bwd_bytes, 'achieved_gbs': bwd_bytes / (k_mean[2] * 1e-3) / 1e9,
+                           'frac': bwd_bytes / (k_mean[2] * 1e-3) / 1e9 / hbm} if k_mean[2] > 0 else None}
 
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
     fast = None

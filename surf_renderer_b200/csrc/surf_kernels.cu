@@ -342,29 +342,64 @@ __device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetVie
                                             PixelRegs<P>& r) {
     int i = 0;
     if (MODE == 0) {
+        // Software-pipelined: the records of group k+1 are fetched from shared memory while group k computes,
+        // and the (rare) branch taken in iteration k tests the filter minimum of group k-1, which finished long
+        // ago - so neither the LDS latency nor the FMNMX3 chain + branch resolution sits on the critical path.
         constexpr int G = (P >= 8) ? 2 : 4;
-        for (; i + G <= count; i += G) {
-            float e[G][P];
-            float m = INFINITY;
+        const int ngroups = count / G;
+        if (ngroups > 0) {
+            float4 A[G], B[G];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float4 A = s[2 * (i + g)];
-                const float4 B = s[2 * (i + g) + 1];
+            for (int g = 0; g < G; ++g) { A[g] = s[2 * g]; B[g] = s[2 * g + 1]; }
+            float m_prev = INFINITY;
+            for (int k = 0; k < ngroups; ++k) {
+                float4 An[G], Bn[G];
+                const int nxt = (k + 1 < ngroups ? k + 1 : k) * G;     // last iteration re-reads its own group
 #pragma unroll
-                for (int q = 0; q < P / 2; ++q) {
-                    unpack2(disk_margin2<P>(A, B, r, q), e[g][2 * q], e[g][2 * q + 1]);
-                    m = fminf(m, fminf(e[g][2 * q], e[g][2 * q + 1]));     // NaN-ignoring min: NaN margins are misses
-                }
-            }
-            if (m <= 0.f) {       // rare: some (disk, pixel) of this group passed the conservative filter
+                for (int g = 0; g < G; ++g) { An[g] = s[2 * (nxt + g)]; Bn[g] = s[2 * (nxt + g) + 1]; }
+                float m = INFINITY;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const float4 A = s[2 * (i + g)];
 #pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        if (e[g][p] <= 0.f) narrow_one<P>(sv, local0 + i + g, A, eye, near_clip, far_clip, r, p);
+                    for (int q = 0; q < P / 2; ++q) {
+                        float e0, e1;
+                        unpack2(disk_margin2<P>(A[g], B[g], r, q), e0, e1);
+                        m = fminf(m, fminf(e0, e1));     // NaN-ignoring min: NaN margins are misses
+                    }
+                }
+                if (m_prev <= 0.f) {       // rare: a pair of the PREVIOUS group passed the conservative filter
+                    const int base = (k - 1) * G;
+#pragma unroll 1
+                    for (int g = 0; g < G; ++g) {
+                        const float4 Ag = s[2 * (base + g)], Bg = s[2 * (base + g) + 1];
+#pragma unroll
+                        for (int q = 0; q < P / 2; ++q) {
+                            float e0, e1;
+                            unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
+                            if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
+                            if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
+                        }
+                    }
+                }
+                m_prev = m;
+#pragma unroll
+                for (int g = 0; g < G; ++g) { A[g] = An[g]; B[g] = Bn[g]; }
+            }
+            if (m_prev <= 0.f) {
+                const int base = (ngroups - 1) * G;
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const float4 Ag = s[2 * (base + g)], Bg = s[2 * (base + g) + 1];
+#pragma unroll
+                    for (int q = 0; q < P / 2; ++q) {
+                        float e0, e1;
+                        unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
+                        if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
+                        if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
+                    }
                 }
             }
+            i = ngroups * G;
         }
     }
     for (; i < count; ++i) {

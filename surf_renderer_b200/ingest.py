@@ -1,0 +1,188 @@
+"""Scene / asset ingest: the data formats on the input side of render().
+
+Mirrors, with the same names and return shapes, the reference's loaders
+    diffrend/model.py:90-211          load_splat, load_obj, load_off, load_model, obj_to_triangle_spec
+    diffrend/torch/render.py:9-107    transform_model, load_scene, make_torch_var
+so that a scene JSON (docs/scene_description.md; scenes/*.json) or a .obj/.off/.splat asset can be fed to
+surf_renderer_b200.render exactly as the reference's CLI does (torch/render.py:103-107).  Parsing is numpy; the
+tensors are created directly on the target device.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+
+# ---------------------------------------------------------------------------------------------------
+# asset files
+# ---------------------------------------------------------------------------------------------------
+def _records(path):
+    """whitespace-tokenised, non-empty, non-comment lines of a text asset"""
+    with open(path, 'r') as fh:
+        for raw in fh:
+            tok = raw.split()
+            if not tok or tok[0].startswith('#'):
+                continue
+            yield tok
+
+
+def load_obj(filename, verbose=False):
+    """Wavefront .obj -> {'v': [V,3] float64, 'f': [F,3] int (0-based)}.  Only `v` and `f` records are read; the
+    vertex index is the part of each face token before the first '/' (diffrend/model.py:119-144)."""
+    verts, faces = [], []
+    for tok in _records(filename):
+        if tok[0] == 'v':
+            verts.append([float(x) for x in tok[1:]])
+        elif tok[0] == 'f':
+            faces.append([int(t.split('/')[0]) - 1 for t in tok[1:]])
+    if verbose:
+        print('Vertex count: {}'.format(len(verts)))
+        print('Face count: {}'.format(len(faces)))
+    return {'v': np.array(verts), 'f': np.array(faces)}
+
+
+def load_off(filename, verbose=False):
+    """Object File Format -> {'v', 'f', 'e'} (diffrend/model.py:147-188).  The counts may share the 'OFF' line."""
+    it = _records(filename)
+    head = next(it)
+    if not head[0].startswith('OFF'):
+        raise ValueError('%s: not an OFF file' % filename)
+    counts = head[1:] if len(head) > 1 else next(it)
+    if head[0] != 'OFF' and len(head[0]) > 3:            # 'OFF123 456 0' written without a space
+        counts = [head[0][3:]] + head[1:]
+    n_v, n_f, n_e = (int(c) for c in counts[:3])
+    verts, faces, edges = [], [], []
+    for tok in it:
+        if len(verts) < n_v:
+            verts.append([float(x) for x in tok])
+        elif len(faces) < n_f:
+            faces.append([int(x) for x in tok[1:]])       # first entry is the vertex count of the face
+        elif len(edges) < n_e:
+            edges.append([int(x) for x in tok])
+    if verbose:
+        print('#V: {}, #F: {}, #E: {}'.format(n_v, n_f, n_e))
+    return {'v': np.array(verts), 'f': np.array(faces), 'e': np.array(edges)}
+
+
+def load_splat(filename, verbose=False):
+    """.splat -> {'v': centres, 'vn': normals, 'r': radii [S,1|2|3], 'type': 'splat'} (diffrend/model.py:90-116)."""
+    out = {'v': [], 'vn': [], 'r': []}
+    for tok in _records(filename):
+        if tok[0] in out:
+            out[tok[0]].append([float(x) for x in tok[1:]])
+    if verbose:
+        print('Vertex count: {}'.format(len(out['v'])))
+    return {'v': np.array(out['v']), 'vn': np.array(out['vn']), 'r': np.array(out['r']), 'type': 'splat'}
+
+
+def load_model(filename, verbose=False):
+    """Dispatch on the extension: .off / .obj / .splat (diffrend/model.py:191-199)."""
+    ext = os.path.splitext(filename)[1][1:]
+    loaders = {'off': load_off, 'obj': load_obj, 'splat': load_splat}
+    if ext not in loaders:
+        raise KeyError(ext)
+    return loaders[ext](filename, verbose)
+
+
+def compute_face_normal(obj, unnormalized=False):
+    """Unit normal of every face, cross(v1-v0, v2-v0); degenerate faces keep a zero normal (model.py:18-32)."""
+    tri = obj['v'][obj['f']]
+    n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    if unnormalized:
+        return n
+    length = np.sqrt(np.sum(n ** 2, axis=-1))[..., None]
+    length[length == 0] = 1
+    return n / length
+
+
+def obj_to_triangle_spec(obj):
+    """{'face': [F,3,4] homogeneous vertices (w=1), 'normal': [F,4] face normals (w=0)} (model.py:202-211)."""
+    faces = obj['v'][obj['f']]
+    normals = compute_face_normal(obj)
+    faces = np.concatenate((faces, np.ones(faces.shape[:-1] + (1,), dtype=faces.dtype)), axis=-1)
+    normals = np.concatenate((normals, np.zeros(normals.shape[:-1] + (1,), dtype=normals.dtype)), axis=-1)
+    return {'face': faces, 'normal': normals}
+
+
+# ---------------------------------------------------------------------------------------------------
+# scene files
+# ---------------------------------------------------------------------------------------------------
+def axis_angle_matrix(axis, angle):
+    """4x4 rotation about `axis` by `angle` radians - the unit-quaternion form the reference uses
+    (diffrend/numpy/quaternion.py:74-86 via numpy/ops.py:29-30)."""
+    a = np.asarray(axis, dtype=np.float64)[:3]
+    a = a / np.sqrt(np.sum(a ** 2))
+    w = np.cos(angle / 2.)
+    x, y, z = a * np.sin(angle / 2.)
+    s = 2. / (w * w + x * x + y * y + z * z)
+    return np.array([[1 - s * (y ** 2 + z ** 2), s * (x * y - w * z), s * (x * z + w * y), 0],
+                     [s * (x * y + w * z), 1 - s * (x ** 2 + z ** 2), s * (y * z - w * x), 0],
+                     [s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x ** 2 + y ** 2), 0],
+                     [0, 0, 0, 1]])
+
+
+def transform_model(obj, scale, rotate, translate):
+    """scale -> rotate -> translate of the vertex array, in place (diffrend/torch/render.py:9-34)."""
+    v = obj['v']
+    if scale is not None:
+        v = v * np.array(scale)[None, :]
+    if rotate is not None:
+        M = axis_angle_matrix(axis=rotate['axis'], angle=np.deg2rad(rotate['angle_deg']))
+        v = np.matmul(v, M.transpose(1, 0)[:3, :3])
+    if translate is not None:
+        v = v + np.array(translate)[None, :]
+    obj['v'] = v
+    return obj
+
+
+def load_scene(scene_filename):
+    """Scene JSON -> scene dict whose `objects.obj` entries are loaded, transformed and merged into one
+    `objects.triangle` set (diffrend/torch/render.py:37-85).  Arrays stay numpy; see make_torch_var."""
+    with open(scene_filename, 'r') as fh:
+        scene = json.load(fh)
+    base = os.path.dirname(scene_filename)
+    parts = {'face': [], 'normal': [], 'material_idx': []}
+    for entry in scene['objects']['obj']:
+        model = load_obj(os.path.join(base, entry['path']))
+        model = transform_model(model, entry.get('scale'), entry.get('rotate'), entry.get('translate'))
+        spec = obj_to_triangle_spec(model)
+        parts['face'].append(spec['face'])
+        parts['normal'].append(spec['normal'])
+        parts['material_idx'].append(np.ones(spec['face'].shape[0]) * entry['material_idx'])
+    scene['objects']['triangle'] = {k: np.concatenate(v) for k, v in parts.items()}
+    del scene['objects']['obj']
+    return scene
+
+
+def make_torch_var(var_dict, device=None):
+    """Lists / arrays -> tensors, recursively: integer lists become int64, everything else float32
+    (diffrend/torch/render.py:81-100).  `device` defaults to the current CUDA device when there is one."""
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+
+    def tensor_of(value):
+        first = value
+        while isinstance(first, list) and first:
+            first = first[0]
+            break
+        if type(first) is int:
+            return torch.tensor(value, dtype=torch.int64, device=device)
+        return torch.tensor(np.asarray(value, dtype=np.float64), dtype=torch.float32, device=device)
+
+    for key, value in var_dict.items():
+        if isinstance(value, dict):
+            make_torch_var(value, device)
+        elif isinstance(value, list):
+            var_dict[key] = tensor_of(value)
+        elif isinstance(value, np.ndarray):
+            var_dict[key] = tensor_of(value.tolist())
+    return var_dict
+
+
+def render_scene(scene_file, **params):
+    """diffrend/torch/render.py:103-107."""
+    from .renderer import render
+    return render(make_torch_var(load_scene(scene_file)), **params)
