@@ -566,11 +566,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_intersect_screen: opt-in fast intersection kernel (math_mode 3, perspective).  Level 1 tests EVERY (pixel, primitive) pair
-// in registers against the primitive's screen-space bounding circle: per pixel pair one FADD2 + one FFMA2
-// (packed f32x2) + one FMNMX3, i.e. 2.25 FMA-pipe lane-instructions per test at P = 8 (the y-term is shared by
-// the P pixels of a thread, which sit in one image row).  The rare flagged pairs run the exact reference-order
-// test.  Same persistent-CTA / TMA-ring / atomicMin z-buffer structure as k_intersect.
+// k_intersect_screen: opt-in fast intersection kernel (math_mode 3, perspective).  Level 1 classifies EVERY (pixel,
+// primitive) pair in registers against the primitive's screen-space bounding circle.  The test is separable: the
+// row term (y - v)^2 - rho^2 is shared by the P pixels of a thread (they sit in one image row) and rules all of
+// them out when positive; otherwise the column terms are evaluated two pixels per instruction (FADD2 + FFMA2 +
+// FMNMX3 per pixel pair).  The rare flagged pairs run the exact reference-order test.  Same persistent-CTA / TMA-ring / atomicMin z-buffer structure as k_intersect.
 //   thread -> P consecutive columns of one row; warp -> 4P x 8 pixels; CTA -> 8P x 32 pixels.
 // ---------------------------------------------------------------------------------------------------
 struct ScreenParams {
@@ -699,13 +699,24 @@ __global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen
         constexpr int G = 4;
         int i = 0;
         for (; i + G <= count; i += G) {
+            // row term first: the P pixels of a thread share one image row, so sy = (y - v)^2 - rho^2 > 0 rules out
+            // all of them at once.  Only when some lane's row crosses one of the G circles are the column terms
+            // evaluated (packed, two pixels per instruction).
+            float4 C[G];
+            float sy[G];
+            float my = INFINITY;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                C[g] = s[i + g];                            // -u, -v, -rho^2, 0   (LDS.128, warp broadcast)
+                const float dy = y + C[g].y;
+                sy[g] = fmaf(dy, dy, C[g].z);
+                my = fminf(my, sy[g]);
+            }
+            if (!__any_sync(0xffffffffu, my <= 0.f)) continue;
             float m = INFINITY;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const float4 C = s[i + g];                  // -u, -v, -rho^2, 0   (LDS.128, warp broadcast)
-                const float dy = y + C.y;
-                const float sy = fmaf(dy, dy, C.z);
-                const unsigned long long mu = pack2(C.x, C.x), sy2 = pack2(sy, sy);
+                const unsigned long long mu = pack2(C[g].x, C[g].x), sy2 = pack2(sy[g], sy[g]);
 #pragma unroll
                 for (int q = 0; q < P / 2; ++q) {
                     const unsigned long long dx = add2(x2[q], mu);
