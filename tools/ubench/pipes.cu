@@ -29,6 +29,18 @@ __global__ void __launch_bounds__(256) k(int iters, float* out){
       for(int j=0;j<8;j++) u[j]=rcpa(u[j]);
     }
     if(MODE==4){ float a0,a1; unpack2(x[i&7?0:1],a0,a1); m=fminf(m,fminf(a0,a1)); }
+    if(MODE==6){   // FFMA2 with a scalar .F32 broadcast multiplicand (as in the intersection kernel)
+      #pragma unroll
+      for(int j=0;j<10;j++) x[j]=fma2(pack2(u[j&7],u[j&7]),x[j],c);
+    }
+    if(MODE==7){   // FFMA2 with a scalar .F32 broadcast addend
+      #pragma unroll
+      for(int j=0;j<10;j++) x[j]=fma2(x[j],b,pack2(u[j&7],u[j&7]));
+    }
+    if(MODE==8){   // square-accumulate form: fma2(x, x, y)
+      #pragma unroll
+      for(int j=0;j<10;j++) x[j]=fma2(x[(j+1)%10],x[(j+1)%10],x[j]);
+    }
     if(MODE==5){
       float a0[20];
       #pragma unroll
@@ -58,5 +70,8 @@ int main(){
   run<3>("8 MUFU.RCP", 0, 8);
   run<4>("10 FFMA2 + 2 MUFU + FMNMX3", 10, 2);
   run<5>("20 FFMA scalar + 2 MUFU", 10, 2);
+  run<6>("10 FFMA2 bcast multiplicand", 10, 0);
+  run<7>("10 FFMA2 bcast addend", 10, 0);
+  run<8>("10 FFMA2 x*x+y", 10, 0);
   return 0;
 }
