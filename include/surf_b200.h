@@ -163,6 +163,33 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
                   const int64_t* nearest, const float* depth,
                   const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads, void* cuda_stream);
 
+/* ---- one-splat-per-pixel renderer: diffrend/torch/renderer.py:537-751 render_splats_along_ray ----
+ * Splat k sits on the ray of flat pixel k at camera-space depth z[k] (negative = in front of the camera,
+ * clamped with -relu(-z)); it is shaded in camera coordinates with the same fragment shader as render()
+ * (no double_sided, no tonemap; use_quartic honoured).  `scene` supplies lights / colours / materials only
+ * (its primitive sets are ignored; light_pos must be homogeneous [L,4], it is multiplied by the view matrix).
+ * Outputs: image [n,3], depth [n] = |pos|, pos [n,3] (camera coordinates), normal [n,3] (copy of the input). */
+typedef struct SurfSplats {
+    int32_t count;            /* must equal width * height */
+    const float* z;           /* [count] depths, or column 2 of a [count,3] position array (z_stride = 3) */
+    int32_t z_stride;         /* 1 or 3 */
+    const float* normal;      /* [count, normal_stride] camera-space normals (used as given, not normalised) */
+    int32_t normal_stride;    /* 3 or 4 */
+    const int32_t* material_idx; /* [count], or NULL = material 0 */
+    const float* light_vis;   /* [L, count] per-light visibility (constant), or NULL */
+} SurfSplats;
+typedef struct SurfSplatGrads {
+    float* z;                 /* same stride as SurfSplats.z; caller zero-initialises, the library adds */
+    float* normal;            /* same stride as SurfSplats.normal */
+} SurfSplatGrads;
+int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                        const SurfSplats* splats, void* workspace, size_t workspace_bytes,
+                        const SurfOutputs* out, void* cuda_stream);
+int surf_splats_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                         const SurfSplats* splats, void* workspace, size_t workspace_bytes,
+                         const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads,
+                         const SurfSplatGrads* splat_grads, void* cuda_stream);
+
 /* ---- host-pointer API (self-contained: H2D, kernels, D2H) ---- */
 typedef struct SurfContext SurfContext;
 SurfContext* surf_context_create(int32_t device);

@@ -431,3 +431,64 @@ def _shadow_visibility(light_pos, frag_p, winner, objects, params, n_pix):
             vis.append((((nearest_t == MISS_SENTINEL) + (blocker == winner[lo:hi])) > 0).float())
         out.append(torch.cat(vis))
     return torch.stack(out, dim=0)
+
+
+# --------------------------------------------------------------------------
+# render_splats_along_ray (renderer.py:537-751): one splat per pixel at depth z along the pixel's ray, shaded in
+# camera coordinates.  Restated for samples == 1 with caller-provided normals (the GAN generator path,
+# GAN/gan.py:563-597); normal estimation (utils.py:886-972) and supersampling are not restated.
+# --------------------------------------------------------------------------
+def view_matrix(eye, at, up):
+    """utils.py:376-382 ``lookat``: world -> camera, the inverse of camera_pose."""
+    return camera_pose(eye, at, up).inverse()
+
+
+def render_along_ray(scene, **params):
+    camera = scene['camera']
+    vp = np.array(camera['viewport'])
+    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    aspect = W / H
+    eye, at, up = camera['eye'][:3], camera['at'][:3], camera['up'][:3]
+    mcam = view_matrix(eye=eye, at=at, up=up)
+    splats = scene['objects']['disk']
+    z_in = splats['pos']
+    normals_cc = splats.get('normal', None)
+    if normals_cc is None:
+        raise NotImplementedError('normal estimation is not restated')
+    if params.get('samples', 1) > 1:
+        raise NotImplementedError('supersampling is not restated')
+    fovy, focal = camera['fovy'], camera['focal_length']
+    h = np.tan(fovy / 2) * 2 * focal
+    w = h * aspect
+    if z_in.dim() == 1:
+        Z = -torch.nn.functional.relu(-z_in)
+    else:
+        Z = -torch.nn.functional.relu(-z_in[:, 2])
+    gx, gy = np.meshgrid(np.linspace(-1, 1, W), np.linspace(1, -1, H))
+    gx *= w / 2
+    gy *= h / 2
+    x = _f32(gx.ravel())
+    y = _f32(gy.ravel())
+    X = -Z * x / focal
+    Y = -Z * y / focal
+    pos_cc = torch.stack((X, Y, Z), dim=1)
+    material_idx = splats['material_idx']
+    visibility = splats.get('light_vis', None)
+    depth = lp_norm(pos_cc[..., :3]).view(H, W)
+    lights = scene['lights']
+    light_rgb = scene['colors'][lights['color_idx']]
+    light_cc = torch.mm(lights['pos'], mcam.transpose(1, 0))
+    frag_n = normals_cc[:, :3]
+    frag_p = pos_cc[:, :3]
+    if material_idx is not None:
+        albedo = torch.index_select(scene['materials']['albedo'], 0, material_idx)
+        coeffs = torch.index_select(scene['materials']['coeffs'], 0, material_idx)
+    else:
+        albedo, coeffs = scene['materials']['albedo'], scene['materials']['coeffs']
+    per_light = phong(frag_normals=frag_n, to_light=light_cc[:, None, :3] - frag_p[:, :3],
+                      to_eye=-unit(frag_p[None, :, :3]), atten=lights['attenuation'], coeffs=coeffs,
+                      light_rgb=light_rgb, ambient=lights['ambient'], albedo=albedo, double_sided=False,
+                      use_quartic=params.get('use_quartic', False), visibility=visibility)
+    im = torch.nn.functional.relu(torch.sum(per_light, dim=0).view(H, W, 3))
+    return {'image': im, 'depth': depth, 'pos': pos_cc[..., :3].view(H, W, 3),
+            'normal': normals_cc[..., :3].contiguous().view(H, W, 3)}

@@ -61,6 +61,15 @@ class SurfSceneGrads(C.Structure):
                 ('colors', C.c_void_p), ('albedo', C.c_void_p), ('coeffs', C.c_void_p), ('gamma', C.c_void_p)]
 
 
+class SurfSplats(C.Structure):
+    _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
+                ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p)]
+
+
+class SurfSplatGrads(C.Structure):
+    _fields_ = [('z', C.c_void_p), ('normal', C.c_void_p)]
+
+
 # every symbol include/surf_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'surf_abi_version': (C.c_int, []),
@@ -71,6 +80,11 @@ SYMBOLS = {
     'surf_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                 C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_splats_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                      C.POINTER(SurfSplats), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
+    'surf_splats_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                       C.POINTER(SurfSplats), C.c_void_p, C.c_size_t, C.POINTER(SurfOutGrads),
+                                       C.POINTER(SurfSceneGrads), C.POINTER(SurfSplatGrads), C.c_void_p]),
     'surf_context_create': (C.c_void_p, [C.c_int32]),
     'surf_context_destroy': (None, [C.c_void_p]),
     'surf_render_host': (C.c_int, [C.c_void_p, C.POINTER(SurfScene), C.POINTER(SurfCamera),

@@ -949,7 +949,12 @@ struct DeviceSink {
             lp[c] = at[c] = col[c] = 0.f;
         }
     }
+    __device__ void end_splat(int m) { flush_scalars(m); }
     __device__ void end_pixel(int set, int local, int idx, int m, const float* g7) {
+        flush_scalars(m);
+        flush_primitive(set, local, idx, g7);
+    }
+    __device__ void flush_scalars(int m) {
         const int lane = threadIdx.x & 31;
         // global scalars
 #pragma unroll
@@ -977,6 +982,9 @@ struct DeviceSink {
                 if (cf[c] != 0.f) atomicAdd(&cta_acc[p.sm.coeffs + m * 3 + c], (double)cf[c]);
             }
         }
+    }
+    __device__ void flush_primitive(int set, int local, int idx, const float* g7) {
+        const int lane = threadIdx.x & 31;
         // per-primitive gradients: warp-segmented reduction keyed by the winner index, then one
         // red.global.add per component from the segment leader
         const unsigned peers = __match_any_sync(0xffffffffu, idx);
@@ -1076,6 +1084,125 @@ __global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant
     else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
     else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
     else { if (p.gp.gamma) p.gp.gamma[0] += v; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// render_splats_along_ray kernels (renderer.py:537-751)
+// ---------------------------------------------------------------------------------------------------
+struct SplatParams {
+    SceneView sc;                 // lights (camera space, stride 3, in the workspace) / colours / materials
+    const CamState* cam;
+    const float* z; int z_stride;
+    const float* normal; int normal_stride;
+    const int* mat;
+    const float* vis;             // [L, n] or null
+    int n;
+    ShadeFlags fl;
+    float* image; float* depth; float* normal_out; float* pos;                       // forward outputs
+    const float* g_image; const float* g_depth; const float* g_normal; const float* g_pos;   // backward inputs
+    float* gz; float* gnormal;    // backward outputs (caller's strides)
+    SlotMap sm; double* acc;
+};
+
+__global__ void k_splat_setup(CamArgs a, CamState* cs, const float* light_pos4, int n_lights, float* light_cc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        camera_setup(a.eye, a.at, a.up, 0, a.W, a.H, a.fovy, a.focal, a.near_clip, a.far_clip, cs);
+    __syncthreads();
+    for (int l = threadIdx.x; l < n_lights; l += blockDim.x) {
+        Vec3 v = light_to_camera(*cs, light_pos4 + 4 * (size_t)l);
+        light_cc[3 * l] = v.x; light_cc[3 * l + 1] = v.y; light_cc[3 * l + 2] = v.z;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_splat_forward(const __grid_constant__ SplatParams p) {
+    __shared__ float sm[256][3];
+    const int base = blockIdx.x * 256;
+    const int k = base + threadIdx.x;
+    const bool live = k < p.n;
+    SplatOut so = SplatOut();
+    float nn[3] = {0.f, 0.f, 0.f};
+    if (live) {
+        float vis_l[16];
+        const float* vis = nullptr;
+        if (p.vis) {
+            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + k];
+            vis = vis_l;
+        }
+        const float* np_ = p.normal + (size_t)k * p.normal_stride;
+        nn[0] = np_[0]; nn[1] = np_[1]; nn[2] = np_[2];
+        so = splat_pixel_forward(p.sc, *p.cam, k, p.z[(size_t)k * p.z_stride], v3(nn[0], nn[1], nn[2]),
+                                 p.mat ? p.mat[k] : 0, p.fl, vis);
+        if (p.depth) p.depth[k] = so.depth;
+    }
+    if (p.image) store3(p.image, sm, base, p.n, so.image);
+    if (p.pos) store3(p.pos, sm, base, p.n, so.pos);
+    if (p.normal_out) store3(p.normal_out, sm, base, p.n, nn);
+}
+
+__global__ void __launch_bounds__(128) k_splat_backward(const __grid_constant__ SplatParams p) {
+    __shared__ double cta_acc[kMaxAccSlots];
+    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < p.n;
+    const int kk = live ? k : p.n - 1;
+    PixelGrads g;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
+        g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
+        g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
+    }
+    g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
+    float vis_l[16];
+    const float* vis = nullptr;
+    if (p.vis) {
+        for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
+        vis = vis_l;
+    }
+    BackwardParams bp_view;          // DeviceSink only reads the slot map from it
+    bp_view.sm = p.sm;
+    DeviceSink sink(bp_view, cta_acc);
+    const float* np_ = p.normal + (size_t)kk * p.normal_stride;
+    float gz, gn[3];
+    splat_pixel_backward(p.sc, *p.cam, kk, p.z[(size_t)kk * p.z_stride], v3(np_[0], np_[1], np_[2]),
+                         p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gn);
+    if (live) {
+        if (p.gz) p.gz[(size_t)k * p.z_stride] += gz;
+        if (p.gnormal)
+            for (int c = 0; c < 3; ++c) p.gnormal[(size_t)k * p.normal_stride + c] += gn[c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x)
+        if (cta_acc[j] != 0.0) atomicAdd(p.acc + j, cta_acc[j]);
+}
+
+struct SplatFinalizeParams { GradPtrs gp; SlotMap sm; const double* acc; const CamState* cam; int L; };
+__global__ void __launch_bounds__(128) k_splat_finalize(const __grid_constant__ SplatFinalizeParams p) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.sm.total) return;
+    const float v = (float)p.acc[j];
+    if (j < p.sm.coeffs) { if (p.gp.albedo) p.gp.albedo[j - p.sm.albedo] += v; }
+    else if (j < p.sm.light_pos) { if (p.gp.coeffs) p.gp.coeffs[j - p.sm.coeffs] += v; }
+    else if (j < p.sm.atten) {
+        // camera -> world: l_cc = R^T l_xyz - l_w R^T eye  =>  d/dl_xyz = R g,  d/dl_w = -(R^T eye) . g
+        const int q = j - p.sm.light_pos;
+        const int l = q / 3, c = q % 3;
+        if (p.gp.light_pos && c == 0) {
+            const CamState& cs = *p.cam;
+            const double g0 = p.acc[j], g1 = p.acc[j + 1], g2 = p.acc[j + 2];
+            float* dst = p.gp.light_pos + 4 * (size_t)l;
+            for (int r = 0; r < 3; ++r) dst[r] += (float)(cs.R[3 * r] * g0 + cs.R[3 * r + 1] * g1 + cs.R[3 * r + 2] * g2);
+            double gw = 0.0;
+            const double gi[3] = {g0, g1, g2};
+            for (int i = 0; i < 3; ++i)
+                gw -= ((double)cs.R[i] * cs.eye[0] + (double)cs.R[3 + i] * cs.eye[1] + (double)cs.R[6 + i] * cs.eye[2]) * gi[i];
+            dst[3] += (float)gw;
+        }
+    }
+    else if (j < p.sm.colors) { if (p.gp.atten) p.gp.atten[j - p.sm.atten] += v; }
+    else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
+    else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
 }
 
 // d/d(image) of mean((image - target)^2) and the loss itself (inverse-rendering step, test_optimization.py:104)
@@ -1376,6 +1503,83 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     return SURF_OK;
 }
 
+static int splat_frame(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
+                       void* workspace, size_t workspace_bytes, SplatParams* p, CamArgs* cam, Workspace* ws, float** light_cc) {
+    if (!scene || !camera || !opt || !sp) return fail(SURF_ERR_BAD_ARG, "null scene/camera/options/splats");
+    std::string err;
+    SceneView sc;
+    if (!build_scene_view(*scene, &sc, &err, true)) return fail(SURF_ERR_BAD_ARG, err);
+    if (!check_camera(*camera, &err)) return fail(SURF_ERR_BAD_ARG, err);
+    if (camera->proj != 0) return fail(SURF_ERR_UNSUPPORTED, "render_splats_along_ray is defined for the perspective frustum");
+    if (scene->light_pos_stride != 4) return fail(SURF_ERR_BAD_ARG, "along-ray lights must be homogeneous [L,4] (torch.mm with the 4x4 view matrix)");
+    if (sp->count != camera->width * camera->height) return fail(SURF_ERR_BAD_ARG, "one splat per pixel: count must equal width*height");
+    if (!sp->z || !sp->normal) return fail(SURF_ERR_UNSUPPORTED, "splat depths and normals are required (normal estimation is not built)");
+    if ((sp->z_stride != 1 && sp->z_stride != 3) || (sp->normal_stride != 3 && sp->normal_stride != 4))
+        return fail(SURF_ERR_BAD_ARG, "z_stride must be 1 or 3, normal_stride 3 or 4");
+    if (sc.n_lights > 16 && sp->light_vis) return fail(SURF_ERR_UNSUPPORTED, "light_vis supports at most 16 lights");
+    if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
+    carve(workspace, 0, sp->count, sc.n_lights, false, ws);
+    if (ws->bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
+    *light_cc = ws->rays;                       // the ray buffer is unused on this path: holds the L x 3 camera-space lights
+    *cam = CamArgs{camera->eye, camera->at, camera->up, 0, camera->width, camera->height, camera->fovy,
+                   camera->focal_length, camera->near_clip, camera->far_clip};
+    p->sc = sc;
+    p->sc.light_pos = *light_cc; p->sc.light_pos_stride = 3; p->sc.gamma = nullptr;
+    p->cam = ws->cam;
+    p->z = sp->z; p->z_stride = sp->z_stride; p->normal = sp->normal; p->normal_stride = sp->normal_stride;
+    p->mat = sp->material_idx; p->vis = sp->light_vis; p->n = sp->count;
+    p->fl = ShadeFlags{0, opt->use_quartic};
+    p->image = p->depth = p->normal_out = p->pos = nullptr;
+    p->g_image = p->g_depth = p->g_normal = p->g_pos = nullptr;
+    p->gz = p->gnormal = nullptr;
+    p->sm = slot_map(sc.n_materials, sc.n_lights, sc.n_colors);
+    p->acc = ws->acc;
+    if (p->sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the backward accumulators");
+    return SURF_OK;
+}
+
+static int splats_forward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
+                               void* workspace, size_t bytes, const SurfOutputs* out, cudaStream_t st) {
+    if (!out) return fail(SURF_ERR_BAD_ARG, "null outputs");
+    SplatParams p; CamArgs cam; Workspace ws; float* lcc;
+    int rc = splat_frame(scene, camera, opt, sp, workspace, bytes, &p, &cam, &ws, &lcc);
+    if (rc) return rc;
+    k_splat_setup<<<1, 64, 0, st>>>(cam, ws.cam, scene->light_pos, scene->n_lights, lcc);
+    SURF_LAUNCHED("k_splat_setup");
+    p.image = out->image; p.depth = out->depth; p.normal_out = out->normal; p.pos = out->pos;
+    timer_mark(1, 0, st);
+    k_splat_forward<<<(p.n + 255) / 256, 256, 0, st>>>(p);
+    timer_mark(1, 1, st);
+    SURF_LAUNCHED("k_splat_forward");
+    return SURF_OK;
+}
+
+static int splats_backward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
+                                void* workspace, size_t bytes, const SurfOutGrads* og, const SurfSceneGrads* sg,
+                                const SurfSplatGrads* spg, cudaStream_t st) {
+    if (!og || !sg || !spg) return fail(SURF_ERR_BAD_ARG, "null out_grads/scene_grads/splat_grads");
+    SplatParams p; CamArgs cam; Workspace ws; float* lcc;
+    int rc = splat_frame(scene, camera, opt, sp, workspace, bytes, &p, &cam, &ws, &lcc);
+    if (rc) return rc;
+    k_splat_setup<<<1, 64, 0, st>>>(cam, ws.cam, scene->light_pos, scene->n_lights, lcc);
+    SURF_LAUNCHED("k_splat_setup");
+    SURF_CUDA(cudaMemsetAsync(ws.acc, 0, sizeof(double) * kMaxAccSlots, st));
+    p.g_image = og->image; p.g_depth = og->depth; p.g_normal = og->normal; p.g_pos = og->pos;
+    p.gz = spg->z; p.gnormal = spg->normal;
+    timer_mark(2, 0, st);
+    k_splat_backward<<<(p.n + 127) / 128, 128, 0, st>>>(p);
+    timer_mark(2, 1, st);
+    SURF_LAUNCHED("k_splat_backward");
+    SplatFinalizeParams fp;
+    for (int s = 0; s < kMaxSets; ++s) fp.gp.prim_pos[s] = fp.gp.prim_normal[s] = fp.gp.prim_radius[s] = nullptr;
+    fp.gp.light_pos = sg->light_pos; fp.gp.atten = sg->light_attenuation; fp.gp.ambient = sg->ambient;
+    fp.gp.colors = sg->colors; fp.gp.albedo = sg->albedo; fp.gp.coeffs = sg->coeffs; fp.gp.gamma = nullptr;
+    fp.sm = p.sm; fp.acc = ws.acc; fp.cam = ws.cam; fp.L = scene->n_lights;
+    k_splat_finalize<<<(p.sm.total + 127) / 128, 128, 0, st>>>(fp);
+    SURF_LAUNCHED("k_splat_finalize");
+    return SURF_OK;
+}
+
 }  // namespace surf
 
 // ===================================================================================================
@@ -1438,6 +1642,21 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
     const bool warm = options && options->forced_nearest == 2;
     return backward_impl(scene, camera, options, workspace, workspace_bytes, nearest, depth, out_grads, scene_grads,
                          (cudaStream_t)cuda_stream, warm);
+}
+
+int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                        const SurfSplats* splats, void* workspace, size_t workspace_bytes, const SurfOutputs* out,
+                        void* cuda_stream) {
+    g_launches = 0;
+    return splats_forward_impl(scene, camera, options, splats, workspace, workspace_bytes, out, (cudaStream_t)cuda_stream);
+}
+
+int surf_splats_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                         const SurfSplats* splats, void* workspace, size_t workspace_bytes, const SurfOutGrads* out_grads,
+                         const SurfSceneGrads* scene_grads, const SurfSplatGrads* splat_grads, void* cuda_stream) {
+    g_launches = 0;
+    return splats_backward_impl(scene, camera, options, splats, workspace, workspace_bytes, out_grads, scene_grads,
+                                splat_grads, (cudaStream_t)cuda_stream);
 }
 
 double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream) {

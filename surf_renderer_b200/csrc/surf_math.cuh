@@ -511,19 +511,15 @@ struct PixelGrads {           // incoming output gradients at one pixel
     float image[3]; float depth; float pos[3]; float normal[3];
 };
 
+// backward of composite + shading at one fragment (P, n, material m): accumulates material / light / colour /
+// ambient / gamma gradients into the sink and ADDS d/dP and d/dn to *gP, *gn.
 template <class Sink>
-SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int idx, bool hit,
-                            ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink) {
+SURF_HD void backward_shading(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int m, bool hit, ShadeFlags fl,
+                              const float* visibility, const float g_image[3], Sink& sink, Vec3* gP_io, Vec3* gn_io) {
     // Control flow is kept uniform across pixels (no early exits around sink calls): the device sink
     // reduces across the warp inside end_light()/end_pixel(), so every lane must reach them.  Inactive
     // pixels compute on (finite-or-not) garbage and contribute selected zeros.
-    Fragment f = fragment_at(sc, idx, o, d);
-    const SetView& sv = sc.sets[f.set];
-    Vec3 P = f.P, n = f.n;
-    Vec3 gP = v3(g.pos[0], g.pos[1], g.pos[2]);
-    Vec3 gn = v3(g.normal[0], g.normal[1], g.normal[2]);
-
-    const int m = f.mat;
+    Vec3 gP = *gP_io, gn = *gn_io;
     const float* A = sc.albedo + 3 * m;
     const float kd = sc.coeffs[3 * m + 0], ks = sc.coeffs[3 * m + 1], sh = sc.coeffs[3 * m + 2];
     // forward recompute of the composite to get dLoss/dI (renderer.py:330-340 backwards)
@@ -538,10 +534,10 @@ SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int i
         if (hit && Ic > 0.f) {
             if (sc.gamma) {
                 float gm = sc.gamma[0];
-                gI[c] = g.image[c] * gm * powf(Ic, gm - 1.f);
-                if (g.image[c] != 0.f) g_gamma += g.image[c] * powf(Ic, gm) * logf(Ic);
+                gI[c] = g_image[c] * gm * powf(Ic, gm - 1.f);
+                if (g_image[c] != 0.f) g_gamma += g_image[c] * powf(Ic, gm) * logf(Ic);
             } else {
-                gI[c] = g.image[c];
+                gI[c] = g_image[c];
             }
         }
         active |= (gI[c] != 0.f);
@@ -629,6 +625,21 @@ SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int i
         gP = v3(gP.x - (gV.x - gv_dot * V.x) / sv_len, gP.y - (gV.y - gv_dot * V.y) / sv_len,
                 gP.z - (gV.z - gv_dot * V.z) / sv_len);
     }
+
+    *gP_io = gP;
+    *gn_io = gn;
+}
+
+template <class Sink>
+SURF_HD void backward_pixel(const SceneView& sc, Vec3 eye, Vec3 o, Vec3 d, int idx, bool hit,
+                            ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink) {
+    Fragment f = fragment_at(sc, idx, o, d);
+    const SetView& sv = sc.sets[f.set];
+    Vec3 P = f.P, n = f.n;
+    Vec3 gP = v3(g.pos[0], g.pos[1], g.pos[2]);
+    Vec3 gn = v3(g.normal[0], g.normal[1], g.normal[2]);
+    const int m = f.mat;
+    backward_shading(sc, eye, P, n, m, hit, fl, visibility, g.image, sink, &gP, &gn);
 
     const float g_depth = hit ? g.depth : 0.f;
     float out7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -747,6 +758,63 @@ SURF_HD float shadow_visibility(const SceneView& sc, Vec3 P, int self_idx, int l
         }
     }
     return ((best_t == kMissSentinel) || (best == self_idx)) ? 1.f : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// render_splats_along_ray (renderer.py:537-751): one splat per pixel at camera-space depth z on the pixel's ray,
+// shaded in camera coordinates (eye at the origin, lights transformed by the view matrix).
+// ---------------------------------------------------------------------------------------------------
+// light l in camera coordinates: row l of torch.mm(light_pos [L,4], Mcam^T) with Mcam = [R^T | -R^T eye]
+SURF_HD Vec3 light_to_camera(const CamState& cs, const float* l4) {
+    Vec3 out;
+    float* o = &out.x;
+    for (int i = 0; i < 3; ++i) {
+        const Vec3 col = v3(cs.R[i], cs.R[3 + i], cs.R[6 + i]);
+        const float ti = -dot_seq(col, v3(cs.eye[0], cs.eye[1], cs.eye[2]));
+        o[i] = xfma(l4[3], ti, xfma(l4[2], col.z, xfma(l4[1], col.y, xmul(l4[0], col.x))));
+    }
+    return out;
+}
+// splat position from its depth: Z = -relu(-z), X = -Z x / f, Y = -Z y / f (renderer.py:566-580); depth = |P|
+SURF_HD void splat_fragment(const CamState& cs, int pix, float z, Vec3* P, float* depth, float* px, float* py) {
+    const float Z = z < 0.f ? z : -0.f;
+    float x, y;
+    pixel_xy(cs, pix, &x, &y);
+    const float f = -cs.neg_focal;
+    *P = v3(xdiv(xmul(-Z, x), f), xdiv(xmul(-Z, y), f), Z);
+    *depth = xsqrt(sq3_seq(*P));
+    *px = x; *py = y;
+}
+struct SplatOut { float image[3]; float depth; float pos[3]; };
+SURF_HD SplatOut splat_pixel_forward(const SceneView& sc, const CamState& cs, int pix, float z, Vec3 n, int mat,
+                                     ShadeFlags fl, const float* visibility) {
+    SplatOut so;
+    Vec3 P;
+    float x, y;
+    splat_fragment(cs, pix, z, &P, &so.depth, &x, &y);
+    float lit[3];
+    shade_pixel(sc, v3(0.f, 0.f, 0.f), P, n, mat, fl, visibility, lit);
+    for (int c = 0; c < 3; ++c) so.image[c] = lit[c] > 0.f ? lit[c] : 0.f;          // relu, no tonemap (:741)
+    so.pos[0] = P.x; so.pos[1] = P.y; so.pos[2] = P.z;
+    return so;
+}
+// backward of one splat: returns d/dz and d/dnormal; light / material gradients go to the sink
+template <class Sink>
+SURF_HD void splat_pixel_backward(const SceneView& sc, const CamState& cs, int pix, float z, Vec3 n, int mat,
+                                  ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink,
+                                  float* gz, float gn_out[3]) {
+    Vec3 P;
+    float depth, x, y;
+    splat_fragment(cs, pix, z, &P, &depth, &x, &y);
+    Vec3 gP = v3(g.pos[0], g.pos[1], g.pos[2]);
+    Vec3 gn = v3(g.normal[0], g.normal[1], g.normal[2]);
+    backward_shading(sc, v3(0.f, 0.f, 0.f), P, n, mat, true, fl, visibility, g.image, sink, &gP, &gn);
+    if (depth > 0.f) gP = faxpy(g.depth / depth, P, gP);
+    const float f = -cs.neg_focal;
+    const float gZ = gP.z - gP.x * x / f - gP.y * y / f;
+    *gz = z < 0.f ? gZ : 0.f;
+    gn_out[0] = gn.x; gn_out[1] = gn.y; gn_out[2] = gn.z;
+    sink.end_splat(mat);
 }
 
 // order-preserving float -> uint32 map for the packed z-buffer key (t_key << 32 | primitive index);

@@ -8,11 +8,12 @@
 
 namespace surf {
 
-inline bool build_scene_view(const SurfScene& s, SceneView* v, std::string* err) {
-    if (s.n_sets < 1 || s.n_sets > SURF_MAX_SETS) { *err = "scene needs 1..8 primitive sets"; return false; }
-    v->n_sets = s.n_sets;
+inline bool build_scene_view(const SurfScene& s, SceneView* v, std::string* err, bool shading_only = false) {
+    const int n_sets = shading_only ? 0 : s.n_sets;       // along-ray splats: only lights / colours / materials
+    if (!shading_only && (s.n_sets < 1 || s.n_sets > SURF_MAX_SETS)) { *err = "scene needs 1..8 primitive sets"; return false; }
+    v->n_sets = n_sets;
     int first = 0, rec = 0;
-    for (int k = 0; k < s.n_sets; ++k) {
+    for (int k = 0; k < n_sets; ++k) {
         const SurfPrimSet& p = s.sets[k];
         SetView& o = v->sets[k];
         if (p.kind < 0 || p.kind > 3) { *err = "unknown primitive kind"; return false; }
@@ -33,7 +34,7 @@ inline bool build_scene_view(const SurfScene& s, SceneView* v, std::string* err)
         // every set's packed records start on a 128-byte boundary (8 float4) for the TMA bulk copies
         rec += ((p.count * rec_f4(p.kind) + 7) / 8) * 8;
     }
-    for (int k = s.n_sets; k < kMaxSets; ++k) { v->sets[k] = SetView(); v->sets[k].first = 0x7fffffff; }
+    for (int k = n_sets; k < kMaxSets; ++k) { v->sets[k] = SetView(); v->sets[k].first = 0x7fffffff; }
     v->total = first;
     if (s.n_lights < 1 || !s.light_pos || !s.light_color_idx || !s.light_attenuation || !s.ambient) {
         *err = "lights: pos, color_idx, attenuation and ambient are required (renderer.py:266-274)";

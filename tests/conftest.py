@@ -17,4 +17,10 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+    """fixtures of render() (make_golden.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('ar_'))
+
+
+def along_ray_cases():
+    """fixtures of render_splats_along_ray() (make_golden_along_ray.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('ar_'))

@@ -65,6 +65,7 @@ struct HostSink {
     }
     // the interface backward_pixel() writes to
     void end_light(int, int) {}
+    void end_splat(int) {}
     void end_pixel(int set, int local, int, int, const float* g7) {
         for (int k = 0; k < 7; ++k) g_prim[set][(size_t)local * 7 + k] += g7[k];
     }
@@ -232,6 +233,90 @@ int emul_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptio
     for (int c = 0; c < 3; ++c)
         if (sg->ambient) sg->ambient[c] += (float)hs.g_amb[c];
     if (sg->gamma) sg->gamma[0] += (float)hs.g_gamma;
+    return 0;
+}
+
+// ---- render_splats_along_ray emulation -----------------------------------------------------------
+struct EmulSplats { int count; const float* z; int z_stride; const float* normal; int normal_stride; const int* mat;
+                    const float* vis; };
+
+static bool splat_setup(const SurfScene* scene, const SurfCamera* cam, SceneView* sc, CamState* cs, std::vector<float>* lcc) {
+    SurfScene tmp = *scene;
+    if (!build_scene_view(tmp, sc, &g_err, true) || !check_camera(*cam, &g_err)) return false;
+    if (scene->light_pos_stride != 4) { g_err = "along-ray lights must be homogeneous [L,4]"; return false; }
+    camera_setup(cam->eye, cam->at, cam->up, 0, cam->width, cam->height, cam->fovy, cam->focal_length,
+                 cam->near_clip, cam->far_clip, cs);
+    lcc->resize((size_t)sc->n_lights * 3);
+    for (int l = 0; l < sc->n_lights; ++l) {
+        Vec3 v = light_to_camera(*cs, scene->light_pos + 4 * (size_t)l);
+        (*lcc)[3 * l] = v.x; (*lcc)[3 * l + 1] = v.y; (*lcc)[3 * l + 2] = v.z;
+    }
+    sc->light_pos = lcc->data(); sc->light_pos_stride = 3; sc->gamma = nullptr;
+    return true;
+}
+
+int emul_splats_forward(const SurfScene* scene, const SurfCamera* cam, const SurfOptions* opt, const EmulSplats* sp,
+                        const SurfOutputs* out) {
+    SceneView sc; CamState cs; std::vector<float> lcc;
+    if (!splat_setup(scene, cam, &sc, &cs, &lcc)) return -1;
+    ShadeFlags fl = {0, opt->use_quartic};
+    std::vector<float> vis(sc.n_lights);
+    for (int k = 0; k < sp->count; ++k) {
+        if (sp->vis) for (int l = 0; l < sc.n_lights; ++l) vis[l] = sp->vis[(size_t)l * sp->count + k];
+        const float* nn = sp->normal + (size_t)k * sp->normal_stride;
+        SplatOut so = splat_pixel_forward(sc, cs, k, sp->z[(size_t)k * sp->z_stride], ld3(nn), sp->mat ? sp->mat[k] : 0, fl,
+                                          sp->vis ? vis.data() : nullptr);
+        memcpy(out->image + 3 * (size_t)k, so.image, 12);
+        out->depth[k] = so.depth;
+        memcpy(out->pos + 3 * (size_t)k, so.pos, 12);
+        memcpy(out->normal + 3 * (size_t)k, nn, 12);
+    }
+    return 0;
+}
+
+int emul_splats_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptions* opt, const EmulSplats* sp,
+                         const SurfOutGrads* og, const SurfSceneGrads* sg, float* gz, float* gnormal) {
+    SceneView sc; CamState cs; std::vector<float> lcc;
+    if (!splat_setup(scene, cam, &sc, &cs, &lcc)) return -1;
+    ShadeFlags fl = {0, opt->use_quartic};
+    HostSink hs(sc);
+    std::vector<float> vis(sc.n_lights);
+    for (int k = 0; k < sp->count; ++k) {
+        if (sp->vis) for (int l = 0; l < sc.n_lights; ++l) vis[l] = sp->vis[(size_t)l * sp->count + k];
+        PixelGrads g;
+        for (int c = 0; c < 3; ++c) {
+            g.image[c] = og->image ? og->image[3 * (size_t)k + c] : 0.f;
+            g.pos[c] = og->pos ? og->pos[3 * (size_t)k + c] : 0.f;
+            g.normal[c] = og->normal ? og->normal[3 * (size_t)k + c] : 0.f;
+        }
+        g.depth = og->depth ? og->depth[k] : 0.f;
+        float gzk, gnk[3];
+        splat_pixel_backward(sc, cs, k, sp->z[(size_t)k * sp->z_stride], ld3(sp->normal + (size_t)k * sp->normal_stride),
+                             sp->mat ? sp->mat[k] : 0, fl, sp->vis ? vis.data() : nullptr, g, hs, &gzk, gnk);
+        gz[(size_t)k * sp->z_stride] += gzk;
+        for (int c = 0; c < 3; ++c) gnormal[(size_t)k * sp->normal_stride + c] += gnk[c];
+    }
+    for (int m = 0; m < sc.n_materials * 3; ++m) {
+        if (sg->albedo) sg->albedo[m] += (float)hs.g_albedo[m];
+        if (sg->coeffs) sg->coeffs[m] += (float)hs.g_coeff[m];
+    }
+    for (int l = 0; l < sc.n_lights; ++l) {
+        const double* gl = &hs.g_lpos[l * 3];
+        if (sg->light_pos) {       // camera -> world: d/dl_xyz = R g, d/dl_w = -(R^T eye) . g
+            for (int j = 0; j < 3; ++j)
+                sg->light_pos[4 * (size_t)l + j] += (float)(cs.R[3 * j] * gl[0] + cs.R[3 * j + 1] * gl[1] + cs.R[3 * j + 2] * gl[2]);
+            double gw = 0;
+            for (int i = 0; i < 3; ++i)
+                gw -= (cs.R[i] * cs.eye[0] + cs.R[3 + i] * cs.eye[1] + cs.R[6 + i] * cs.eye[2]) * gl[i];
+            sg->light_pos[4 * (size_t)l + 3] += (float)gw;
+        }
+        for (int c = 0; c < 3; ++c)
+            if (sg->light_attenuation) sg->light_attenuation[l * 3 + c] += (float)hs.g_atten[l * 3 + c];
+    }
+    for (int r = 0; r < sc.n_colors * 3; ++r)
+        if (sg->colors) sg->colors[r] += (float)hs.g_color[r];
+    for (int c = 0; c < 3; ++c)
+        if (sg->ambient) sg->ambient[c] += (float)hs.g_amb[c];
     return 0;
 }
 

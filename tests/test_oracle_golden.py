@@ -63,3 +63,28 @@ def test_oracle_matches_live_reference_on_fresh_random_scene():
         b = torch_oracle.render(scene_io.clone_scene(scene), **kw)
         for k in ('nearest', 'depth', 'pos', 'normal', 'image', 'ray_dir'):
             assert torch.equal(a[k], b[k]) or np.array_equal(a[k].numpy(), b[k].numpy(), equal_nan=True), k
+
+
+from conftest import along_ray_cases   # noqa: E402
+
+
+@pytest.mark.parametrize('name', along_ray_cases())
+def test_oracle_along_ray_matches_reference_golden(name):
+    scene, params, outs, grads, extra = scene_io.load_case(os.path.join(GOLDEN_DIR, name + '.npz'))
+    sc = scene_io.clone_scene(scene, requires_grad=True)
+    if 'light_vis' in sc['objects']['disk']:
+        sc['objects']['disk']['light_vis'] = sc['objects']['disk']['light_vis'].detach()
+    res = torch_oracle.render_along_ray(sc, **params)
+    for k in ('image', 'depth', 'pos', 'normal'):
+        assert np.array_equal(res[k].detach().numpy(), outs[k], equal_nan=True), k
+    H, W = res['depth'].shape
+    w = scene_io.loss_weights((H, W), extra['loss_seed'])
+    loss = sum((res[k] * w[k]).sum() for k in ('image', 'depth', 'pos', 'normal'))
+    leaves = {'objects/disk/pos': sc['objects']['disk']['pos'], 'objects/disk/normal': sc['objects']['disk']['normal'],
+              'materials/albedo': sc['materials']['albedo'], 'materials/coeffs': sc['materials']['coeffs'],
+              'lights/pos': sc['lights']['pos'], 'lights/attenuation': sc['lights']['attenuation'],
+              'lights/ambient': sc['lights']['ambient'], 'colors': sc['colors']}
+    gs = torch.autograd.grad(loss, [leaves[k] for k in grads], allow_unused=True)
+    for k, g in zip(grads, gs):
+        scale = max(1e-12, float(np.abs(grads[k]).max()))
+        np.testing.assert_allclose(g.numpy() / scale, grads[k] / scale, rtol=1e-5, atol=1e-6, err_msg=k)
