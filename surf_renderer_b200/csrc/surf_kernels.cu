@@ -97,6 +97,9 @@ struct Workspace {
     double* acc;                 // backward scalar accumulators
     double* prim_acc;            // backward per-primitive accumulators [total_prims, 7]
     float* vis;                  // [L, n] shadow visibility
+    float* gray;                 // [7, n] generic rays: origin xyz, direction xyz, t_max (orthographic / shadow rays)
+    unsigned long long* zbuf2;   // [n] z-buffer keys of the shadow rays
+    float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
     size_t bytes;
 };
 constexpr int kMaxAccSlots = 512;
@@ -120,6 +123,10 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
     ws->vis = (float*)(p + off);
     if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
+    // generic-ray buffers: always carved (orthographic frames need them too); 36 B per pixel
+    ws->gray = (float*)(p + off); off += align_up((size_t)7 * n_pix * sizeof(float), 256);
+    ws->zbuf2 = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
+    ws->obound = (float*)(p + off); off += 256;
     ws->bytes = off;
 }
 
@@ -769,6 +776,228 @@ __global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen
     flush();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_intersect_rays: the same fused intersection + z-buffer structure for rays with PER-RAY origins
+// (orthographic camera pixels, shadow rays).  Disk filter per ray pair: 17 packed FMA-pipe instructions
+// (n.o 3, numer 1, n.d 3, t 1, P = o + t d 3, rel = P - c 3, |rel|^2 - r^2 3) + 2 MUFU.RCP.
+// MODE 0: camera rays, near <= t <= far;  MODE 1: shadow rays, 0 < t < tmax[ray] (renderer.py:306).
+// ---------------------------------------------------------------------------------------------------
+struct RayParams {
+    SceneView sc;
+    const CamState* cam;
+    const float4* packed;            // origin-independent records (k_prep_rays)
+    const float* gray;               // [7, n]: ox oy oz dx dy dz tmax
+    unsigned long long* zbuf;        // [n]
+    int n_pix, n_tiles, n_chunks, stage_f4;
+    int chunks_before[kMaxSets + 1];
+};
+
+__global__ void __launch_bounds__(256) k_prep_rays(const __grid_constant__ SceneView sc, const float* __restrict__ obound,
+                                                   float4* __restrict__ packed) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= sc.total) return;
+    const int s = find_set(sc, g);
+    const SetView& sv = sc.sets[s];
+    const int i = g - sv.first;
+    const float ob = obound[0];
+    F4 r[4];
+    if (sv.kind == KIND_DISK) {
+        prep_disk_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], ob,
+                       &r[0], &r[1]);
+    } else if (sv.kind == KIND_PLANE) {
+        prep_plane_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), &r[0]);
+    } else if (sv.kind == KIND_SPHERE) {
+        prep_sphere_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], ob, &r[0]);
+    } else {
+        const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
+        prep_triangle_rays(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                           ld3(sv.normal + (size_t)i * sv.normal_stride), ob, &r[0], &r[1], &r[2], &r[3]);
+    }
+    const int nf4 = rec_f4(sv.kind);
+    float4* dst = packed + sv.rec_off + (size_t)i * nf4;
+    for (int k = 0; k < nf4; ++k) dst[k] = make_float4(r[k].x, r[k].y, r[k].z, r[k].w);
+}
+
+template <int P>
+struct RayRegs {
+    unsigned long long ox[P / 2], oy[P / 2], oz[P / 2], dx[P / 2], dy[P / 2], dz[P / 2];
+    float tmax[P];
+    float best_t[P];
+    int best_i[P];
+};
+template <int P>
+__device__ __forceinline__ void ray_of(const RayRegs<P>& r, int p, Vec3* o, Vec3* d) {
+    float lo, hi;
+    unpack2(r.ox[p >> 1], lo, hi); o->x = (p & 1) ? hi : lo;
+    unpack2(r.oy[p >> 1], lo, hi); o->y = (p & 1) ? hi : lo;
+    unpack2(r.oz[p >> 1], lo, hi); o->z = (p & 1) ? hi : lo;
+    unpack2(r.dx[p >> 1], lo, hi); d->x = (p & 1) ? hi : lo;
+    unpack2(r.dy[p >> 1], lo, hi); d->y = (p & 1) ? hi : lo;
+    unpack2(r.dz[p >> 1], lo, hi); d->z = (p & 1) ? hi : lo;
+}
+
+template <int P, int MODE>
+__device__ __forceinline__ void narrow_ray(const RayParams& prm, const SetView& sv, int local, RayRegs<P>& r, int p) {
+    Vec3 o, d, nn;
+    float numer, t;
+    ray_of<P>(r, p, &o, &d);
+    plane_consts_for_origin(sv, local, o, &nn, &numer);
+    bool hit;
+    if (MODE == 0) {
+        hit = exact_hit(sv, local, nn, numer, o, d, prm.cam->near_clip, prm.cam->far_clip, &t);
+    } else {
+        hit = exact_hit(sv, local, nn, numer, o, d, -INFINITY, INFINITY, &t) && t > 0.f && t < r.tmax[p];
+    }
+    if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
+}
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_constant__ RayParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    const int tid = threadIdx.x;
+    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
+    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    if (lo >= hi) return;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int c, int* set, int* local0, int* count) {
+        int s = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxSets; ++k)
+            if (k < prm.sc.n_sets && c >= prm.chunks_before[k]) s = k;
+        const SetView& sv = prm.sc.sets[s];
+        const int ppc = prm.stage_f4 / rec_f4(sv.kind);
+        const int j = c - prm.chunks_before[s];
+        *set = s; *local0 = j * ppc; *count = min(ppc, sv.count - j * ppc);
+    };
+    auto issue = [&](int item, int stage) {
+        int set, local0, count;
+        decode(item % prm.n_chunks, &set, &local0, &count);
+        const SetView& sv = prm.sc.sets[set];
+        const int nf4 = rec_f4(sv.kind);
+        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(stage_buf + (size_t)stage * prm.stage_f4, prm.packed + sv.rec_off + (size_t)local0 * nf4, bytes, &full_bar[stage]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
+
+    constexpr int TILE = kThreads * P;
+    RayRegs<P> r;
+    int cur_tile = -1;
+    auto flush = [&]() {
+        if (cur_tile < 0) return;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int pix = cur_tile * TILE + p * kThreads + tid;
+            if (r.best_i[p] >= 0 && pix < prm.n_pix)
+                atomicMin(prm.zbuf + pix, ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
+        }
+    };
+
+    for (int it = lo; it < hi; ++it) {
+        const int kk = it - lo;
+        const int stage = kk % kStages;
+        const uint32_t parity = (uint32_t)((kk / kStages) & 1);
+        __syncthreads();
+        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (kk + kStages - 1) % kStages);
+        const int tile = it / prm.n_chunks;
+        if (tile != cur_tile) {
+            flush();
+            cur_tile = tile;
+            float v[6][P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int pix = tile * TILE + p * kThreads + tid;
+                const bool ok = pix < prm.n_pix;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v[c][p] = ok ? prm.gray[(size_t)c * prm.n_pix + pix] : 0.f;
+                r.tmax[p] = ok ? prm.gray[(size_t)6 * prm.n_pix + pix] : 0.f;
+                r.best_t[p] = INFINITY;
+                r.best_i[p] = -1;
+            }
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) {
+                r.ox[q] = pack2(v[0][2 * q], v[0][2 * q + 1]); r.oy[q] = pack2(v[1][2 * q], v[1][2 * q + 1]);
+                r.oz[q] = pack2(v[2][2 * q], v[2][2 * q + 1]); r.dx[q] = pack2(v[3][2 * q], v[3][2 * q + 1]);
+                r.dy[q] = pack2(v[4][2 * q], v[4][2 * q + 1]); r.dz[q] = pack2(v[5][2 * q], v[5][2 * q + 1]);
+            }
+        }
+        int set, local0, count;
+        decode(it % prm.n_chunks, &set, &local0, &count);
+        const SetView& sv = prm.sc.sets[set];
+        mbar_wait(&full_bar[stage], parity);
+        const float4* __restrict__ s = stage_buf + (size_t)stage * prm.stage_f4;
+        if (sv.kind == KIND_DISK) {
+            for (int i = 0; i < count; ++i) {
+                const float4 A = s[2 * i], B = s[2 * i + 1];
+                const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z);
+                float m = INFINITY;
+                float e[P];
+#pragma unroll
+                for (int q = 0; q < P / 2; ++q) {
+                    const unsigned long long no = fma2(nz, r.oz[q], fma2(ny, r.oy[q], mul2(nx, r.ox[q])));
+                    const unsigned long long numer = fma2(no, pack2(-1.f, -1.f), pack2(A.w, A.w));
+                    const unsigned long long b2 = fma2(nz, r.dz[q], fma2(ny, r.dy[q], mul2(nx, r.dx[q])));
+                    float b0, b1;
+                    unpack2(b2, b0, b1);
+                    const unsigned long long t2 = mul2(numer, pack2(rcp_approx(b0), rcp_approx(b1)));
+                    const unsigned long long rx = add2(fma2(t2, r.dx[q], r.ox[q]), pack2(B.x, B.x));
+                    const unsigned long long ry = add2(fma2(t2, r.dy[q], r.oy[q]), pack2(B.y, B.y));
+                    const unsigned long long rz = add2(fma2(t2, r.dz[q], r.oz[q]), pack2(B.z, B.z));
+                    unpack2(fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, pack2(B.w, B.w)))), e[2 * q], e[2 * q + 1]);
+                    m = fminf(m, fminf(e[2 * q], e[2 * q + 1]));
+                }
+                if (m <= 0.f) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        if (e[p] <= 0.f) narrow_ray<P, MODE>(prm, sv, local0 + i, r, p);
+                }
+            }
+        } else {
+            const int nf4 = rec_f4(sv.kind);
+            for (int i = 0; i < count; ++i) {
+                const float4* rec = s + (size_t)i * nf4;
+                const F4 A = f4(rec[0].x, rec[0].y, rec[0].z, rec[0].w);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    Vec3 o, d;
+                    ray_of<P>(r, p, &o, &d);
+                    bool pass = true;
+                    if (sv.kind == KIND_SPHERE) pass = sphere_filter_rays(A, o, d);
+                    else if (sv.kind == KIND_TRIANGLE)
+                        pass = triangle_filter_rays(A, f4(rec[1].x, rec[1].y, rec[1].z, rec[1].w), f4(rec[2].x, rec[2].y, rec[2].z, rec[2].w),
+                                                    f4(rec[3].x, rec[3].y, rec[3].z, rec[3].w), o, d);
+                    if (pass) narrow_ray<P, MODE>(prm, sv, local0 + i, r, p);
+                }
+            }
+        }
+    }
+    flush();
+}
+
+// generic rays of an orthographic frame: per-pixel origins, one direction
+__global__ void __launch_bounds__(256) k_rays_ortho(const CamState* __restrict__ cs, int pix0, int n, float* __restrict__ gray,
+                                                    float* __restrict__ obound) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float len = 0.f;
+    if (k < n) {
+        const Vec3 o = pixel_ray_origin_ortho(*cs, pix0 + k);
+        gray[k] = o.x; gray[(size_t)n + k] = o.y; gray[2 * (size_t)n + k] = o.z;
+        gray[3 * (size_t)n + k] = cs->odir[0]; gray[4 * (size_t)n + k] = cs->odir[1]; gray[5 * (size_t)n + k] = cs->odir[2];
+        gray[6 * (size_t)n + k] = INFINITY;
+        len = sqrtf(o.x * o.x + o.y * o.y + o.z * o.z);
+    }
+    for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
+    if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
+}
+
 // generic-origin variant (orthographic camera: per-pixel origins, one direction).  Exact tests only; the
 // reference itself only supports this projection up to one tile of pixels.
 __global__ void __launch_bounds__(256) k_intersect_generic(const __grid_constant__ SceneView sc,
@@ -878,6 +1107,47 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowPa
     const int self = key == kMissKey ? 0 : (int)(key & 0xFFFFFFFFull);
     Fragment f = fragment_at(p.sc, self, o, d);
     p.vis[(size_t)l * p.n + k] = shadow_visibility(p.sc, f.P, self, l);
+}
+
+// shadow rays of light l (renderer.py:293-299): origin frag_pos + 0.1 L, direction L, t_max = |light - frag_pos|.
+// Miss pixels get a null direction (no hits): their visibility never reaches an output (image is masked).
+__global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, int l, float* __restrict__ gray,
+                                                     unsigned long long* __restrict__ zbuf2, float* __restrict__ obound) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float len = 0.f;
+    if (k < p.n) {
+        const size_t n = (size_t)p.n;
+        zbuf2[k] = kMissKey;
+        const unsigned long long key = p.zbuf[k];
+        Vec3 so = v3(0.f, 0.f, 0.f), L = v3(0.f, 0.f, 0.f);
+        float dist = 0.f;
+        if (key != kMissKey) {
+            Vec3 o, d;
+            pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
+            Fragment f = fragment_at(p.sc, (int)(key & 0xFFFFFFFFull), o, d);
+            Vec3 Lv = vsub(ld3(p.sc.light_pos + (size_t)l * p.sc.light_pos_stride), f.P);
+            dist = xsqrt(sq3_seq(Lv));
+            L = v3(xdiv(Lv.x, dist), xdiv(Lv.y, dist), xdiv(Lv.z, dist));
+            so = vadd(f.P, vscale(0.1f, L));
+            len = sqrtf(so.x * so.x + so.y * so.y + so.z * so.z);
+            if (!(len == len) || !(dist == dist) || isinf(len)) { L = v3(0.f, 0.f, 0.f); len = 0.f; }
+        }
+        gray[k] = so.x; gray[n + k] = so.y; gray[2 * n + k] = so.z;
+        gray[3 * n + k] = L.x; gray[4 * n + k] = L.y; gray[5 * n + k] = L.z;
+        gray[6 * n + k] = dist;
+    }
+    for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
+    if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
+}
+
+// visible iff nothing was hit inside (0, |L|), or the nearest such hit is the fragment's own primitive (:306-309)
+__global__ void __launch_bounds__(256) k_shadow_resolve(const unsigned long long* __restrict__ zbuf,
+                                                        const unsigned long long* __restrict__ zbuf2, int n, float* __restrict__ vis_l) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long self = zbuf[k], hit = zbuf2[k];
+    const bool visible = hit == kMissKey || self == kMissKey || (unsigned)(hit & 0xFFFFFFFFull) == (unsigned)(self & 0xFFFFFFFFull);
+    vis_l[k] = visible ? 1.f : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1313,6 +1583,9 @@ static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaS
     return SURF_OK;
 }
 
+template <int MODE>
+static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st);
+
 template <int P>
 static int launch_screen(const ScreenParams& prm, int grid, size_t smem, cudaStream_t st) {
     auto kern = k_intersect_screen<P>;
@@ -1353,9 +1626,15 @@ static int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStre
 
 static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st) {
     if (f.cam.proj != 0) {
-        k_intersect_generic<<<(f.n + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.pix0, f.n, f.ws.zbuf);
-        SURF_LAUNCHED("k_intersect_generic");
-        return SURF_OK;
+        if (opt->math_mode == 1) {       // exact-only fallback kept for cross-checking the filtered kernel
+            k_intersect_generic<<<(f.n + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.pix0, f.n, f.ws.zbuf);
+            SURF_LAUNCHED("k_intersect_generic");
+            return SURF_OK;
+        }
+        SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4, st));
+        k_rays_ortho<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.cam, f.pix0, f.n, f.ws.gray, f.ws.obound);
+        SURF_LAUNCHED("k_rays_ortho");
+        return run_intersect_rays<0>(f, f.ws.zbuf, st);
     }
     if (opt->math_mode == 3) return run_intersect_screen(f, opt, st);
     IsectParams prm;
@@ -1420,6 +1699,47 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     return fail(SURF_ERR_BAD_ARG, "unsupported pixels_per_thread");
 }
 
+template <int MODE>
+static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st) {
+    k_prep_rays<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.obound, f.ws.packed);
+    SURF_LAUNCHED("k_prep_rays");
+    constexpr int P = 4;
+    RayParams prm;
+    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.gray = f.ws.gray; prm.zbuf = zbuf; prm.n_pix = f.n;
+    const int tile = kThreads * P;
+    prm.n_tiles = (f.n + tile - 1) / tile;
+    const int grid_max = sm_count() * 2;
+    int chunk = 1024;
+    while (chunk > 64) {
+        long long items = 0;
+        for (int s = 0; s < f.sc.n_sets; ++s) {
+            const int ppc = (chunk * 2) / rec_f4(f.sc.sets[s].kind);
+            items += (f.sc.sets[s].count + ppc - 1) / ppc;
+        }
+        if (items * prm.n_tiles >= 4LL * grid_max) break;
+        chunk /= 2;
+    }
+    prm.stage_f4 = chunk * 2;
+    int nchunks = 0;
+    for (int s = 0; s < kMaxSets; ++s) {
+        prm.chunks_before[s] = nchunks;
+        if (s < f.sc.n_sets) {
+            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
+            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
+        }
+    }
+    prm.chunks_before[kMaxSets] = nchunks;
+    prm.n_chunks = nchunks;
+    const long long items = (long long)prm.n_tiles * nchunks;
+    const int grid = (int)std::min<long long>(items, grid_max);
+    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
+    auto kern = k_intersect_rays<P, MODE>;
+    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(prm);
+    SURF_LAUNCHED("k_intersect_rays");
+    return SURF_OK;
+}
+
 static int run_common_prologue(const Frame& f, float* ray_out, cudaStream_t st, bool need_rays_and_zbuf) {
     k_setup<<<1, 32, 0, st>>>(f.cam, f.ws.cam);
     SURF_LAUNCHED("k_setup");
@@ -1447,9 +1767,20 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
     if ((rc = run_intersect(f, opt, st))) return rc;
     if (f.shadow) {
         ShadowParams sp{f.sc, f.ws.cam, f.ws.rays, f.ws.zbuf, f.ws.vis, f.pix0, f.n};
-        dim3 grid((f.n + 127) / 128, f.sc.n_lights);
-        k_shadow<<<grid, 128, 0, st>>>(sp);
-        SURF_LAUNCHED("k_shadow");
+        if (opt->math_mode == 1) {       // exact-only brute force kept for cross-checking
+            dim3 grid((f.n + 127) / 128, f.sc.n_lights);
+            k_shadow<<<grid, 128, 0, st>>>(sp);
+            SURF_LAUNCHED("k_shadow");
+        } else {
+            for (int l = 0; l < f.sc.n_lights; ++l) {
+                SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4, st));
+                k_rays_shadow<<<(f.n + 255) / 256, 256, 0, st>>>(sp, l, f.ws.gray, f.ws.zbuf2, f.ws.obound);
+                SURF_LAUNCHED("k_rays_shadow");
+                if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st))) return rc;
+                k_shadow_resolve<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, f.n, f.ws.vis + (size_t)l * f.n);
+                SURF_LAUNCHED("k_shadow_resolve");
+            }
+        }
     }
     ShadeParams sh;
     sh.sc = f.sc; sh.cam = f.ws.cam; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf; sh.vis = f.shadow ? f.ws.vis : nullptr;

@@ -42,6 +42,16 @@ SURF_HD float xsqrt(float a) { return sqrtf(a); }
 SURF_HD float xfma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
+// approximate reciprocal of the conservative filters: MUFU.RCP on the device, 1/x in the host emulation
+SURF_HD float approx_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 struct Vec3 {
     float x, y, z;
 };
@@ -300,18 +310,79 @@ SURF_HD bool screen_filter(const F4& C, float x, float y) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// origin-independent filter records for rays with per-ray origins (orthographic camera, shadow rays).
+// `obound` bounds |origin| over the rays of the launch; it only enters the conservative slack.
+//   DISK: A = (n, p.n)  B = (-c, -(r+slack)^2)     PLANE: A           SPHERE: S = (c, (r+slack)^2)
+//   TRIANGLE: A = (n, v0.n), W_i = (n x e_i, -v_i.(n x e_i) + slack)   (test: P.W_i.xyz + W_i.w >= 0)
+// ---------------------------------------------------------------------------------------------------
+SURF_HD void prep_disk_rays(Vec3 p, Vec3 nraw, float r, float obound, F4* A, F4* B) {
+    PlaneConst pc = plane_const(p, nraw);
+    *A = f4(pc.n.x, pc.n.y, pc.n.z, pc.dist);
+    double scale = 2.0 * (double)obound + 2.0 * dlen(p.x, p.y, p.z) + fabs((double)r);
+    double rs = fabs((double)r) + 4e-6 * scale;
+    *B = f4(-p.x, -p.y, -p.z, -f_round_up(rs * rs * (1.0 + 1e-6)));
+}
+SURF_HD void prep_plane_rays(Vec3 p, Vec3 nraw, F4* A) {
+    PlaneConst pc = plane_const(p, nraw);
+    *A = f4(pc.n.x, pc.n.y, pc.n.z, pc.dist);
+}
+SURF_HD void prep_sphere_rays(Vec3 c, float r, float obound, F4* S) {
+    double scale = 2.0 * (double)obound + 2.0 * dlen(c.x, c.y, c.z) + fabs((double)r);
+    double rs = fabs((double)r) + 8e-6 * scale;
+    *S = f4(c.x, c.y, c.z, f_round_up(rs * rs * (1.0 + 1e-5) + 1e-6 * scale * scale));   // hb^2 - |oc|^2 cancels: 2^-22 |oc|^2 noise
+}
+SURF_HD void prep_triangle_rays(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, float obound, F4* A, F4* W0, F4* W1, F4* W2) {
+    PlaneConst pc = plane_const(v0, nraw);
+    *A = f4(pc.n.x, pc.n.y, pc.n.z, pc.dist);
+    const Vec3 vs[3] = {v0, v1, v2};
+    F4* outs[3] = {W0, W1, W2};
+    double e[3][3], el[3], emax = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        const Vec3& a = vs[i];
+        const Vec3& b = vs[(i + 1) % 3];
+        e[i][0] = (double)b.x - a.x; e[i][1] = (double)b.y - a.y; e[i][2] = (double)b.z - a.z;
+        el[i] = dlen(e[i][0], e[i][1], e[i][2]);
+        emax = el[i] > emax ? el[i] : emax;
+    }
+    const double nx = pc.n.x, ny = pc.n.y, nz = pc.n.z;
+    for (int i = 0; i < 3; ++i) {
+        const double wx = ny * e[i][2] - nz * e[i][1];
+        const double wy = nz * e[i][0] - nx * e[i][2];
+        const double wz = nx * e[i][1] - ny * e[i][0];
+        const Vec3& v = vs[i];
+        const double k = -(v.x * wx + v.y * wy + v.z * wz);
+        const double scale = 2.0 * (double)obound + 3.0 * dlen(v.x, v.y, v.z) + emax;
+        *outs[i] = f4((float)wx, (float)wy, (float)wz, f_round_up(k + 8e-6 * el[i] * scale + 1e-30));
+    }
+}
+SURF_HD bool disk_filter_rays(const F4& A, const F4& B, Vec3 o, Vec3 d) {
+    float no = fmaf(A.z, o.z, fmaf(A.y, o.y, A.x * o.x));
+    float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
+    float t = (A.w - no) * approx_rcp(b);
+    float rx = fmaf(t, d.x, o.x) + B.x, ry = fmaf(t, d.y, o.y) + B.y, rz = fmaf(t, d.z, o.z) + B.z;
+    return fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, B.w))) <= 0.f;
+}
+SURF_HD bool sphere_filter_rays(const F4& S, Vec3 o, Vec3 d) {
+    float ox = o.x - S.x, oy = o.y - S.y, oz = o.z - S.z;
+    float hb = fmaf(oz, d.z, fmaf(oy, d.y, ox * d.x));
+    float oc2 = fmaf(oz, oz, fmaf(oy, oy, ox * ox));
+    return fmaf(hb, hb, S.w - oc2) >= 0.f;
+}
+SURF_HD bool triangle_filter_rays(const F4& A, const F4& W0, const F4& W1, const F4& W2, Vec3 o, Vec3 d) {
+    float no = fmaf(A.z, o.z, fmaf(A.y, o.y, A.x * o.x));
+    float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
+    float t = (A.w - no) * approx_rcp(b);
+    float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
+    float c0 = fmaf(W0.z, pz, fmaf(W0.y, py, fmaf(W0.x, px, W0.w)));
+    float c1 = fmaf(W1.z, pz, fmaf(W1.y, py, fmaf(W1.x, px, W1.w)));
+    float c2 = fmaf(W2.z, pz, fmaf(W2.y, py, fmaf(W2.x, px, W2.w)));
+    return (c0 >= 0.f) & (c1 >= 0.f) & (c2 >= 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // coarse (conservative) filters - scalar forms; the intersection kernel has packed f32x2 versions of the
 // disk filter.  `rcp` is an approximate reciprocal on the device (MUFU.RCP), 1/x on the host.
 // ---------------------------------------------------------------------------------------------------
-SURF_HD float approx_rcp(float x) {
-#if defined(__CUDA_ARCH__)
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return 1.0f / x;
-#endif
-}
 SURF_HD bool disk_filter(const F4& A, const F4& B, Vec3 d) {
     float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
     float t = A.w * approx_rcp(b);

@@ -43,6 +43,36 @@ void pack_all(const SceneView& sc, Vec3 o, Packed* pk) {
     }
 }
 
+void pack_all_rays(const SceneView& sc, float obound, Packed* pk) {
+    pk->rec.assign(packed_f4_total(sc), f4(0, 0, 0, 0));
+    for (int s = 0; s < sc.n_sets; ++s) {
+        const SetView& sv = sc.sets[s];
+        for (int i = 0; i < sv.count; ++i) {
+            F4* r = &pk->rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)];
+            if (sv.kind == KIND_DISK)
+                prep_disk_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], obound, r, r + 1);
+            else if (sv.kind == KIND_PLANE)
+                prep_plane_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), r);
+            else if (sv.kind == KIND_SPHERE)
+                prep_sphere_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], obound, r);
+            else {
+                const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
+                prep_triangle_rays(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                                   ld3(sv.normal + (size_t)i * sv.normal_stride), obound, r, r + 1, r + 2, r + 3);
+            }
+        }
+    }
+}
+
+bool filter_pass_rays(const SetView& sv, const F4* r, Vec3 o, Vec3 d) {
+    switch (sv.kind) {
+        case KIND_DISK: return disk_filter_rays(r[0], r[1], o, d);
+        case KIND_PLANE: return true;
+        case KIND_SPHERE: return sphere_filter_rays(r[0], o, d);
+        default: return triangle_filter_rays(r[0], r[1], r[2], r[3], o, d);
+    }
+}
+
 bool filter_pass(const SetView& sv, const F4* r, Vec3 d) {
     switch (sv.kind) {
         case KIND_DISK: return disk_filter(r[0], r[1], d);
@@ -112,6 +142,14 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
     Packed pk;
     const Vec3 eye = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
     if (cs.proj == 0) pack_all(sc, eye, &pk);
+    else {
+        float ob = 0.f;
+        for (int pix = p0; pix < p1; ++pix) {
+            Vec3 oo = pixel_ray_origin_ortho(cs, pix);
+            ob = fmaxf(ob, sqrtf(oo.x * oo.x + oo.y * oo.y + oo.z * oo.z));
+        }
+        pack_all_rays(sc, ob, &pk);
+    }
     long long filter_misses = 0;
     std::vector<F4> circ;
     if (cs.proj == 0) {
@@ -136,6 +174,7 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
                     n = v3(r[0].x, r[0].y, r[0].z); numer = r[0].w;
                 } else {
                     plane_consts_for_origin(sv, i, o, &n, &numer);
+                    pass = filter_pass_rays(sv, &pk.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)], o, d);
                 }
                 float t;
                 bool hit = exact_hit(sv, i, n, numer, o, d, cs.near_clip, cs.far_clip, &t);
@@ -234,6 +273,50 @@ int emul_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptio
         if (sg->ambient) sg->ambient[c] += (float)hs.g_amb[c];
     if (sg->gamma) sg->gamma[0] += (float)hs.g_gamma;
     return 0;
+}
+
+// Counts shadow-ray (pixel, light, primitive) triples whose exact test reports an occluder but whose conservative
+// per-ray-origin filter rejects the pair (must be 0).  `keys` are the z-buffer keys emul_forward produced.
+long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* cam, const unsigned long long* keys) {
+    SceneView sc;
+    if (!build_scene_view(*scene, &sc, &g_err) || !check_camera(*cam, &g_err)) return -1;
+    CamState cs;
+    camera_setup(cam->eye, cam->at, cam->up, cam->proj, cam->width, cam->height, cam->fovy, cam->focal_length,
+                 cam->near_clip, cam->far_clip, &cs);
+    const int N = cam->width * cam->height;
+    long long misses = 0;
+    for (int l = 0; l < sc.n_lights; ++l) {
+        std::vector<Vec3> so(N), dir(N);
+        std::vector<float> tmax(N, 0.f);
+        float ob = 0.f;
+        for (int pix = 0; pix < N; ++pix) {
+            if (keys[pix] == kMissKey) continue;
+            Vec3 o, d;
+            pixel_ray(cs, pix, &o, &d);
+            Fragment f = fragment_at(sc, (int)(keys[pix] & 0xFFFFFFFFull), o, d);
+            Vec3 Lv = vsub(ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), f.P);
+            float dist = xsqrt(sq3_seq(Lv));
+            dir[pix] = v3(xdiv(Lv.x, dist), xdiv(Lv.y, dist), xdiv(Lv.z, dist));
+            so[pix] = vadd(f.P, vscale(0.1f, dir[pix]));
+            tmax[pix] = dist;
+            ob = fmaxf(ob, sqrtf(so[pix].x * so[pix].x + so[pix].y * so[pix].y + so[pix].z * so[pix].z));
+        }
+        Packed pk;
+        pack_all_rays(sc, ob, &pk);
+        for (int pix = 0; pix < N; ++pix) {
+            if (keys[pix] == kMissKey) continue;
+            for (int s = 0; s < sc.n_sets; ++s) {
+                const SetView& sv = sc.sets[s];
+                for (int i = 0; i < sv.count; ++i) {
+                    Vec3 nn; float numer, t;
+                    plane_consts_for_origin(sv, i, so[pix], &nn, &numer);
+                    bool hit = exact_hit(sv, i, nn, numer, so[pix], dir[pix], -INFINITY, INFINITY, &t) && t > 0.f && t < tmax[pix];
+                    if (hit && !filter_pass_rays(sv, &pk.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)], so[pix], dir[pix])) ++misses;
+                }
+            }
+        }
+    }
+    return misses;
 }
 
 // ---- render_splats_along_ray emulation -----------------------------------------------------------

@@ -38,9 +38,17 @@ def forward(scene, **params):
            'ray_dir': torch.empty(3, n if m.proj == 0 else 1)}
     co = _abi.SurfOutputs(*[out[k].data_ptr() for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir')])
     sc, cam, opt = m.c_scene(), m.c_camera(), make_options(params)
-    misses = lib().emul_forward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(co), None)
+    keys = torch.empty(n, dtype=torch.int64)
+    misses = lib().emul_forward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(co), keys.data_ptr())
     if misses < 0:
         raise RuntimeError(lib().emul_last_error().decode())
+    if params.get('shadow', False) and m.proj == 0:
+        lib().emul_shadow_filter_misses.restype = C.c_longlong
+        lib().emul_shadow_filter_misses.argtypes = [C.POINTER(_abi.SurfScene), C.POINTER(_abi.SurfCamera), C.c_void_p]
+        sm = lib().emul_shadow_filter_misses(C.byref(sc), C.byref(cam), keys.data_ptr())
+        if sm < 0:
+            raise RuntimeError(lib().emul_last_error().decode())
+        misses += sm
     H, W = m.height, m.width
     res = {'image': out['image'].view(H, W, 3), 'depth': out['depth'].view(H, W), 'normal': out['normal'].view(H, W, 3),
            'pos': out['pos'].view(H, W, 3), 'nearest': out['nearest'].view(H, W), 'ray_dir': out['ray_dir']}

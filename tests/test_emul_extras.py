@@ -85,6 +85,7 @@ def test_sphere_forward_matches_reference_semantics():
 def test_shadow_visibility_matches_oracle_restatement(seed):
     scene = synth.random_mixed_scene(seed, width=36, height=28, n_disk=10, n_sphere=0, n_tri=6, n_plane=1)
     res, misses, m = emul_driver.forward(scene, shadow=True)
+    assert misses == 0, 'a conservative filter (camera or shadow rays) rejected %d exact hits' % misses
     ref = torch_oracle.render(scene_io.clone_scene(scene), shadow=True)
     rep = parity.compare_forward(res, {k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}, scene, atol=2e-5)
     no_shadow, _, _ = emul_driver.forward(scene)

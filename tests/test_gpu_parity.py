@@ -412,3 +412,39 @@ def test_outputs_are_deterministic_and_stream_ordered():
     st.synchronize()
     for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_filtered_ray_kernel_equals_exact_only_kernels():
+    """Shadow rays and the orthographic camera run through k_intersect_rays (conservative per-ray-origin filter + exact
+    narrow phase); math_mode=1 keeps the exact-only brute-force kernels - both must give the same bits."""
+    from surf_renderer_b200 import scenes as synth
+    scene = scene_io.clone_scene(synth.random_mixed_scene(33, width=72, height=56, n_disk=300, n_tri=120, n_sphere=10, n_plane=1),
+                                 device='cuda')
+    a = _cpu(_render(scene, shadow=True))
+    b = _cpu(_render(scene, shadow=True, _math_mode=1))
+    for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+        assert torch.equal(a[k], b[k]), k
+    plain = _cpu(_render(scene))
+    assert not torch.equal(plain['image'], a['image'])
+    ortho = scene_io.clone_scene(synth.random_mixed_scene(34, width=64, height=48, n_disk=200, n_tri=80, n_sphere=6, proj='orthographic'),
+                                 device='cuda')
+    a = _cpu(_render(ortho))
+    b = _cpu(_render(ortho, _math_mode=1))
+    for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+        assert torch.equal(a[k], b[k]), k
+    assert int((a['depth'] <= 1000).sum()) > 100
+    # and the orthographic frame agrees with the oracle beyond the reference's one-tile limit (tiled over origins)
+    ocpu = scene_io.clone_scene(ortho, device='cpu')
+    ref = torch_oracle.render(ocpu)
+    parity.compare_forward(a, _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), ocpu,
+                           ortho_origins=torch_oracle.make_rays(ocpu['camera'])[0])
+
+
+def test_shadow_rays_at_splat_scale():
+    """bunny-sized splat scene with shadows (the demos' default, full_diff_renderer_demo.py:378): fast path vs oracle."""
+    scene, params, outs, grads, extra = _load('b_bunny_48')
+    scene['camera']['viewport'] = [0, 0, 96, 96]
+    res = _cpu(_render(scene_io.clone_scene(scene, device='cuda'), shadow=True))
+    ref = torch_oracle.render(scene_io.clone_scene(scene), shadow=True)
+    rep = parity.compare_forward(res, _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), scene, atol=2e-5)
+    assert rep['hit_pixels'] > 1500
