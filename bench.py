@@ -325,7 +325,10 @@ def main():
         ach_lane = tests_launch * FMA_INSTR_PER_DISK_TEST / (isect_ms * 1e-3)
         fma_meas = max(lib().surf_fma_peak(0, 8192, None), lib().surf_fma_peak(1, 8192, None))
         roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
-                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane, 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane,
+                    # dram__bytes_read+write of one k_intersect launch, ncu --set full (profiles/r1_ncu_full_step_kernels.json);
+                    # only meaningful for the default single-GPU config it was captured on
+                    'traffic': 22395904 if (world == 1 and M == 100_000 and H == 1024 and args.math == 0) else None,
                     'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no fp32 entry)' % peak_src,
                     'peak_measured': fma_meas * 2 / 1e12, 'frac_of_measured': ach_lane / fma_meas if fma_meas > 0 else None,
                     'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),

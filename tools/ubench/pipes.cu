@@ -41,6 +41,16 @@ __global__ void __launch_bounds__(256) k(int iters, float* out){
       #pragma unroll
       for(int j=0;j<10;j++) x[j]=fma2(x[(j+1)%10],x[(j+1)%10],x[j]);
     }
+    if(MODE==9){   // three distinct register pairs per FFMA2 (register-file read-port pressure)
+      unsigned long long yy[10], zz[10];
+      #pragma unroll
+      for(int j=0;j<10;j++){ yy[j]=pack2(u[j&7]+j, u[(j+1)&7]); zz[j]=pack2(u[(j+2)&7], u[(j+3)&7]-j); }
+      #pragma unroll
+      for(int r=0;r<4;r++){
+        #pragma unroll
+        for(int j=0;j<10;j++) x[j]=fma2(yy[j],zz[(j+r)%10],x[j]);
+      }
+    }
     if(MODE==5){
       float a0[20];
       #pragma unroll
@@ -73,5 +83,6 @@ int main(){
   run<6>("10 FFMA2 bcast multiplicand", 10, 0);
   run<7>("10 FFMA2 bcast addend", 10, 0);
   run<8>("10 FFMA2 x*x+y", 10, 0);
+  run<9>("40 FFMA2, 3 distinct reg pairs", 40, 0);
   return 0;
 }
