@@ -344,8 +344,6 @@ def render(scene, **params):
         n_pix = subset.numel()
     if params.get('vis_stat', False):
         raise RuntimeError('Removed Support for vis_stat')
-    if params.get('norm_depth_image_only', False):
-        raise NotImplementedError('norm_depth_image_only: broken in the reference under tiling (SURVEY A.6-8)')
     persp = origin.shape[0] == 1
 
     near, far = camera['near'], camera['far']
@@ -364,6 +362,14 @@ def render(scene, **params):
         mat, last_t = parts[-1][4], parts[-1][5]
     else:
         depth, winner, frag_n, frag_p, mat, last_t = _zbuffer_tile(origin, direction, objects, near, far)
+
+    if params.get('norm_depth_image_only', False):
+        # renderer.py:245-260 (the reference reaches this only with tiled=False)
+        im_depth = depth.view(H, W) if subset is None else depth.view(1, n_pix)
+        min_depth = torch.min(im_depth)
+        norm = blend(im_depth >= camera['far'], min_depth, im_depth)
+        norm = (norm - min_depth) / (torch.max(im_depth) - min_depth)
+        return {'image': norm, 'depth': im_depth, 'nearest': winner.view(*im_depth.shape), 'ray_dir': direction}
 
     lights = scene['lights']
     light_pos = lights['pos'][:, :3]

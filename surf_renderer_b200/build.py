@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 SO = os.path.join(PKG, 'libsurf_b200.so')
 SOURCES = [os.path.join(CSRC, 'surf_kernels.cu')]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ('surf_math.cuh', 'surf_view.h')] + \
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))] + \
     [os.path.join(PKG, '..', 'include', 'surf_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -29,1472 +29,13 @@
 
 namespace surf {
 
-// ---------------------------------------------------------------------------------------------------
-// error handling (thread-local string) / launch accounting and optional timers (process-wide counters)
-// ---------------------------------------------------------------------------------------------------
-static thread_local std::string g_error;
-static int g_launches = 0;   // process-wide: autograd runs backward on its own thread
-
-// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg): a ring of
-// event pairs per kernel kind so that a whole timed region can be averaged without synchronising inside it
-constexpr int kTimerRing = 256;
-struct KernelTimers {
-    bool enabled = false;
-    bool created = false;
-    cudaEvent_t ev[3][kTimerRing][2] = {};
-    long long count[3] = {0, 0, 0};     // launches recorded since timing was (re-)enabled
-};
-static KernelTimers g_timers;   // process-wide (see g_launches)
-static void timer_mark(int which, int edge, cudaStream_t st) {
-    if (!g_timers.enabled) return;
-    if (!g_timers.created) {
-        for (int k = 0; k < 3; ++k)
-            for (int r = 0; r < kTimerRing; ++r)
-                for (int e = 0; e < 2; ++e) cudaEventCreate(&g_timers.ev[k][r][e]);
-        g_timers.created = true;
-    }
-    const int slot = (int)(g_timers.count[which] % kTimerRing);
-    cudaEventRecord(g_timers.ev[which][slot][edge], st);
-    if (edge == 1) ++g_timers.count[which];
-}
-static double timer_ms(int which, long long index) {
-    const int slot = (int)(index % kTimerRing);
-    if (cudaEventSynchronize(g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_timers.ev[which][slot][0], g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
-    return (double)ms;
-}
-
-static int fail(int code, const std::string& msg) {
-    g_error = msg;
-    return code;
-}
-static int cuda_fail(cudaError_t e, const char* where) {
-    g_error = std::string(where) + ": " + cudaGetErrorString(e);
-    return SURF_ERR_CUDA;
-}
-#define SURF_CUDA(call)                                     \
-    do {                                                    \
-        cudaError_t e_ = (call);                            \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
-    } while (0)
-#define SURF_LAUNCHED(name)                                      \
-    do {                                                         \
-        ++g_launches;                                            \
-        cudaError_t e_ = cudaPeekAtLastError();                  \
-        if (e_ != cudaSuccess) return cuda_fail(e_, name);       \
-    } while (0)
-
-// ---------------------------------------------------------------------------------------------------
-// workspace layout
-// ---------------------------------------------------------------------------------------------------
-struct Workspace {
-    CamState* cam;
-    float4* packed;              // plane-filter records, per set, 128-byte aligned (math_mode 1..3)
-    float4* circ;                // level-1 screen-circle records, one float4 per primitive in global order
-    float* rays;                 // [3, n] SoA unit directions (perspective)
-    unsigned long long* zbuf;    // [n] packed (depth key << 32 | primitive index)
-    double* acc;                 // backward scalar accumulators
-    double* prim_acc;            // backward per-primitive accumulators [total_prims, 7]
-    float* vis;                  // [L, n] shadow visibility
-    float* gray;                 // [7, n] generic rays: origin xyz, direction xyz, t_max (orthographic / shadow rays)
-    unsigned long long* zbuf2;   // [n] z-buffer keys of the shadow rays
-    float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
-    size_t bytes;
-};
-constexpr int kMaxAccSlots = 512;
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-static size_t packed_bytes_bound(int total_prims) {
-    // worst case: all triangles (4 float4 each) + 8 sets x 128-byte padding
-    return (size_t)total_prims * 64 + kMaxSets * 128 + 256;
-}
-
-static void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws) {
-    char* p = (char*)base;
-    size_t off = 0;
-    ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
-    ws->packed = (float4*)(p + off); off += align_up(packed_bytes_bound(total_prims), 256);
-    ws->circ = (float4*)(p + off); off += align_up((size_t)total_prims * 16 + 256, 256);
-    ws->rays = (float*)(p + off); off += align_up((size_t)3 * n_pix * sizeof(float), 256);
-    ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
-    ws->acc = (double*)(p + off); off += align_up((size_t)kMaxAccSlots * 8, 256);
-    ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
-    ws->vis = (float*)(p + off);
-    if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
-    // generic-ray buffers: always carved (orthographic frames need them too); 36 B per pixel
-    ws->gray = (float*)(p + off); off += align_up((size_t)7 * n_pix * sizeof(float), 256);
-    ws->zbuf2 = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
-    ws->obound = (float*)(p + off); off += 256;
-    ws->bytes = off;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// small PTX helpers: mbarrier, TMA bulk copy, packed f32x2 math
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-// Blackwell packed fp32: one instruction, two lane-FMAs (SASS: FFMA2 / FMUL2)
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_setup / k_prep / k_raygen
-// ---------------------------------------------------------------------------------------------------
-struct CamArgs {
-    const float* eye; const float* at; const float* up;
-    int proj, W, H;
-    double fovy, focal;
-    float near_clip, far_clip;
-};
-
-__global__ void k_setup(CamArgs a, CamState* cs) {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        camera_setup(a.eye, a.at, a.up, a.proj, a.W, a.H, a.fovy, a.focal, a.near_clip, a.far_clip, cs);
-}
-
-__global__ void __launch_bounds__(256) k_prep(const __grid_constant__ SceneView sc, const CamState* __restrict__ cs,
-                                              float4* __restrict__ packed) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= sc.total) return;
-    const int s = find_set(sc, g);
-    const SetView& sv = sc.sets[s];
-    const int i = g - sv.first;
-    const Vec3 o = v3(cs->eye[0], cs->eye[1], cs->eye[2]);
-    F4 r[4];
-    if (sv.kind == KIND_DISK) {
-        prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], o,
-                  &r[0], &r[1]);
-    } else if (sv.kind == KIND_PLANE) {
-        prep_plane(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), o, &r[0]);
-    } else if (sv.kind == KIND_SPHERE) {
-        prep_sphere(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], o, &r[0]);
-    } else {
-        const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
-        prep_triangle(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
-                      ld3(sv.normal + (size_t)i * sv.normal_stride), o, &r[0], &r[1], &r[2], &r[3]);
-    }
-    const int nf4 = rec_f4(sv.kind);
-    float4* dst = packed + sv.rec_off + (size_t)i * nf4;
-    for (int k = 0; k < nf4; ++k) dst[k] = make_float4(r[k].x, r[k].y, r[k].z, r[k].w);
-}
-
-__global__ void __launch_bounds__(256) k_raygen(const CamState* __restrict__ cs, int pix0, int n,
-                                                float* __restrict__ rays, float* __restrict__ ray_out,
-                                                unsigned long long* __restrict__ zbuf) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    zbuf[k] = kMissKey;
-    if (cs->proj == 0) {
-        Vec3 d = pixel_ray_dir(*cs, pix0 + k);
-        rays[k] = d.x; rays[(size_t)n + k] = d.y; rays[2 * (size_t)n + k] = d.z;
-        if (ray_out) { ray_out[k] = d.x; ray_out[(size_t)n + k] = d.y; ray_out[2 * (size_t)n + k] = d.z; }
-    } else if (k == 0 && ray_out) {
-        ray_out[0] = cs->odir[0]; ray_out[1] = cs->odir[1]; ray_out[2] = cs->odir[2];
-    }
-}
-
-__global__ void __launch_bounds__(256) k_prep_screen(const __grid_constant__ SceneView sc, const CamState* __restrict__ cs,
-                                                     float4* __restrict__ circ) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= sc.total) return;
-    const int s = find_set(sc, g);
-    const F4 r = prep_screen(*cs, sc.sets[s], g - sc.sets[s].first);
-    circ[g] = make_float4(r.x, r.y, r.z, r.w);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_intersect: the fused intersection + z-buffer kernel (perspective: one common ray origin)
-// ---------------------------------------------------------------------------------------------------
-constexpr int kThreads = 256;
-constexpr int kStages = 3;
-
-struct IsectParams {
-    SceneView sc;
-    const CamState* cam;
-    const float4* packed;
-    const float* rays;               // [3, n]
-    unsigned long long* zbuf;        // [n]
-    int n_pix;                       // pixels in this launch's range
-    int n_tiles, n_chunks;           // work grid: items = n_tiles * n_chunks
-    int stage_f4;                    // float4 capacity of one smem stage
-    int chunks_before[kMaxSets + 1]; // prefix sum of chunks per set
-};
-
-__device__ __forceinline__ int prims_per_chunk(int stage_f4, int kind) { return stage_f4 / rec_f4(kind); }
-
-// decode a global chunk id -> (set, first local primitive, count)
-__device__ __forceinline__ void decode_chunk(const IsectParams& p, int c, int* set, int* local0, int* count) {
-    int s = 0;
-#pragma unroll
-    for (int k = 1; k < kMaxSets; ++k)
-        if (k < p.sc.n_sets && c >= p.chunks_before[k]) s = k;
-    const SetView& sv = p.sc.sets[s];
-    const int ppc = prims_per_chunk(p.stage_f4, sv.kind);
-    const int j = c - p.chunks_before[s];
-    *set = s;
-    *local0 = j * ppc;
-    *count = min(ppc, sv.count - j * ppc);
-}
-
-template <int P>
-struct PixelRegs {
-    // ray directions of the P pixels this thread owns, stored as packed pairs (pixel 2q, 2q+1)
-    unsigned long long dx[P / 2], dy[P / 2], dz[P / 2];
-    float best_t[P];
-    int best_i[P];
-};
-
-template <int P>
-__device__ __forceinline__ Vec3 ray_of(const PixelRegs<P>& r, int p) {
-    float lo, hi;
-    Vec3 d;
-    unpack2(r.dx[p >> 1], lo, hi); d.x = (p & 1) ? hi : lo;
-    unpack2(r.dy[p >> 1], lo, hi); d.y = (p & 1) ? hi : lo;
-    unpack2(r.dz[p >> 1], lo, hi); d.z = (p & 1) ? hi : lo;
-    return d;
-}
-
-// exact narrow phase for all P pixels of this thread against one candidate primitive
-template <int P>
-__device__ __forceinline__ void narrow(const IsectParams& prm, const SetView& sv, int local, float4 A, Vec3 eye,
-                                       float near_clip, float far_clip, PixelRegs<P>& r) {
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        float t;
-        Vec3 d = ray_of<P>(r, p);
-        bool hit = exact_hit(sv, local, v3(A.x, A.y, A.z), A.w, eye, d, near_clip, far_clip, &t);
-        if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
-    }
-}
-
-// filter margin e = |(o-c) + t d|^2 - (r+slack)^2 of one disk for pixel pair q (two pixels per instruction)
-template <int P>
-__device__ __forceinline__ unsigned long long disk_margin2(const float4& A, const float4& B, const PixelRegs<P>& r, int q) {
-    const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z);
-    unsigned long long b2 = fma2(nz, r.dz[q], fma2(ny, r.dy[q], mul2(nx, r.dx[q])));
-    float b0, b1;
-    unpack2(b2, b0, b1);
-    unsigned long long t2 = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
-    unsigned long long rx = fma2(t2, r.dx[q], pack2(B.x, B.x));
-    unsigned long long ry = fma2(t2, r.dy[q], pack2(B.y, B.y));
-    unsigned long long rz = fma2(t2, r.dz[q], pack2(B.z, B.z));
-    return fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, pack2(B.w, B.w))));
-}
-
-// exact narrow phase of one pixel against one disk
-template <int P>
-__device__ __forceinline__ void narrow_one(const SetView& sv, int local, const float4& A, Vec3 eye, float near_clip,
-                                           float far_clip, PixelRegs<P>& r, int p) {
-    float t;
-    Vec3 d = ray_of<P>(r, p);
-    bool hit = exact_hit(sv, local, v3(A.x, A.y, A.z), A.w, eye, d, near_clip, far_clip, &t);
-    if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
-}
-
-// MODE 0: packed FFMA2 filter, G disks per branch (no per-primitive control dependency, ILP across disks)
-// MODE 1: scalar FFMA filter, one branch per disk          MODE 2: packed FFMA2 filter, one branch per disk
-template <int P, int MODE>
-__device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                            int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                            PixelRegs<P>& r) {
-    int i = 0;
-    if (MODE == 0) {
-        // Software-pipelined: the records of group k+1 are fetched from shared memory while group k computes,
-        // and the (rare) branch taken in iteration k tests the filter minimum of group k-1, which finished long
-        // ago - so neither the LDS latency nor the FMNMX3 chain + branch resolution sits on the critical path.
-        constexpr int G = (P >= 8) ? 2 : 4;
-        const int ngroups = count / G;
-        if (ngroups > 0) {
-            float4 A[G], B[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) { A[g] = s[2 * g]; B[g] = s[2 * g + 1]; }
-            float m_prev = INFINITY;
-            for (int k = 0; k < ngroups; ++k) {
-                float4 An[G], Bn[G];
-                const int nxt = (k + 1 < ngroups ? k + 1 : k) * G;     // last iteration re-reads its own group
-#pragma unroll
-                for (int g = 0; g < G; ++g) { An[g] = s[2 * (nxt + g)]; Bn[g] = s[2 * (nxt + g) + 1]; }
-                float m = INFINITY;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-#pragma unroll
-                    for (int q = 0; q < P / 2; ++q) {
-                        float e0, e1;
-                        unpack2(disk_margin2<P>(A[g], B[g], r, q), e0, e1);
-                        m = fminf(m, fminf(e0, e1));     // NaN-ignoring min: NaN margins are misses
-                    }
-                }
-                if (m_prev <= 0.f) {       // rare: a pair of the PREVIOUS group passed the conservative filter
-                    const int base = (k - 1) * G;
-#pragma unroll 1
-                    for (int g = 0; g < G; ++g) {
-                        const float4 Ag = s[2 * (base + g)], Bg = s[2 * (base + g) + 1];
-#pragma unroll
-                        for (int q = 0; q < P / 2; ++q) {
-                            float e0, e1;
-                            unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
-                            if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
-                            if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
-                        }
-                    }
-                }
-                m_prev = m;
-#pragma unroll
-                for (int g = 0; g < G; ++g) { A[g] = An[g]; B[g] = Bn[g]; }
-            }
-            if (m_prev <= 0.f) {
-                const int base = (ngroups - 1) * G;
-#pragma unroll 1
-                for (int g = 0; g < G; ++g) {
-                    const float4 Ag = s[2 * (base + g)], Bg = s[2 * (base + g) + 1];
-#pragma unroll
-                    for (int q = 0; q < P / 2; ++q) {
-                        float e0, e1;
-                        unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
-                        if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
-                        if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
-                    }
-                }
-            }
-            i = ngroups * G;
-        }
-    }
-    for (; i < count; ++i) {
-        const float4 A = s[2 * i];       // n.x n.y n.z numer      (LDS.128, warp-broadcast)
-        const float4 B = s[2 * i + 1];   // oc.x oc.y oc.z -(r+slack)^2
-        bool any = false;
-        if (MODE != 1) {
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                float e0, e1;
-                unpack2(disk_margin2<P>(A, B, r, q), e0, e1);
-                any |= (e0 <= 0.f) | (e1 <= 0.f);
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                Vec3 d = ray_of<P>(r, p);
-                float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
-                float t = A.w * rcp_approx(b);
-                float rx = fmaf(t, d.x, B.x), ry = fmaf(t, d.y, B.y), rz = fmaf(t, d.z, B.z);
-                any |= fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, B.w))) <= 0.f;
-            }
-        }
-        if (any) narrow<P>(prm, sv, local0 + i, A, eye, near_clip, far_clip, r);
-    }
-}
-
-template <int P>
-__device__ __forceinline__ void chunk_planes(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                             int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                             PixelRegs<P>& r) {
-    for (int i = 0; i < count; ++i) narrow<P>(prm, sv, local0 + i, s[i], eye, near_clip, far_clip, r);
-}
-
-template <int P>
-__device__ __forceinline__ void chunk_spheres(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                              int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                              PixelRegs<P>& r) {
-    for (int i = 0; i < count; ++i) {
-        const float4 S = s[i];
-        bool any = false;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            Vec3 d = ray_of<P>(r, p);
-            float hb = fmaf(S.z, d.z, fmaf(S.y, d.y, S.x * d.x));
-            any |= fmaf(hb, hb, -S.w) >= 0.f;
-        }
-        if (any) narrow<P>(prm, sv, local0 + i, S, eye, near_clip, far_clip, r);
-    }
-}
-
-template <int P>
-__device__ __forceinline__ void chunk_triangles(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                                int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                                PixelRegs<P>& r) {
-    for (int i = 0; i < count; ++i) {
-        const float4 A = s[4 * i], W0 = s[4 * i + 1], W1 = s[4 * i + 2], W2 = s[4 * i + 3];
-        bool any = false;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            Vec3 d = ray_of<P>(r, p);
-            float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
-            float t = A.w * rcp_approx(b);
-            float c0 = fmaf(t, fmaf(W0.z, d.z, fmaf(W0.y, d.y, W0.x * d.x)), W0.w);
-            float c1 = fmaf(t, fmaf(W1.z, d.z, fmaf(W1.y, d.y, W1.x * d.x)), W1.w);
-            float c2 = fmaf(t, fmaf(W2.z, d.z, fmaf(W2.y, d.y, W2.x * d.x)), W2.w);
-            any |= (c0 >= 0.f) & (c1 >= 0.f) & (c2 >= 0.f);
-        }
-        if (any) narrow<P>(prm, sv, local0 + i, A, eye, near_clip, far_clip, r);
-    }
-}
-
-template <int P, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant__ IsectParams prm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-
-    const int tid = threadIdx.x;
-    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
-    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
-    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
-    if (lo >= hi) return;
-
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int item, int stage) {
-        int set, local0, count;
-        decode_chunk(prm, item % prm.n_chunks, &set, &local0, &count);
-        const SetView& sv = prm.sc.sets[set];
-        const int nf4 = rec_f4(sv.kind);
-        const float4* src = prm.packed + sv.rec_off + (size_t)local0 * nf4;
-        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
-        mbar_expect_tx(&full_bar[stage], bytes);
-        tma_bulk_g2s(stage_buf + (size_t)stage * prm.stage_f4, src, bytes, &full_bar[stage]);
-    };
-    if (tid == 0)
-        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
-
-    const Vec3 eye = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
-    const float near_clip = prm.cam->near_clip, far_clip = prm.cam->far_clip;
-    constexpr int TILE = kThreads * P;
-
-    PixelRegs<P> r;
-    int cur_tile = -1;
-
-    auto flush = [&]() {
-        if (cur_tile < 0) return;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int pix = cur_tile * TILE + p * kThreads + tid;
-            if (r.best_i[p] >= 0 && pix < prm.n_pix) {
-                unsigned long long key = ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p];
-                atomicMin(prm.zbuf + pix, key);
-            }
-        }
-    };
-
-    for (int it = lo; it < hi; ++it) {
-        const int k = it - lo;
-        const int stage = k % kStages;
-        const uint32_t parity = (uint32_t)((k / kStages) & 1);
-        __syncthreads();   // every thread is done with item it-1, whose stage is the one refilled below
-        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (k + kStages - 1) % kStages);
-
-        const int tile = it / prm.n_chunks;
-        if (tile != cur_tile) {
-            flush();
-            cur_tile = tile;
-            float d[3][P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int pix = tile * TILE + p * kThreads + tid;
-                const bool ok = pix < prm.n_pix;
-                d[0][p] = ok ? prm.rays[pix] : 0.f;
-                d[1][p] = ok ? prm.rays[(size_t)prm.n_pix + pix] : 0.f;
-                d[2][p] = ok ? prm.rays[2 * (size_t)prm.n_pix + pix] : 0.f;
-                r.best_t[p] = INFINITY;
-                r.best_i[p] = -1;
-            }
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                r.dx[q] = pack2(d[0][2 * q], d[0][2 * q + 1]);
-                r.dy[q] = pack2(d[1][2 * q], d[1][2 * q + 1]);
-                r.dz[q] = pack2(d[2][2 * q], d[2][2 * q + 1]);
-            }
-        }
-
-        int set, local0, count;
-        decode_chunk(prm, it % prm.n_chunks, &set, &local0, &count);
-        const SetView& sv = prm.sc.sets[set];
-        mbar_wait(&full_bar[stage], parity);
-        const float4* s = stage_buf + (size_t)stage * prm.stage_f4;
-        if (sv.kind == KIND_DISK) chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
-        else if (sv.kind == KIND_TRIANGLE) chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
-        else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
-        else chunk_planes<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
-    }
-    flush();
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_intersect_screen: opt-in fast intersection kernel (math_mode 3, perspective).  Level 1 classifies EVERY (pixel,
-// primitive) pair in registers against the primitive's screen-space bounding circle.  The test is separable: the
-// row term (y - v)^2 - rho^2 is shared by the P pixels of a thread (they sit in one image row) and rules all of
-// them out when positive; otherwise the column terms are evaluated two pixels per instruction (FADD2 + FFMA2 +
-// FMNMX3 per pixel pair).  The rare flagged pairs run the exact reference-order test.  Same persistent-CTA / TMA-ring / atomicMin z-buffer structure as k_intersect.
-//   thread -> P consecutive columns of one row; warp -> 4P x 8 pixels; CTA -> 8P x 32 pixels.
-// ---------------------------------------------------------------------------------------------------
-struct ScreenParams {
-    SceneView sc;
-    const CamState* cam;
-    const float4* circ;              // [total] level-1 records
-    const float* rays;               // [3, n]
-    unsigned long long* zbuf;        // [n]
-    int pix0, n_pix, W, row0;
-    int tiles_x, n_tiles, n_chunks, chunk, total;
-};
-
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
-// exact test of one (pixel, primitive) pair; returns true and *t on a valid hit.  Out of line: rare path.
-__device__ __noinline__ bool exact_pair(const ScreenParams& prm, int idx, int k, float* t_out) {
-    const int set = find_set(prm.sc, idx);
-    const SetView& sv = prm.sc.sets[set];
-    const int local = idx - sv.first;
-    const Vec3 o = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
-    const Vec3 d = v3(prm.rays[k], prm.rays[(size_t)prm.n_pix + k], prm.rays[2 * (size_t)prm.n_pix + k]);
-    Vec3 nn;
-    float numer;
-    plane_consts_for_origin(sv, local, o, &nn, &numer);
-    return exact_hit(sv, local, nn, numer, o, d, prm.cam->near_clip, prm.cam->far_clip, t_out);
-}
-
-template <int P>
-__global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen(const __grid_constant__ ScreenParams prm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-
-    const int tid = threadIdx.x;
-    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
-    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
-    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
-    if (lo >= hi) return;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int item, int stage) {
-        const int c = item % prm.n_chunks;
-        const int first = c * prm.chunk;
-        const int count = min(prm.chunk, prm.total - first);
-        const uint32_t bytes = (uint32_t)count * 16u;
-        mbar_expect_tx(&full_bar[stage], bytes);
-        tma_bulk_g2s(stage_buf + (size_t)stage * prm.chunk, prm.circ + first, bytes, &full_bar[stage]);
-    };
-    if (tid == 0)
-        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
-
-    // thread geometry inside the CTA tile
-    const int warp = tid >> 5, lane = tid & 31;
-    const int tcol = (warp & 1) * 4 * P + (lane & 3) * P;     // first column of this thread inside the tile
-    const int trow = (warp >> 1) * 8 + (lane >> 2);
-    constexpr int TW = 8 * P, TH = 32;
-
-    unsigned long long x2[P / 2];       // image-plane x of the thread's pixels, packed pairs
-    float y = 0.f;
-    float best_t[P];
-    int best_i[P];
-    int kbase = 0;                      // output index of the thread's first pixel
-    unsigned valid = 0;                 // bit p: pixel p is inside the frame and the launch's pixel range
-    int cur_tile = -1;
-
-    auto flush = [&]() {
-        if (cur_tile < 0) return;
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-            if (best_i[p] >= 0) {
-                unsigned long long key = ((unsigned long long)float_order_key(best_t[p]) << 32) | (unsigned)best_i[p];
-                atomicMin(prm.zbuf + kbase + p, key);
-            }
-    };
-
-    for (int it = lo; it < hi; ++it) {
-        const int kk = it - lo;
-        const int stage = kk % kStages;
-        const uint32_t parity = (uint32_t)((kk / kStages) & 1);
-        __syncthreads();
-        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (kk + kStages - 1) % kStages);
-
-        const int tile = it / prm.n_chunks;
-        if (tile != cur_tile) {
-            flush();
-            cur_tile = tile;
-            const int ty = tile / prm.tiles_x, tx = tile - ty * prm.tiles_x;
-            const int row = prm.row0 + ty * TH + trow;
-            const int col0 = tx * TW + tcol;
-            kbase = row * prm.W + col0 - prm.pix0;
-            valid = 0;
-            float xs[P];
-            float yy = 0.f;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int col = col0 + p;
-                const int k = kbase + p;
-                const bool ok = col < prm.W && row < prm.cam->H && k >= 0 && k < prm.n_pix;
-                float xv = 3.0e18f;                   // far outside any circle: never flagged
-                if (ok) {
-                    pixel_xy(*prm.cam, row * prm.W + col, &xv, &yy);
-                    valid |= 1u << p;
-                }
-                xs[p] = xv;
-                best_t[p] = INFINITY;
-                best_i[p] = -1;
-            }
-            y = valid ? yy : 3.0e18f;
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) x2[q] = pack2(xs[2 * q], xs[2 * q + 1]);
-        }
-
-        const int first = (it % prm.n_chunks) * prm.chunk;
-        const int count = min(prm.chunk, prm.total - first);
-        mbar_wait(&full_bar[stage], parity);
-        const float4* __restrict__ s = stage_buf + (size_t)stage * prm.chunk;
-
-        constexpr int G = 4;
-        int i = 0;
-        for (; i + G <= count; i += G) {
-            // row term first: the P pixels of a thread share one image row, so sy = (y - v)^2 - rho^2 > 0 rules out
-            // all of them at once.  Only when some lane's row crosses one of the G circles are the column terms
-            // evaluated (packed, two pixels per instruction).
-            float4 C[G];
-            float sy[G];
-            float my = INFINITY;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                C[g] = s[i + g];                            // -u, -v, -rho^2, 0   (LDS.128, warp broadcast)
-                const float dy = y + C[g].y;
-                sy[g] = fmaf(dy, dy, C[g].z);
-                my = fminf(my, sy[g]);
-            }
-            if (!__any_sync(0xffffffffu, my <= 0.f)) continue;
-            float m = INFINITY;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const unsigned long long mu = pack2(C[g].x, C[g].x), sy2 = pack2(sy[g], sy[g]);
-#pragma unroll
-                for (int q = 0; q < P / 2; ++q) {
-                    const unsigned long long dx = add2(x2[q], mu);
-                    float e0, e1;
-                    unpack2(fma2(dx, dx, sy2), e0, e1);
-                    m = fminf(m, fminf(e0, e1));
-                }
-            }
-            if (m <= 0.f) {          // rare: some pair of this group lies inside its screen circle
-#pragma unroll 1
-                for (int g = 0; g < G; ++g) {
-                    const float4 C = s[i + g];
-                    const float dy = y + C.y;
-                    const float sy = fmaf(dy, dy, C.z);
-#pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        float lo_, hi_;
-                        unpack2(x2[p >> 1], lo_, hi_);
-                        const float dx = ((p & 1) ? hi_ : lo_) + C.x;
-                        if (fmaf(dx, dx, sy) <= 0.f) {
-                            float t;
-                            if (exact_pair(prm, first + i + g, kbase + p, &t) && t < best_t[p]) {
-                                best_t[p] = t;
-                                best_i[p] = first + i + g;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        for (; i < count; ++i) {     // chunk tail
-            const float4 C = s[i];
-            const float dy = y + C.y;
-            const float sy = fmaf(dy, dy, C.z);
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                float lo_, hi_;
-                unpack2(x2[p >> 1], lo_, hi_);
-                const float dx = ((p & 1) ? hi_ : lo_) + C.x;
-                if (fmaf(dx, dx, sy) <= 0.f) {
-                    float t;
-                    if (exact_pair(prm, first + i, kbase + p, &t) && t < best_t[p]) {
-                        best_t[p] = t;
-                        best_i[p] = first + i;
-                    }
-                }
-            }
-        }
-    }
-    flush();
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_intersect_rays: the same fused intersection + z-buffer structure for rays with PER-RAY origins
-// (orthographic camera pixels, shadow rays).  Disk filter per ray pair: 17 packed FMA-pipe instructions
-// (n.o 3, numer 1, n.d 3, t 1, P = o + t d 3, rel = P - c 3, |rel|^2 - r^2 3) + 2 MUFU.RCP.
-// MODE 0: camera rays, near <= t <= far;  MODE 1: shadow rays, 0 < t < tmax[ray] (renderer.py:306).
-// ---------------------------------------------------------------------------------------------------
-struct RayParams {
-    SceneView sc;
-    const CamState* cam;
-    const float4* packed;            // origin-independent records (k_prep_rays)
-    const float* gray;               // [7, n]: ox oy oz dx dy dz tmax
-    unsigned long long* zbuf;        // [n]
-    int n_pix, n_tiles, n_chunks, stage_f4;
-    int chunks_before[kMaxSets + 1];
-};
-
-__global__ void __launch_bounds__(256) k_prep_rays(const __grid_constant__ SceneView sc, const float* __restrict__ obound,
-                                                   float4* __restrict__ packed) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= sc.total) return;
-    const int s = find_set(sc, g);
-    const SetView& sv = sc.sets[s];
-    const int i = g - sv.first;
-    const float ob = obound[0];
-    F4 r[4];
-    if (sv.kind == KIND_DISK) {
-        prep_disk_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], ob,
-                       &r[0], &r[1]);
-    } else if (sv.kind == KIND_PLANE) {
-        prep_plane_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), &r[0]);
-    } else if (sv.kind == KIND_SPHERE) {
-        prep_sphere_rays(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], ob, &r[0]);
-    } else {
-        const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
-        prep_triangle_rays(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
-                           ld3(sv.normal + (size_t)i * sv.normal_stride), ob, &r[0], &r[1], &r[2], &r[3]);
-    }
-    const int nf4 = rec_f4(sv.kind);
-    float4* dst = packed + sv.rec_off + (size_t)i * nf4;
-    for (int k = 0; k < nf4; ++k) dst[k] = make_float4(r[k].x, r[k].y, r[k].z, r[k].w);
-}
-
-template <int P>
-struct RayRegs {
-    unsigned long long ox[P / 2], oy[P / 2], oz[P / 2], dx[P / 2], dy[P / 2], dz[P / 2];
-    float tmax[P];
-    float best_t[P];
-    int best_i[P];
-};
-template <int P>
-__device__ __forceinline__ void ray_of(const RayRegs<P>& r, int p, Vec3* o, Vec3* d) {
-    float lo, hi;
-    unpack2(r.ox[p >> 1], lo, hi); o->x = (p & 1) ? hi : lo;
-    unpack2(r.oy[p >> 1], lo, hi); o->y = (p & 1) ? hi : lo;
-    unpack2(r.oz[p >> 1], lo, hi); o->z = (p & 1) ? hi : lo;
-    unpack2(r.dx[p >> 1], lo, hi); d->x = (p & 1) ? hi : lo;
-    unpack2(r.dy[p >> 1], lo, hi); d->y = (p & 1) ? hi : lo;
-    unpack2(r.dz[p >> 1], lo, hi); d->z = (p & 1) ? hi : lo;
-}
-
-template <int P, int MODE>
-__device__ __forceinline__ void narrow_ray(const RayParams& prm, const SetView& sv, int local, RayRegs<P>& r, int p) {
-    Vec3 o, d, nn;
-    float numer, t;
-    ray_of<P>(r, p, &o, &d);
-    plane_consts_for_origin(sv, local, o, &nn, &numer);
-    bool hit;
-    if (MODE == 0) {
-        hit = exact_hit(sv, local, nn, numer, o, d, prm.cam->near_clip, prm.cam->far_clip, &t);
-    } else {
-        hit = exact_hit(sv, local, nn, numer, o, d, -INFINITY, INFINITY, &t) && t > 0.f && t < r.tmax[p];
-    }
-    if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
-}
-
-template <int P, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_constant__ RayParams prm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    const int tid = threadIdx.x;
-    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
-    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
-    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
-    if (lo >= hi) return;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto decode = [&](int c, int* set, int* local0, int* count) {
-        int s = 0;
-#pragma unroll
-        for (int k = 1; k < kMaxSets; ++k)
-            if (k < prm.sc.n_sets && c >= prm.chunks_before[k]) s = k;
-        const SetView& sv = prm.sc.sets[s];
-        const int ppc = prm.stage_f4 / rec_f4(sv.kind);
-        const int j = c - prm.chunks_before[s];
-        *set = s; *local0 = j * ppc; *count = min(ppc, sv.count - j * ppc);
-    };
-    auto issue = [&](int item, int stage) {
-        int set, local0, count;
-        decode(item % prm.n_chunks, &set, &local0, &count);
-        const SetView& sv = prm.sc.sets[set];
-        const int nf4 = rec_f4(sv.kind);
-        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
-        mbar_expect_tx(&full_bar[stage], bytes);
-        tma_bulk_g2s(stage_buf + (size_t)stage * prm.stage_f4, prm.packed + sv.rec_off + (size_t)local0 * nf4, bytes, &full_bar[stage]);
-    };
-    if (tid == 0)
-        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
-
-    constexpr int TILE = kThreads * P;
-    RayRegs<P> r;
-    int cur_tile = -1;
-    auto flush = [&]() {
-        if (cur_tile < 0) return;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int pix = cur_tile * TILE + p * kThreads + tid;
-            if (r.best_i[p] >= 0 && pix < prm.n_pix)
-                atomicMin(prm.zbuf + pix, ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
-        }
-    };
-
-    for (int it = lo; it < hi; ++it) {
-        const int kk = it - lo;
-        const int stage = kk % kStages;
-        const uint32_t parity = (uint32_t)((kk / kStages) & 1);
-        __syncthreads();
-        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (kk + kStages - 1) % kStages);
-        const int tile = it / prm.n_chunks;
-        if (tile != cur_tile) {
-            flush();
-            cur_tile = tile;
-            float v[6][P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int pix = tile * TILE + p * kThreads + tid;
-                const bool ok = pix < prm.n_pix;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) v[c][p] = ok ? prm.gray[(size_t)c * prm.n_pix + pix] : 0.f;
-                r.tmax[p] = ok ? prm.gray[(size_t)6 * prm.n_pix + pix] : 0.f;
-                r.best_t[p] = INFINITY;
-                r.best_i[p] = -1;
-            }
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                r.ox[q] = pack2(v[0][2 * q], v[0][2 * q + 1]); r.oy[q] = pack2(v[1][2 * q], v[1][2 * q + 1]);
-                r.oz[q] = pack2(v[2][2 * q], v[2][2 * q + 1]); r.dx[q] = pack2(v[3][2 * q], v[3][2 * q + 1]);
-                r.dy[q] = pack2(v[4][2 * q], v[4][2 * q + 1]); r.dz[q] = pack2(v[5][2 * q], v[5][2 * q + 1]);
-            }
-        }
-        int set, local0, count;
-        decode(it % prm.n_chunks, &set, &local0, &count);
-        const SetView& sv = prm.sc.sets[set];
-        mbar_wait(&full_bar[stage], parity);
-        const float4* __restrict__ s = stage_buf + (size_t)stage * prm.stage_f4;
-        if (sv.kind == KIND_DISK) {
-            for (int i = 0; i < count; ++i) {
-                const float4 A = s[2 * i], B = s[2 * i + 1];
-                const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z);
-                float m = INFINITY;
-                float e[P];
-#pragma unroll
-                for (int q = 0; q < P / 2; ++q) {
-                    const unsigned long long no = fma2(nz, r.oz[q], fma2(ny, r.oy[q], mul2(nx, r.ox[q])));
-                    const unsigned long long numer = fma2(no, pack2(-1.f, -1.f), pack2(A.w, A.w));
-                    const unsigned long long b2 = fma2(nz, r.dz[q], fma2(ny, r.dy[q], mul2(nx, r.dx[q])));
-                    float b0, b1;
-                    unpack2(b2, b0, b1);
-                    const unsigned long long t2 = mul2(numer, pack2(rcp_approx(b0), rcp_approx(b1)));
-                    const unsigned long long rx = add2(fma2(t2, r.dx[q], r.ox[q]), pack2(B.x, B.x));
-                    const unsigned long long ry = add2(fma2(t2, r.dy[q], r.oy[q]), pack2(B.y, B.y));
-                    const unsigned long long rz = add2(fma2(t2, r.dz[q], r.oz[q]), pack2(B.z, B.z));
-                    unpack2(fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, pack2(B.w, B.w)))), e[2 * q], e[2 * q + 1]);
-                    m = fminf(m, fminf(e[2 * q], e[2 * q + 1]));
-                }
-                if (m <= 0.f) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        if (e[p] <= 0.f) narrow_ray<P, MODE>(prm, sv, local0 + i, r, p);
-                }
-            }
-        } else {
-            const int nf4 = rec_f4(sv.kind);
-            for (int i = 0; i < count; ++i) {
-                const float4* rec = s + (size_t)i * nf4;
-                const F4 A = f4(rec[0].x, rec[0].y, rec[0].z, rec[0].w);
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    Vec3 o, d;
-                    ray_of<P>(r, p, &o, &d);
-                    bool pass = true;
-                    if (sv.kind == KIND_SPHERE) pass = sphere_filter_rays(A, o, d);
-                    else if (sv.kind == KIND_TRIANGLE)
-                        pass = triangle_filter_rays(A, f4(rec[1].x, rec[1].y, rec[1].z, rec[1].w), f4(rec[2].x, rec[2].y, rec[2].z, rec[2].w),
-                                                    f4(rec[3].x, rec[3].y, rec[3].z, rec[3].w), o, d);
-                    if (pass) narrow_ray<P, MODE>(prm, sv, local0 + i, r, p);
-                }
-            }
-        }
-    }
-    flush();
-}
-
-// generic rays of an orthographic frame: per-pixel origins, one direction
-__global__ void __launch_bounds__(256) k_rays_ortho(const CamState* __restrict__ cs, int pix0, int n, float* __restrict__ gray,
-                                                    float* __restrict__ obound) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float len = 0.f;
-    if (k < n) {
-        const Vec3 o = pixel_ray_origin_ortho(*cs, pix0 + k);
-        gray[k] = o.x; gray[(size_t)n + k] = o.y; gray[2 * (size_t)n + k] = o.z;
-        gray[3 * (size_t)n + k] = cs->odir[0]; gray[4 * (size_t)n + k] = cs->odir[1]; gray[5 * (size_t)n + k] = cs->odir[2];
-        gray[6 * (size_t)n + k] = INFINITY;
-        len = sqrtf(o.x * o.x + o.y * o.y + o.z * o.z);
-    }
-    for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
-    if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
-}
-
-// generic-origin variant (orthographic camera: per-pixel origins, one direction).  Exact tests only; the
-// reference itself only supports this projection up to one tile of pixels.
-__global__ void __launch_bounds__(256) k_intersect_generic(const __grid_constant__ SceneView sc,
-                                                           const CamState* __restrict__ cs, int pix0, int n,
-                                                           unsigned long long* __restrict__ zbuf) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const Vec3 o = pixel_ray_origin_ortho(*cs, pix0 + k);
-    const Vec3 d = v3(cs->odir[0], cs->odir[1], cs->odir[2]);
-    float best_t = INFINITY;
-    int best = -1;
-    for (int s = 0; s < sc.n_sets; ++s) {
-        const SetView& sv = sc.sets[s];
-        for (int i = 0; i < sv.count; ++i) {
-            Vec3 nn; float numer, t;
-            plane_consts_for_origin(sv, i, o, &nn, &numer);
-            if (exact_hit(sv, i, nn, numer, o, d, cs->near_clip, cs->far_clip, &t) && t < best_t) {
-                best_t = t; best = sv.first + i;
-            }
-        }
-    }
-    if (best >= 0) zbuf[k] = ((unsigned long long)float_order_key(best_t) << 32) | (unsigned)best;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_shade: resolve + Phong shading epilogue
-// ---------------------------------------------------------------------------------------------------
-struct ShadeParams {
-    SceneView sc;
-    const CamState* cam;
-    const float* rays;
-    const unsigned long long* zbuf;
-    const float* vis;     // [L, n] or null
-    int pix0, n;
-    ShadeFlags fl;
-    float* image; float* depth; float* normal; float* pos; long long* nearest;
-};
-
-__device__ __forceinline__ void pixel_ray(const CamState& cs, const float* rays, int n, int pix0, int k, Vec3* o, Vec3* d) {
-    if (cs.proj == 0) {
-        *o = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
-        *d = v3(rays[k], rays[(size_t)n + k], rays[2 * (size_t)n + k]);
-    } else {
-        *o = pixel_ray_origin_ortho(cs, pix0 + k);
-        *d = v3(cs.odir[0], cs.odir[1], cs.odir[2]);
-    }
-}
-
-// cooperative [256,3] -> coalesced store through shared memory
-__device__ __forceinline__ void store3(float* __restrict__ dst, float (*sm)[3], int base, int n, const float v[3]) {
-    const int tid = threadIdx.x;
-    __syncthreads();
-    sm[tid][0] = v[0]; sm[tid][1] = v[1]; sm[tid][2] = v[2];
-    __syncthreads();
-    const float* flat = &sm[0][0];
-    const int lim = min(256, n - base) * 3;
-    for (int j = tid; j < lim; j += 256) dst[(size_t)base * 3 + j] = flat[j];
-}
-
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ShadeParams p) {
-    __shared__ float sm[256][3];
-    const int base = blockIdx.x * 256;
-    const int k = base + threadIdx.x;
-    const bool live = k < p.n;
-    PixelOut po;
-    if (live) {
-        Vec3 o, d;
-        pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
-        float vis_l[16];
-        const float* vis = nullptr;
-        if (p.vis) {
-            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + k];
-            vis = vis_l;
-        }
-        po = resolve_pixel(p.sc, *p.cam, o, d, p.zbuf[k], p.fl, vis);
-        if (p.depth) p.depth[k] = po.depth;
-        if (p.nearest) p.nearest[k] = po.nearest;
-    } else {
-        po = PixelOut();
-    }
-    if (p.image) store3(p.image, sm, base, p.n, po.image);
-    if (p.normal) store3(p.normal, sm, base, p.n, po.normal);
-    if (p.pos) store3(p.pos, sm, base, p.n, po.pos);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// shadow rays (renderer.py:291-314): per light, a ray from frag_pos + 0.1 L toward the light against all
-// primitives; the light is visible iff nothing is hit strictly between 0 and |L|, or the nearest such hit
-// is the fragment's own primitive.  Per-pixel origins -> exact tests over the raw arrays.
-// ---------------------------------------------------------------------------------------------------
-struct ShadowParams {
-    SceneView sc;
-    const CamState* cam;
-    const float* rays;
-    const unsigned long long* zbuf;
-    float* vis;      // [L, n]
-    int pix0, n;
-};
-
-__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowParams p) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y;
-    if (k >= p.n) return;
-    Vec3 o, d;
-    pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
-    const unsigned long long key = p.zbuf[k];
-    const int self = key == kMissKey ? 0 : (int)(key & 0xFFFFFFFFull);
-    Fragment f = fragment_at(p.sc, self, o, d);
-    p.vis[(size_t)l * p.n + k] = shadow_visibility(p.sc, f.P, self, l);
-}
-
-// shadow rays of light l (renderer.py:293-299): origin frag_pos + 0.1 L, direction L, t_max = |light - frag_pos|.
-// Miss pixels get a null direction (no hits): their visibility never reaches an output (image is masked).
-__global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, int l, float* __restrict__ gray,
-                                                     unsigned long long* __restrict__ zbuf2, float* __restrict__ obound) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    float len = 0.f;
-    if (k < p.n) {
-        const size_t n = (size_t)p.n;
-        zbuf2[k] = kMissKey;
-        const unsigned long long key = p.zbuf[k];
-        Vec3 so = v3(0.f, 0.f, 0.f), L = v3(0.f, 0.f, 0.f);
-        float dist = 0.f;
-        if (key != kMissKey) {
-            Vec3 o, d;
-            pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
-            Fragment f = fragment_at(p.sc, (int)(key & 0xFFFFFFFFull), o, d);
-            Vec3 Lv = vsub(ld3(p.sc.light_pos + (size_t)l * p.sc.light_pos_stride), f.P);
-            dist = xsqrt(sq3_seq(Lv));
-            L = v3(xdiv(Lv.x, dist), xdiv(Lv.y, dist), xdiv(Lv.z, dist));
-            so = vadd(f.P, vscale(0.1f, L));
-            len = sqrtf(so.x * so.x + so.y * so.y + so.z * so.z);
-            if (!(len == len) || !(dist == dist) || isinf(len)) { L = v3(0.f, 0.f, 0.f); len = 0.f; }
-        }
-        gray[k] = so.x; gray[n + k] = so.y; gray[2 * n + k] = so.z;
-        gray[3 * n + k] = L.x; gray[4 * n + k] = L.y; gray[5 * n + k] = L.z;
-        gray[6 * n + k] = dist;
-    }
-    for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
-    if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
-}
-
-// visible iff nothing was hit inside (0, |L|), or the nearest such hit is the fragment's own primitive (:306-309)
-__global__ void __launch_bounds__(256) k_shadow_resolve(const unsigned long long* __restrict__ zbuf,
-                                                        const unsigned long long* __restrict__ zbuf2, int n, float* __restrict__ vis_l) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const unsigned long long self = zbuf[k], hit = zbuf2[k];
-    const bool visible = hit == kMissKey || self == kMissKey || (unsigned)(hit & 0xFFFFFFFFull) == (unsigned)(self & 0xFFFFFFFFull);
-    vis_l[k] = visible ? 1.f : 0.f;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_backward
-// ---------------------------------------------------------------------------------------------------
-struct GradPtrs {
-    float* prim_pos[kMaxSets]; float* prim_normal[kMaxSets]; float* prim_radius[kMaxSets];
-    float* light_pos; float* atten; float* ambient; float* colors; float* albedo; float* coeffs; float* gamma;
-};
-// accumulator slot map (doubles): [albedo K*3][coeffs K*3][light_pos L*3][atten L*3][colors C*3][ambient 3][gamma 1]
-struct SlotMap { int albedo, coeffs, light_pos, atten, colors, ambient, gamma, total; };
-
-__host__ __device__ inline SlotMap slot_map(int K, int L, int Cn) {
-    SlotMap m;
-    m.albedo = 0; m.coeffs = K * 3; m.light_pos = m.coeffs + K * 3; m.atten = m.light_pos + L * 3;
-    m.colors = m.atten + L * 3; m.ambient = m.colors + Cn * 3; m.gamma = m.ambient + 3; m.total = m.gamma + 1;
-    return m;
-}
-
-struct BackwardParams {
-    SceneView sc;
-    const CamState* cam;
-    const float* rays;
-    const float* vis;
-    const long long* nearest;
-    const float* depth;
-    const float* g_image; const float* g_depth; const float* g_normal; const float* g_pos;
-    int pix0, n;
-    ShadeFlags fl;
-    GradPtrs gp;
-    SlotMap sm;
-    double* acc;
-    double* prim_acc;
-};
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-struct DeviceSink {
-    const BackwardParams& p;
-    double* cta_acc;           // shared, [sm.total]
-    float alb[3], cf[3], amb[3], gam;
-    float lp[3], at[3], col[3];
-    __device__ DeviceSink(const BackwardParams& prm, double* shared_acc) : p(prm), cta_acc(shared_acc) {
-        for (int c = 0; c < 3; ++c) alb[c] = cf[c] = amb[c] = lp[c] = at[c] = col[c] = 0.f;
-        gam = 0.f;
-    }
-    __device__ void albedo(int, int c, float v) { alb[c] += v; }
-    __device__ void coeff(int, int c, float v) { cf[c] += v; }
-    __device__ void ambient(int c, float v) { amb[c] += v; }
-    __device__ void gamma(float v) { gam += v; }
-    __device__ void light_pos(int, int c, float v) { lp[c] += v; }
-    __device__ void atten(int, int c, float v) { at[c] += v; }
-    __device__ void color(int, int c, float v) { col[c] += v; }
-    __device__ void add_cta(int slot, float warp_total) { atomicAdd(&cta_acc[slot], (double)warp_total); }
-    __device__ void end_light(int l, int crow) {
-        const int lane = threadIdx.x & 31;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = warp_sum(lp[c]), b = warp_sum(at[c]), e = warp_sum(col[c]);
-            if (lane == 0) {
-                if (a != 0.f) add_cta(p.sm.light_pos + l * 3 + c, a);
-                if (b != 0.f) add_cta(p.sm.atten + l * 3 + c, b);
-                if (e != 0.f) add_cta(p.sm.colors + crow * 3 + c, e);
-            }
-            lp[c] = at[c] = col[c] = 0.f;
-        }
-    }
-    __device__ void end_splat(int m) { flush_scalars(m); }
-    __device__ void end_pixel(int set, int local, int idx, int m, const float* g7) {
-        flush_scalars(m);
-        flush_primitive(set, local, idx, g7);
-    }
-    __device__ void flush_scalars(int m) {
-        const int lane = threadIdx.x & 31;
-        // global scalars
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = warp_sum(amb[c]);
-            if (lane == 0 && a != 0.f) add_cta(p.sm.ambient + c, a);
-        }
-        float gsum = warp_sum(gam);
-        if (lane == 0 && gsum != 0.f) add_cta(p.sm.gamma, gsum);
-        // per-material rows: warp-uniform material is the common case (splat scenes use one material)
-        const int m0 = __shfl_sync(0xffffffffu, m, 0);
-        if (__all_sync(0xffffffffu, m == m0)) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float a = warp_sum(alb[c]), b = warp_sum(cf[c]);
-                if (lane == 0) {
-                    if (a != 0.f) add_cta(p.sm.albedo + m0 * 3 + c, a);
-                    if (b != 0.f) add_cta(p.sm.coeffs + m0 * 3 + c, b);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (alb[c] != 0.f) atomicAdd(&cta_acc[p.sm.albedo + m * 3 + c], (double)alb[c]);
-                if (cf[c] != 0.f) atomicAdd(&cta_acc[p.sm.coeffs + m * 3 + c], (double)cf[c]);
-            }
-        }
-    }
-    __device__ void flush_primitive(int set, int local, int idx, const float* g7) {
-        const int lane = threadIdx.x & 31;
-        // per-primitive gradients: warp-segmented reduction keyed by the winner index, then one
-        // red.global.add per component from the segment leader
-        const unsigned peers = __match_any_sync(0xffffffffu, idx);
-        const int leader = __ffs(peers) - 1;
-        float v[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) v[c] = g7[c];
-        unsigned rest = peers & ~(1u << leader);
-        // every lane walks the union of peer sets in lock-step (max 31 steps, usually 0-3)
-        const unsigned any_rest = __reduce_or_sync(0xffffffffu, rest);
-        if (any_rest) {
-            for (int src = 0; src < 32; ++src) {
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    float o = __shfl_sync(0xffffffffu, g7[c], src);
-                    if (lane == leader && ((rest >> src) & 1u)) v[c] += o;
-                }
-            }
-        }
-        if (lane == leader) {
-            // double accumulation: per-pixel contributions of a grazing primitive cancel heavily, and a
-            // sequential fp32 atomic sum would carry ~1e-4 relative noise (the reference sums pairwise)
-            double* dst = p.prim_acc + (size_t)idx * 7;
-#pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (v[c] != 0.f) atomicAdd(dst + c, (double)v[c]);
-        }
-        (void)set; (void)local;
-    }
-};
-
-__global__ void __launch_bounds__(128) k_backward(const __grid_constant__ BackwardParams p) {
-    __shared__ double cta_acc[kMaxAccSlots];
-    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = k < p.n;
-    const int kk = live ? k : p.n - 1;      // dead lanes shadow the last pixel with zero incoming gradients
-    Vec3 o, d;
-    pixel_ray(*p.cam, p.rays, p.n, p.pix0, kk, &o, &d);
-    PixelGrads g;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
-        g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
-        g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
-    }
-    g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
-    const float dep = p.depth[kk];
-    const bool hit = dep <= p.cam->far_clip && dep >= p.cam->near_clip;
-    float vis_l[16];
-    const float* vis = nullptr;
-    if (p.vis) {
-        for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
-        vis = vis_l;
-    }
-    DeviceSink sink(p, cta_acc);
-    backward_pixel(p.sc, v3(p.cam->eye[0], p.cam->eye[1], p.cam->eye[2]), o, d, (int)p.nearest[kk], hit, p.fl, vis, g, sink);
-    __syncthreads();
-    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x)
-        if (cta_acc[j] != 0.0) atomicAdd(p.acc + j, cta_acc[j]);
-}
-
-struct FinalizeParams {
-    GradPtrs gp; SlotMap sm; const double* acc; int K, L, Cn, light_pos_stride;
-    SceneView sc; const double* prim_acc;
-};
-__global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant__ FinalizeParams p) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < p.sc.total) {      // per-primitive accumulators -> fp32 leaves (caller's strides)
-        const int s = find_set(p.sc, j);
-        const SetView& sv = p.sc.sets[s];
-        const int local = j - sv.first;
-        const double* a = p.prim_acc + (size_t)j * 7;
-        float* gpos = p.gp.prim_pos[s];
-        if (gpos) {
-            const size_t row = sv.kind == KIND_TRIANGLE ? (size_t)local * 3 * sv.pos_stride : (size_t)local * sv.pos_stride;
-            for (int c = 0; c < 3; ++c) gpos[row + c] += (float)a[c];
-        }
-        float* gnr = p.gp.prim_normal[s];
-        if (gnr && sv.kind != KIND_SPHERE)
-            for (int c = 0; c < 3; ++c) gnr[(size_t)local * sv.normal_stride + c] += (float)a[3 + c];
-        float* grd = p.gp.prim_radius[s];
-        if (grd && sv.kind == KIND_SPHERE) grd[local] += (float)a[6];
-        return;
-    }
-    j -= p.sc.total;
-    if (j >= p.sm.total) return;
-    const float v = (float)p.acc[j];
-    if (j < p.sm.coeffs) { if (p.gp.albedo) p.gp.albedo[j - p.sm.albedo] += v; }
-    else if (j < p.sm.light_pos) { if (p.gp.coeffs) p.gp.coeffs[j - p.sm.coeffs] += v; }
-    else if (j < p.sm.atten) {
-        const int q = j - p.sm.light_pos;
-        if (p.gp.light_pos) p.gp.light_pos[(size_t)(q / 3) * p.light_pos_stride + q % 3] += v;
-    }
-    else if (j < p.sm.colors) { if (p.gp.atten) p.gp.atten[j - p.sm.atten] += v; }
-    else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
-    else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
-    else { if (p.gp.gamma) p.gp.gamma[0] += v; }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// render_splats_along_ray kernels (renderer.py:537-751)
-// ---------------------------------------------------------------------------------------------------
-struct SplatParams {
-    SceneView sc;                 // lights (camera space, stride 3, in the workspace) / colours / materials
-    const CamState* cam;
-    const float* z; int z_stride;
-    const float* normal; int normal_stride;
-    const int* mat;
-    const float* vis;             // [L, n] or null
-    int n;
-    ShadeFlags fl;
-    float* image; float* depth; float* normal_out; float* pos;                       // forward outputs
-    const float* g_image; const float* g_depth; const float* g_normal; const float* g_pos;   // backward inputs
-    float* gz; float* gnormal;    // backward outputs (caller's strides)
-    SlotMap sm; double* acc;
-};
-
-__global__ void k_splat_setup(CamArgs a, CamState* cs, const float* light_pos4, int n_lights, float* light_cc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        camera_setup(a.eye, a.at, a.up, 0, a.W, a.H, a.fovy, a.focal, a.near_clip, a.far_clip, cs);
-    __syncthreads();
-    for (int l = threadIdx.x; l < n_lights; l += blockDim.x) {
-        Vec3 v = light_to_camera(*cs, light_pos4 + 4 * (size_t)l);
-        light_cc[3 * l] = v.x; light_cc[3 * l + 1] = v.y; light_cc[3 * l + 2] = v.z;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_splat_forward(const __grid_constant__ SplatParams p) {
-    __shared__ float sm[256][3];
-    const int base = blockIdx.x * 256;
-    const int k = base + threadIdx.x;
-    const bool live = k < p.n;
-    SplatOut so = SplatOut();
-    float nn[3] = {0.f, 0.f, 0.f};
-    if (live) {
-        float vis_l[16];
-        const float* vis = nullptr;
-        if (p.vis) {
-            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + k];
-            vis = vis_l;
-        }
-        const float* np_ = p.normal + (size_t)k * p.normal_stride;
-        nn[0] = np_[0]; nn[1] = np_[1]; nn[2] = np_[2];
-        so = splat_pixel_forward(p.sc, *p.cam, k, p.z[(size_t)k * p.z_stride], v3(nn[0], nn[1], nn[2]),
-                                 p.mat ? p.mat[k] : 0, p.fl, vis);
-        if (p.depth) p.depth[k] = so.depth;
-    }
-    if (p.image) store3(p.image, sm, base, p.n, so.image);
-    if (p.pos) store3(p.pos, sm, base, p.n, so.pos);
-    if (p.normal_out) store3(p.normal_out, sm, base, p.n, nn);
-}
-
-__global__ void __launch_bounds__(128) k_splat_backward(const __grid_constant__ SplatParams p) {
-    __shared__ double cta_acc[kMaxAccSlots];
-    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = k < p.n;
-    const int kk = live ? k : p.n - 1;
-    PixelGrads g;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
-        g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
-        g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
-    }
-    g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
-    float vis_l[16];
-    const float* vis = nullptr;
-    if (p.vis) {
-        for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
-        vis = vis_l;
-    }
-    BackwardParams bp_view;          // DeviceSink only reads the slot map from it
-    bp_view.sm = p.sm;
-    DeviceSink sink(bp_view, cta_acc);
-    const float* np_ = p.normal + (size_t)kk * p.normal_stride;
-    float gz, gn[3];
-    splat_pixel_backward(p.sc, *p.cam, kk, p.z[(size_t)kk * p.z_stride], v3(np_[0], np_[1], np_[2]),
-                         p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gn);
-    if (live) {
-        if (p.gz) p.gz[(size_t)k * p.z_stride] += gz;
-        if (p.gnormal)
-            for (int c = 0; c < 3; ++c) p.gnormal[(size_t)k * p.normal_stride + c] += gn[c];
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x)
-        if (cta_acc[j] != 0.0) atomicAdd(p.acc + j, cta_acc[j]);
-}
-
-struct SplatFinalizeParams { GradPtrs gp; SlotMap sm; const double* acc; const CamState* cam; int L; };
-__global__ void __launch_bounds__(128) k_splat_finalize(const __grid_constant__ SplatFinalizeParams p) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.sm.total) return;
-    const float v = (float)p.acc[j];
-    if (j < p.sm.coeffs) { if (p.gp.albedo) p.gp.albedo[j - p.sm.albedo] += v; }
-    else if (j < p.sm.light_pos) { if (p.gp.coeffs) p.gp.coeffs[j - p.sm.coeffs] += v; }
-    else if (j < p.sm.atten) {
-        // camera -> world: l_cc = R^T l_xyz - l_w R^T eye  =>  d/dl_xyz = R g,  d/dl_w = -(R^T eye) . g
-        const int q = j - p.sm.light_pos;
-        const int l = q / 3, c = q % 3;
-        if (p.gp.light_pos && c == 0) {
-            const CamState& cs = *p.cam;
-            const double g0 = p.acc[j], g1 = p.acc[j + 1], g2 = p.acc[j + 2];
-            float* dst = p.gp.light_pos + 4 * (size_t)l;
-            for (int r = 0; r < 3; ++r) dst[r] += (float)(cs.R[3 * r] * g0 + cs.R[3 * r + 1] * g1 + cs.R[3 * r + 2] * g2);
-            double gw = 0.0;
-            const double gi[3] = {g0, g1, g2};
-            for (int i = 0; i < 3; ++i)
-                gw -= ((double)cs.R[i] * cs.eye[0] + (double)cs.R[3 + i] * cs.eye[1] + (double)cs.R[6 + i] * cs.eye[2]) * gi[i];
-            dst[3] += (float)gw;
-        }
-    }
-    else if (j < p.sm.colors) { if (p.gp.atten) p.gp.atten[j - p.sm.atten] += v; }
-    else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
-    else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
-}
-
-// d/d(image) of mean((image - target)^2) and the loss itself (inverse-rendering step, test_optimization.py:104)
-__global__ void __launch_bounds__(256) k_mse_grad(const float* __restrict__ image, const float* __restrict__ target,
-                                                  int count, float* __restrict__ g_image, double* __restrict__ loss_acc) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    float e = 0.f;
-    if (j < count) {
-        const float diff = image[j] - target[j];
-        g_image[j] = 2.f * diff / (float)count;
-        e = diff * diff;
-    }
-    e = warp_sum(e);
-    __shared__ float part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = e;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += part[w];
-        atomicAdd(loss_acc, (double)s / (double)count);
-    }
-}
+#include "surf_runtime.cuh"
+#include "surf_ptx.cuh"
+#include "surf_frame_kernels.cuh"
+#include "surf_intersect.cuh"
+#include "surf_shade.cuh"
+#include "surf_backward.cuh"
+#include "surf_splats.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // FP32 FMA-pipe microbenchmark (roofline denominator check)
@@ -2274,3 +815,4 @@ int surf_render_backward_host(SurfContext* ctx, const SurfScene* scene, const Su
 }
 
 }  // extern "C"
+

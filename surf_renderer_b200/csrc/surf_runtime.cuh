@@ -1,0 +1,105 @@
+// surf_runtime.cuh - part of libsurf_b200.so (single translation unit: included by surf_kernels.cu inside namespace surf).
+// error handling, launch accounting, kernel timers, workspace layout
+#pragma once
+
+// ---------------------------------------------------------------------------------------------------
+// error handling (thread-local string) / launch accounting and optional timers (process-wide counters)
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+static int g_launches = 0;   // process-wide: autograd runs backward on its own thread
+
+// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg): a ring of
+// event pairs per kernel kind so that a whole timed region can be averaged without synchronising inside it
+constexpr int kTimerRing = 256;
+struct KernelTimers {
+    bool enabled = false;
+    bool created = false;
+    cudaEvent_t ev[3][kTimerRing][2] = {};
+    long long count[3] = {0, 0, 0};     // launches recorded since timing was (re-)enabled
+};
+static KernelTimers g_timers;   // process-wide (see g_launches)
+static void timer_mark(int which, int edge, cudaStream_t st) {
+    if (!g_timers.enabled) return;
+    if (!g_timers.created) {
+        for (int k = 0; k < 3; ++k)
+            for (int r = 0; r < kTimerRing; ++r)
+                for (int e = 0; e < 2; ++e) cudaEventCreate(&g_timers.ev[k][r][e]);
+        g_timers.created = true;
+    }
+    const int slot = (int)(g_timers.count[which] % kTimerRing);
+    cudaEventRecord(g_timers.ev[which][slot][edge], st);
+    if (edge == 1) ++g_timers.count[which];
+}
+static double timer_ms(int which, long long index) {
+    const int slot = (int)(index % kTimerRing);
+    if (cudaEventSynchronize(g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_timers.ev[which][slot][0], g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+    g_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return SURF_ERR_CUDA;
+}
+#define SURF_CUDA(call)                                     \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+#define SURF_LAUNCHED(name)                                      \
+    do {                                                         \
+        ++g_launches;                                            \
+        cudaError_t e_ = cudaPeekAtLastError();                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_, name);       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------------
+struct Workspace {
+    CamState* cam;
+    float4* packed;              // plane-filter records, per set, 128-byte aligned (math_mode 1..3)
+    float4* circ;                // level-1 screen-circle records, one float4 per primitive in global order
+    float* rays;                 // [3, n] SoA unit directions (perspective)
+    unsigned long long* zbuf;    // [n] packed (depth key << 32 | primitive index)
+    double* acc;                 // backward scalar accumulators
+    double* prim_acc;            // backward per-primitive accumulators [total_prims, 7]
+    float* vis;                  // [L, n] shadow visibility
+    float* gray;                 // [7, n] generic rays: origin xyz, direction xyz, t_max (orthographic / shadow rays)
+    unsigned long long* zbuf2;   // [n] z-buffer keys of the shadow rays
+    float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
+    size_t bytes;
+};
+constexpr int kMaxAccSlots = 512;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t packed_bytes_bound(int total_prims) {
+    // worst case: all triangles (4 float4 each) + 8 sets x 128-byte padding
+    return (size_t)total_prims * 64 + kMaxSets * 128 + 256;
+}
+
+static void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws) {
+    char* p = (char*)base;
+    size_t off = 0;
+    ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
+    ws->packed = (float4*)(p + off); off += align_up(packed_bytes_bound(total_prims), 256);
+    ws->circ = (float4*)(p + off); off += align_up((size_t)total_prims * 16 + 256, 256);
+    ws->rays = (float*)(p + off); off += align_up((size_t)3 * n_pix * sizeof(float), 256);
+    ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
+    ws->acc = (double*)(p + off); off += align_up((size_t)kMaxAccSlots * 8, 256);
+    ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
+    ws->vis = (float*)(p + off);
+    if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
+    // generic-ray buffers: always carved (orthographic frames need them too); 36 B per pixel
+    ws->gray = (float*)(p + off); off += align_up((size_t)7 * n_pix * sizeof(float), 256);
+    ws->zbuf2 = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
+    ws->obound = (float*)(p + off); off += 256;
+    ws->bytes = off;
+}
+

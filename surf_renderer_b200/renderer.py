@@ -114,9 +114,6 @@ def render_flat(scene, pixel_range=None, **params):
     Returns flat tensors (image [n,3], depth [n], normal [n,3], pos [n,3], nearest [n], ray_dir) and (H, W)."""
     if get_param_value('vis_stat', params, False):
         raise RuntimeError('Removed Support for vis_stat')                      # renderer.py:233-234
-    if get_param_value('norm_depth_image_only', params, False):
-        raise NotImplementedError('norm_depth_image_only is broken in the reference under the default '
-                                  'tiling (renderer.py:245-260 reads untiled temporaries)')
     dev = _resolve_device(scene)
     m = Marshalled(scene, dev)
     outs = _RenderFn.apply(m, dict(params), pixel_range, *m.floats)
@@ -126,12 +123,25 @@ def render_flat(scene, pixel_range=None, **params):
 def render(scene, **params):
     """Render.  Reference: diffrend/torch/renderer.py:136 ``render(scene, **params)``.
 
-    params honoured: double_sided, use_quartic, shadow.  Accepted and semantically no-ops here: tiled, tile_size
-    (the pixel tiling only bounded the reference's [M,N] temporaries), backface_culling (the reference only
-    labels the scene, renderer.py:152-159 - output unchanged).  vis_stat raises RuntimeError like the
-    reference; norm_depth_image_only raises NotImplementedError.
+    params honoured: double_sided, use_quartic, shadow, norm_depth_image_only.  Accepted and semantically no-ops
+    here: tiled, tile_size (the pixel tiling only bounded the reference's [M,N] temporaries), backface_culling (the
+    reference only labels the scene, renderer.py:152-159 - output unchanged).  vis_stat raises RuntimeError like
+    the reference.
     """
     (image, depth, normal, pos, nearest, ray_dir), (H, W) = render_flat(scene, None, **params)
+    if get_param_value('norm_depth_image_only', params, False):
+        # renderer.py:245-260: depth normalised to [0, 1] with misses mapped to the minimum.  (In the reference
+        # this branch only runs with tiled=False and for scenes whose intersectors ignore disable_normals; here
+        # it is defined for every scene.)  Same arithmetic: blend, subtract, divide.
+        im_depth = depth.view(H, W)
+        far = float(scene['camera']['far'])
+        min_depth = torch.min(im_depth)
+        is_far = (im_depth >= far).float()
+        norm = is_far * min_depth + (1 - is_far) * im_depth
+        norm = (norm - min_depth) / (torch.max(im_depth) - min_depth)
+        return {'image': norm, 'depth': im_depth, 'ray_dist': None, 'obj_dist': None, 'nearest': nearest.view(H, W),
+                'ray_dir': ray_dir, 'valid_pixels': None, 'obj_pixel_count': None, 'pixel_obj_count': None,
+                'valid_pixels_mask': None}
     return {
         'image': image.view(H, W, 3),
         'depth': depth.view(H, W),

@@ -111,8 +111,6 @@ def test_render_kwargs_behaviour_without_gpu():
     scene = synth.scene_basic(16, 12)
     with pytest.raises(RuntimeError):
         surf_renderer_b200.render(scene, vis_stat=True)                 # renderer.py:233-234
-    with pytest.raises(NotImplementedError):
-        surf_renderer_b200.render(scene, norm_depth_image_only=True)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match='no CPU path'):
             surf_renderer_b200.render(scene)                            # fails loudly, never falls back

@@ -449,3 +449,13 @@ def test_shadow_rays_at_splat_scale():
     ref = torch_oracle.render(scene_io.clone_scene(scene), shadow=True)
     rep = parity.compare_forward(res, _cpu({k: v for k, v in ref.items() if isinstance(v, torch.Tensor)}), scene, atol=2e-5)
     assert rep['hit_pixels'] > 1500
+
+
+def test_norm_depth_image_only_matches_oracle():
+    scene, params, outs, grads, extra = _load('c_torus_64')
+    res = _render(scene_io.clone_scene(scene, device='cuda'), norm_depth_image_only=True, double_sided=True)
+    ref = torch_oracle.render(scene_io.clone_scene(scene), tiled=False, norm_depth_image_only=True, double_sided=True)
+    assert set(ref.keys()) <= set(res.keys())
+    assert torch.equal(res['nearest'].cpu(), ref['nearest'])
+    assert torch.allclose(res['image'].cpu(), ref['image'], rtol=1e-4, atol=1e-5)
+    assert float(res['image'].min()) == 0.0 and float(res['image'].max()) <= 1.0

@@ -88,3 +88,16 @@ def test_oracle_along_ray_matches_reference_golden(name):
     for k, g in zip(grads, gs):
         scale = max(1e-12, float(np.abs(grads[k]).max()))
         np.testing.assert_allclose(g.numpy() / scale, grads[k] / scale, rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='reference tree not present')
+def test_oracle_norm_depth_image_only_matches_live_reference():
+    """renderer.py:245-260 runs in the reference with tiled=False on triangle scenes (their intersector ignores
+    disable_normals)."""
+    import sys
+    sys.path.insert(0, '/root/reference')
+    from diffrend.torch.renderer import render as ref_render
+    scene, params, outs, grads, extra = scene_io.load_case(os.path.join(GOLDEN_DIR, 'c_torus_64.npz'))
+    a = ref_render(scene_io.clone_scene(scene), tiled=False, norm_depth_image_only=True, double_sided=True)
+    b = torch_oracle.render(scene_io.clone_scene(scene), tiled=False, norm_depth_image_only=True, double_sided=True)
+    assert torch.equal(a['image'], b['image']) and torch.equal(a['depth'], b['depth']) and torch.equal(a['nearest'], b['nearest'])
