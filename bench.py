@@ -431,7 +431,7 @@ def main():
     line = {'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)', 'value': value, 'unit': 'tests/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss),
+            'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
             'gpu_launches': int(sum(launches)), 'gpu_launches_per_step': int(launches[-1]) if launches else 0,
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'fast_mode': fast,
             'wall_s_timed_region': wall}

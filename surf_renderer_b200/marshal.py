@@ -187,6 +187,27 @@ class Marshalled:
         return sg
 
 
+# process-wide default of the intersection-kernel variant (SurfOptions.math_mode); a call's `_math_mode` kwarg wins.
+# 0 = ray-plane FFMA2 filter (default), 3 = screen-space level-1 test (fastest).  Also settable through the
+# environment variable SURF_INTERSECT_MODE for drop-in use without touching call sites.
+import os as _os
+
+_DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3}.get(_os.environ.get('SURF_INTERSECT_MODE', 'plane'), None)
+if _DEFAULT_MATH_MODE is None:
+    _DEFAULT_MATH_MODE = int(_os.environ['SURF_INTERSECT_MODE'])
+
+
+def set_default_intersect_mode(mode):
+    """'plane' (0, default) or 'screen' (3); returns the previous value.  All modes give bit-identical outputs."""
+    global _DEFAULT_MATH_MODE
+    prev = _DEFAULT_MATH_MODE
+    _DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3}.get(mode, mode)
+    if _DEFAULT_MATH_MODE not in (0, 1, 2, 3):
+        _DEFAULT_MATH_MODE = prev
+        raise ValueError("mode must be 'plane', 'screen' or 0..3")
+    return prev
+
+
 def make_options(params, pixel_range=None, forced_nearest=False):
     opt = _abi.SurfOptions()
     opt.double_sided = int(bool(params.get('double_sided', False)))
@@ -197,5 +218,5 @@ def make_options(params, pixel_range=None, forced_nearest=False):
     opt.forced_nearest = int(forced_nearest)
     opt.pixels_per_thread = int(params.get('_pixels_per_thread', 0))
     opt.chunk_prims = int(params.get('_chunk_prims', 0))
-    opt.math_mode = int(params.get('_math_mode', 0))
+    opt.math_mode = int(params.get('_math_mode', _DEFAULT_MATH_MODE))
     return opt
