@@ -138,33 +138,43 @@ struct DeviceSink {
     }
 };
 
+// Persistent grid-stride CTAs: the light / material / colour accumulators live in shared memory for the whole life
+// of the CTA and are flushed with one double atomicAdd per slot per CTA.  (One flush per 128 pixels put ~8000
+// same-address double atomics per slot on the L2 and made the kernel 5x slower than its instruction count.)
 __global__ void __launch_bounds__(128) k_backward(const __grid_constant__ BackwardParams p) {
     __shared__ double cta_acc[kMaxAccSlots];
     for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
     __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = k < p.n;
-    const int kk = live ? k : p.n - 1;      // dead lanes shadow the last pixel with zero incoming gradients
-    Vec3 o, d;
-    pixel_ray(*p.cam, p.rays, p.n, p.pix0, kk, &o, &d);
-    PixelGrads g;
+    const Vec3 eye = v3(p.cam->eye[0], p.cam->eye[1], p.cam->eye[2]);
+    for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {   // uniform trip count per CTA
+        const int k = base + threadIdx.x;
+        const bool live = k < p.n;
+        const int kk = live ? k : p.n - 1;      // dead lanes shadow the last pixel with zero incoming gradients
+        const float dep = p.depth[kk];
+        const bool hit = live && dep <= p.cam->far_clip && dep >= p.cam->near_clip;
+        PixelGrads g;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
-        g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
-        g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
+        for (int c = 0; c < 3; ++c) {
+            g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
+            g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
+            g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
+        }
+        g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
+        // a warp whose pixels are all misses with no incoming geometry gradient has nothing to contribute
+        const bool needed = hit || g.pos[0] != 0.f || g.pos[1] != 0.f || g.pos[2] != 0.f ||
+                            g.normal[0] != 0.f || g.normal[1] != 0.f || g.normal[2] != 0.f;
+        if (!__any_sync(0xffffffffu, needed)) continue;
+        Vec3 o, d;
+        pixel_ray(*p.cam, p.rays, p.n, p.pix0, kk, &o, &d);
+        float vis_l[16];
+        const float* vis = nullptr;
+        if (p.vis) {
+            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
+            vis = vis_l;
+        }
+        DeviceSink sink(p, cta_acc);
+        backward_pixel(p.sc, eye, o, d, (int)p.nearest[kk], hit, p.fl, vis, g, sink);
     }
-    g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
-    const float dep = p.depth[kk];
-    const bool hit = dep <= p.cam->far_clip && dep >= p.cam->near_clip;
-    float vis_l[16];
-    const float* vis = nullptr;
-    if (p.vis) {
-        for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
-        vis = vis_l;
-    }
-    DeviceSink sink(p, cta_acc);
-    backward_pixel(p.sc, v3(p.cam->eye[0], p.cam->eye[1], p.cam->eye[2]), o, d, (int)p.nearest[kk], hit, p.fl, vis, g, sink);
     __syncthreads();
     for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x)
         if (cta_acc[j] != 0.0) atomicAdd(p.acc + j, cta_acc[j]);

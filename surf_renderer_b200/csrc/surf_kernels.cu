@@ -365,7 +365,7 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     bp.gp.light_pos = sg->light_pos; bp.gp.atten = sg->light_attenuation; bp.gp.ambient = sg->ambient;
     bp.gp.colors = sg->colors; bp.gp.albedo = sg->albedo; bp.gp.coeffs = sg->coeffs; bp.gp.gamma = sg->gamma;
     timer_mark(2, 0, st);
-    k_backward<<<(f.n + 127) / 128, 128, 0, st>>>(bp);
+    k_backward<<<std::min((f.n + 127) / 128, sm_count() * 8), 128, 0, st>>>(bp);
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_backward");
     FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
@@ -439,7 +439,7 @@ static int splats_backward_impl(const SurfScene* scene, const SurfCamera* camera
     p.g_image = og->image; p.g_depth = og->depth; p.g_normal = og->normal; p.g_pos = og->pos;
     p.gz = spg->z; p.gnormal = spg->normal;
     timer_mark(2, 0, st);
-    k_splat_backward<<<(p.n + 127) / 128, 128, 0, st>>>(p);
+    k_splat_backward<<<std::min((p.n + 127) / 128, sm_count() * 8), 128, 0, st>>>(p);
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_splat_backward");
     SplatFinalizeParams fp;

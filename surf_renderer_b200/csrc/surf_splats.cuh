@@ -59,34 +59,36 @@ __global__ void __launch_bounds__(128) k_splat_backward(const __grid_constant__ 
     __shared__ double cta_acc[kMaxAccSlots];
     for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
     __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = k < p.n;
-    const int kk = live ? k : p.n - 1;
-    PixelGrads g;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
-        g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
-        g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
-    }
-    g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
-    float vis_l[16];
-    const float* vis = nullptr;
-    if (p.vis) {
-        for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
-        vis = vis_l;
-    }
     BackwardParams bp_view;          // DeviceSink only reads the slot map from it
     bp_view.sm = p.sm;
-    DeviceSink sink(bp_view, cta_acc);
-    const float* np_ = p.normal + (size_t)kk * p.normal_stride;
-    float gz, gn[3];
-    splat_pixel_backward(p.sc, *p.cam, kk, p.z[(size_t)kk * p.z_stride], v3(np_[0], np_[1], np_[2]),
-                         p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gn);
-    if (live) {
-        if (p.gz) p.gz[(size_t)k * p.z_stride] += gz;
-        if (p.gnormal)
-            for (int c = 0; c < 3; ++c) p.gnormal[(size_t)k * p.normal_stride + c] += gn[c];
+    for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {   // persistent, see k_backward
+        const int k = base + threadIdx.x;
+        const bool live = k < p.n;
+        const int kk = live ? k : p.n - 1;
+        PixelGrads g;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            g.image[c] = (live && p.g_image) ? p.g_image[(size_t)kk * 3 + c] : 0.f;
+            g.pos[c] = (live && p.g_pos) ? p.g_pos[(size_t)kk * 3 + c] : 0.f;
+            g.normal[c] = (live && p.g_normal) ? p.g_normal[(size_t)kk * 3 + c] : 0.f;
+        }
+        g.depth = (live && p.g_depth) ? p.g_depth[kk] : 0.f;
+        float vis_l[16];
+        const float* vis = nullptr;
+        if (p.vis) {
+            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + kk];
+            vis = vis_l;
+        }
+        DeviceSink sink(bp_view, cta_acc);
+        const float* np_ = p.normal + (size_t)kk * p.normal_stride;
+        float gz, gn[3];
+        splat_pixel_backward(p.sc, *p.cam, kk, p.z[(size_t)kk * p.z_stride], v3(np_[0], np_[1], np_[2]),
+                             p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gn);
+        if (live) {
+            if (p.gz) p.gz[(size_t)k * p.z_stride] += gz;
+            if (p.gnormal)
+                for (int c = 0; c < 3; ++c) p.gnormal[(size_t)k * p.normal_stride + c] += gn[c];
+        }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x)
