@@ -24,9 +24,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, 'tests')):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
@@ -156,10 +155,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_step(scene, target_scene, subset, threads):
     """One bounded sample of the workload on the CPU: fwd + loss + bwd over `subset` pixels of the frame."""
-    import scene_io
     from oracle import torch_oracle
+    from surf_renderer_b200.scenes import clone_scene
     torch.set_num_threads(threads)
-    sc = scene_io.clone_scene(scene, requires_grad=False)
+    sc = clone_scene(scene, requires_grad=False)
     leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
     for t in leaves:
         t.requires_grad_(True)
@@ -242,8 +241,8 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     import torch.distributed as dist
-    import scene_io
     import surf_renderer_b200
+    from surf_renderer_b200.scenes import clone_scene
     from surf_renderer_b200 import _abi, dist as sdist
     from surf_renderer_b200._lib import check, lib
     from surf_renderer_b200.marshal import Marshalled, make_options
@@ -255,13 +254,13 @@ def main():
     peaks, peak_src = measured_peaks()
     params = {'_pixels_per_thread': args.ppt, '_chunk_prims': args.chunk, '_math_mode': args.math}
 
-    sc = scene_io.clone_scene(scene, device=dev)
+    sc = clone_scene(scene, device=dev)
     leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
     for t in leaves:
         t.requires_grad_(True)
     opt = torch.optim.Adam(leaves, lr=1e-4, fused=True)
     with torch.no_grad():
-        tgt = surf_renderer_b200.render(scene_io.clone_scene(target_scene, device=dev), **params)['image']
+        tgt = surf_renderer_b200.render(clone_scene(target_scene, device=dev), **params)['image']
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     lib().surf_set_kernel_timing(1)
     launches = []
@@ -371,7 +370,7 @@ def main():
     # ---- e2e: C-ABI host-pointer call, pinned host buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        hs = scene_io.clone_scene(scene)
+        hs = clone_scene(scene)
         m = Marshalled(hs, 'cpu')
         m.floats = [t.pin_memory() for t in m.floats]
         m.ints = {k: v.pin_memory() for k, v in m.ints.items()}

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -470,7 +471,7 @@ extern "C" {
 
 int surf_abi_version(void) { return SURF_ABI_VERSION; }
 const char* surf_last_error(void) { return g_error.c_str(); }
-int surf_last_launch_count(void) { return g_launches; }
+int surf_last_launch_count(void) { return g_launches.load(); }
 void surf_set_kernel_timing(int32_t enabled) {
     g_timers.enabled = enabled != 0;
     for (int k = 0; k < 3; ++k) g_timers.count[k] = 0;

@@ -6,7 +6,7 @@
 // error handling (thread-local string) / launch accounting and optional timers (process-wide counters)
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string g_error;
-static int g_launches = 0;   // process-wide: autograd runs backward on its own thread
+static std::atomic<int> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg): a ring of
 // event pairs per kernel kind so that a whole timed region can be averaged without synchronising inside it

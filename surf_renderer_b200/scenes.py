@@ -195,3 +195,27 @@ def random_mixed_scene(seed, width=48, height=40, n_disk=12, n_plane=1, n_sphere
         s['camera']['fovy'] = float(np.deg2rad(120.))
         s['camera']['focal_length'] = 3.0
     return s
+
+
+def clone_scene(scene, device=None, requires_grad=False):
+    """Deep copy; tensors are detached clones (optionally moved / made leaves requiring grad)."""
+    def rec(v):
+        if isinstance(v, dict):
+            return {k: rec(x) for k, x in v.items()}
+        if isinstance(v, torch.Tensor):
+            t = v.detach().clone()
+            if device is not None:
+                t = t.to(device)
+            if requires_grad and t.is_floating_point():
+                t.requires_grad_(True)
+            return t
+        if isinstance(v, list):
+            return list(v)
+        return v
+    out = rec(scene)
+    if requires_grad:
+        # the reference cannot differentiate w.r.t. the camera (in-place op, utils.py:476)
+        for k in ('eye', 'at', 'up'):
+            if isinstance(out['camera'].get(k), torch.Tensor):
+                out['camera'][k] = out['camera'][k].detach()
+    return out

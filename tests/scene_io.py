@@ -115,28 +115,7 @@ def grad_leaves(scene):
     return leaves
 
 
-def clone_scene(scene, device=None, requires_grad=False):
-    """Deep copy; tensors are detached clones (optionally moved / made leaves requiring grad)."""
-    def rec(v):
-        if isinstance(v, dict):
-            return {k: rec(x) for k, x in v.items()}
-        if isinstance(v, torch.Tensor):
-            t = v.detach().clone()
-            if device is not None:
-                t = t.to(device)
-            if requires_grad and t.is_floating_point():
-                t.requires_grad_(True)
-            return t
-        if isinstance(v, list):
-            return list(v)
-        return v
-    out = rec(scene)
-    if requires_grad:
-        # the reference cannot differentiate w.r.t. the camera (in-place op, utils.py:476)
-        for k in ('eye', 'at', 'up'):
-            if isinstance(out['camera'].get(k), torch.Tensor):
-                out['camera'][k] = out['camera'][k].detach()
-    return out
+from surf_renderer_b200.scenes import clone_scene   # noqa: E402,F401  (kept here for the tests' convenience)
 
 
 def loss_weights(shape_hw, seed):
