@@ -163,6 +163,17 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
                   const int64_t* nearest, const float* depth,
                   const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads, void* cuda_stream);
 
+/* ---- batches of independent scenes: the per-element loop of GAN.get_real_samples (GAN/gan.py:326-377) ----
+ * Arrays of n_scenes scenes / cameras / workspaces / outputs (one shared SurfOptions).  All kernels of all scenes are
+ * launched by this one call, fanned out over internal streams that fork from and join to `cuda_stream`; gradients of
+ * parameters shared between scenes may alias (the accumulation is atomic). */
+int surf_forward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCamera* cameras, const SurfOptions* options,
+                       void* const* workspaces, const size_t* workspace_bytes, const SurfOutputs* outs, void* cuda_stream);
+int surf_backward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCamera* cameras, const SurfOptions* options,
+                        void* const* workspaces, const size_t* workspace_bytes, const int64_t* const* nearest,
+                        const float* const* depth, const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads,
+                        void* cuda_stream);
+
 /* ---- one-splat-per-pixel renderer: diffrend/torch/renderer.py:537-751 render_splats_along_ray ----
  * Splat k sits on the ray of flat pixel k at camera-space depth z[k] (negative = in front of the camera,
  * clamped with -relu(-z)); it is shaded in camera coordinates with the same fragment shader as render()

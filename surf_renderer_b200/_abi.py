@@ -80,6 +80,11 @@ SYMBOLS = {
     'surf_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                 C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_forward_batch': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(SurfOutputs), C.c_void_p]),
+    'surf_backward_batch': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p), C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
     'surf_splats_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                       C.POINTER(SurfSplats), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
     'surf_splats_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),

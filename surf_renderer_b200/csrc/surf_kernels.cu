@@ -23,6 +23,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -515,6 +516,83 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
     const bool warm = options && options->forced_nearest == 2;
     return backward_impl(scene, camera, options, workspace, workspace_bytes, nearest, depth, out_grads, scene_grads,
                          (cudaStream_t)cuda_stream, warm);
+}
+
+// ---- batches of independent scenes (GAN real-sample batches, GAN/gan.py:326-377; BASELINE configs[3]) ----
+// One host call launches every scene's kernels back to back, fanned out over a small pool of internal streams that
+// fork from / join to the caller's stream with events, so the small per-scene kernels overlap and the host pays one
+// call instead of one Python round trip per scene.
+}  // extern "C"
+
+namespace {
+constexpr int kBatchStreams = 4;
+struct StreamPool {
+    int device = -1;
+    cudaStream_t st[kBatchStreams] = {};
+    cudaEvent_t fork = nullptr, join[kBatchStreams] = {};
+};
+static std::mutex g_pool_mutex;
+static std::vector<StreamPool*> g_pools;
+
+static StreamPool* stream_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (StreamPool* p : g_pools)
+        if (p->device == dev) return p;
+    StreamPool* p = new StreamPool();
+    p->device = dev;
+    bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < kBatchStreams && ok; ++k)
+        ok = cudaStreamCreateWithFlags(&p->st[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete p; return nullptr; }
+    g_pools.push_back(p);
+    return p;
+}
+
+template <class PerScene>
+static int run_batch(int32_t n_scenes, cudaStream_t caller, PerScene&& per_scene) {
+    if (n_scenes < 1) return fail(SURF_ERR_BAD_ARG, "empty batch");
+    StreamPool* pool = stream_pool();
+    if (!pool) return fail(SURF_ERR_CUDA, "could not create the batch stream pool");
+    const int lanes = std::min<int>(kBatchStreams, n_scenes);
+    SURF_CUDA(cudaEventRecord(pool->fork, caller));
+    for (int k = 0; k < lanes; ++k) SURF_CUDA(cudaStreamWaitEvent(pool->st[k], pool->fork, 0));
+    int rc = SURF_OK;
+    for (int b = 0; b < n_scenes && rc == SURF_OK; ++b) rc = per_scene(b, pool->st[b % lanes]);
+    for (int k = 0; k < lanes; ++k) {       // always re-join, also on error, so the caller's stream stays ordered
+        cudaEventRecord(pool->join[k], pool->st[k]);
+        cudaStreamWaitEvent(caller, pool->join[k], 0);
+    }
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int surf_forward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCamera* cameras, const SurfOptions* options,
+                       void* const* workspaces, const size_t* workspace_bytes, const SurfOutputs* outs, void* cuda_stream) {
+    g_launches = 0;
+    if (!scenes || !cameras || !options || !workspaces || !workspace_bytes || !outs)
+        return fail(SURF_ERR_BAD_ARG, "null batch argument");
+    return run_batch(n_scenes, (cudaStream_t)cuda_stream, [&](int b, cudaStream_t st) {
+        return forward_impl(&scenes[b], &cameras[b], options, workspaces[b], workspace_bytes[b], &outs[b], st);
+    });
+}
+
+int surf_backward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCamera* cameras, const SurfOptions* options,
+                        void* const* workspaces, const size_t* workspace_bytes, const int64_t* const* nearest,
+                        const float* const* depth, const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads,
+                        void* cuda_stream) {
+    g_launches = 0;
+    if (!scenes || !cameras || !options || !workspaces || !workspace_bytes || !nearest || !depth || !out_grads || !scene_grads)
+        return fail(SURF_ERR_BAD_ARG, "null batch argument");
+    const bool warm = options->forced_nearest == 2;
+    return run_batch(n_scenes, (cudaStream_t)cuda_stream, [&](int b, cudaStream_t st) {
+        return backward_impl(&scenes[b], &cameras[b], options, workspaces[b], workspace_bytes[b], nearest[b], depth[b],
+                             &out_grads[b], &scene_grads[b], st, warm);
+    });
 }
 
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,

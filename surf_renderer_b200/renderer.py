@@ -151,3 +151,103 @@ def render(scene, **params):
         'nearest': nearest.view(H, W),
         'ray_dir': ray_dir,
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batches of independent scenes
+# ---------------------------------------------------------------------------------------------------------------
+class _RenderBatchFn(torch.autograd.Function):
+    """surf_forward_batch / surf_backward_batch over a list of marshalled scenes: one host call per direction."""
+
+    @staticmethod
+    def forward(ctx, ms, params, *floats):
+        dev = floats[0].device
+        n = len(ms)
+        opt = make_options(params)
+        offs, o = [], 0
+        for m in ms:
+            offs.append(o)
+            o += len(m.floats)
+        scenes = (_abi.SurfScene * n)()
+        cams = (_abi.SurfCamera * n)()
+        outs = (_abi.SurfOutputs * n)()
+        ws_ptrs = (C.c_void_p * n)()
+        ws_sizes = (C.c_size_t * n)()
+        results, workspaces = [], []
+        for b, m in enumerate(ms):
+            fl = floats[offs[b]:offs[b] + len(m.floats)]
+            scenes[b], cams[b] = m.c_scene(fl), m.c_camera()
+            npx = m.n_pixels
+            ws_bytes = lib().surf_workspace_bytes(m.total_prims, npx, int(fl[m.i_light_pos].shape[0]), int(opt.shadow))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            t = (torch.empty(npx, 3, device=dev), torch.empty(npx, device=dev), torch.empty(npx, 3, device=dev),
+                 torch.empty(npx, 3, device=dev), torch.empty(npx, dtype=torch.int64, device=dev),
+                 torch.empty(3, npx if m.proj == 0 else 1, device=dev))
+            outs[b] = _abi.SurfOutputs(*[x.data_ptr() for x in t])
+            ws_ptrs[b], ws_sizes[b] = ws.data_ptr(), ws_bytes
+            results.append(t)
+            workspaces.append(ws)
+        with torch.cuda.device(dev):
+            check(lib().surf_forward_batch(n, scenes, cams, C.byref(opt), ws_ptrs, ws_sizes, outs, _stream_ptr()))
+        ctx.ms, ctx.params, ctx.offs, ctx.workspaces = ms, params, offs, workspaces
+        ctx.n_float = len(floats)
+        flat = [x for t in results for x in t]
+        ctx.save_for_backward(*floats, *[t[4] for t in results], *[t[1] for t in results])
+        ctx.mark_non_differentiable(*[t[4] for t in results], *[t[5] for t in results])
+        return tuple(flat)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        ms, n = ctx.ms, len(ctx.ms)
+        saved = ctx.saved_tensors
+        floats = saved[:ctx.n_float]
+        nearest, depth = saved[ctx.n_float:ctx.n_float + n], saved[ctx.n_float + n:]
+        dev = floats[0].device
+        opt = make_options(ctx.params)
+        opt.forced_nearest = 2
+        grads = [torch.zeros_like(t) if ctx.needs_input_grad[2 + i] else None for i, t in enumerate(floats)]
+        scenes = (_abi.SurfScene * n)()
+        cams = (_abi.SurfCamera * n)()
+        ogs = (_abi.SurfOutGrads * n)()
+        sgs = (_abi.SurfSceneGrads * n)()
+        ws_ptrs = (C.c_void_p * n)()
+        ws_sizes = (C.c_size_t * n)()
+        near_p = (C.c_void_p * n)()
+        depth_p = (C.c_void_p * n)()
+        keep = []
+        for b, m in enumerate(ms):
+            lo = ctx.offs[b]
+            fl = floats[lo:lo + len(m.floats)]
+            scenes[b], cams[b] = m.c_scene(fl), m.c_camera()
+            g_image, g_depth, g_normal, g_pos = (None if g is None else g.contiguous() for g in gouts[6 * b:6 * b + 4])
+            keep += [g_image, g_depth, g_normal, g_pos]
+            ogs[b] = _abi.SurfOutGrads(*[(t.data_ptr() if t is not None else None) for t in (g_image, g_depth, g_normal, g_pos)])
+            sgs[b] = m.c_grads(grads[lo:lo + len(m.floats)])
+            ws_ptrs[b], ws_sizes[b] = ctx.workspaces[b].data_ptr(), ctx.workspaces[b].numel()
+            near_p[b], depth_p[b] = nearest[b].data_ptr(), depth[b].data_ptr()
+        with torch.cuda.device(dev):
+            check(lib().surf_backward_batch(n, scenes, cams, C.byref(opt), ws_ptrs, ws_sizes, near_p, depth_p, ogs, sgs,
+                                            _stream_ptr()))
+        return (None, None) + tuple(grads)
+
+
+def render_batch(scenes, **params):
+    """Render a list of independent scenes with ONE library call per direction (the reference renders a GAN batch
+    in a Python loop of render() calls, GAN/gan.py:326-377).  Returns a list of render()-style result dicts.  A tensor
+    shared by several scenes (e.g. common lights / materials) receives the sum of its gradients, as autograd would."""
+    if get_param_value('vis_stat', params, False):
+        raise RuntimeError('Removed Support for vis_stat')
+    if get_param_value('norm_depth_image_only', params, False):
+        raise NotImplementedError('norm_depth_image_only is per-frame: call render() for it')
+    if len(scenes) == 0:
+        return []
+    dev = _resolve_device(scenes[0])
+    ms = [Marshalled(sc, dev) for sc in scenes]
+    flat = _RenderBatchFn.apply(ms, dict(params), *[t for m in ms for t in m.floats])
+    out = []
+    for b, m in enumerate(ms):
+        image, depth, normal, pos, nearest, ray_dir = flat[6 * b:6 * b + 6]
+        H, W = m.height, m.width
+        out.append({'image': image.view(H, W, 3), 'depth': depth.view(H, W), 'normal': normal.view(H, W, 3),
+                    'pos': pos.view(H, W, 3), 'ray_dist': None, 'nearest': nearest.view(H, W), 'ray_dir': ray_dir})
+    return out

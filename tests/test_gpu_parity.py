@@ -459,3 +459,33 @@ def test_norm_depth_image_only_matches_oracle():
     assert torch.equal(res['nearest'].cpu(), ref['nearest'])
     assert torch.allclose(res['image'].cpu(), ref['image'], rtol=1e-4, atol=1e-5)
     assert float(res['image'].min()) == 0.0 and float(res['image'].max()) <= 1.0
+
+
+def test_render_batch_equals_per_scene_render():
+    """render_batch (one library call, internal stream fan-out) == a loop of render() calls, forward and backward,
+    including a parameter tensor shared by all scenes of the batch."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    shared_albedo = torch.tensor([[0.6, 0.5, 0.4]], device='cuda', requires_grad=True)
+    shared_albedo2 = shared_albedo.detach().clone().requires_grad_(True)
+
+    def build(albedo):
+        out = []
+        for i in range(9):
+            sc = scene_io.clone_scene(synth.config_d_scene(i, m=800, width=48, height=40), device='cuda', requires_grad=True)
+            sc['materials']['albedo'] = albedo
+            out.append(sc)
+        return out
+    a_scenes, b_scenes = build(shared_albedo), build(shared_albedo2)
+    batch = surf_renderer_b200.render_batch(a_scenes, double_sided=True)
+    loop = [surf_renderer_b200.render(sc, double_sided=True) for sc in b_scenes]
+    for ra, rb in zip(batch, loop):
+        for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+            assert torch.equal(ra[k], rb[k]), k
+    sum((r['image'] * (i + 1)).sum() + r['depth'].clamp(max=50).sum() for i, r in enumerate(batch)).backward()
+    sum((r['image'] * (i + 1)).sum() + r['depth'].clamp(max=50).sum() for i, r in enumerate(loop)).backward()
+    for sa, sb in zip(a_scenes, b_scenes):
+        assert torch.allclose(sa['objects']['disk']['pos'].grad, sb['objects']['disk']['pos'].grad, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(sa['lights']['pos'].grad, sb['lights']['pos'].grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(shared_albedo.grad, shared_albedo2.grad, rtol=1e-4, atol=1e-5)
+    assert surf_renderer_b200.render_batch([]) == []
