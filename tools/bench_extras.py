@@ -51,5 +51,24 @@ for size in (128, 1024):
     n = size * size
     out['along_ray_%d' % size] = {'forward_ms': tf, 'fwd_bwd_ms': tfb, 'forward_gbs': n * 60 / (tf * 1e-3) / 1e9}
     print('along_ray', size, out['along_ray_%d' % size], flush=True)
+# config D: 64 scenes x 5000 splats at 128x128, double sided, fwd + bwd (BASELINE configs[3]); loop of render() vs render_batch()
+batch = [scene_io.clone_scene(synth.config_d_scene(i), device='cuda', requires_grad=True) for i in range(64)]
+
+
+def loop_fb():
+    rs = [surf_renderer_b200.render(sc, double_sided=True) for sc in batch]
+    sum(r['image'].sum() for r in rs).backward()
+
+
+def batch_fb():
+    rs = surf_renderer_b200.render_batch(batch, double_sided=True)
+    sum(r['image'].sum() for r in rs).backward()
+
+
+t_loop = timed(loop_fb, reps=3, warm=1)
+t_batch = timed(batch_fb, reps=3, warm=1)
+tests = 64 * 5000 * 128 * 128
+out['config_d_64x5000_128'] = {'loop_fwd_bwd_ms': t_loop, 'batch_fwd_bwd_ms': t_batch, 'batch_tests_per_s': tests / (t_batch * 1e-3)}
+print('config_d', out['config_d_64x5000_128'], flush=True)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bench_extras.json'), 'w'), indent=1)
