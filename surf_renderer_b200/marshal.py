@@ -7,6 +7,7 @@ or python numbers (torch/render.py:88-107 make_torch_var produces tensors; the d
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -29,16 +30,31 @@ def _as_float_tensor(v, device):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_INT_CACHE = {}          # (id(src), version, device) -> (weakref(src), int32 tensor); index arrays rarely change
+_INT_CACHE_MAX = 256
+
+
 def _as_int_tensor(v, device):
-    """index arrays may arrive as long or float tensors, lists or numpy arrays (renderer.py:128,284)."""
+    """index arrays may arrive as long or float tensors, lists or numpy arrays (renderer.py:128,284).  The int32
+    device copy of a tensor is cached until the tensor is modified in place or collected."""
     if isinstance(v, torch.Tensor):
+        key = (id(v), v._version, str(device))
+        hit = _INT_CACHE.get(key)
+        if hit is not None and hit[0]() is v:
+            return hit[1]
         t = v.detach()
     else:
+        key = None
         t = torch.tensor(np.asarray(v))
     t = t.long().to(torch.int32)          # .long() truncation first, like the reference's material_idx.long()
     if t.device != device:
         t = t.to(device)
-    return t.contiguous()
+    t = t.contiguous()
+    if key is not None:
+        if len(_INT_CACHE) >= _INT_CACHE_MAX:
+            _INT_CACHE.clear()
+        _INT_CACHE[key] = (weakref.ref(v), t)
+    return t
 
 
 def _scalar(v):
