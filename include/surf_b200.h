@@ -188,10 +188,13 @@ typedef struct SurfSplats {
     int32_t normal_stride;    /* 3 or 4 */
     const int32_t* material_idx; /* [count], or NULL = material 0 */
     const float* light_vis;   /* [L, count] per-light visibility (constant), or NULL */
+    const float* pos;         /* optional [count,3] explicit camera-space positions (supersampled fragments,
+                                 renderer.py:603-673); when non-NULL `z` is ignored and count need not equal W*H */
 } SurfSplats;
 typedef struct SurfSplatGrads {
     float* z;                 /* same stride as SurfSplats.z; caller zero-initialises, the library adds */
     float* normal;            /* same stride as SurfSplats.normal */
+    float* pos;               /* [count,3], only with explicit positions */
 } SurfSplatGrads;
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
                         const SurfSplats* splats, void* workspace, size_t workspace_bytes,

@@ -449,6 +449,58 @@ def view_matrix(eye, at, up):
     return camera_pose(eye, at, up).inverse()
 
 
+def _pad_reflect(x):
+    """utils.py:748-769 ``pad2d(x, (1,1,1,1), 'reflect')`` for an [H, W, C] tensor."""
+    xx = x[None, ...].transpose(3, 1)
+    xx = torch.nn.ReflectionPad2d((1, 1, 1, 1))(xx).transpose(1, 3)
+    return xx[0]
+
+
+def neighbour_diffs(x):
+    """utils.py:772-792 ``grad_spatial2d``: [8, H, W, C] differences to the 8 neighbours (reflect padding)."""
+    xp = _pad_reflect(x)
+    Hp, Wp = xp.shape[:2]
+    centre = xp[1:-1, 1:-1, :]
+    out = []
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dx == 0 and dy == 0:
+                continue
+            out.append(xp[1 + dy:Hp + dy - 1, 1 + dx:Wp + dx - 1, :] - centre)
+    return torch.stack(out, dim=0)
+
+
+def normals_plane_fit(pos):
+    """utils.py:886-923 ``estimate_surface_normals_plane_fit``: constrained least-squares plane through each splat."""
+    nd = unit(neighbour_diffs(pos), 1e-10)
+    nd = nd.view(nd.shape[0], -1, 3)
+    M = nd[:, :, :2].transpose(1, 0)
+    Mt = M.transpose(2, 1)
+    MtM = Mt.matmul(M)
+    det = MtM[:, 0, 0] * MtM[:, 1, 1] - MtM[:, 0, 1] * MtM[:, 1, 0]
+    flip = torch.tensor([1, 0])
+    adj = MtM.index_select(1, flip).transpose(2, 1).index_select(1, flip) * _f32([[1, -1], [-1, 1]])[None, ...]
+    inv = adj / (det[:, None, None] + 1e-12)
+    nxy = inv.matmul(Mt.matmul(-nd[..., 2].transpose(1, 0)[:, :, None])).squeeze()
+    n = torch.cat([nxy, _f32(np.ones((nxy.shape[0], 1)))], dim=1).view(pos.shape)
+    return unit(n)
+
+
+def normals_average(pos):
+    """utils.py:854-883 ``find_average_normal``."""
+    nd = unit(neighbour_diffs(pos), 1e-10)
+    order = ((4, 2), (2, 1), (1, 0), (0, 3), (3, 5), (5, 6), (6, 7), (7, 4))
+    n = torch.stack([torch.cross(nd[a], nd[b], dim=-1) for a, b in order], dim=0)
+    return torch.clamp(unit(torch.mean(n, dim=0), 1e-10), 0.0, 1.0)
+
+
+def _upsampled(x, H, W, C, K):
+    """renderer.py:476-481 ``reshape_upsampled_data``."""
+    x = x.view(H, W, C, K, K)
+    x = x.transpose(3, 1).transpose(3, 2).transpose(4, 3)
+    return x.contiguous().view(H * W * K * K, C)
+
+
 def render_along_ray(scene, **params):
     camera = scene['camera']
     vp = np.array(camera['viewport'])
@@ -459,10 +511,6 @@ def render_along_ray(scene, **params):
     splats = scene['objects']['disk']
     z_in = splats['pos']
     normals_cc = splats.get('normal', None)
-    if normals_cc is None:
-        raise NotImplementedError('normal estimation is not restated')
-    if params.get('samples', 1) > 1:
-        raise NotImplementedError('supersampling is not restated')
     fovy, focal = camera['fovy'], camera['focal_length']
     h = np.tan(fovy / 2) * 2 * focal
     w = h * aspect
@@ -478,8 +526,39 @@ def render_along_ray(scene, **params):
     X = -Z * x / focal
     Y = -Z * y / focal
     pos_cc = torch.stack((X, Y, Z), dim=1)
+    if normals_cc is None:                                               # renderer.py:591-594
+        method = params.get('normal_estimation_method', 'plane')
+        est = {'plane': normals_plane_fit, 'avg_normal': normals_average}[method]
+        normals_cc = est(pos_cc.view(H, W, 3))[..., :3].view(-1, 3)
     material_idx = splats['material_idx']
     visibility = splats.get('light_vis', None)
+    samples = params.get('samples', 1)
+    if samples > 1:                                                      # renderer.py:603-673
+        plane_d = torch.sum(pos_cc * normals_cc[:, :3], dim=1)
+        zz = _f32(np.ones(x.shape) * -focal)
+        sub_w = w / (samples * W - 1)
+        sub_h = h / (samples * H - 1)
+        p_ss, n_ss, m_ss, v_ss = [], [], [], []
+        if visibility is not None:
+            visibility = visibility.transpose(1, 0)
+        for deltax in np.linspace(-1, 1, samples):
+            xx = x + deltax * sub_w / 2
+            for deltay in np.linspace(1, -1, samples):
+                yy = y + deltay * sub_h / 2
+                ray = unit(torch.stack((xx, yy, zz), dim=1))
+                t = plane_d / torch.sum(ray * normals_cc[:, :3], dim=1)
+                p_ss.append(t[:, None] * ray)
+                n_ss.append(normals_cc[:, :3])
+                m_ss.append(material_idx[:, None])
+                if visibility is not None:
+                    v_ss.append(visibility)
+        pos_cc = _upsampled(torch.stack(p_ss, dim=2), H, W, 3, samples)
+        normals_cc = _upsampled(torch.stack(n_ss, dim=2), H, W, 3, samples)
+        material_idx = _upsampled(torch.stack(m_ss, dim=2), H, W, 1, samples).view(-1)
+        if visibility is not None:
+            visibility = _upsampled(torch.stack(v_ss, dim=2), H, W, visibility.shape[1], samples).transpose(1, 0)
+        H *= samples
+        W *= samples
     depth = lp_norm(pos_cc[..., :3]).view(H, W)
     lights = scene['lights']
     light_rgb = scene['colors'][lights['color_idx']]

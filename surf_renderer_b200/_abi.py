@@ -63,11 +63,11 @@ class SurfSceneGrads(C.Structure):
 
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
-                ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p)]
+                ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p)]
 
 
 class SurfSplatGrads(C.Structure):
-    _fields_ = [('z', C.c_void_p), ('normal', C.c_void_p)]
+    _fields_ = [('z', C.c_void_p), ('normal', C.c_void_p), ('pos', C.c_void_p)]
 
 
 # every symbol include/surf_b200.h declares: name -> (restype, argtypes)

@@ -386,9 +386,10 @@ static int splat_frame(const SurfScene* scene, const SurfCamera* camera, const S
     if (!check_camera(*camera, &err)) return fail(SURF_ERR_BAD_ARG, err);
     if (camera->proj != 0) return fail(SURF_ERR_UNSUPPORTED, "render_splats_along_ray is defined for the perspective frustum");
     if (scene->light_pos_stride != 4) return fail(SURF_ERR_BAD_ARG, "along-ray lights must be homogeneous [L,4] (torch.mm with the 4x4 view matrix)");
-    if (sp->count != camera->width * camera->height) return fail(SURF_ERR_BAD_ARG, "one splat per pixel: count must equal width*height");
-    if (!sp->z || !sp->normal) return fail(SURF_ERR_UNSUPPORTED, "splat depths and normals are required (normal estimation is not built)");
-    if ((sp->z_stride != 1 && sp->z_stride != 3) || (sp->normal_stride != 3 && sp->normal_stride != 4))
+    if (!sp->pos && sp->count != camera->width * camera->height) return fail(SURF_ERR_BAD_ARG, "one splat per pixel: count must equal width*height");
+    if (sp->count < 1) return fail(SURF_ERR_BAD_ARG, "no splats");
+    if ((!sp->z && !sp->pos) || !sp->normal) return fail(SURF_ERR_BAD_ARG, "splat depths (or positions) and normals are required");
+    if ((!sp->pos && sp->z_stride != 1 && sp->z_stride != 3) || (sp->normal_stride != 3 && sp->normal_stride != 4))
         return fail(SURF_ERR_BAD_ARG, "z_stride must be 1 or 3, normal_stride 3 or 4");
     if (sc.n_lights > 16 && sp->light_vis) return fail(SURF_ERR_UNSUPPORTED, "light_vis supports at most 16 lights");
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
@@ -402,6 +403,7 @@ static int splat_frame(const SurfScene* scene, const SurfCamera* camera, const S
     p->cam = ws->cam;
     p->z = sp->z; p->z_stride = sp->z_stride; p->normal = sp->normal; p->normal_stride = sp->normal_stride;
     p->mat = sp->material_idx; p->vis = sp->light_vis; p->n = sp->count;
+    p->pos_in = sp->pos; p->gpos = nullptr;
     p->fl = ShadeFlags{0, opt->use_quartic};
     p->image = p->depth = p->normal_out = p->pos = nullptr;
     p->g_image = p->g_depth = p->g_normal = p->g_pos = nullptr;
@@ -439,7 +441,7 @@ static int splats_backward_impl(const SurfScene* scene, const SurfCamera* camera
     SURF_LAUNCHED("k_splat_setup");
     SURF_CUDA(cudaMemsetAsync(ws.acc, 0, sizeof(double) * kMaxAccSlots, st));
     p.g_image = og->image; p.g_depth = og->depth; p.g_normal = og->normal; p.g_pos = og->pos;
-    p.gz = spg->z; p.gnormal = spg->normal;
+    p.gz = spg->z; p.gnormal = spg->normal; p.gpos = spg->pos;
     timer_mark(2, 0, st);
     k_splat_backward<<<std::min((p.n + 127) / 128, sm_count() * 8), 128, 0, st>>>(p);
     timer_mark(2, 1, st);

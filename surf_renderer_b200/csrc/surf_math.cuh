@@ -857,33 +857,38 @@ SURF_HD void splat_fragment(const CamState& cs, int pix, float z, Vec3* P, float
     *px = x; *py = y;
 }
 struct SplatOut { float image[3]; float depth; float pos[3]; };
-SURF_HD SplatOut splat_pixel_forward(const SceneView& sc, const CamState& cs, int pix, float z, Vec3 n, int mat,
-                                     ShadeFlags fl, const float* visibility) {
+// `pos_opt` (explicit camera-space position, used by the supersampled path) overrides the z-derived position
+SURF_HD SplatOut splat_pixel_forward(const SceneView& sc, const CamState& cs, int pix, float z, const float* pos_opt,
+                                     Vec3 n, int mat, ShadeFlags fl, const float* visibility) {
     SplatOut so;
     Vec3 P;
     float x, y;
-    splat_fragment(cs, pix, z, &P, &so.depth, &x, &y);
+    if (pos_opt) { P = ld3(pos_opt); so.depth = xsqrt(sq3_seq(P)); }
+    else splat_fragment(cs, pix, z, &P, &so.depth, &x, &y);
     float lit[3];
     shade_pixel(sc, v3(0.f, 0.f, 0.f), P, n, mat, fl, visibility, lit);
     for (int c = 0; c < 3; ++c) so.image[c] = lit[c] > 0.f ? lit[c] : 0.f;          // relu, no tonemap (:741)
     so.pos[0] = P.x; so.pos[1] = P.y; so.pos[2] = P.z;
     return so;
 }
-// backward of one splat: returns d/dz and d/dnormal; light / material gradients go to the sink
+// backward of one splat: returns d/dz (or d/dpos when the position was explicit) and d/dnormal; light / material
+// gradients go to the sink
 template <class Sink>
-SURF_HD void splat_pixel_backward(const SceneView& sc, const CamState& cs, int pix, float z, Vec3 n, int mat,
-                                  ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink,
-                                  float* gz, float gn_out[3]) {
+SURF_HD void splat_pixel_backward(const SceneView& sc, const CamState& cs, int pix, float z, const float* pos_opt, Vec3 n,
+                                  int mat, ShadeFlags fl, const float* visibility, const PixelGrads& g, Sink& sink,
+                                  float* gz, float gpos_out[3], float gn_out[3]) {
     Vec3 P;
-    float depth, x, y;
-    splat_fragment(cs, pix, z, &P, &depth, &x, &y);
+    float depth, x = 0.f, y = 0.f;
+    if (pos_opt) { P = ld3(pos_opt); depth = xsqrt(sq3_seq(P)); }
+    else splat_fragment(cs, pix, z, &P, &depth, &x, &y);
     Vec3 gP = v3(g.pos[0], g.pos[1], g.pos[2]);
     Vec3 gn = v3(g.normal[0], g.normal[1], g.normal[2]);
     backward_shading(sc, v3(0.f, 0.f, 0.f), P, n, mat, true, fl, visibility, g.image, sink, &gP, &gn);
     if (depth > 0.f) gP = faxpy(g.depth / depth, P, gP);
     const float f = -cs.neg_focal;
     const float gZ = gP.z - gP.x * x / f - gP.y * y / f;
-    *gz = z < 0.f ? gZ : 0.f;
+    *gz = (!pos_opt && z < 0.f) ? gZ : 0.f;
+    gpos_out[0] = gP.x; gpos_out[1] = gP.y; gpos_out[2] = gP.z;
     gn_out[0] = gn.x; gn_out[1] = gn.y; gn_out[2] = gn.z;
     sink.end_splat(mat);
 }

@@ -12,6 +12,8 @@ struct SplatParams {
     const float* normal; int normal_stride;
     const int* mat;
     const float* vis;             // [L, n] or null
+    const float* pos_in;          // [n, 3] explicit positions or null
+    float* gpos;                  // [n, 3] gradient of the explicit positions or null
     int n;
     ShadeFlags fl;
     float* image; float* depth; float* normal_out; float* pos;                       // forward outputs
@@ -46,7 +48,8 @@ __global__ void __launch_bounds__(256) k_splat_forward(const __grid_constant__ S
         }
         const float* np_ = p.normal + (size_t)k * p.normal_stride;
         nn[0] = np_[0]; nn[1] = np_[1]; nn[2] = np_[2];
-        so = splat_pixel_forward(p.sc, *p.cam, k, p.z[(size_t)k * p.z_stride], v3(nn[0], nn[1], nn[2]),
+        so = splat_pixel_forward(p.sc, *p.cam, k, p.pos_in ? 0.f : p.z[(size_t)k * p.z_stride],
+                                 p.pos_in ? p.pos_in + 3 * (size_t)k : nullptr, v3(nn[0], nn[1], nn[2]),
                                  p.mat ? p.mat[k] : 0, p.fl, vis);
         if (p.depth) p.depth[k] = so.depth;
     }
@@ -81,11 +84,14 @@ __global__ void __launch_bounds__(128) k_splat_backward(const __grid_constant__ 
         }
         DeviceSink sink(bp_view, cta_acc);
         const float* np_ = p.normal + (size_t)kk * p.normal_stride;
-        float gz, gn[3];
-        splat_pixel_backward(p.sc, *p.cam, kk, p.z[(size_t)kk * p.z_stride], v3(np_[0], np_[1], np_[2]),
-                             p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gn);
+        float gz, gpos[3], gn[3];
+        splat_pixel_backward(p.sc, *p.cam, kk, p.pos_in ? 0.f : p.z[(size_t)kk * p.z_stride],
+                             p.pos_in ? p.pos_in + 3 * (size_t)kk : nullptr, v3(np_[0], np_[1], np_[2]),
+                             p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gpos, gn);
         if (live) {
-            if (p.gz) p.gz[(size_t)k * p.z_stride] += gz;
+            if (p.gz && !p.pos_in) p.gz[(size_t)k * p.z_stride] += gz;
+            if (p.gpos && p.pos_in)
+                for (int c = 0; c < 3; ++c) p.gpos[(size_t)k * 3 + c] += gpos[c];
             if (p.gnormal)
                 for (int c = 0; c < 3; ++c) p.gnormal[(size_t)k * p.normal_stride + c] += gn[c];
         }

@@ -321,7 +321,7 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
 
 // ---- render_splats_along_ray emulation -----------------------------------------------------------
 struct EmulSplats { int count; const float* z; int z_stride; const float* normal; int normal_stride; const int* mat;
-                    const float* vis; };
+                    const float* vis; const float* pos; };
 
 static bool splat_setup(const SurfScene* scene, const SurfCamera* cam, SceneView* sc, CamState* cs, std::vector<float>* lcc) {
     SurfScene tmp = *scene;
@@ -347,7 +347,8 @@ int emul_splats_forward(const SurfScene* scene, const SurfCamera* cam, const Sur
     for (int k = 0; k < sp->count; ++k) {
         if (sp->vis) for (int l = 0; l < sc.n_lights; ++l) vis[l] = sp->vis[(size_t)l * sp->count + k];
         const float* nn = sp->normal + (size_t)k * sp->normal_stride;
-        SplatOut so = splat_pixel_forward(sc, cs, k, sp->z[(size_t)k * sp->z_stride], ld3(nn), sp->mat ? sp->mat[k] : 0, fl,
+        SplatOut so = splat_pixel_forward(sc, cs, k, sp->pos ? 0.f : sp->z[(size_t)k * sp->z_stride],
+                                          sp->pos ? sp->pos + 3 * (size_t)k : nullptr, ld3(nn), sp->mat ? sp->mat[k] : 0, fl,
                                           sp->vis ? vis.data() : nullptr);
         memcpy(out->image + 3 * (size_t)k, so.image, 12);
         out->depth[k] = so.depth;
@@ -358,7 +359,7 @@ int emul_splats_forward(const SurfScene* scene, const SurfCamera* cam, const Sur
 }
 
 int emul_splats_backward(const SurfScene* scene, const SurfCamera* cam, const SurfOptions* opt, const EmulSplats* sp,
-                         const SurfOutGrads* og, const SurfSceneGrads* sg, float* gz, float* gnormal) {
+                         const SurfOutGrads* og, const SurfSceneGrads* sg, float* gz, float* gnormal, float* gpos) {
     SceneView sc; CamState cs; std::vector<float> lcc;
     if (!splat_setup(scene, cam, &sc, &cs, &lcc)) return -1;
     ShadeFlags fl = {0, opt->use_quartic};
@@ -373,10 +374,12 @@ int emul_splats_backward(const SurfScene* scene, const SurfCamera* cam, const Su
             g.normal[c] = og->normal ? og->normal[3 * (size_t)k + c] : 0.f;
         }
         g.depth = og->depth ? og->depth[k] : 0.f;
-        float gzk, gnk[3];
-        splat_pixel_backward(sc, cs, k, sp->z[(size_t)k * sp->z_stride], ld3(sp->normal + (size_t)k * sp->normal_stride),
-                             sp->mat ? sp->mat[k] : 0, fl, sp->vis ? vis.data() : nullptr, g, hs, &gzk, gnk);
-        gz[(size_t)k * sp->z_stride] += gzk;
+        float gzk, gpk[3], gnk[3];
+        splat_pixel_backward(sc, cs, k, sp->pos ? 0.f : sp->z[(size_t)k * sp->z_stride], sp->pos ? sp->pos + 3 * (size_t)k : nullptr,
+                             ld3(sp->normal + (size_t)k * sp->normal_stride),
+                             sp->mat ? sp->mat[k] : 0, fl, sp->vis ? vis.data() : nullptr, g, hs, &gzk, gpk, gnk);
+        if (sp->pos) { for (int c = 0; c < 3; ++c) gpos[(size_t)k * 3 + c] += gpk[c]; }
+        else gz[(size_t)k * sp->z_stride] += gzk;
         for (int c = 0; c < 3; ++c) gnormal[(size_t)k * sp->normal_stride + c] += gnk[c];
     }
     for (int m = 0; m < sc.n_materials * 3; ++m) {

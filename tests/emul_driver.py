@@ -73,14 +73,15 @@ def backward(m, params, nearest, depth, gouts):
 
 class _EmulSplats(C.Structure):
     _fields_ = [('count', C.c_int), ('z', C.c_void_p), ('z_stride', C.c_int), ('normal', C.c_void_p),
-                ('normal_stride', C.c_int), ('mat', C.c_void_p), ('vis', C.c_void_p)]
+                ('normal_stride', C.c_int), ('mat', C.c_void_p), ('vis', C.c_void_p), ('pos', C.c_void_p)]
 
 
-def _splat_setup(scene, params):
-    from surf_renderer_b200.along_ray import _SplatInputs
-    inp = _SplatInputs(scene, torch.device('cpu'))
+def _splat_setup(scene, params, inp=None):
+    from surf_renderer_b200.along_ray import build_inputs
+    if inp is None:
+        inp = build_inputs(scene, params, torch.device('cpu'))
     sc, cam, sp, opt = inp.structs(inp.floats, params)
-    es = _EmulSplats(sp.count, sp.z, sp.z_stride, sp.normal, sp.normal_stride, sp.material_idx, sp.light_vis)
+    es = _EmulSplats(sp.count, sp.z, sp.z_stride, sp.normal, sp.normal_stride, sp.material_idx, sp.light_vis, sp.pos)
     L = lib()
     L.emul_splats_forward.restype = C.c_int
     L.emul_splats_forward.argtypes = [C.POINTER(_abi.SurfScene), C.POINTER(_abi.SurfCamera), C.POINTER(_abi.SurfOptions),
@@ -88,12 +89,12 @@ def _splat_setup(scene, params):
     L.emul_splats_backward.restype = C.c_int
     L.emul_splats_backward.argtypes = [C.POINTER(_abi.SurfScene), C.POINTER(_abi.SurfCamera), C.POINTER(_abi.SurfOptions),
                                        C.POINTER(_EmulSplats), C.POINTER(_abi.SurfOutGrads), C.POINTER(_abi.SurfSceneGrads),
-                                       C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
     return inp, sc, cam, es, opt
 
 
-def splats_forward(scene, **params):
-    inp, sc, cam, es, opt = _splat_setup(scene, params)
+def splats_forward(scene, _inp=None, **params):
+    inp, sc, cam, es, opt = _splat_setup(scene, params, _inp)
     n = inp.n
     out = {'image': torch.empty(n, 3), 'depth': torch.empty(n), 'normal': torch.empty(n, 3), 'pos': torch.empty(n, 3)}
     co = _abi.SurfOutputs(out['image'].data_ptr(), out['depth'].data_ptr(), out['normal'].data_ptr(), out['pos'].data_ptr(), None, None)
@@ -104,8 +105,9 @@ def splats_forward(scene, **params):
             'normal': out['normal'].view(H, W, 3)}, inp
 
 
-def splats_backward(scene, params, gouts):
-    inp, sc, cam, es, opt = _splat_setup(scene, params)
+def splats_backward(scene, params, gouts, _inp=None):
+    """gradients w.r.t. inp.floats (for explicit fragments: floats[0] = positions, floats[1] = normals)"""
+    inp, sc, cam, es, opt = _splat_setup(scene, params, _inp)
     grads = [torch.zeros_like(t) for t in inp.floats]
     keep = {k: v.contiguous() for k, v in gouts.items()}
     og = _abi.SurfOutGrads(keep['image'].data_ptr(), keep['depth'].data_ptr(), keep['normal'].data_ptr(), keep['pos'].data_ptr())
@@ -114,6 +116,6 @@ def splats_backward(scene, params, gouts):
     sg.colors, sg.albedo, sg.coeffs = grads[5].data_ptr(), grads[6].data_ptr(), grads[7].data_ptr()
     gz = grads[0].data_ptr() + (8 if inp.z_stride == 3 else 0)
     if lib().emul_splats_backward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(es), C.byref(og), C.byref(sg), gz,
-                                  grads[1].data_ptr()) != 0:
+                                  grads[1].data_ptr(), grads[0].data_ptr()) != 0:
         raise RuntimeError(lib().emul_last_error().decode())
     return dict(zip(inp.names, grads))

