@@ -489,3 +489,64 @@ def test_render_batch_equals_per_scene_render():
         assert torch.allclose(sa['lights']['pos'].grad, sb['lights']['pos'].grad, rtol=1e-4, atol=1e-6)
     assert torch.allclose(shared_albedo.grad, shared_albedo2.grad, rtol=1e-4, atol=1e-5)
     assert surf_renderer_b200.render_batch([]) == []
+
+
+def _camera_basis(cam):
+    eye, at, up = (cam[k][:3].double().cpu() for k in ('eye', 'at', 'up'))
+    z = (eye - at) / (eye - at).norm()
+    upn = up / up.norm()
+    x = torch.linalg.cross(upn, z)
+    x = x / x.norm()
+    y = torch.linalg.cross(z, x)
+    return eye, x, y, z
+
+
+@pytest.mark.parametrize('which', ['mixed', 'config_e_full'])
+def test_hit_points_project_back_onto_their_pixels(which):
+    """Size-independent geometric property (the consistency the reference checks in projection_layer.py:461-606):
+    every hit point, transformed to camera coordinates and projected onto the image plane, lands on the pixel that
+    produced it; depth equals the distance from the eye; the hit point lies on the reported primitive."""
+    from surf_renderer_b200 import scenes as synth
+    scene = synth.random_mixed_scene(91, width=160, height=120, n_disk=60, n_tri=40, n_sphere=6) if which == 'mixed' \
+        else synth.config_e()
+    res = _cpu(_render(scene_io.clone_scene(scene, device='cuda')))
+    cam = scene['camera']
+    H, W = res['depth'].shape
+    hit = res['depth'] <= cam['far']
+    assert int(hit.sum()) > 1000
+    eye, xc, yc, zc = _camera_basis(cam)
+    P = res['pos'].double()[hit]
+    q = P - eye
+    qx, qy, qz = q @ xc, q @ yc, q @ zc
+    f = cam['focal_length']
+    h = float(np.tan(cam['fovy'] / 2) * 2 * f)
+    w = h * W / H
+    rows, cols = torch.nonzero(hit, as_tuple=True)
+    x_pix = (-1 + 2 * cols.double() / (W - 1)) * (w / 2)
+    y_pix = (1 - 2 * rows.double() / (H - 1)) * (h / 2)
+    x_img, y_img = -f * qx / qz, -f * qy / qz
+    pix = w / (W - 1)
+    assert float((x_img - x_pix).abs().max()) < 2e-3 * pix + 1e-6
+    assert float((y_img - y_pix).abs().max()) < 2e-3 * pix + 1e-6
+    assert torch.allclose(q.norm(dim=1), res['depth'].double()[hit], rtol=2e-6, atol=1e-6)
+    # the winner really contains the hit point (disks: within the radius, on the plane)
+    if which == 'config_e_full':
+        d = scene['objects']['disk']
+        idx = res['nearest'][hit]
+        c, n, r = d['pos'].double()[idx], d['normal'].double()[idx], d['radius'].double()[idx]
+        n = n / n.norm(dim=1, keepdim=True)
+        rel = P - c
+        assert float(((rel * n).sum(1)).abs().max()) < 2e-5
+        assert float((rel.norm(dim=1) - r).max()) < 2e-5
+        # and no splat strictly in front of the winner along the same ray contains the ray (spot check, 64 pixels)
+        g = torch.Generator().manual_seed(5)
+        pick = torch.randperm(P.shape[0], generator=g)[:64]
+        dirs = q[pick] / q[pick].norm(dim=1, keepdim=True)
+        call, nall, rall = d['pos'].double(), d['normal'].double(), d['radius'].double()
+        nall = nall / nall.norm(dim=1, keepdim=True)
+        for j, k in enumerate(pick.tolist()):
+            t = ((call - eye) @ nall.T).diagonal() / (nall @ dirs[j])
+            Pj = eye + t[:, None] * dirs[j]
+            inside = ((Pj - call).norm(dim=1) <= rall) & (t >= cam['near']) & (t <= cam['far'])
+            t_best = float(res['depth'].double()[hit][k])
+            assert float(t[inside].min()) >= t_best - 1e-5 * t_best
