@@ -545,7 +545,7 @@ def test_hit_points_project_back_onto_their_pixels(which):
         call, nall, rall = d['pos'].double(), d['normal'].double(), d['radius'].double()
         nall = nall / nall.norm(dim=1, keepdim=True)
         for j, k in enumerate(pick.tolist()):
-            t = ((call - eye) @ nall.T).diagonal() / (nall @ dirs[j])
+            t = ((call - eye) * nall).sum(1) / (nall @ dirs[j])
             Pj = eye + t[:, None] * dirs[j]
             inside = ((Pj - call).norm(dim=1) <= rall) & (t >= cam['near']) & (t <= cam['far'])
             t_best = float(res['depth'].double()[hit][k])
