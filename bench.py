@@ -208,6 +208,25 @@ def run_cpu_baseline(scene, target_scene, budget_s, threads, steps=1, warmup=0):
             'fwd_tests_per_s': tests / tf, 'ms_per_sample_step': 1e3 * (tf + tb)}, n_pix, tf + tb
 
 
+def run_numpy_baseline(scene, n_pix=96, reps=2):
+    """The reference's second CPU renderer (diffrend/numpy/renderer.py, restated in oracle/numpy_oracle.py): forward
+    only (it has no gradients), float64, Lambertian, and it materialises the whole [M, N, 4] tensor - so the sample is
+    a small pixel subset of the same frame and the same splats."""
+    from oracle import numpy_oracle
+    hs = numpy_oracle.homogeneous_scene(scene)
+    m = int(hs['objects']['disk']['pos'].shape[0])
+    sub = cpu_sample(scene, n_pix).numpy()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        numpy_oracle.render(hs, pixel_subset=sub)
+        best = min(best, time.perf_counter() - t0)
+    return {'value': float(m) * len(sub) / best, 'unit': 'tests/s (forward only)', 'cores': 1, 'kind': 'port',
+            'sample': '%d random pixels of the frame x %d splats, forward, best of %d (%.2fs); numpy float64 port of '
+                      'the reference numpy twin (no tiling: [M,N,4] temporaries; elementwise numpy is single-threaded)'
+                      % (len(sub), m, reps, best)}
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -235,6 +254,7 @@ def main():
                 'ms_per_step': 1e3 * step_s, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'cpu_baseline': cb,
                 'frames_per_s_extrapolated': cb['value'] / tests_per_step,
+                'cpu_baseline_numpy': run_numpy_baseline(scene),
                 'e2e': {'value': cb['value'], 'unit': 'tests/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return 0
@@ -423,16 +443,18 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    cpu_baseline = None
+    cpu_baseline = cpu_baseline_numpy = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline, _, _ = run_cpu_baseline(scene, target_scene, budget_s=20.0, threads=os.cpu_count() or 1)
+        cpu_baseline_numpy = run_numpy_baseline(scene)
 
     line = {'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)', 'value': value, 'unit': 'tests/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
             'gpu_launches': int(sum(launches)), 'gpu_launches_per_step': int(launches[-1]) if launches else 0,
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'fast_mode': fast,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'cpu_baseline_numpy': cpu_baseline_numpy, 'e2e': e2e,
+            'fast_mode': fast,
             'wall_s_timed_region': wall}
     print(json.dumps(line))
     if world > 1:

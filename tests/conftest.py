@@ -18,9 +18,15 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 def golden_cases():
     """fixtures of render() (make_golden.py)"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('ar_'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith('.npz') and not f.startswith(('ar_', 'np_', 'b200_')))
 
 
 def along_ray_cases():
     """fixtures of render_splats_along_ray() (make_golden_along_ray.py)"""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('ar_'))
+
+
+def numpy_twin_cases():
+    """fixtures of the reference's numpy twin renderer (make_golden_numpy.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('np_'))

@@ -501,6 +501,18 @@ def _camera_basis(cam):
     return eye, x, y, z
 
 
+def test_stored_b200_render_is_current():
+    """tests/golden/b200_halfbox_160x120.npz is the frame the reference's own projection_layer tests were run on
+    (tests/test_projection_pins.py, build container only).  The current kernels must still produce it."""
+    stored = np.load(os.path.join(GOLDEN_DIR, 'b200_halfbox_160x120.npz'))
+    scene, _, _, _, _ = _load('halfbox_sphere_cube_48x36')
+    scene['camera']['viewport'] = [0, 0, 160, 120]
+    res = _cpu(_render(scene_io.clone_scene(scene, device='cuda')))
+    assert np.array_equal(res['nearest'].numpy(), stored['nearest'])
+    for k in ('image', 'depth', 'pos', 'normal'):
+        assert np.allclose(res[k].numpy(), stored[k], rtol=parity.RTOL, atol=parity.ATOL), k
+
+
 @pytest.mark.parametrize('which', ['mixed', 'config_e_full'])
 def test_hit_points_project_back_onto_their_pixels(which):
     """Size-independent geometric property (the consistency the reference checks in projection_layer.py:461-606):
