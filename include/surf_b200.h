@@ -174,6 +174,27 @@ int surf_backward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCam
                         const float* const* depth, const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads,
                         void* cuda_stream);
 
+/* ---- strided batches: one scene description + element strides between consecutive scenes ----
+ * The GAN workload holds a batch as stacked tensors (splat positions [B,M,3], camera eyes [B,3], shared lights and
+ * materials).  Scene b reads every pointer of `scene0` / `camera0` advanced by b * stride ELEMENTS (floats / int32);
+ * a stride of 0 means all scenes share that array (its gradient then receives the sum over the batch).  All scenes
+ * have the same primitive counts, light / colour / material counts, viewport and scalar camera parameters.
+ * Outputs, `nearest`, `depth`, incoming gradients are contiguous per scene: [B, n, ...] (ray_dir [B,3,n] or [B,3,1]);
+ * `workspace` holds B slices of `workspace_bytes_per_scene` (>= surf_workspace_bytes, rounded up to 256).
+ * Gradient accumulators in `grads0` have the layout (and strides) of the inputs they belong to. */
+typedef struct SurfBatchLayout {
+    int64_t set_pos[SURF_MAX_SETS], set_normal[SURF_MAX_SETS], set_radius[SURF_MAX_SETS], set_material_idx[SURF_MAX_SETS];
+    int64_t light_pos, light_color_idx, light_attenuation, ambient, colors, albedo, coeffs, gamma;
+    int64_t eye, at, up;
+} SurfBatchLayout;
+int surf_forward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                         const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
+                         size_t workspace_bytes_per_scene, const SurfOutputs* out0, void* cuda_stream);
+int surf_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                          const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
+                          size_t workspace_bytes_per_scene, const int64_t* nearest0, const float* depth0,
+                          const SurfOutGrads* out_grads0, const SurfSceneGrads* grads0, void* cuda_stream);
+
 /* ---- one-splat-per-pixel renderer: diffrend/torch/renderer.py:537-751 render_splats_along_ray ----
  * Splat k sits on the ray of flat pixel k at camera-space depth z[k] (negative = in front of the camera,
  * clamped with -relu(-z)); it is shaded in camera coordinates with the same fragment shader as render()

@@ -61,6 +61,15 @@ class SurfSceneGrads(C.Structure):
                 ('colors', C.c_void_p), ('albedo', C.c_void_p), ('coeffs', C.c_void_p), ('gamma', C.c_void_p)]
 
 
+class SurfBatchLayout(C.Structure):
+    """element strides between consecutive scenes of a strided batch (0 = shared by all scenes)"""
+    _fields_ = [('set_pos', C.c_int64 * SURF_MAX_SETS), ('set_normal', C.c_int64 * SURF_MAX_SETS),
+                ('set_radius', C.c_int64 * SURF_MAX_SETS), ('set_material_idx', C.c_int64 * SURF_MAX_SETS),
+                ('light_pos', C.c_int64), ('light_color_idx', C.c_int64), ('light_attenuation', C.c_int64),
+                ('ambient', C.c_int64), ('colors', C.c_int64), ('albedo', C.c_int64), ('coeffs', C.c_int64),
+                ('gamma', C.c_int64), ('eye', C.c_int64), ('at', C.c_int64), ('up', C.c_int64)]
+
+
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
                 ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p)]
@@ -85,6 +94,11 @@ SYMBOLS = {
     'surf_backward_batch': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_void_p), C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_forward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfBatchLayout),
+                                       C.POINTER(SurfOptions), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
+    'surf_backward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfBatchLayout),
+                                        C.POINTER(SurfOptions), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
     'surf_splats_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                       C.POINTER(SurfSplats), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
     'surf_splats_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),

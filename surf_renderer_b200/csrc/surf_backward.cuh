@@ -141,8 +141,50 @@ struct DeviceSink {
 // Persistent grid-stride CTAs: the light / material / colour accumulators live in shared memory for the whole life
 // of the CTA and are flushed with one double atomicAdd per slot per CTA.  (One flush per 128 pixels put ~8000
 // same-address double atomics per slot on the L2 and made the kernel 5x slower than its instruction count.)
+__device__ __forceinline__ void backward_body(const BackwardParams& p, double* cta_acc);
+
 __global__ void __launch_bounds__(128) k_backward(const __grid_constant__ BackwardParams p) {
     __shared__ double cta_acc[kMaxAccSlots];
+    backward_body(p, cta_acc);
+}
+
+__device__ __forceinline__ void grads_at(GradPtrs* gp, const BatchArgs& ba, int b) {
+    for (int k = 0; k < kMaxSets; ++k) {
+        gp->prim_pos[k] = adv(gp->prim_pos[k], b * ba.set_pos[k]);
+        gp->prim_normal[k] = adv(gp->prim_normal[k], b * ba.set_normal[k]);
+        gp->prim_radius[k] = adv(gp->prim_radius[k], b * ba.set_radius[k]);
+    }
+    gp->light_pos = adv(gp->light_pos, b * ba.light_pos);
+    gp->atten = adv(gp->atten, b * ba.light_atten);
+    gp->ambient = adv(gp->ambient, b * ba.ambient);
+    gp->colors = adv(gp->colors, b * ba.colors);
+    gp->albedo = adv(gp->albedo, b * ba.albedo);
+    gp->coeffs = adv(gp->coeffs, b * ba.coeffs);
+    gp->gamma = adv(gp->gamma, b * ba.gamma);
+}
+
+// strided batch: blockIdx.y = scene; nearest / depth / incoming gradients are [B, n, ...]
+__global__ void __launch_bounds__(128) k_backward_batch(const __grid_constant__ BackwardParams p0,
+                                                        const __grid_constant__ BatchArgs ba) {
+    __shared__ double cta_acc[kMaxAccSlots];
+    __shared__ BackwardParams p;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        p = p0;
+        scene_at(&p.sc, ba, b);
+        grads_at(&p.gp, ba, b);
+        p.cam = ws_at(p0.cam, ba, b); p.rays = ws_at(p0.rays, ba, b);
+        p.acc = ws_at(p0.acc, ba, b); p.prim_acc = ws_at(p0.prim_acc, ba, b);
+        const long long n = p0.n;
+        p.nearest = adv(p0.nearest, b * n); p.depth = adv(p0.depth, b * n);
+        p.g_image = adv(p0.g_image, b * n * 3); p.g_depth = adv(p0.g_depth, b * n);
+        p.g_normal = adv(p0.g_normal, b * n * 3); p.g_pos = adv(p0.g_pos, b * n * 3);
+    }
+    __syncthreads();
+    backward_body(p, cta_acc);
+}
+
+__device__ __forceinline__ void backward_body(const BackwardParams& p, double* cta_acc) {
     for (int j = threadIdx.x; j < p.sm.total; j += blockDim.x) cta_acc[j] = 0.0;
     __syncthreads();
     const Vec3 eye = v3(p.cam->eye[0], p.cam->eye[1], p.cam->eye[2]);
@@ -184,8 +226,9 @@ struct FinalizeParams {
     GradPtrs gp; SlotMap sm; const double* acc; int K, L, Cn, light_pos_stride;
     SceneView sc; const double* prim_acc;
 };
-__global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant__ FinalizeParams p) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+// The leaves are updated with atomics: in a batch several scenes (concurrent streams, or the scene dimension of
+// k_backward_finalize_batch) may share one gradient array (SurfBatchLayout stride 0, or aliased pointers).
+__device__ __forceinline__ void finalize_body(const FinalizeParams& p, int j) {
     if (j < p.sc.total) {      // per-primitive accumulators -> fp32 leaves (caller's strides)
         const int s = find_set(p.sc, j);
         const SetView& sv = p.sc.sets[s];
@@ -194,27 +237,44 @@ __global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant
         float* gpos = p.gp.prim_pos[s];
         if (gpos) {
             const size_t row = sv.kind == KIND_TRIANGLE ? (size_t)local * 3 * sv.pos_stride : (size_t)local * sv.pos_stride;
-            for (int c = 0; c < 3; ++c) gpos[row + c] += (float)a[c];
+            for (int c = 0; c < 3; ++c) atomicAdd(gpos + row + c, (float)a[c]);
         }
         float* gnr = p.gp.prim_normal[s];
         if (gnr && sv.kind != KIND_SPHERE)
-            for (int c = 0; c < 3; ++c) gnr[(size_t)local * sv.normal_stride + c] += (float)a[3 + c];
+            for (int c = 0; c < 3; ++c) atomicAdd(gnr + (size_t)local * sv.normal_stride + c, (float)a[3 + c]);
         float* grd = p.gp.prim_radius[s];
-        if (grd && sv.kind == KIND_SPHERE) grd[local] += (float)a[6];
+        if (grd && sv.kind == KIND_SPHERE) atomicAdd(grd + local, (float)a[6]);
         return;
     }
     j -= p.sc.total;
     if (j >= p.sm.total) return;
     const float v = (float)p.acc[j];
-    if (j < p.sm.coeffs) { if (p.gp.albedo) p.gp.albedo[j - p.sm.albedo] += v; }
-    else if (j < p.sm.light_pos) { if (p.gp.coeffs) p.gp.coeffs[j - p.sm.coeffs] += v; }
+    if (j < p.sm.coeffs) { if (p.gp.albedo) atomicAdd(p.gp.albedo + (j - p.sm.albedo), v); }
+    else if (j < p.sm.light_pos) { if (p.gp.coeffs) atomicAdd(p.gp.coeffs + (j - p.sm.coeffs), v); }
     else if (j < p.sm.atten) {
         const int q = j - p.sm.light_pos;
-        if (p.gp.light_pos) p.gp.light_pos[(size_t)(q / 3) * p.light_pos_stride + q % 3] += v;
+        if (p.gp.light_pos) atomicAdd(p.gp.light_pos + (size_t)(q / 3) * p.light_pos_stride + q % 3, v);
     }
-    else if (j < p.sm.colors) { if (p.gp.atten) p.gp.atten[j - p.sm.atten] += v; }
-    else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
-    else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
-    else { if (p.gp.gamma) p.gp.gamma[0] += v; }
+    else if (j < p.sm.colors) { if (p.gp.atten) atomicAdd(p.gp.atten + (j - p.sm.atten), v); }
+    else if (j < p.sm.ambient) { if (p.gp.colors) atomicAdd(p.gp.colors + (j - p.sm.colors), v); }
+    else if (j < p.sm.gamma) { if (p.gp.ambient) atomicAdd(p.gp.ambient + (j - p.sm.ambient), v); }
+    else { if (p.gp.gamma) atomicAdd(p.gp.gamma, v); }
 }
 
+__global__ void __launch_bounds__(128) k_backward_finalize(const __grid_constant__ FinalizeParams p) {
+    finalize_body(p, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(128) k_backward_finalize_batch(const __grid_constant__ FinalizeParams p0,
+                                                                 const __grid_constant__ BatchArgs ba) {
+    __shared__ FinalizeParams p;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        p = p0;
+        scene_at(&p.sc, ba, b);
+        grads_at(&p.gp, ba, b);
+        p.acc = ws_at(p0.acc, ba, b); p.prim_acc = ws_at(p0.prim_acc, ba, b);
+    }
+    __syncthreads();
+    finalize_body(p, blockIdx.x * blockDim.x + threadIdx.x);
+}

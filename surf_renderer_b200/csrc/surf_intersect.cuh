@@ -18,6 +18,7 @@ struct IsectParams {
     int n_tiles, n_chunks;           // work grid: items = n_tiles * n_chunks
     int stage_f4;                    // float4 capacity of one smem stage
     int chunks_before[kMaxSets + 1]; // prefix sum of chunks per set
+    int tiles_per_scene;             // k_intersect_batch: n_tiles = n_scenes * tiles_per_scene (else = n_tiles)
 };
 
 __device__ __forceinline__ int prims_per_chunk(int stage_f4, int kind) { return stage_f4 / rec_f4(kind); }
@@ -354,6 +355,133 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant
         else chunk_planes<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
     }
     flush();
+}
+
+// k_intersect_batch: the same kernel over a strided batch of scenes.  The work grid is [scene][tile][chunk]; all
+// scenes share the chunking of scene 0, and the per-scene pointers - primitive arrays for the exact narrow phase,
+// camera, rays, z-buffer - live in a shared-memory copy `sprm` of the parameter block that is re-pointed whenever the
+// CTA's contiguous item range crosses into the next scene.  (Kept as a separate body: ptxas schedules the packed-FMA
+// loop of k_intersect differently - 3 % slower - when the single-scene kernel is instantiated from a shared template.)
+template <int P, int MODE, bool BATCH>
+__device__ __forceinline__ void intersect_body(const IsectParams& prm0, const BatchArgs* ba, IsectParams* sprm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    const IsectParams& prm = BATCH ? *sprm : prm0;
+
+    const int tid = threadIdx.x;
+    const long long n_items = (long long)prm0.n_tiles * prm0.n_chunks;
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
+    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    if (lo >= hi) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int item, int stage) {      // chunking (prm0) is the same for every scene of a batch
+        int set, local0, count;
+        decode_chunk(prm0, item % prm0.n_chunks, &set, &local0, &count);
+        const SetView& sv = prm0.sc.sets[set];
+        const int nf4 = rec_f4(sv.kind);
+        const float4* packed = BATCH ? ws_at(prm0.packed, *ba, (item / prm0.n_chunks) / prm0.tiles_per_scene) : prm0.packed;
+        const float4* src = packed + sv.rec_off + (size_t)local0 * nf4;
+        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(stage_buf + (size_t)stage * prm0.stage_f4, src, bytes, &full_bar[stage]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
+
+    Vec3 eye = v3(prm0.cam->eye[0], prm0.cam->eye[1], prm0.cam->eye[2]);
+    const float near_clip = prm0.cam->near_clip, far_clip = prm0.cam->far_clip;    // camera scalars are batch-wide
+    constexpr int TILE = kThreads * P;
+
+    PixelRegs<P> r;
+    int cur_tile = -1;       // global tile id ([scene][tile] in a batch)
+    int cur_lt = 0;          // the same tile counted inside its scene
+    int cur_b = -1;
+
+    auto flush = [&]() {
+        if (cur_tile < 0) return;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int pix = cur_lt * TILE + p * kThreads + tid;
+            if (r.best_i[p] >= 0 && pix < prm.n_pix) {
+                unsigned long long key = ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p];
+                atomicMin(prm.zbuf + pix, key);
+            }
+        }
+    };
+
+    for (int it = lo; it < hi; ++it) {
+        const int k = it - lo;
+        const int stage = k % kStages;
+        const uint32_t parity = (uint32_t)((k / kStages) & 1);
+        __syncthreads();   // every thread is done with item it-1, whose stage is the one refilled below
+        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (k + kStages - 1) % kStages);
+
+        const int tile = it / prm0.n_chunks;
+        if (tile != cur_tile) {
+            flush();
+            cur_tile = tile;
+            cur_lt = tile;
+            if (BATCH) {
+                const int b = tile / prm0.tiles_per_scene;
+                cur_lt = tile - b * prm0.tiles_per_scene;
+                if (b != cur_b) {        // CTA-uniform: `tile` depends on the item index only
+                    __syncthreads();     // flush() above still used the previous scene's pointers
+                    if (tid == 0) {
+                        *sprm = prm0;
+                        scene_at(&sprm->sc, *ba, b);
+                        sprm->cam = ws_at(prm0.cam, *ba, b);
+                        sprm->rays = ws_at(prm0.rays, *ba, b);
+                        sprm->zbuf = ws_at(prm0.zbuf, *ba, b);
+                    }
+                    __syncthreads();
+                    cur_b = b;
+                    eye = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
+                }
+            }
+            float d[3][P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int pix = cur_lt * TILE + p * kThreads + tid;
+                const bool ok = pix < prm.n_pix;
+                d[0][p] = ok ? prm.rays[pix] : 0.f;
+                d[1][p] = ok ? prm.rays[(size_t)prm.n_pix + pix] : 0.f;
+                d[2][p] = ok ? prm.rays[2 * (size_t)prm.n_pix + pix] : 0.f;
+                r.best_t[p] = INFINITY;
+                r.best_i[p] = -1;
+            }
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) {
+                r.dx[q] = pack2(d[0][2 * q], d[0][2 * q + 1]);
+                r.dy[q] = pack2(d[1][2 * q], d[1][2 * q + 1]);
+                r.dz[q] = pack2(d[2][2 * q], d[2][2 * q + 1]);
+            }
+        }
+
+        int set, local0, count;
+        decode_chunk(prm0, it % prm0.n_chunks, &set, &local0, &count);
+        const SetView& sv = prm.sc.sets[set];
+        mbar_wait(&full_bar[stage], parity);
+        const float4* s = stage_buf + (size_t)stage * prm0.stage_f4;
+        if (sv.kind == KIND_DISK) chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+        else if (sv.kind == KIND_TRIANGLE) chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+        else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+        else chunk_planes<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+    }
+    flush();
+}
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) k_intersect_batch(const __grid_constant__ IsectParams prm0,
+                                                                 const __grid_constant__ BatchArgs ba) {
+    __shared__ IsectParams sprm;
+    intersect_body<P, MODE, true>(prm0, &ba, &sprm);
 }
 
 // ---------------------------------------------------------------------------------------------------

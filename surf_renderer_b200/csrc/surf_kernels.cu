@@ -116,7 +116,16 @@ static int make_frame(const SurfScene* scene, const SurfCamera* camera, const Su
 }
 
 template <int P, int MODE>
-static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaStream_t st) {
+static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaStream_t st, const BatchArgs* ba) {
+    if (ba) {
+        auto kern = k_intersect_batch<P, MODE>;
+        SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        timer_mark(0, 0, st);
+        kern<<<grid, kThreads, smem, st>>>(prm, *ba);
+        timer_mark(0, 1, st);
+        SURF_LAUNCHED("k_intersect_batch");
+        return SURF_OK;
+    }
     auto kern = k_intersect<P, MODE>;
     SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timer_mark(0, 0, st);
@@ -167,7 +176,9 @@ static int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStre
     return launch_screen<16>(prm, grid, smem, st);
 }
 
-static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st) {
+// `ba` non-null: strided batch (perspective, plane-filter modes only) - the work grid gets a scene dimension
+static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const BatchArgs* ba = nullptr) {
+    if (ba && (f.cam.proj != 0 || opt->math_mode == 3)) return fail(SURF_ERR_UNSUPPORTED, "no fused batch for this mode");
     if (f.cam.proj != 0) {
         if (opt->math_mode == 1) {       // exact-only fallback kept for cross-checking the filtered kernel
             k_intersect_generic<<<(f.n + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.pix0, f.n, f.ws.zbuf);
@@ -186,7 +197,8 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
     if (P != 2 && P != 4 && P != 8) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 2, 4 or 8");
     const int tile = kThreads * P;
-    prm.n_tiles = (f.n + tile - 1) / tile;
+    prm.tiles_per_scene = (f.n + tile - 1) / tile;
+    prm.n_tiles = prm.tiles_per_scene * (ba ? ba->n_scenes : 1);
     // stage capacity: chunk_prims disk records (2 float4 each); keep >= 4x grid items for balance on small frames
     int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
     if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
@@ -231,9 +243,9 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..3");
 #define SURF_DISPATCH(PP)                                                      \
     if (P == PP) {                                                             \
-        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st);    \
-        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st);    \
-        return launch_intersect<PP, 2>(prm, grid, smem, st);                   \
+        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st, ba); \
+        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st, ba); \
+        return launch_intersect<PP, 2>(prm, grid, smem, st, ba);                \
     }
     SURF_DISPATCH(2)
     SURF_DISPATCH(4)
@@ -527,7 +539,7 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
 }  // extern "C"
 
 namespace {
-constexpr int kBatchStreams = 4;
+constexpr int kBatchStreams = 16;
 struct StreamPool {
     int device = -1;
     cudaStream_t st[kBatchStreams] = {};
@@ -594,6 +606,193 @@ int surf_backward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCam
     return run_batch(n_scenes, (cudaStream_t)cuda_stream, [&](int b, cudaStream_t st) {
         return backward_impl(&scenes[b], &cameras[b], options, workspaces[b], workspace_bytes[b], nearest[b], depth[b],
                              &out_grads[b], &scene_grads[b], st, warm);
+    });
+}
+
+}  // extern "C"
+namespace {
+template <class T>
+inline T* advance(T* base, int64_t elems) { return base ? base + elems : nullptr; }
+
+// scene / camera / gradient structs of element b of a strided batch
+void strided_scene(const SurfScene& s0, const SurfBatchLayout& L, int64_t b, SurfScene* s) {
+    *s = s0;
+    for (int k = 0; k < s0.n_sets && k < SURF_MAX_SETS; ++k) {
+        s->sets[k].pos = advance(s0.sets[k].pos, b * L.set_pos[k]);
+        s->sets[k].normal = advance(s0.sets[k].normal, b * L.set_normal[k]);
+        s->sets[k].radius = advance(s0.sets[k].radius, b * L.set_radius[k]);
+        s->sets[k].material_idx = advance(s0.sets[k].material_idx, b * L.set_material_idx[k]);
+    }
+    s->light_pos = advance(s0.light_pos, b * L.light_pos);
+    s->light_color_idx = advance(s0.light_color_idx, b * L.light_color_idx);
+    s->light_attenuation = advance(s0.light_attenuation, b * L.light_attenuation);
+    s->ambient = advance(s0.ambient, b * L.ambient);
+    s->colors = advance(s0.colors, b * L.colors);
+    s->albedo = advance(s0.albedo, b * L.albedo);
+    s->coeffs = advance(s0.coeffs, b * L.coeffs);
+    s->gamma = advance(s0.gamma, b * L.gamma);
+}
+void strided_camera(const SurfCamera& c0, const SurfBatchLayout& L, int64_t b, SurfCamera* c) {
+    *c = c0;
+    c->eye = advance(c0.eye, b * L.eye);
+    c->at = advance(c0.at, b * L.at);
+    c->up = advance(c0.up, b * L.up);
+}
+void strided_grads(const SurfSceneGrads& g0, int n_sets, const SurfBatchLayout& L, int64_t b, SurfSceneGrads* g) {
+    *g = g0;
+    for (int k = 0; k < n_sets && k < SURF_MAX_SETS; ++k) {
+        g->sets[k].pos = advance(g0.sets[k].pos, b * L.set_pos[k]);
+        g->sets[k].normal = advance(g0.sets[k].normal, b * L.set_normal[k]);
+        g->sets[k].radius = advance(g0.sets[k].radius, b * L.set_radius[k]);
+    }
+    g->light_pos = advance(g0.light_pos, b * L.light_pos);
+    g->light_attenuation = advance(g0.light_attenuation, b * L.light_attenuation);
+    g->ambient = advance(g0.ambient, b * L.ambient);
+    g->colors = advance(g0.colors, b * L.colors);
+    g->albedo = advance(g0.albedo, b * L.albedo);
+    g->coeffs = advance(g0.coeffs, b * L.coeffs);
+    g->gamma = advance(g0.gamma, b * L.gamma);
+}
+int64_t frame_pixels(const SurfCamera& c, const SurfOptions& o) {
+    return (o.pixel_begin == 0 && o.pixel_end == 0) ? (int64_t)c.width * c.height : (int64_t)o.pixel_end - o.pixel_begin;
+}
+BatchArgs batch_args(const SurfBatchLayout& L, int n_scenes, size_t ws_stride) {
+    BatchArgs ba;
+    ba.n_scenes = n_scenes;
+    ba.ws_stride = (long long)ws_stride;
+    for (int k = 0; k < kMaxSets; ++k) {
+        ba.set_pos[k] = L.set_pos[k]; ba.set_normal[k] = L.set_normal[k];
+        ba.set_radius[k] = L.set_radius[k]; ba.set_mat[k] = L.set_material_idx[k];
+    }
+    ba.light_pos = L.light_pos; ba.light_color_idx = L.light_color_idx; ba.light_atten = L.light_attenuation;
+    ba.ambient = L.ambient; ba.colors = L.colors; ba.albedo = L.albedo; ba.coeffs = L.coeffs; ba.gamma = L.gamma;
+    ba.eye = L.eye; ba.at = L.at; ba.up = L.up;
+    return ba;
+}
+
+// the fused batch kernels cover the GAN case: perspective, no shadow rays, ray-plane filter modes
+bool fused_batch_ok(const SurfCamera& c, const SurfOptions& o, int n_scenes) {
+    return c.proj == 0 && !o.shadow && o.math_mode != 3 && n_scenes <= 65535;
+}
+
+// Whole batch in FIVE launches: every kernel gets a scene dimension (blockIdx.y; k_intersect_batch: the work item).
+int forward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfBatchLayout* layout,
+                          const SurfOptions* opt, void* workspace, size_t ws_stride, const SurfOutputs* out0, cudaStream_t st) {
+    Frame f;
+    int rc = make_frame(scene0, camera0, opt, workspace, ws_stride, &f);
+    if (rc) return rc;
+    const BatchArgs ba = batch_args(*layout, n_scenes, ws_stride);
+    const unsigned B = (unsigned)n_scenes;
+    k_setup_batch<<<B, 32, 0, st>>>(f.cam, ba, f.ws.cam);
+    SURF_LAUNCHED("k_setup_batch");
+    k_raygen_batch<<<dim3((f.n + 255) / 256, B), 256, 0, st>>>(f.ws.cam, ba, f.pix0, f.n, f.ws.rays, out0->ray_dir,
+                                                              3LL * f.n, f.ws.zbuf);
+    SURF_LAUNCHED("k_raygen_batch");
+    k_prep_batch<<<dim3((f.sc.total + 255) / 256, B), 256, 0, st>>>(f.sc, ba, f.ws.cam, f.ws.packed);
+    SURF_LAUNCHED("k_prep_batch");
+    if ((rc = run_intersect(f, opt, st, &ba))) return rc;
+    ShadeParams sh;
+    sh.sc = f.sc; sh.cam = f.ws.cam; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf; sh.vis = nullptr;
+    sh.pix0 = f.pix0; sh.n = f.n; sh.fl = f.fl;
+    sh.image = out0->image; sh.depth = out0->depth; sh.normal = out0->normal; sh.pos = out0->pos;
+    sh.nearest = (long long*)out0->nearest;
+    timer_mark(1, 0, st);
+    k_shade_batch<<<dim3((f.n + 255) / 256, B), 256, 0, st>>>(sh, ba);
+    timer_mark(1, 1, st);
+    SURF_LAUNCHED("k_shade_batch");
+    return SURF_OK;
+}
+
+int backward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfBatchLayout* layout,
+                           const SurfOptions* opt, void* workspace, size_t ws_stride, const int64_t* nearest0,
+                           const float* depth0, const SurfOutGrads* og, const SurfSceneGrads* sg, cudaStream_t st, bool warm) {
+    Frame f;
+    int rc = make_frame(scene0, camera0, opt, workspace, ws_stride, &f);
+    if (rc) return rc;
+    const SlotMap sm = slot_map(f.sc.n_materials, f.sc.n_lights, f.sc.n_colors);
+    if (sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the backward accumulators");
+    const BatchArgs ba = batch_args(*layout, n_scenes, ws_stride);
+    const unsigned B = (unsigned)n_scenes;
+    if (!warm) {
+        k_setup_batch<<<B, 32, 0, st>>>(f.cam, ba, f.ws.cam);
+        SURF_LAUNCHED("k_setup_batch");
+        k_raygen_batch<<<dim3((f.n + 255) / 256, B), 256, 0, st>>>(f.ws.cam, ba, f.pix0, f.n, f.ws.rays, nullptr, 0, f.ws.zbuf);
+        SURF_LAUNCHED("k_raygen_batch");
+    }
+    // the accumulators of all scenes sit at the same offsets of their workspaces: two strided memsets
+    SURF_CUDA(cudaMemset2DAsync(f.ws.acc, ws_stride, 0, sizeof(double) * kMaxAccSlots, B, st));
+    SURF_CUDA(cudaMemset2DAsync(f.ws.prim_acc, ws_stride, 0, sizeof(double) * 7 * (size_t)f.sc.total, B, st));
+    BackwardParams bp;
+    bp.sc = f.sc; bp.cam = f.ws.cam; bp.rays = f.ws.rays; bp.vis = nullptr;
+    bp.nearest = (const long long*)nearest0; bp.depth = depth0;
+    bp.g_image = og->image; bp.g_depth = og->depth; bp.g_normal = og->normal; bp.g_pos = og->pos;
+    bp.pix0 = f.pix0; bp.n = f.n; bp.fl = f.fl; bp.sm = sm; bp.acc = f.ws.acc; bp.prim_acc = f.ws.prim_acc;
+    for (int s = 0; s < kMaxSets; ++s) {
+        bp.gp.prim_pos[s] = sg->sets[s].pos; bp.gp.prim_normal[s] = sg->sets[s].normal; bp.gp.prim_radius[s] = sg->sets[s].radius;
+    }
+    bp.gp.light_pos = sg->light_pos; bp.gp.atten = sg->light_attenuation; bp.gp.ambient = sg->ambient;
+    bp.gp.colors = sg->colors; bp.gp.albedo = sg->albedo; bp.gp.coeffs = sg->coeffs; bp.gp.gamma = sg->gamma;
+    const int gx = std::max(1, std::min((f.n + 127) / 128, (sm_count() * 8 + n_scenes - 1) / n_scenes));
+    timer_mark(2, 0, st);
+    k_backward_batch<<<dim3(gx, B), 128, 0, st>>>(bp, ba);
+    timer_mark(2, 1, st);
+    SURF_LAUNCHED("k_backward_batch");
+    FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
+                      f.sc, f.ws.prim_acc};
+    k_backward_finalize_batch<<<dim3((f.sc.total + sm.total + 127) / 128, B), 128, 0, st>>>(fp, ba);
+    SURF_LAUNCHED("k_backward_finalize_batch");
+    return SURF_OK;
+}
+}  // namespace
+extern "C" {
+
+int surf_forward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                         const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
+                         size_t workspace_bytes_per_scene, const SurfOutputs* out0, void* cuda_stream) {
+    g_launches = 0;
+    if (!scene0 || !camera0 || !layout || !options || !workspace || !out0) return fail(SURF_ERR_BAD_ARG, "null batch argument");
+    if (workspace_bytes_per_scene % 256) return fail(SURF_ERR_BAD_ARG, "workspace_bytes_per_scene must be a multiple of 256");
+    if (n_scenes < 1) return fail(SURF_ERR_BAD_ARG, "empty batch");
+    if (fused_batch_ok(*camera0, *options, n_scenes))
+        return forward_strided_fused(n_scenes, scene0, camera0, layout, options, workspace, workspace_bytes_per_scene, out0,
+                                     (cudaStream_t)cuda_stream);
+    const int64_t n = frame_pixels(*camera0, *options);
+    const int64_t rd = camera0->proj == 0 ? 3 * n : 3;
+    return run_batch(n_scenes, (cudaStream_t)cuda_stream, [&](int b, cudaStream_t st) {
+        SurfScene s; SurfCamera c; SurfOutputs o;
+        strided_scene(*scene0, *layout, b, &s);
+        strided_camera(*camera0, *layout, b, &c);
+        o.image = advance(out0->image, b * n * 3); o.depth = advance(out0->depth, b * n);
+        o.normal = advance(out0->normal, b * n * 3); o.pos = advance(out0->pos, b * n * 3);
+        o.nearest = advance(out0->nearest, b * n); o.ray_dir = advance(out0->ray_dir, b * rd);
+        return forward_impl(&s, &c, options, (char*)workspace + (size_t)b * workspace_bytes_per_scene,
+                            workspace_bytes_per_scene, &o, st);
+    });
+}
+
+int surf_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                          const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
+                          size_t workspace_bytes_per_scene, const int64_t* nearest0, const float* depth0,
+                          const SurfOutGrads* out_grads0, const SurfSceneGrads* grads0, void* cuda_stream) {
+    g_launches = 0;
+    if (!scene0 || !camera0 || !layout || !options || !workspace || !nearest0 || !depth0 || !out_grads0 || !grads0)
+        return fail(SURF_ERR_BAD_ARG, "null batch argument");
+    if (workspace_bytes_per_scene % 256) return fail(SURF_ERR_BAD_ARG, "workspace_bytes_per_scene must be a multiple of 256");
+    if (n_scenes < 1) return fail(SURF_ERR_BAD_ARG, "empty batch");
+    const bool warm = options->forced_nearest == 2;
+    if (fused_batch_ok(*camera0, *options, n_scenes))
+        return backward_strided_fused(n_scenes, scene0, camera0, layout, options, workspace, workspace_bytes_per_scene,
+                                      nearest0, depth0, out_grads0, grads0, (cudaStream_t)cuda_stream, warm);
+    const int64_t n = frame_pixels(*camera0, *options);
+    return run_batch(n_scenes, (cudaStream_t)cuda_stream, [&](int b, cudaStream_t st) {
+        SurfScene s; SurfCamera c; SurfOutGrads og; SurfSceneGrads sg;
+        strided_scene(*scene0, *layout, b, &s);
+        strided_camera(*camera0, *layout, b, &c);
+        strided_grads(*grads0, scene0->n_sets, *layout, b, &sg);
+        og.image = advance(out_grads0->image, b * n * 3); og.depth = advance(out_grads0->depth, b * n);
+        og.normal = advance(out_grads0->normal, b * n * 3); og.pos = advance(out_grads0->pos, b * n * 3);
+        return backward_impl(&s, &c, options, (char*)workspace + (size_t)b * workspace_bytes_per_scene,
+                             workspace_bytes_per_scene, nearest0 + b * n, depth0 + b * n, &og, &sg, st, warm);
     });
 }
 

@@ -37,9 +37,32 @@ __device__ __forceinline__ void store3(float* __restrict__ dst, float (*sm)[3], 
     for (int j = tid; j < lim; j += 256) dst[(size_t)base * 3 + j] = flat[j];
 }
 
+__device__ __forceinline__ void shade_body(const ShadeParams& p, float (*sm)[3], int block);
+
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ShadeParams p) {
     __shared__ float sm[256][3];
-    const int base = blockIdx.x * 256;
+    shade_body(p, sm, blockIdx.x);
+}
+
+// strided batch: blockIdx.y = scene; outputs are [B, n, ...]
+__global__ void __launch_bounds__(256) k_shade_batch(const __grid_constant__ ShadeParams p0, const __grid_constant__ BatchArgs ba) {
+    __shared__ float sm[256][3];
+    __shared__ ShadeParams p;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        p = p0;
+        scene_at(&p.sc, ba, b);
+        p.cam = ws_at(p0.cam, ba, b); p.rays = ws_at(p0.rays, ba, b); p.zbuf = ws_at(p0.zbuf, ba, b);
+        const long long n = p0.n;
+        p.image = adv(p0.image, b * n * 3); p.depth = adv(p0.depth, b * n); p.normal = adv(p0.normal, b * n * 3);
+        p.pos = adv(p0.pos, b * n * 3); p.nearest = adv(p0.nearest, b * n);
+    }
+    __syncthreads();
+    shade_body(p, sm, blockIdx.x);
+}
+
+__device__ __forceinline__ void shade_body(const ShadeParams& p, float (*sm)[3], int block) {
+    const int base = block * 256;
     const int k = base + threadIdx.x;
     const bool live = k < p.n;
     PixelOut po;

@@ -38,6 +38,8 @@ def _as_int_tensor(v, device):
     """index arrays may arrive as long or float tensors, lists or numpy arrays (renderer.py:128,284).  The int32
     device copy of a tensor is cached until the tensor is modified in place or collected."""
     if isinstance(v, torch.Tensor):
+        if v.dtype == torch.int32 and v.device == device and v.is_contiguous():
+            return v                        # already in the library's format (e.g. a slice of a marshalled batch)
         key = (id(v), v._version, str(device))
         hit = _INT_CACHE.get(key)
         if hit is not None and hit[0]() is v:
@@ -201,6 +203,122 @@ class Marshalled:
         sg.light_pos, sg.light_attenuation, sg.ambient = ptr(self.i_light_pos), ptr(self.i_atten), ptr(self.i_ambient)
         sg.colors, sg.albedo, sg.coeffs, sg.gamma = ptr(self.i_colors), ptr(self.i_albedo), ptr(self.i_coeffs), ptr(self.i_gamma)
         return sg
+
+
+class MarshalledBatch:
+    """Strided batch (include/surf_b200.h, SurfBatchLayout): ONE scene dict in which any tensor may carry a leading
+    batch dimension B - splat positions [B,M,3], camera eyes [B,4], ... - and everything else is shared by all B
+    scenes.  `m` is the Marshalled view of scene 0 (validation, slot order, base pointers); `fulls` are the whole
+    (batched or shared) float tensors aligned with `m.floats`; `strides` their per-scene element strides."""
+
+    _NDIM = {'pos': 2, 'normal': 2, 'radius': 1, 'face': 3}
+
+    def __init__(self, scene, device):
+        device = torch.device(device)
+        self.batch = None
+        owners = {}                       # id(scene-0 view) -> (full tensor, stride)
+
+        def split(v, base_ndim, as_int=False):
+            full = _as_int_tensor(v, device) if as_int else _as_float_tensor(v, device)
+            if full.dim() == base_ndim + 1:
+                if self.batch is None:
+                    self.batch = int(full.shape[0])
+                elif int(full.shape[0]) != self.batch:
+                    raise ValueError('batched scene: leading dimensions %d and %d disagree' % (self.batch, full.shape[0]))
+                view, stride = full[0], int(full.stride(0))
+            elif full.dim() == base_ndim or (base_ndim == 1 and full.dim() == 0):
+                view, stride = full, 0
+            else:
+                raise ValueError('batched scene: unexpected tensor rank %d (expected %d or %d)' % (full.dim(), base_ndim, base_ndim + 1))
+            owners[id(view)] = (full, stride, view)
+            return view
+
+        s0 = {'objects': {}}
+        self.int_strides = {}
+        for kind, prim in scene['objects'].items():
+            if kind not in PRIM_FIELDS:
+                raise KeyError(kind)
+            o = {f: split(prim[f], self._NDIM[f]) for f in PRIM_FIELDS[kind]}
+            o['material_idx'] = split(prim['material_idx'], 1, as_int=True)
+            self.int_strides['objects/%s/material_idx' % kind] = owners[id(o['material_idx'])][1]
+            s0['objects'][kind] = o
+        lights = scene['lights']
+        s0['lights'] = {'pos': split(lights['pos'], 2), 'attenuation': split(lights['attenuation'], 2),
+                        'ambient': split(lights['ambient'], 1), 'color_idx': split(lights['color_idx'], 1, as_int=True)}
+        self.int_strides['lights/color_idx'] = owners[id(s0['lights']['color_idx'])][1]
+        s0['colors'] = split(scene['colors'], 2)
+        s0['materials'] = {'albedo': split(scene['materials']['albedo'], 2), 'coeffs': split(scene['materials']['coeffs'], 2)}
+        if 'tonemap' in scene:
+            tm = scene['tonemap']
+            g = tm['gamma'] if isinstance(tm['gamma'], torch.Tensor) else [float(tm['gamma'])]
+            s0['tonemap'] = {'type': tm['type'], 'gamma': split(g, 1)}
+        cam = dict(scene['camera'])
+        self.cam_strides = {}
+        for k in ('eye', 'at', 'up'):
+            cam[k] = split(cam[k], 1)
+            self.cam_strides[k] = owners[id(cam[k])][1]
+        s0['camera'] = cam
+        if self.batch is None:
+            raise ValueError('batched scene: no tensor carries a batch dimension')
+        self.m = Marshalled(s0, device)
+        for k in ('eye', 'at', 'up'):         # Marshalled re-slices the camera vectors; they must still alias the batch
+            if self.m.cam_vecs[k].data_ptr() != cam[k].data_ptr():
+                raise AssertionError('camera vector was copied while marshalling')
+        self.fulls, self.strides = [], []
+        for t in self.m.floats:
+            full, stride, _ = owners[id(t)]
+            self.fulls.append(full)
+            self.strides.append(stride)
+
+    def views0(self, fulls):
+        """scene-0 views of the (autograd-unpacked) full tensors, for Marshalled.c_scene"""
+        return [f[0] if st else f for f, st in zip(fulls, self.strides)]
+
+    def c_layout(self):
+        lay = _abi.SurfBatchLayout()
+        m = self.m
+        for k, (kind, _count, _ps, _ns, slots) in enumerate(m.sets):
+            lay.set_pos[k] = self.strides[slots['face' if kind == 'triangle' else 'pos']]
+            if 'normal' in slots:
+                lay.set_normal[k] = self.strides[slots['normal']]
+            if 'radius' in slots:
+                lay.set_radius[k] = self.strides[slots['radius']]
+            lay.set_material_idx[k] = self.int_strides['objects/%s/material_idx' % kind]
+        lay.light_pos, lay.light_attenuation = self.strides[m.i_light_pos], self.strides[m.i_atten]
+        lay.ambient, lay.light_color_idx = self.strides[m.i_ambient], self.int_strides['lights/color_idx']
+        lay.colors, lay.albedo, lay.coeffs = self.strides[m.i_colors], self.strides[m.i_albedo], self.strides[m.i_coeffs]
+        lay.gamma = self.strides[m.i_gamma] if m.i_gamma is not None else 0
+        lay.eye, lay.at, lay.up = (self.cam_strides[k] for k in ('eye', 'at', 'up'))
+        return lay
+
+
+_BATCH_BASE_NDIM = {('objects', 'pos'): 2, ('objects', 'normal'): 2, ('objects', 'radius'): 1, ('objects', 'face'): 3,
+                    ('objects', 'material_idx'): 1, ('lights', 'pos'): 2, ('lights', 'attenuation'): 2,
+                    ('lights', 'ambient'): 1, ('lights', 'color_idx'): 1, ('colors', None): 2,
+                    ('materials', 'albedo'): 2, ('materials', 'coeffs'): 2, ('tonemap', 'gamma'): 1,
+                    ('camera', 'eye'): 1, ('camera', 'at'): 1, ('camera', 'up'): 1}
+
+
+def select_scenes(scene, index):
+    """Sub-batch of a batched scene dict (see MarshalledBatch): every tensor that carries the batch dimension is
+    indexed with `index` (a list / LongTensor / slice of scene numbers), shared tensors are passed through.  Used to
+    shard a batch over ranks (dist.shard_scenes) - the selection is differentiable like any tensor indexing."""
+    def pick(group, field, v):
+        base = _BATCH_BASE_NDIM.get((group, field))
+        if base is not None and isinstance(v, torch.Tensor) and v.dim() == base + 1:
+            return v[index]
+        return v
+    out = {}
+    for key, val in scene.items():
+        if key == 'objects':
+            out[key] = {kind: {f: pick('objects', f, v) for f, v in prim.items()} for kind, prim in val.items()}
+        elif key == 'colors':
+            out[key] = pick('colors', None, val)
+        elif isinstance(val, dict):
+            out[key] = {f: pick(key, f, v) for f, v in val.items()}
+        else:
+            out[key] = val
+    return out
 
 
 # process-wide default of the intersection-kernel variant (SurfOptions.math_mode); a call's `_math_mode` kwarg wins.

@@ -11,11 +11,12 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _abi
 from ._lib import check, lib
-from .marshal import Marshalled, make_options
+from .marshal import Marshalled, MarshalledBatch, make_options
 
 
 def get_param_value(key, dict_var, default_val, required=False):
@@ -231,16 +232,163 @@ class _RenderBatchFn(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+class _RenderStridedFn(torch.autograd.Function):
+    """surf_forward_strided / surf_backward_strided: a batch held as stacked tensors, one allocation per output and
+    per gradient for the whole batch."""
+
+    @staticmethod
+    def forward(ctx, mb, params, *fulls):
+        m, B = mb.m, mb.batch
+        dev = fulls[0].device
+        opt = make_options(params)
+        npx = m.n_pixels
+        views = mb.views0(fulls)
+        ws_bytes = lib().surf_workspace_bytes(m.total_prims, npx, int(views[m.i_light_pos].shape[0]), int(opt.shadow))
+        ws_bytes = (ws_bytes + 255) // 256 * 256
+        workspace = torch.empty(B, ws_bytes, dtype=torch.uint8, device=dev)
+        image = torch.empty(B, npx, 3, device=dev)
+        depth = torch.empty(B, npx, device=dev)
+        normal = torch.empty(B, npx, 3, device=dev)
+        pos = torch.empty(B, npx, 3, device=dev)
+        nearest = torch.empty(B, npx, dtype=torch.int64, device=dev)
+        ray_dir = torch.empty(B, 3, npx if m.proj == 0 else 1, device=dev)
+        out = _abi.SurfOutputs(image.data_ptr(), depth.data_ptr(), normal.data_ptr(), pos.data_ptr(),
+                               nearest.data_ptr(), ray_dir.data_ptr())
+        sc, cam, lay = m.c_scene(views), m.c_camera(), mb.c_layout()
+        with torch.cuda.device(dev):
+            check(lib().surf_forward_strided(B, C.byref(sc), C.byref(cam), C.byref(lay), C.byref(opt),
+                                             workspace.data_ptr(), ws_bytes, C.byref(out), _stream_ptr()))
+        ctx.mb, ctx.params, ctx.workspace = mb, params, workspace
+        ctx.save_for_backward(nearest, depth, *fulls)
+        ctx.mark_non_differentiable(nearest, ray_dir)
+        return image, depth, normal, pos, nearest, ray_dir
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_normal, g_pos, _g_nearest, _g_ray):
+        saved = ctx.saved_tensors
+        nearest, depth, fulls = saved[0], saved[1], saved[2:]
+        mb = ctx.mb
+        m, B = mb.m, mb.batch
+        dev = depth.device
+        opt = make_options(ctx.params)
+        opt.forced_nearest = 2
+        grads = [torch.zeros_like(t) if ctx.needs_input_grad[2 + i] else None for i, t in enumerate(fulls)]
+        gs = [None if g is None else g.contiguous() for g in (g_image, g_depth, g_normal, g_pos)]
+        og = _abi.SurfOutGrads(*[(t.data_ptr() if t is not None else None) for t in gs])
+        sg = m.c_grads(grads)                       # base pointers; the layout strides apply to them as well
+        sc, cam, lay = m.c_scene(mb.views0(fulls)), m.c_camera(), mb.c_layout()
+        ws = ctx.workspace
+        with torch.cuda.device(dev):
+            check(lib().surf_backward_strided(B, C.byref(sc), C.byref(cam), C.byref(lay), C.byref(opt), ws.data_ptr(),
+                                              ws.shape[1], nearest.data_ptr(), depth.data_ptr(), C.byref(og),
+                                              C.byref(sg), _stream_ptr()))
+        return (None, None) + tuple(grads)
+
+
+def _render_strided(scene, params):
+    dev = _resolve_device(scene)
+    mb = MarshalledBatch(scene, dev)
+    image, depth, normal, pos, nearest, ray_dir = _RenderStridedFn.apply(mb, dict(params), *mb.fulls)
+    B, H, W = mb.batch, mb.m.height, mb.m.width
+    return {'image': image.view(B, H, W, 3), 'depth': depth.view(B, H, W), 'normal': normal.view(B, H, W, 3),
+            'pos': pos.view(B, H, W, 3), 'ray_dist': None, 'nearest': nearest.view(B, H, W), 'ray_dir': ray_dir}
+
+
+def _stack_scenes(scenes):
+    """A list of scene dicts with identical structure -> one batched scene dict (leaves that are the SAME tensor
+    object in every scene stay shared, the others are stacked, differentiably), or None when the scenes differ in
+    structure and must be rendered one by one."""
+    first = scenes[0]
+
+    def leaves(sc):
+        out = []
+        for kind, prim in sc['objects'].items():
+            for f in sorted(prim):
+                out.append(('objects', kind, f, prim[f]))
+        for f in ('pos', 'attenuation', 'ambient', 'color_idx'):
+            out.append(('lights', f, None, sc['lights'][f]))
+        out.append(('colors', None, None, sc['colors']))
+        for f in ('albedo', 'coeffs'):
+            out.append(('materials', f, None, sc['materials'][f]))
+        if 'tonemap' in sc:
+            out.append(('tonemap', 'gamma', None, sc['tonemap']['gamma']))
+        for f in ('eye', 'at', 'up'):
+            out.append(('camera', f, None, sc['camera'][f]))
+        return out
+
+    def scalars(sc):
+        cam = sc['camera']
+        vp = cam['viewport']
+        return (cam.get('proj_type'), tuple(int(x) for x in vp), float(cam['fovy']), float(cam['focal_length']),
+                float(cam['near']), float(cam['far']), tuple(sc['objects'].keys()), 'tonemap' in sc,
+                sc['tonemap']['type'] if 'tonemap' in sc else None)
+
+    try:
+        ref_leaves, ref_scalars = leaves(first), scalars(first)
+        columns = [[v] for (_, _, _, v) in ref_leaves]
+        for sc in scenes[1:]:
+            if scalars(sc) != ref_scalars:
+                return None
+            lv = leaves(sc)
+            if len(lv) != len(ref_leaves):
+                return None
+            for col, (a, b, c, v), (a0, b0, c0, v0) in zip(columns, lv, ref_leaves):
+                if (a, b, c) != (a0, b0, c0):
+                    return None
+                if v is not v0:
+                    if not isinstance(v, torch.Tensor):      # lists / numpy arrays / numbers (the demos mix them)
+                        v = torch.as_tensor(np.asarray(v))
+                    if not isinstance(col[0], torch.Tensor):
+                        col[0] = torch.as_tensor(np.asarray(col[0]))
+                    if v.shape != col[0].shape or v.dtype != col[0].dtype or v.device != col[0].device:
+                        return None
+                col.append(v)
+    except (KeyError, TypeError, ValueError):
+        return None                      # let the per-scene path raise the reference-style error
+    batched = {'objects': {k: {} for k in first['objects']}, 'lights': {}, 'materials': {}, 'camera': dict(first['camera'])}
+    for (a, b, c, v0), col in zip(ref_leaves, columns):
+        shared = all(v is v0 for v in col)
+        if not shared and col[0].dim() == 0:
+            col = [v.reshape(1) for v in col]
+        val = v0 if shared else torch.stack(col, 0)
+        if a == 'objects':
+            batched['objects'][b][c] = val
+        elif a == 'colors':
+            batched['colors'] = val
+        elif a == 'tonemap':
+            batched['tonemap'] = {'type': first['tonemap']['type'], 'gamma': val}
+        else:
+            batched[a][b] = val
+    return batched
+
+
 def render_batch(scenes, **params):
-    """Render a list of independent scenes with ONE library call per direction (the reference renders a GAN batch
-    in a Python loop of render() calls, GAN/gan.py:326-377).  Returns a list of render()-style result dicts.  A tensor
-    shared by several scenes (e.g. common lights / materials) receives the sum of its gradients, as autograd would."""
+    """Render a batch of independent scenes with ONE library call per direction (the reference renders a GAN batch
+    in a Python loop of render() calls, GAN/gan.py:326-377).
+
+    `scenes` is either
+      * a list of scene dicts -> returns a list of render()-style result dicts.  Scenes of identical structure
+        (same primitive kinds and counts, same camera scalars - the GAN case) are stacked and rendered through the
+        strided-batch entry points; otherwise each scene is marshalled on its own.  A tensor shared by several
+        scenes (e.g. common lights / materials) receives the sum of its gradients, as autograd would; or
+      * ONE scene dict whose tensors may carry a leading batch dimension B (splat positions [B,M,3], camera eyes
+        [B,4], ...; everything else shared) -> returns one dict of stacked outputs (image [B,H,W,3], depth [B,H,W],
+        normal, pos, nearest [B,H,W], ray_dir [B,3,n]).  This is the cheapest form: no per-scene host work at all."""
     if get_param_value('vis_stat', params, False):
         raise RuntimeError('Removed Support for vis_stat')
     if get_param_value('norm_depth_image_only', params, False):
         raise NotImplementedError('norm_depth_image_only is per-frame: call render() for it')
+    if isinstance(scenes, dict):
+        return _render_strided(scenes, params)
     if len(scenes) == 0:
         return []
+    stacked = _stack_scenes(scenes) if len(scenes) > 1 else None
+    if stacked is not None:
+        res = _render_strided(stacked, params)
+        cols = {k: torch.unbind(res[k], 0) for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir')}
+        return [{'image': cols['image'][b], 'depth': cols['depth'][b], 'normal': cols['normal'][b], 'pos': cols['pos'][b],
+                 'ray_dist': None, 'nearest': cols['nearest'][b], 'ray_dir': cols['ray_dir'][b]}
+                for b in range(len(scenes))]
     dev = _resolve_device(scenes[0])
     ms = [Marshalled(sc, dev) for sc in scenes]
     flat = _RenderBatchFn.apply(ms, dict(params), *[t for m in ms for t in m.floats])

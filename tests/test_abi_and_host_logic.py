@@ -56,7 +56,7 @@ def test_struct_layouts_match_c():
     """ctypes mirrors must have the C compiler's layout: check sizes against a tiny C program."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu", sizeof(SurfPrimSet), sizeof(SurfScene), sizeof(SurfCamera), sizeof(SurfOptions), sizeof(SurfOutputs), sizeof(SurfOutGrads), sizeof(SurfSceneGrads));return 0;}\n' % HEADER
+    src = '#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu", sizeof(SurfPrimSet), sizeof(SurfScene), sizeof(SurfCamera), sizeof(SurfOptions), sizeof(SurfOutputs), sizeof(SurfOutGrads), sizeof(SurfSceneGrads), sizeof(SurfBatchLayout), sizeof(SurfSplats), sizeof(SurfSplatGrads));return 0;}\n' % HEADER
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, 'a.c')
         open(c, 'w').write(src)
@@ -64,7 +64,8 @@ def test_struct_layouts_match_c():
         subprocess.check_call(['gcc', '-std=c99', c, '-o', exe])        # the header is plain C
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mine = [C.sizeof(t) for t in (_abi.SurfPrimSet, _abi.SurfScene, _abi.SurfCamera, _abi.SurfOptions,
-                                  _abi.SurfOutputs, _abi.SurfOutGrads, _abi.SurfSceneGrads)]
+                                  _abi.SurfOutputs, _abi.SurfOutGrads, _abi.SurfSceneGrads, _abi.SurfBatchLayout,
+                                  _abi.SurfSplats, _abi.SurfSplatGrads)]
     assert sizes == mine
 
 
@@ -85,6 +86,60 @@ def test_marshal_accepts_reference_style_inputs():
     assert sc.gamma is not None
     cam = m.c_camera()
     assert cam.proj == 0 and abs(cam.fovy - scene['camera']['fovy']) < 1e-12
+
+
+def test_strided_batch_marshalling():
+    """render_batch host logic: a list of same-shaped scenes stacks into one batched dict (shared objects stay
+    shared), and MarshalledBatch turns it into scene-0 pointers + per-scene element strides without copying."""
+    from surf_renderer_b200.marshal import MarshalledBatch
+    from surf_renderer_b200.renderer import _stack_scenes
+    shared_lights = torch.rand(3, 4)
+    scenes = []
+    for i in range(5):
+        sc = synth.config_d_scene(i, m=40, width=16, height=12)
+        sc['lights']['pos'] = shared_lights
+        sc['lights']['attenuation'] = sc['lights']['attenuation'][:3]
+        sc['lights']['color_idx'] = [1, 2, 3]                       # a python list, equal in every scene
+        scenes.append(sc)
+    stacked = _stack_scenes(scenes)
+    assert stacked is not None
+    assert stacked['objects']['disk']['pos'].shape == (5, 40, 3) and stacked['objects']['disk']['radius'].shape == (5, 40)
+    assert stacked['lights']['pos'] is shared_lights
+    assert stacked['camera']['eye'].shape[0] == 5 and stacked['tonemap']['gamma'].shape == (5, 1)
+    assert torch.equal(stacked['objects']['disk']['pos'][3], scenes[3]['objects']['disk']['pos'])
+
+    mb = MarshalledBatch(stacked, 'cpu')
+    assert mb.batch == 5 and mb.m.total_prims == 40 and (mb.m.width, mb.m.height) == (16, 12)
+    lay = mb.c_layout()
+    assert lay.set_pos[0] == 120 and lay.set_normal[0] == 120 and lay.set_radius[0] == 40 and lay.set_material_idx[0] == 40
+    assert lay.light_pos == 0 and lay.light_attenuation == 9 and lay.light_color_idx == 3
+    assert lay.eye == stacked['camera']['eye'].shape[1] and lay.gamma == 1
+    sc0 = mb.m.c_scene(mb.views0(mb.fulls))
+    i_pos = mb.m.sets[0][4]['pos']
+    assert sc0.sets[0].pos == mb.fulls[i_pos].data_ptr() and sc0.n_lights == 3
+    assert mb.m.c_camera().eye == mb.m.cam_vecs['eye'].data_ptr()
+
+    # sub-batches (scenes over ranks, dist.shard_scenes): batched leaves are indexed, shared ones passed through
+    from surf_renderer_b200 import select_scenes
+    from surf_renderer_b200.dist import shard_scenes
+    idx = shard_scenes(5, 1, 2)
+    part = select_scenes(stacked, idx)
+    assert part['objects']['disk']['pos'].shape == (2, 40, 3) and part['lights']['pos'] is shared_lights
+    assert torch.equal(part['camera']['eye'][1], stacked['camera']['eye'][3])
+    assert part['camera']['viewport'] == stacked['camera']['viewport']
+    assert MarshalledBatch(part, 'cpu').batch == 2
+
+    # different primitive counts, a different viewport or a different kind order cannot be stacked
+    odd = synth.config_d_scene(9, m=41, width=16, height=12)
+    assert _stack_scenes(scenes + [odd]) is None
+    wide = synth.config_d_scene(9, m=40, width=20, height=12)
+    assert _stack_scenes(scenes + [wide]) is None
+    with pytest.raises(ValueError):
+        MarshalledBatch(synth.config_d_scene(0, m=40, width=16, height=12), 'cpu')     # nothing batched
+    bad = dict(stacked)
+    bad['colors'] = torch.rand(4, 3, 3)
+    with pytest.raises(ValueError):
+        MarshalledBatch(bad, 'cpu')                                                      # 4 != 5
 
 
 def test_marshal_errors_mirror_reference():

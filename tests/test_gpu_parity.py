@@ -491,6 +491,73 @@ def test_render_batch_equals_per_scene_render():
     assert surf_renderer_b200.render_batch([]) == []
 
 
+def test_render_batch_of_differently_shaped_scenes_falls_back_to_per_scene_marshalling():
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    from surf_renderer_b200.renderer import _stack_scenes
+    scenes = [scene_io.clone_scene(synth.config_d_scene(i, m=300 + 50 * i, width=40, height=32), device='cuda',
+                                   requires_grad=True) for i in range(4)]
+    scenes.append(scene_io.clone_scene(synth.random_mixed_scene(3, width=40, height=32, n_disk=30, n_tri=20, n_sphere=3),
+                                       device='cuda', requires_grad=True))
+    assert _stack_scenes(scenes) is None
+    twins = [scene_io.clone_scene(sc, device='cuda', requires_grad=True) for sc in scenes]
+    batch = surf_renderer_b200.render_batch(scenes, double_sided=True)
+    loop = [surf_renderer_b200.render(sc, double_sided=True) for sc in twins]
+    for ra, rb in zip(batch, loop):
+        for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+            assert torch.equal(ra[k], rb[k]), k
+    sum(r['image'].sum() for r in batch).backward()
+    sum(r['image'].sum() for r in loop).backward()
+    for sa, sb in zip(scenes, twins):
+        ga, gb = scene_io.grad_leaves(sa), scene_io.grad_leaves(sb)
+        for name in ga:
+            if gb[name].grad is not None:
+                assert torch.allclose(ga[name].grad, gb[name].grad, rtol=1e-4, atol=1e-6), name
+
+
+def test_render_batch_of_stacked_tensors():
+    """One scene dict with batched leaves (positions [B,M,3], normals, camera eyes [B,4]) and shared lights /
+    materials == a loop of render() over its slices: same bits forward, same gradients, shared leaves summed."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    B = 7
+    parts = [synth.config_d_scene(i, m=600, width=56, height=40) for i in range(B)]
+    base = scene_io.clone_scene(parts[0], device='cuda')
+
+    def leaf(t):
+        return t.detach().clone().cuda().requires_grad_(True)
+    pos = leaf(torch.stack([p['objects']['disk']['pos'] for p in parts]))
+    nrm = leaf(torch.stack([p['objects']['disk']['normal'] for p in parts]))
+    eye = torch.stack([torch.as_tensor(p['camera']['eye'], dtype=torch.float32) for p in parts]).cuda()
+    lights, albedo = leaf(base['lights']['pos']), leaf(base['materials']['albedo'])
+    batched = scene_io.clone_scene(parts[0], device='cuda')
+    batched['objects']['disk']['pos'], batched['objects']['disk']['normal'] = pos, nrm
+    batched['camera']['eye'] = eye
+    batched['lights']['pos'], batched['materials']['albedo'] = lights, albedo
+    res = surf_renderer_b200.render_batch(batched, double_sided=True)
+    assert res['image'].shape == (B, 40, 56, 3) and res['nearest'].shape == (B, 40, 56) and res['ray_dir'].shape == (B, 3, 40 * 56)
+    w = torch.linspace(0.5, 1.5, B, device='cuda')
+    ((res['image'] * w[:, None, None, None]).sum() + res['depth'].clamp(max=50).sum() + res['pos'].sum()).backward()
+
+    pos2, nrm2, lights2, albedo2 = leaf(pos), leaf(nrm), leaf(lights), leaf(albedo)
+    total = 0
+    for b in range(B):
+        sc = scene_io.clone_scene(parts[0], device='cuda')
+        sc['objects']['disk']['pos'], sc['objects']['disk']['normal'] = pos2[b], nrm2[b]
+        sc['camera']['eye'] = eye[b]
+        sc['lights']['pos'], sc['materials']['albedo'] = lights2, albedo2
+        r = surf_renderer_b200.render(sc, double_sided=True)
+        for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+            assert torch.equal(r[k], res[k][b]), (k, b)
+        assert torch.equal(r['ray_dir'], res['ray_dir'][b])
+        total = total + (r['image'] * w[b]).sum() + r['depth'].clamp(max=50).sum() + r['pos'].sum()
+    total.backward()
+    assert torch.allclose(pos.grad, pos2.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(nrm.grad, nrm2.grad, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(lights.grad, lights2.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(albedo.grad, albedo2.grad, rtol=1e-4, atol=1e-4)
+
+
 def _camera_basis(cam):
     eye, at, up = (cam[k][:3].double().cpu() for k in ('eye', 'at', 'up'))
     z = (eye - at) / (eye - at).norm()

@@ -65,10 +65,23 @@ def batch_fb():
     sum(r['image'].sum() for r in rs).backward()
 
 
+from surf_renderer_b200.renderer import _stack_scenes
+stacked = _stack_scenes([scene_io.clone_scene(synth.config_d_scene(i), device='cuda') for i in range(64)])
+for f in ('pos', 'normal'):
+    stacked['objects']['disk'][f].requires_grad_(True)
+
+
+def stacked_fb():
+    surf_renderer_b200.render_batch(stacked, double_sided=True)['image'].sum().backward()
+
+
 t_loop = timed(loop_fb, reps=3, warm=1)
 t_batch = timed(batch_fb, reps=3, warm=1)
+t_stacked = timed(stacked_fb, reps=5, warm=2)
 tests = 64 * 5000 * 128 * 128
-out['config_d_64x5000_128'] = {'loop_fwd_bwd_ms': t_loop, 'batch_fwd_bwd_ms': t_batch, 'batch_tests_per_s': tests / (t_batch * 1e-3)}
+out['config_d_64x5000_128'] = {'loop_fwd_bwd_ms': t_loop, 'batch_list_fwd_bwd_ms': t_batch, 'batch_stacked_fwd_bwd_ms': t_stacked,
+                               'stacked_tests_per_s': tests / (t_stacked * 1e-3),
+                               'note': 'loop/list: every float leaf of every scene requires grad; stacked: pos + normal'}
 print('config_d', out['config_d_64x5000_128'], flush=True)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bench_extras.json'), 'w'), indent=1)
