@@ -6,7 +6,9 @@ row-major pixel bands with replicated scene inputs and no halo:
   * tiles over GPUs  - rank r renders flat pixels [r*N/G, (r+1)*N/G) against all primitives; the output bands
     are all-gathered, and after backward the partial scene gradients are summed with ONE all-reduce over a
     single packed fp32 buffer.  No collective sits inside the intersection kernel's data path.
-  * scenes over GPUs - a batch of independent scenes is split round-robin; outputs are all-gathered.
+  * scenes over GPUs - a batch of independent scenes is split over ranks (render_batch_sharded: contiguous blocks of
+    a stacked batch; shard_scenes / gather_scene_outputs: round-robin helpers for lists); outputs are all-gathered,
+    gradients of parameters shared by all scenes are all-reduced.
 
 The collectives are plain torch.distributed calls (payloads are a few MB; latency-bound).  The render function is
 injectable so the host-side logic is testable on CPU with gloo (tests use the oracle as the stand-in).
@@ -75,6 +77,31 @@ def render_bands(scene, render_flat_fn=None, group=None, gather=('image', 'depth
             out[k] = full.view(*shapes[k])
         else:
             out[k] = v
+    return out
+
+
+def render_batch_sharded(scene, render_batch_fn=None, group=None, gather=('image', 'depth', 'nearest'), **params):
+    """Scenes-over-GPUs render of a batched scene dict (render_batch's stacked form; BASELINE config D: 64 scenes
+    over 8 GPUs).  Rank r renders the contiguous block band_range(B, r, world) of scenes; the outputs named in
+    `gather` come back as full [B, H, W, ...] tensors on every rank (one all_gather each), the others hold this
+    rank's block.  Differentiable like render_bands: each rank back-propagates through its own block; gradients of
+    tensors shared by all scenes are partial per rank - sum them with allreduce_gradients()."""
+    from .marshal import batched_scene_size, select_scenes
+    if render_batch_fn is None:
+        from .renderer import render_batch as render_batch_fn
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = batched_scene_size(scene)
+    if B is None:
+        raise ValueError('render_batch_sharded needs a batched scene dict')
+    if B < world:
+        raise ValueError('fewer scenes (%d) than ranks (%d)' % (B, world))
+    b0, b1 = band_range(B, rank, world)
+    res = render_batch_fn(select_scenes(scene, slice(b0, b1)), **params)
+    sizes = [band_range(B, r, world)[1] - band_range(B, r, world)[0] for r in range(world)]
+    out = {'block': (b0, b1), 'ray_dist': None}
+    for k, v in res.items():
+        out[k] = _GatherBands.apply(v, sizes, rank, group) if (k in gather and v is not None) else v
     return out
 
 

@@ -299,6 +299,27 @@ _BATCH_BASE_NDIM = {('objects', 'pos'): 2, ('objects', 'normal'): 2, ('objects',
                     ('camera', 'eye'): 1, ('camera', 'at'): 1, ('camera', 'up'): 1}
 
 
+def batched_scene_size(scene):
+    """Batch size B of a batched scene dict (the leading dimension of its batched tensors); None if nothing is batched."""
+    def walk(group, d):
+        for f, v in d.items():
+            base = _BATCH_BASE_NDIM.get((group, f))
+            if base is not None and isinstance(v, torch.Tensor) and v.dim() == base + 1:
+                return int(v.shape[0])
+        return None
+    for kind, prim in scene['objects'].items():
+        b = walk('objects', prim)
+        if b is not None:
+            return b
+    for group in ('camera', 'lights', 'materials', 'tonemap'):
+        if group in scene:
+            b = walk(group, scene[group])
+            if b is not None:
+                return b
+    v = scene.get('colors')
+    return int(v.shape[0]) if isinstance(v, torch.Tensor) and v.dim() == 3 else None
+
+
 def select_scenes(scene, index):
     """Sub-batch of a batched scene dict (see MarshalledBatch): every tensor that carries the batch dimension is
     indexed with `index` (a list / LongTensor / slice of scene numbers), shared tensors are passed through.  Used to

@@ -23,6 +23,46 @@ def _oracle_render_flat(scene, pixel_range, **params):
             res['nearest'].reshape(n), res['ray_dir']), (H, W)
 
 
+def _oracle_render_batch(scene, **params):
+    """stand-in for render_batch(stacked dict): the oracle, scene by scene"""
+    from oracle import torch_oracle
+    from surf_renderer_b200.marshal import batched_scene_size, select_scenes
+    rs = [torch_oracle.render(select_scenes(scene, b), **params) for b in range(batched_scene_size(scene))]
+    return {k: torch.stack([r[k] for r in rs]) for k in ('image', 'depth', 'normal', 'pos', 'nearest')}
+
+
+def _check_scene_sharding(rank, world):
+    """scenes over ranks (config D): 5 stacked scenes on 2 ranks (blocks of 3 and 2), shared lights"""
+    from surf_renderer_b200 import dist as sdist, scenes as synth
+    from surf_renderer_b200.renderer import _stack_scenes
+
+    def build():
+        lights = torch.tensor([[2., 3., 4., 1.], [-3., 1., 5., 1.]], requires_grad=True)
+        parts = []
+        for i in range(5):
+            sc = synth.config_d_scene(i, m=60, width=12, height=10, radius=0.12)
+            sc['lights'] = {'pos': lights, 'color_idx': sc['lights']['color_idx'][:2],
+                            'attenuation': sc['lights']['attenuation'][:2], 'ambient': sc['lights']['ambient']}
+            parts.append(sc)
+        st = _stack_scenes(parts)
+        st['objects']['disk']['pos'] = st['objects']['disk']['pos'].detach().requires_grad_(True)
+        return st, lights
+    w = torch.rand(5, 10, 12, 3, generator=torch.Generator().manual_seed(3))
+    st, lights = build()
+    res = sdist.render_batch_sharded(st, render_batch_fn=_oracle_render_batch, double_sided=True)
+    (res['image'] * w).sum().backward()
+    sdist.allreduce_gradients([st['objects']['disk']['pos'], lights])
+    st1, lights1 = build()
+    ref = _oracle_render_batch(st1, double_sided=True)
+    (ref['image'] * w).sum().backward()
+    b0, b1 = res['block']
+    ok = res['image'].shape == (5, 10, 12, 3) and torch.equal(res['image'], ref['image'])
+    ok = ok and torch.equal(res['nearest'], ref['nearest']) and res['pos'].shape[0] == b1 - b0
+    ok = ok and torch.allclose(st['objects']['disk']['pos'].grad, st1['objects']['disk']['pos'].grad, rtol=1e-4, atol=1e-7)
+    ok = ok and torch.allclose(lights.grad, lights1.grad, rtol=1e-4, atol=1e-6)
+    return bool(ok)
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -58,6 +98,7 @@ def _worker(rank, world, port, tmp):
     stack = torch.tensor([[float(i)] for i in mine])
     full = sdist.gather_scene_outputs(stack, 5)
     ok = ok and torch.equal(full.reshape(-1), torch.arange(5.0)) and nbytes > 0
+    ok = ok and _check_scene_sharding(rank, world)
     open(os.path.join(tmp, 'ok%d' % rank), 'w').write('1' if ok else '0')
     dist.destroy_process_group()
 
