@@ -560,6 +560,11 @@ def render_along_ray(scene, **params):
         H *= samples
         W *= samples
     depth = lp_norm(pos_cc[..., :3]).view(H, W)
+    if params.get('norm_depth_image_only', False):                       # renderer.py:677-686
+        lo = torch.min(depth)
+        norm = blend(depth >= camera['far'], lo, depth)
+        norm = (norm - lo) / (torch.max(depth) - lo)
+        return {'image': norm, 'depth': depth, 'pos': pos_cc, 'normal': normals_cc}
     lights = scene['lights']
     light_rgb = scene['colors'][lights['color_idx']]
     light_cc = torch.mm(lights['pos'], mcam.transpose(1, 0))

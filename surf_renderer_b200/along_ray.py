@@ -245,10 +245,18 @@ def build_inputs(scene, params, device):
 
 def render_splats_along_ray(scene, **params):
     """Reference: diffrend/torch/renderer.py:537 ``render_splats_along_ray(scene, **params)``."""
-    if get_param_value('norm_depth_image_only', params, False):
-        raise NotImplementedError('norm_depth_image_only is not built for the along-ray renderer')
     dev = _resolve_device(scene)
     inp = build_inputs(scene, params, dev)
     image, depth, pos, normal = _AlongRayFn.apply(inp, dict(params), *inp.floats)
     H, W = inp.height, inp.width
+    if get_param_value('norm_depth_image_only', params, False):
+        # renderer.py:677-686: depth normalised to [0, 1], fragments at or beyond `far` mapped to the minimum; `pos`
+        # and `normal` are returned flat ([N,3]) like the reference's pos_CC / normals_CC.  Same arithmetic as `where`
+        # (utils.py:58-60): blend, subtract, divide.
+        im_depth = depth.view(H, W)
+        min_depth = torch.min(im_depth)
+        is_far = (im_depth >= float(_scalar(scene['camera'].get('far', 1000.0)))).float()
+        norm = is_far * min_depth + (1 - is_far) * im_depth
+        norm = (norm - min_depth) / (torch.max(im_depth) - min_depth)
+        return {'image': norm, 'depth': im_depth, 'pos': pos, 'normal': normal}
     return {'image': image.view(H, W, 3), 'depth': depth.view(H, W), 'pos': pos.view(H, W, 3), 'normal': normal.view(H, W, 3)}

@@ -85,11 +85,22 @@ def test_emulated_along_ray_matches_reference_golden(name):
     parity.compare_grads(g, grads)
 
 
-def test_along_ray_unsupported_options_raise():
+@pytest.mark.gpu
+def test_gpu_along_ray_norm_depth_image_only():
+    """renderer.py:677-686: normalised depth image; fragments at or beyond `far` take the minimum."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_golden_along_ray_scene import along_ray_scene
     import surf_renderer_b200
-    scene, params, outs, grads, extra = _load('ar_basic_32x24')
-    with pytest.raises(NotImplementedError):
-        surf_renderer_b200.render_splats_along_ray(scene, norm_depth_image_only=True)
+    from oracle import torch_oracle
+    scene = along_ray_scene(13, 26, 18)
+    scene['camera']['far'] = 4.0
+    ref = torch_oracle.render_along_ray(scene_io.clone_scene(scene), norm_depth_image_only=True)
+    res = surf_renderer_b200.render_splats_along_ray(scene_io.clone_scene(scene, device='cuda'), norm_depth_image_only=True)
+    assert res['image'].shape == (18, 26) and res['pos'].shape == (26 * 18, 3)
+    for k in ('image', 'depth', 'pos', 'normal'):
+        a, b = res[k].cpu().double(), ref[k][..., :3].double() if k in ('pos', 'normal') else ref[k].double()
+        assert torch.allclose(a, b, rtol=parity.RTOL, atol=parity.ATOL), k
 
 
 @pytest.mark.gpu

@@ -107,3 +107,20 @@ def test_oracle_norm_depth_image_only_matches_live_reference():
     a = ref_render(scene_io.clone_scene(scene), tiled=False, norm_depth_image_only=True, double_sided=True)
     b = torch_oracle.render(scene_io.clone_scene(scene), tiled=False, norm_depth_image_only=True, double_sided=True)
     assert torch.equal(a['image'], b['image']) and torch.equal(a['depth'], b['depth']) and torch.equal(a['nearest'], b['nearest'])
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='reference tree not present')
+def test_oracle_along_ray_norm_depth_matches_live_reference():
+    """renderer.py:677-686, the depth-only branch of render_splats_along_ray."""
+    import sys
+    sys.path.insert(0, '/root/reference')
+    sys.path.insert(0, GOLDEN_DIR)
+    from diffrend.torch.renderer import render_splats_along_ray as ref_fn
+    from make_golden_along_ray_scene import along_ray_scene
+    scene = along_ray_scene(13, 26, 18)
+    scene['camera']['far'] = 4.0                     # some fragments beyond `far`
+    a = ref_fn(scene_io.clone_scene(scene), norm_depth_image_only=True)
+    b = torch_oracle.render_along_ray(scene_io.clone_scene(scene), norm_depth_image_only=True)
+    assert float((a['depth'] >= 4.0).float().mean()) > 0.02
+    for k in ('image', 'depth', 'pos', 'normal'):
+        assert torch.equal(a[k], b[k]), k
