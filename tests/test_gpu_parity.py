@@ -558,6 +558,44 @@ def test_render_batch_of_stacked_tensors():
     assert torch.allclose(albedo.grad, albedo2.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('variant', ['shadow', 'ortho', 'screen', 'single'])
+def test_strided_batch_fallback_paths(variant):
+    """Strided batches outside the fused kernels' envelope (shadow rays, orthographic camera, math_mode 3) run scene
+    by scene inside the library; a batch of one goes through the same entry points.  Same bits as render()."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    from surf_renderer_b200.renderer import _stack_scenes
+    B = 1 if variant == 'single' else 3
+    parts = [scene_io.clone_scene(synth.config_d_scene(i, m=300, width=40, height=28, radius=0.08), device='cuda') for i in range(B)]
+    params = {'double_sided': True}
+    if variant == 'shadow':
+        params['shadow'] = True
+    if variant == 'screen':
+        params['_math_mode'] = 3
+    if variant == 'ortho':
+        for p in parts:
+            p['camera']['proj_type'] = 'orthographic'
+            p['camera']['fovy'] = float(np.deg2rad(60.))
+            p['camera']['focal_length'] = 1.0
+    if B == 1:
+        st = scene_io.clone_scene(parts[0], device='cuda')
+        st['objects']['disk']['pos'] = st['objects']['disk']['pos'][None]
+    else:
+        st = _stack_scenes(parts)
+    st['objects']['disk']['pos'] = st['objects']['disk']['pos'].detach().requires_grad_(True)
+    res = surf_renderer_b200.render_batch(st, **params)
+    assert res['image'].shape == (B, 28, 40, 3)
+    res['image'].sum().backward()
+    for b, p in enumerate(parts):
+        sc = scene_io.clone_scene(p, device='cuda', requires_grad=True)
+        r = surf_renderer_b200.render(sc, **params)
+        for k in ('image', 'depth', 'nearest', 'pos', 'normal'):
+            assert torch.equal(r[k], res[k][b]), (k, b)
+        r['image'].sum().backward()
+        assert torch.allclose(st['objects']['disk']['pos'].grad[b], sc['objects']['disk']['pos'].grad, rtol=1e-5, atol=1e-7)
+    assert int((res['depth'] <= 1000).sum()) > 50
+
+
 def _camera_basis(cam):
     eye, at, up = (cam[k][:3].double().cpu() for k in ('eye', 'at', 'up'))
     z = (eye - at) / (eye - at).norm()
