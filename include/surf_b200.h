@@ -175,8 +175,9 @@ int surf_backward_batch(int32_t n_scenes, const SurfScene* scenes, const SurfCam
                         void* cuda_stream);
 
 /* ---- strided batches: one scene description + element strides between consecutive scenes ----
- * The GAN workload holds a batch as stacked tensors (splat positions [B,M,3], camera eyes [B,3], shared lights and
- * materials).  Scene b reads every pointer of `scene0` / `camera0` advanced by b * stride ELEMENTS (floats / int32);
+ * Replaces the same per-element loop (GAN.get_real_samples, diffrend/torch/GAN/gan.py:326-377: one render() call per
+ * batch element over scenes that differ only in splat positions / normals and camera eye) for callers that hold
+ * the batch as stacked tensors (splat positions [B,M,3], camera eyes [B,3], shared lights and materials).  Scene b reads every pointer of `scene0` / `camera0` advanced by b * stride ELEMENTS (floats / int32);
  * a stride of 0 means all scenes share that array (its gradient then receives the sum over the batch).  All scenes
  * have the same primitive counts, light / colour / material counts, viewport and scalar camera parameters.
  * Outputs, `nearest`, `depth`, incoming gradients are contiguous per scene: [B, n, ...] (ray_dir [B,3,n] or [B,3,1]);
