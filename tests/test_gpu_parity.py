@@ -596,6 +596,51 @@ def test_strided_batch_fallback_paths(variant):
     assert int((res['depth'] <= 1000).sum()) > 50
 
 
+@pytest.mark.parametrize('batched', [False, True])
+def test_whole_step_replays_from_a_cuda_graph(batched):
+    """The library never synchronises or reads device data on the host, so render + loss + backward + Adam captures
+    into ONE CUDA graph (surf_renderer_b200.GraphedStep); replaying it walks the same parameter trajectory, bit for
+    bit, as stepping eagerly - single frames and strided batches (fork/join over the internal streams included)."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    from surf_renderer_b200.renderer import _stack_scenes
+
+    def make():
+        if batched:
+            sc = _stack_scenes([scene_io.clone_scene(synth.config_d_scene(i, m=500, width=48, height=40, radius=0.06), device='cuda')
+                                for i in range(4)])
+            call = lambda: surf_renderer_b200.render_batch(sc, double_sided=True)['image']      # noqa: E731
+        else:
+            sc = scene_io.clone_scene(synth.config_e(m=3000, width=64, height=64, radius=0.03), device='cuda')
+            call = lambda: surf_renderer_b200.render(sc)['image']                                 # noqa: E731
+        with torch.no_grad():
+            target = call().clone()
+        pos = sc['objects']['disk']['pos']
+        g = torch.Generator(device='cuda').manual_seed(4)
+        pos = (pos + 0.003 * torch.randn(pos.shape, device='cuda', generator=g)).requires_grad_(True)
+        sc['objects']['disk']['pos'] = pos
+        pos.grad = torch.zeros_like(pos)
+        opt = torch.optim.Adam([pos], lr=2e-4, capturable=True)
+
+        def step():
+            opt.zero_grad(set_to_none=False)
+            loss = ((call() - target) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss
+        return pos, step
+    pos_a, step_a = make()
+    for _ in range(3 + 10):
+        loss_a = step_a()
+    pos_b, step_b = make()
+    graphed = surf_renderer_b200.GraphedStep(step_b, warmup=3)
+    for _ in range(10):
+        loss_b = graphed()
+    torch.cuda.synchronize()
+    assert torch.equal(pos_a.detach(), pos_b.detach())
+    assert float(loss_a.detach()) == float(loss_b.detach()) and float(loss_b.detach()) > 0
+
+
 def _camera_basis(cam):
     eye, at, up = (cam[k][:3].double().cpu() for k in ('eye', 'at', 'up'))
     z = (eye - at) / (eye - at).norm()
