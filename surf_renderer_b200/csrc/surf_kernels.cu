@@ -198,6 +198,12 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     if (P != 2 && P != 4 && P != 8) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 2, 4 or 8");
     const int tile = kThreads * P;
     prm.tiles_per_scene = (f.n + tile - 1) / tile;
+    prm.tiles_x = 0; prm.W = f.cam.W; prm.pix0 = f.pix0;
+    if (ba && P == 8 && f.cam.W % 64 == 0) {       // 2-D tiles for the batch kernel (see IsectParams)
+        const int row0 = f.pix0 / f.cam.W, row1 = (f.pix0 + f.n - 1) / f.cam.W;
+        prm.tiles_x = f.cam.W / 64;
+        prm.tiles_per_scene = prm.tiles_x * ((row1 - row0 + 1 + 31) / 32);
+    }
     prm.n_tiles = prm.tiles_per_scene * (ba ? ba->n_scenes : 1);
     // stage capacity: chunk_prims disk records (2 float4 each); keep >= 4x grid items for balance on small frames
     int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;

@@ -515,13 +515,15 @@ def test_render_batch_of_differently_shaped_scenes_falls_back_to_per_scene_marsh
                 assert torch.allclose(ga[name].grad, gb[name].grad, rtol=1e-4, atol=1e-6), name
 
 
-def test_render_batch_of_stacked_tensors():
+@pytest.mark.parametrize('width,height', [(56, 40), (64, 40), (128, 72)])
+def test_render_batch_of_stacked_tensors(width, height):
     """One scene dict with batched leaves (positions [B,M,3], normals, camera eyes [B,4]) and shared lights /
-    materials == a loop of render() over its slices: same bits forward, same gradients, shared leaves summed."""
+    materials == a loop of render() over its slices: same bits forward, same gradients, shared leaves summed.
+    Widths that are multiples of 64 take k_intersect_batch's 2-D pixel tiles (partial last tile row included)."""
     import surf_renderer_b200
     from surf_renderer_b200 import scenes as synth
     B = 7
-    parts = [synth.config_d_scene(i, m=600, width=56, height=40) for i in range(B)]
+    parts = [synth.config_d_scene(i, m=600, width=width, height=height) for i in range(B)]
     base = scene_io.clone_scene(parts[0], device='cuda')
 
     def leaf(t):
@@ -535,7 +537,7 @@ def test_render_batch_of_stacked_tensors():
     batched['camera']['eye'] = eye
     batched['lights']['pos'], batched['materials']['albedo'] = lights, albedo
     res = surf_renderer_b200.render_batch(batched, double_sided=True)
-    assert res['image'].shape == (B, 40, 56, 3) and res['nearest'].shape == (B, 40, 56) and res['ray_dir'].shape == (B, 3, 40 * 56)
+    assert res['image'].shape == (B, height, width, 3) and res['nearest'].shape == (B, height, width) and res['ray_dir'].shape == (B, 3, height * width)
     w = torch.linspace(0.5, 1.5, B, device='cuda')
     ((res['image'] * w[:, None, None, None]).sum() + res['depth'].clamp(max=50).sum() + res['pos'].sum()).backward()
 
