@@ -16,7 +16,7 @@ import torch
 
 from . import _abi
 from ._lib import check, lib
-from .marshal import Marshalled, MarshalledBatch, make_options
+from .marshal import Marshalled, MarshalledBatch, batched_scene_size, make_options
 
 
 def get_param_value(key, dict_var, default_val, required=False):
@@ -383,6 +383,8 @@ def render_batch(scenes, **params):
     if len(scenes) == 0:
         return []
     stacked = _stack_scenes(scenes) if len(scenes) > 1 else None
+    if stacked is not None and batched_scene_size(stacked) != len(scenes):
+        stacked = None                   # e.g. the same scene object repeated: nothing to stack along
     if stacked is not None:
         res = _render_strided(stacked, params)
         cols = {k: torch.unbind(res[k], 0) for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir')}

@@ -129,6 +129,11 @@ def test_strided_batch_marshalling():
     assert part['camera']['viewport'] == stacked['camera']['viewport']
     assert MarshalledBatch(part, 'cpu').batch == 2
 
+    # the same scene object repeated has nothing to stack along: render_batch then marshals scene by scene
+    from surf_renderer_b200.marshal import batched_scene_size
+    same = _stack_scenes([scenes[0], scenes[0], scenes[0]])
+    assert same is not None and batched_scene_size(same) is None and batched_scene_size(stacked) == 5
+
     # different primitive counts, a different viewport or a different kind order cannot be stacked
     odd = synth.config_d_scene(9, m=41, width=16, height=12)
     assert _stack_scenes(scenes + [odd]) is None
