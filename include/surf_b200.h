@@ -105,7 +105,9 @@ typedef struct SurfOptions {
     int32_t math_mode;       /* intersection kernel.  0 = default: ray-plane disk filter, packed FFMA2, grouped
                                 branch - 10 FMA-pipe lane-instr per ray-disk test, the SURVEY 8(d) formulation;
                                 1 = same, scalar FFMA; 2 = same, packed, one branch per primitive;
-                                3 = fast: per-pair screen-space bounding-circle test (2.25 lane-instr per test).
+                                3 = fast: per-pair screen-space bounding-circle test (2.25 lane-instr per test);
+                                4 = dense: mode 0's filter with 2-D pixel tiles and per-disk minima (the strided
+                                batch kernel on one scene) for small frames with splats several pixels wide.
                                 All modes run the same exact narrow phase and give bit-identical results.      */
 } SurfOptions;
 

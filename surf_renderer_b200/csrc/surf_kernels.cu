@@ -191,6 +191,18 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
         return run_intersect_rays<0>(f, f.ws.zbuf, st);
     }
     if (opt->math_mode == 3) return run_intersect_screen(f, opt, st);
+    // math_mode 4 ("dense"): the batch kernel's body - 2-D pixel tiles, per-disk filter minima - on a single scene,
+    // i.e. a batch of one.  For small frames with splats several pixels wide (bunny 256x256: -11 %).
+    int mode = opt->math_mode;
+    BatchArgs one_scene;
+    if (mode == 4) {
+        mode = 0;
+        if (!ba) {
+            std::memset(&one_scene, 0, sizeof(one_scene));
+            one_scene.n_scenes = 1;
+            ba = &one_scene;
+        }
+    }
     IsectParams prm;
     prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.n_pix = f.n;
@@ -245,8 +257,7 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     const long long items = (long long)prm.n_tiles * nchunks;
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    const int mode = opt->math_mode;
-    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..3");
+    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
 #define SURF_DISPATCH(PP)                                                      \
     if (P == PP) {                                                             \
         if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st, ba); \

@@ -343,23 +343,24 @@ def select_scenes(scene, index):
 
 
 # process-wide default of the intersection-kernel variant (SurfOptions.math_mode); a call's `_math_mode` kwarg wins.
-# 0 = ray-plane FFMA2 filter (default), 3 = screen-space level-1 test (fastest).  Also settable through the
+# 0 = ray-plane FFMA2 filter (default), 3 = screen-space level-1 test (fastest), 4 = dense small frames.  Also settable through the
 # environment variable SURF_INTERSECT_MODE for drop-in use without touching call sites.
 import os as _os
 
-_DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3}.get(_os.environ.get('SURF_INTERSECT_MODE', 'plane'), None)
+_DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3, 'dense': 4}.get(_os.environ.get('SURF_INTERSECT_MODE', 'plane'), None)
 if _DEFAULT_MATH_MODE is None:
     _DEFAULT_MATH_MODE = int(_os.environ['SURF_INTERSECT_MODE'])
 
 
 def set_default_intersect_mode(mode):
-    """'plane' (0, default) or 'screen' (3); returns the previous value.  All modes give bit-identical outputs."""
+    """'plane' (0, default), 'screen' (3) or 'dense' (4: small frames with wide splats); returns the previous value.
+    All modes give bit-identical outputs."""
     global _DEFAULT_MATH_MODE
     prev = _DEFAULT_MATH_MODE
-    _DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3}.get(mode, mode)
-    if _DEFAULT_MATH_MODE not in (0, 1, 2, 3):
+    _DEFAULT_MATH_MODE = {'plane': 0, 'screen': 3, 'dense': 4}.get(mode, mode)
+    if _DEFAULT_MATH_MODE not in (0, 1, 2, 3, 4):
         _DEFAULT_MATH_MODE = prev
-        raise ValueError("mode must be 'plane', 'screen' or 0..3")
+        raise ValueError("mode must be 'plane', 'screen', 'dense' or 0..4")
     return prev
 
 

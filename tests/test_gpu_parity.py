@@ -87,12 +87,13 @@ def test_radius_has_no_gradient_and_camera_is_constant():
     assert sc['objects']['disk']['pos'].grad is not None
 
 
-@pytest.mark.parametrize('ppt,chunk,mode', [(4, 64, 3), (16, 2048, 3), (8, 96, 3), (8, 0, 0), (2, 32, 1), (4, 256, 2), (4, 2048, 0)])
+@pytest.mark.parametrize('ppt,chunk,mode', [(4, 64, 3), (16, 2048, 3), (8, 96, 3), (8, 0, 0), (2, 32, 1), (4, 256, 2), (4, 2048, 0),
+                                            (8, 0, 4), (4, 128, 4)])
 def test_kernel_variants_are_bit_identical(ppt, chunk, mode):
     """pixels/thread, TMA chunk size and the level-1 filter formulation (screen circle / ray-plane, packed / scalar)
     are tuning knobs: the exact narrow phase decides, so every variant yields the same winners and the same bits."""
     from surf_renderer_b200 import scenes as synth
-    scene = scene_io.clone_scene(synth.config_e(m=6000, width=96, height=80, radius=0.03), device='cuda')
+    scene = scene_io.clone_scene(synth.config_e(m=6000, width=128 if mode == 4 else 96, height=80, radius=0.03), device='cuda')
     base = _cpu(_render(scene))
     var = _cpu(_render(scene, _pixels_per_thread=ppt, _chunk_prims=chunk, _math_mode=mode))
     for k in ('nearest', 'depth', 'image', 'pos', 'normal'):

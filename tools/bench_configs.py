@@ -77,6 +77,7 @@ sc, _ = fixture('a_basic_mixed_64', 64, [('disk', 'pos')])
 rows.append(measure("A' plane+sphere+disk 64x64", sc, {}))
 sc, p = fixture('b_bunny_48', 256, [('disk', 'pos'), ('disk', 'normal')])
 rows.append(measure('B bunny.splat 256x256', sc, {}))
+rows.append(measure('B bunny.splat 256x256, math_mode 4 (dense)', sc, {'_math_mode': 4}))
 sc, p = fixture('c_torus_64', 512, [('triangle', 'face'), ('triangle', 'normal')])
 rows.append(measure('C torus_1K.obj 512x512', sc, {'double_sided': True}))
 st = _stack_scenes([scene_io.clone_scene(synth.config_d_scene(i), device='cuda') for i in range(64)])

@@ -12,7 +12,7 @@ L = lib()
 for scale in (1.0, 0.25, 0.001):
     sc = scene_io.clone_scene(scene, device='cuda')
     sc['objects']['disk']['radius'] = sc['objects']['disk']['radius'] * scale
-    for chunk, mode in ((0, 0), (64, 0), (256, 0)):
+    for chunk, mode in ((0, 0), (64, 0), (0, 4), (64, 4)):
         L.surf_set_kernel_timing(1)
         with torch.no_grad():
             for _ in range(5):
