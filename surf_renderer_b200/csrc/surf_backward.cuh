@@ -143,7 +143,7 @@ struct DeviceSink {
 // same-address double atomics per slot on the L2 and made the kernel 5x slower than its instruction count.)
 __device__ __forceinline__ void backward_body(const BackwardParams& p, double* cta_acc);
 
-__global__ void __launch_bounds__(128) k_backward(const __grid_constant__ BackwardParams p) {
+__global__ void __launch_bounds__(128, 6) k_backward(const __grid_constant__ BackwardParams p) {
     __shared__ double cta_acc[kMaxAccSlots];
     backward_body(p, cta_acc);
 }
@@ -164,7 +164,7 @@ __device__ __forceinline__ void grads_at(GradPtrs* gp, const BatchArgs& ba, int 
 }
 
 // strided batch: blockIdx.y = scene; nearest / depth / incoming gradients are [B, n, ...]
-__global__ void __launch_bounds__(128) k_backward_batch(const __grid_constant__ BackwardParams p0,
+__global__ void __launch_bounds__(128, 6) k_backward_batch(const __grid_constant__ BackwardParams p0,
                                                         const __grid_constant__ BatchArgs ba) {
     __shared__ double cta_acc[kMaxAccSlots];
     __shared__ BackwardParams p;

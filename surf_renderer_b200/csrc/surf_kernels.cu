@@ -396,7 +396,7 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     bp.gp.light_pos = sg->light_pos; bp.gp.atten = sg->light_attenuation; bp.gp.ambient = sg->ambient;
     bp.gp.colors = sg->colors; bp.gp.albedo = sg->albedo; bp.gp.coeffs = sg->coeffs; bp.gp.gamma = sg->gamma;
     timer_mark(2, 0, st);
-    k_backward<<<std::min((f.n + 127) / 128, sm_count() * 8), 128, 0, st>>>(bp);
+    k_backward<<<std::min((f.n + 127) / 128, sm_count() * 16), 128, 0, st>>>(bp);
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_backward");
     FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
@@ -749,7 +749,7 @@ int backward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCame
     }
     bp.gp.light_pos = sg->light_pos; bp.gp.atten = sg->light_attenuation; bp.gp.ambient = sg->ambient;
     bp.gp.colors = sg->colors; bp.gp.albedo = sg->albedo; bp.gp.coeffs = sg->coeffs; bp.gp.gamma = sg->gamma;
-    const int gx = std::max(1, std::min((f.n + 127) / 128, (sm_count() * 8 + n_scenes - 1) / n_scenes));
+    const int gx = std::max(1, std::min((f.n + 127) / 128, (sm_count() * 16 + n_scenes - 1) / n_scenes));
     timer_mark(2, 0, st);
     k_backward_batch<<<dim3(gx, B), 128, 0, st>>>(bp, ba);
     timer_mark(2, 1, st);
