@@ -229,6 +229,40 @@ def _prepare_fragments(scene, inp0, params, device):
     return pos.contiguous(), normals.contiguous(), mat, vis, H, W
 
 
+def z_to_pcl_CC(z, camera):
+    """Reference: diffrend/torch/renderer.py:484-507.  Camera-space point cloud [N,3] of one depth per pixel
+    (z negative in front of the camera, clamped with -relu(-z)); differentiable in z, runs on z's device.  The GAN
+    trainer imports it next to render / render_splats_along_ray (GAN/gan.py:28-29, :446)."""
+    vp = camera['viewport']
+    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
+    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    focal = _scalar(camera['focal_length'])
+    h = np.tan(_scalar(camera['fovy']) / 2) * 2 * focal
+    w = h * (W / H)
+    Z = -torch.nn.functional.relu(-z)
+    gx, gy = np.meshgrid(np.linspace(-1, 1, W), np.linspace(1, -1, H))
+    gx *= w / 2
+    gy *= h / 2
+    x = torch.tensor(gx.ravel(), dtype=torch.float32, device=z.device)
+    y = torch.tensor(gy.ravel(), dtype=torch.float32, device=z.device)
+    return torch.stack((-Z * x / focal, -Z * y / focal, Z), dim=1)
+
+
+def z_to_pcl_CC_batched(z, camera):
+    """Reference: diffrend/torch/renderer.py:510-534, z is [B, H*W]; returns [B, H*W, 3]."""
+    vp = camera['viewport']
+    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
+    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    focal = _scalar(camera['focal_length'])
+    h = np.tan(_scalar(camera['fovy']) / 2) * 2 * focal
+    w = h * (W / H)
+    Z = -torch.nn.functional.relu(-z)
+    y, x = torch.meshgrid(torch.linspace(1, -1, H, device=z.device), torch.linspace(-1, 1, W, device=z.device), indexing='ij')
+    x = (x * w / 2).flatten().repeat(z.shape[0], 1)
+    y = (y * h / 2).flatten().repeat(z.shape[0], 1)
+    return torch.stack((-Z * x / focal, -Z * y / focal, Z), dim=-1)
+
+
 def build_inputs(scene, params, device):
     """_SplatInputs of a call: the plain z-per-pixel form, or explicit fragments when normals are estimated / samples > 1"""
     disk = scene['objects']['disk']

@@ -139,3 +139,25 @@ def test_gpu_along_ray_gan_shape_vs_oracle():
                           'l': sc['lights']['pos'].grad.cpu()},
                          {'z': osc['objects']['disk']['pos'].grad, 'n': osc['objects']['disk']['normal'].grad,
                           'l': osc['lights']['pos'].grad})
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='reference tree not present')
+def test_z_to_pcl_cc_matches_live_reference():
+    """renderer.py:484-534 (imported by the GAN trainer next to the renderers): pure tensor programs, bit-exact."""
+    import sys
+    sys.path.insert(0, '/root/reference')
+    from diffrend.torch.renderer import z_to_pcl_CC as ref_fn, z_to_pcl_CC_batched as ref_batched
+    import surf_renderer_b200
+    cam = {'viewport': [0, 0, 37, 23], 'fovy': float(np.deg2rad(33.)), 'focal_length': 0.7}
+    g = torch.Generator().manual_seed(2)
+    z = -(torch.rand(37 * 23, generator=g) * 4 + 0.5)
+    z[::7] = 0.3                                             # behind the camera: clamped to 0
+    za = z.clone().requires_grad_(True)
+    zb = z.clone().requires_grad_(True)
+    a, b = ref_fn(za, cam), surf_renderer_b200.z_to_pcl_CC(zb, cam)
+    assert torch.equal(a, b)
+    (a * torch.arange(3.)).sum().backward()
+    (b * torch.arange(3.)).sum().backward()
+    assert torch.equal(za.grad, zb.grad)
+    zz = torch.stack((z, z * 0.5, z * 2))
+    assert torch.equal(ref_batched(zz, cam), surf_renderer_b200.z_to_pcl_CC_batched(zz, cam))
