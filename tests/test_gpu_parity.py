@@ -178,6 +178,67 @@ def test_config_e_100k_splats_1024_sampled_vs_oracle():
     assert rep['hit_pixels'] > 300
 
 
+def _oracle_subset_gradient_check(scene, params, n_samples, seed, leaves_of):
+    """Gradients at full size: the loss touches `n_samples` random pixels (random weights on image, depth of hit
+    pixels); the GPU renders the whole frame, the oracle only those pixels (pixels are independent).  Pixels whose
+    winner differs (classified eps-ties) would send gradient to another primitive, so the sample keeps the pixels on
+    which both agree - the forward checks above bound how many are dropped."""
+    sc = scene_io.clone_scene(scene, device='cuda')
+    osc = scene_io.clone_scene(scene)
+    for t in leaves_of(sc) + leaves_of(osc):
+        t.requires_grad_(True)
+    res = _render(sc, **params)
+    H, W = res['depth'].shape
+    g = torch.Generator().manual_seed(seed)
+    subset = torch.randperm(H * W, generator=g)[:n_samples].sort().values
+    ref = torch_oracle.render(osc, pixel_subset=subset, tile_size=512, **params)
+    far = scene['camera']['far']
+    near_gpu = res['nearest'].reshape(-1)[subset.cuda()].cpu()
+    same = (near_gpu == ref['nearest'].reshape(-1)) & ((res['depth'].reshape(-1)[subset.cuda()].cpu() <= far) == (ref['depth'].reshape(-1) <= far))
+    assert float(same.float().mean()) > 0.995
+    w_img = (torch.rand(n_samples, 3, generator=g) - 0.3) * same[:, None]
+    w_dep = (torch.rand(n_samples, generator=g) - 0.5) * same * (ref['depth'].reshape(-1).detach() <= far)
+    loss_ref = (ref['image'].reshape(-1, 3) * w_img).sum() + (ref['depth'].reshape(-1) * w_dep).sum()
+    loss_ref.backward()
+    sub = subset.cuda()
+    loss = (res['image'].reshape(-1, 3)[sub] * w_img.cuda()).sum() + (res['depth'].reshape(-1)[sub] * w_dep.cuda()).sum()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-4 * abs(float(loss_ref.detach())) + 1e-4
+    names = ['leaf%d' % i for i in range(len(leaves_of(sc)))]
+    return parity.compare_grads({n: t.grad.cpu() for n, t in zip(names, leaves_of(sc))},
+                                {n: t.grad for n, t in zip(names, leaves_of(osc))}, rtol=1e-4, atol_scale=2e-5)
+
+
+def _splat_leaves(sc):
+    return [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
+
+
+def test_config_b_bunny_256_gradients_full_size():
+    """BASELINE configs[1] backward at full size: bunny.splat 256x256, 7 lights, Phong - gradients of disk positions
+    and normals, albedo and light positions against the oracle's autograd on 6000 sampled pixels."""
+    scene, params, outs, grads, extra = _load('b_bunny_48')
+    scene['camera']['viewport'] = [0, 0, 256, 256]
+    worst = _oracle_subset_gradient_check(scene, {}, 6000, 21, _splat_leaves)
+    print('bunny256 grads', worst)
+
+
+def test_config_e_100k_splats_1024_gradients_full_size():
+    """BASELINE configs[4] backward at full size: 100K splats at 1024x1024 - gradients against the oracle's autograd
+    on 1500 sampled pixels (1.5e8 ray-splat pairs on the CPU)."""
+    from surf_renderer_b200 import scenes as synth
+    worst = _oracle_subset_gradient_check(synth.config_e(), {}, 1500, 22, _splat_leaves)
+    print('configE grads', worst)
+
+
+def test_config_c_torus_512_gradients_full_size():
+    """BASELINE configs[2] backward at full size: torus_1K.obj 512x512, double sided - face / normal / albedo."""
+    scene, params, outs, grads, extra = _load('c_torus_64')
+    scene['camera']['viewport'] = [0, 0, 512, 512]
+    worst = _oracle_subset_gradient_check(scene, params, 20000, 23,
+                                          lambda sc: [sc['objects']['triangle']['face'], sc['objects']['triangle']['normal'], sc['materials']['albedo']])
+    print('torus512 grads', worst)
+
+
 def test_host_pointer_api_matches_device_api():
     """surf_render_host / surf_render_backward_host (host buffers in, host buffers out) vs the torch path."""
     from surf_renderer_b200 import _abi
