@@ -394,6 +394,42 @@ def test_batch_of_scenes_config_d_shape():
     assert torch.isfinite(sc['objects']['disk']['pos'].grad).all()
 
 
+def test_config_d_full_batch_through_the_strided_kernels():
+    """BASELINE configs[3] at full size as ONE stacked batch (64 scenes x 5000 splats, 128x128, double sided - the
+    five-launch k_*_batch path with 2-D pixel tiles): scenes 0, 17 and 63 of the batch output against the oracle on
+    3000 sampled pixels each, and the gradient of scene 17's splat positions against the oracle's autograd."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    from surf_renderer_b200.renderer import _stack_scenes
+    parts = [synth.config_d_scene(i) for i in range(64)]
+    st = _stack_scenes([scene_io.clone_scene(p, device='cuda') for p in parts])
+    st['objects']['disk']['pos'] = st['objects']['disk']['pos'].detach().requires_grad_(True)
+    res = surf_renderer_b200.render_batch(st, double_sided=True)
+    assert res['image'].shape == (64, 128, 128, 3)
+    g = torch.Generator().manual_seed(77)
+    weights = {}
+    for idx in (0, 17, 63):
+        subset = torch.randperm(128 * 128, generator=g)[:3000].sort().values
+        osc = scene_io.clone_scene(parts[idx])
+        osc['objects']['disk']['pos'].requires_grad_(True)
+        ref = torch_oracle.render(osc, pixel_subset=subset, tile_size=512, double_sided=True)
+        cand = {k: res[k][idx].detach().cpu().reshape(128 * 128, -1)[subset].reshape(ref[k].shape)
+                for k in ('image', 'depth', 'pos', 'normal', 'nearest')}
+        cand['ray_dir'] = res['ray_dir'][idx].detach().cpu()[:, subset]
+        rep = parity.compare_forward(cand, _cpu(ref), parts[idx])
+        assert rep['hit_pixels'] > 50
+        if idx == 17:
+            same = cand['nearest'].reshape(-1) == ref['nearest'].reshape(-1)
+            w = (torch.rand(3000, 3, generator=g) - 0.3) * same[:, None]
+            (ref['image'].reshape(-1, 3) * w).sum().backward()
+            weights = (subset, w, osc['objects']['disk']['pos'].grad)
+    subset, w, ref_grad = weights
+    (res['image'][17].reshape(-1, 3)[subset.cuda()] * w.cuda()).sum().backward()
+    got = st['objects']['disk']['pos'].grad
+    parity.compare_grads({'pos': got[17].cpu()}, {'pos': ref_grad}, rtol=1e-4, atol_scale=2e-5)
+    assert float(got[16].abs().max()) == 0.0 and float(got[18].abs().max()) == 0.0     # other scenes untouched
+
+
 def test_ingested_json_scene_matches_oracle(tmp_path):
     """Scene JSON + OBJ -> ingest.load_scene -> make_torch_var(cuda) -> render: the CLI flow of torch/render.py:103-107."""
     import json
