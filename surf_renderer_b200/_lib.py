@@ -8,7 +8,8 @@ import os
 from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libsurf_b200.so')
+# SURF_B200_LIB points the loader at another build of the library (A/B runs of kernel variants); default = in-tree
+LIB_PATH = os.environ.get('SURF_B200_LIB') or os.path.join(_PKG, 'libsurf_b200.so')
 _lib = None
 
 
