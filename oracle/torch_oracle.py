@@ -21,6 +21,10 @@ Parity pinning: ``tests/golden/*.npz`` were produced by importing the real
 reference from ``/root/reference`` (script: ``tests/golden/make_golden.py``);
 ``tests/test_oracle_golden.py`` checks this restatement bit-for-bit against
 them, and (when ``/root/reference`` is present) against the live reference.
+The shadow-ray branch (renderer.py:291-314) is pinned by ``sh_*.npz``
+(``make_golden_shadow.py``: the stock branch run on CPU with the one attribute
+``torch.cuda.FloatTensor`` it casts with pointed at ``torch.FloatTensor``),
+``render_along_ray`` by ``ar_*.npz`` (``make_golden_along_ray.py``).
 
 Extensions that the reference does not have (used by the tests only):
   * ``pixel_subset``: render only the listed flat pixel indices (pixels are
@@ -419,7 +423,7 @@ def render(scene, **params):
 
 
 def _shadow_visibility(light_pos, frag_p, winner, objects, params, n_pix):
-    """renderer.py:291-314 (device-agnostic restatement; the reference needs CUDA at :311)."""
+    """renderer.py:291-314 (the reference casts with torch.cuda.FloatTensor at :311; pinned by tests/golden/sh_*.npz)."""
     tile = params.get('tile_size', 4096)
     out = []
     for li in range(light_pos.shape[0]):

@@ -2,7 +2,7 @@
   * sphere gradients - NaN in the reference; checked against float64 autograd of the oracle's
     NaN-free sphere variant (oracle-only switch SAFE_SPHERE),
   * shadow rays      - the reference's shadow branch needs CUDA (renderer.py:311); checked against the oracle's
-    device-agnostic restatement (parity-unpinned)."""
+    device-agnostic restatement (itself bit-exact on the reference-generated sh_* shadow fixtures)."""
 import numpy as np
 import pytest
 import torch

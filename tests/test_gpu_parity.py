@@ -317,7 +317,7 @@ def test_fma_peak_microbenchmark_runs():
 @pytest.mark.parametrize('seed', [31, 32])
 def test_shadow_rays_match_oracle_restatement(seed):
     """shadow=True (renderer.py:291-314).  The reference's own shadow branch only runs on CUDA (:311), so the oracle's
-    device-agnostic restatement is the checker (parity-unpinned for this row)."""
+    device-agnostic restatement is the checker (itself bit-exact on the reference-generated sh_* shadow fixtures)."""
     from surf_renderer_b200 import scenes as synth
     scene = synth.random_mixed_scene(seed, width=36, height=28, n_disk=10, n_sphere=0, n_tri=6, n_plane=1)
     sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
