@@ -155,6 +155,10 @@ def main():
     sc['camera']['focal_length'] = 1.0
     run_case('scene2_persp_60x45', sc, {}, 21, with_grad=False)
 
+    # orthographic camera WITH gradients: no spheres (their gradients are NaN in the reference), 56x40 <= one tile
+    run_case('ortho_mixed_nosphere_56x40', synth.random_mixed_scene(8, width=56, height=40, n_sphere=0, n_disk=25, n_tri=20,
+                                                                    proj='orthographic'), {'double_sided': True}, 27)
+
     # E (reduced): 3000 synthetic sphere-shell splats at 40x40 with the config-E camera
     run_case('e_synth_3000_40', synth.config_e(m=3000, width=40, height=40, radius=0.03), {}, 22)
 
