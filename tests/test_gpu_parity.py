@@ -306,6 +306,35 @@ def test_error_behaviour_matches_reference():
     assert torch.equal(a['image'], b['image'])
 
 
+def test_strided_entry_points_reject_bad_arguments():
+    """surf_forward_strided through ctypes: empty batch, misaligned per-scene workspace stride, workspace too small."""
+    from surf_renderer_b200 import _abi, scenes as synth
+    from surf_renderer_b200._lib import lib
+    from surf_renderer_b200.marshal import MarshalledBatch, make_options
+    from surf_renderer_b200.renderer import _stack_scenes
+    st = _stack_scenes([scene_io.clone_scene(synth.config_d_scene(i, m=100, width=32, height=24), device='cuda') for i in range(3)])
+    mb = MarshalledBatch(st, torch.device('cuda', 0))
+    m = mb.m
+    sc, cam, lay, opt = m.c_scene(mb.views0(mb.fulls)), m.c_camera(), mb.c_layout(), make_options({})
+    n = m.n_pixels
+    need = (lib().surf_workspace_bytes(m.total_prims, n, 7, 0) + 255) // 256 * 256
+    ws = torch.empty(3 * need, dtype=torch.uint8, device='cuda')
+    bufs = [torch.empty(3, n, 3, device='cuda'), torch.empty(3, n, device='cuda'), torch.empty(3, n, 3, device='cuda'),
+            torch.empty(3, n, 3, device='cuda'), torch.empty(3, n, dtype=torch.int64, device='cuda'), torch.empty(3, 3, n, device='cuda')]
+    out = _abi.SurfOutputs(*[b.data_ptr() for b in bufs])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call(b, stride):
+        return lib().surf_forward_strided(b, C.byref(sc), C.byref(cam), C.byref(lay), C.byref(opt), ws.data_ptr(), stride,
+                                          C.byref(out), stream)
+    assert call(3, need) == 0
+    torch.cuda.synchronize()
+    assert call(0, need) == -1 and b'empty batch' in lib().surf_last_error()
+    assert call(3, need + 8) == -1 and b'multiple of 256' in lib().surf_last_error()
+    assert call(3, 256) == -4 and b'workspace too small' in lib().surf_last_error()
+    assert lib().surf_forward_strided(3, None, C.byref(cam), C.byref(lay), C.byref(opt), ws.data_ptr(), need, C.byref(out), stream) == -1
+
+
 def test_fma_peak_microbenchmark_runs():
     from surf_renderer_b200._lib import lib
     scalar = lib().surf_fma_peak(0, 4096, None)
