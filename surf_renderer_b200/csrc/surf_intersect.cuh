@@ -909,6 +909,8 @@ struct RayParams {
     unsigned long long* zbuf;        // [n]
     int n_pix, n_tiles, n_chunks, stage_f4;
     int chunks_before[kMaxSets + 1];
+    const int* n_live;               // device count of rays actually stored (compacted shadow rays), or null = n_pix.
+                                     // n_pix stays the row stride of `gray`; the work grid shrinks to the live rays.
 };
 
 __global__ void __launch_bounds__(256) k_prep_rays(const __grid_constant__ SceneView sc, const float* __restrict__ obound,
@@ -976,7 +978,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_con
     float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[kStages];
     const int tid = threadIdx.x;
-    const long long n_items = (long long)prm.n_tiles * prm.n_chunks;
+    constexpr int TILE = kThreads * P;
+    const int n_rays = prm.n_live ? *prm.n_live : prm.n_pix;
+    const long long n_items = (long long)((n_rays + TILE - 1) / TILE) * prm.n_chunks;
     const int lo = (int)(n_items * blockIdx.x / gridDim.x);
     const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
     if (lo >= hi) return;
@@ -1007,7 +1011,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_con
     if (tid == 0)
         for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
 
-    constexpr int TILE = kThreads * P;
     RayRegs<P> r;
     int cur_tile = -1;
     auto flush = [&]() {
@@ -1015,7 +1018,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_con
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const int pix = cur_tile * TILE + p * kThreads + tid;
-            if (r.best_i[p] >= 0 && pix < prm.n_pix)
+            if (r.best_i[p] >= 0 && pix < n_rays)
                 atomicMin(prm.zbuf + pix, ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
         }
     };
@@ -1034,7 +1037,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_rays(const __grid_con
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const int pix = tile * TILE + p * kThreads + tid;
-                const bool ok = pix < prm.n_pix;
+                const bool ok = pix < n_rays;
 #pragma unroll
                 for (int c = 0; c < 6; ++c) v[c][p] = ok ? prm.gray[(size_t)c * prm.n_pix + pix] : 0.f;
                 r.tmax[p] = ok ? prm.gray[(size_t)6 * prm.n_pix + pix] : 0.f;

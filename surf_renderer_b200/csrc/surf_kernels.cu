@@ -136,7 +136,7 @@ static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaS
 }
 
 template <int MODE>
-static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st);
+static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live = nullptr);
 
 template <int P>
 static int launch_screen(const ScreenParams& prm, int grid, size_t smem, cudaStream_t st) {
@@ -275,12 +275,13 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
 }
 
 template <int MODE>
-static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st) {
+static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live) {
     k_prep_rays<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.obound, f.ws.packed);
     SURF_LAUNCHED("k_prep_rays");
     constexpr int P = 4;
     RayParams prm;
     prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.gray = f.ws.gray; prm.zbuf = zbuf; prm.n_pix = f.n;
+    prm.n_live = n_live;
     const int tile = kThreads * P;
     prm.n_tiles = (f.n + tile - 1) / tile;
     const int grid_max = sm_count() * 2;
@@ -348,11 +349,13 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
             SURF_LAUNCHED("k_shadow");
         } else {
             for (int l = 0; l < f.sc.n_lights; ++l) {
-                SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4, st));
-                k_rays_shadow<<<(f.n + 255) / 256, 256, 0, st>>>(sp, l, f.ws.gray, f.ws.zbuf2, f.ws.obound);
+                int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1] = live-ray counter
+                int* slot_of = (int*)(f.ws.gray + (size_t)7 * f.n);
+                SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 8, st));
+                k_rays_shadow<<<(f.n + 255) / 256, 256, 0, st>>>(sp, l, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of);
                 SURF_LAUNCHED("k_rays_shadow");
-                if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st))) return rc;
-                k_shadow_resolve<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, f.n, f.ws.vis + (size_t)l * f.n);
+                if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live))) return rc;
+                k_shadow_resolve<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, slot_of, f.n, f.ws.vis + (size_t)l * f.n);
                 SURF_LAUNCHED("k_shadow_resolve");
             }
         }

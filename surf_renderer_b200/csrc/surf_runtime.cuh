@@ -70,7 +70,8 @@ struct Workspace {
     double* acc;                 // backward scalar accumulators
     double* prim_acc;            // backward per-primitive accumulators [total_prims, 7]
     float* vis;                  // [L, n] shadow visibility
-    float* gray;                 // [7, n] generic rays: origin xyz, direction xyz, t_max (orthographic / shadow rays)
+    float* gray;                 // [8, n] generic rays: origin xyz, direction xyz, t_max (orthographic / shadow rays);
+                                 // row 7 = int slot_of[n]: where pixel k's compacted shadow ray is stored (-1: none)
     unsigned long long* zbuf2;   // [n] z-buffer keys of the shadow rays
     float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
     size_t bytes;
@@ -97,7 +98,7 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->vis = (float*)(p + off);
     if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
     // generic-ray buffers: always carved (orthographic frames need them too); 36 B per pixel
-    ws->gray = (float*)(p + off); off += align_up((size_t)7 * n_pix * sizeof(float), 256);
+    ws->gray = (float*)(p + off); off += align_up((size_t)8 * n_pix * sizeof(float), 256);
     ws->zbuf2 = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
     ws->obound = (float*)(p + off); off += 256;
     ws->bytes = off;

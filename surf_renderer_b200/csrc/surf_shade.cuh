@@ -113,18 +113,22 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowPa
 }
 
 // shadow rays of light l (renderer.py:293-299): origin frag_pos + 0.1 L, direction L, t_max = |light - frag_pos|.
-// Miss pixels get a null direction (no hits): their visibility never reaches an output (image is masked).
+// Only HIT pixels cast a shadow ray (a miss pixel's visibility never reaches an output: its image is masked), and the
+// rays are COMPACTED: pixel k stores its ray in slot j = slot_of[k] of `gray` / `zbuf2` (warp-aggregated atomic
+// counter), so k_intersect_rays only walks *n_live rays - half the work on config E, a quarter on the bunny frame.
+// The order of the slots varies from run to run; every ray's result is independent of its slot.
 __global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, int l, float* __restrict__ gray,
-                                                     unsigned long long* __restrict__ zbuf2, float* __restrict__ obound) {
+                                                     unsigned long long* __restrict__ zbuf2, float* __restrict__ obound,
+                                                     int* __restrict__ n_live, int* __restrict__ slot_of) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     float len = 0.f;
+    Vec3 so = v3(0.f, 0.f, 0.f), L = v3(0.f, 0.f, 0.f);
+    float dist = 0.f;
+    bool live = false;
     if (k < p.n) {
-        const size_t n = (size_t)p.n;
-        zbuf2[k] = kMissKey;
         const unsigned long long key = p.zbuf[k];
-        Vec3 so = v3(0.f, 0.f, 0.f), L = v3(0.f, 0.f, 0.f);
-        float dist = 0.f;
         if (key != kMissKey) {
+            live = true;
             Vec3 o, d;
             pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
             Fragment f = fragment_at(p.sc, (int)(key & 0xFFFFFFFFull), o, d);
@@ -135,21 +139,35 @@ __global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ Sha
             len = sqrtf(so.x * so.x + so.y * so.y + so.z * so.z);
             if (!(len == len) || !(dist == dist) || isinf(len)) { L = v3(0.f, 0.f, 0.f); len = 0.f; }
         }
-        gray[k] = so.x; gray[n + k] = so.y; gray[2 * n + k] = so.z;
-        gray[3 * n + k] = L.x; gray[4 * n + k] = L.y; gray[5 * n + k] = L.z;
-        gray[6 * n + k] = dist;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(n_live, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k < p.n) {
+        const int j = live ? base + __popc(ballot & ((1u << lane) - 1u)) : -1;
+        slot_of[k] = j;
+        if (live) {
+            const size_t n = (size_t)p.n;
+            zbuf2[j] = kMissKey;
+            gray[j] = so.x; gray[n + j] = so.y; gray[2 * n + j] = so.z;
+            gray[3 * n + j] = L.x; gray[4 * n + j] = L.y; gray[5 * n + j] = L.z;
+            gray[6 * n + j] = dist;
+        }
     }
     for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
-    if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
+    if (lane == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
 }
 
 // visible iff nothing was hit inside (0, |L|), or the nearest such hit is the fragment's own primitive (:306-309)
 __global__ void __launch_bounds__(256) k_shadow_resolve(const unsigned long long* __restrict__ zbuf,
-                                                        const unsigned long long* __restrict__ zbuf2, int n, float* __restrict__ vis_l) {
+                                                        const unsigned long long* __restrict__ zbuf2,
+                                                        const int* __restrict__ slot_of, int n, float* __restrict__ vis_l) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const unsigned long long self = zbuf[k], hit = zbuf2[k];
+    const int j = slot_of[k];
+    const unsigned long long self = zbuf[k], hit = j >= 0 ? zbuf2[j] : kMissKey;
     const bool visible = hit == kMissKey || self == kMissKey || (unsigned)(hit & 0xFFFFFFFFull) == (unsigned)(self & 0xFFFFFFFFull);
     vis_l[k] = visible ? 1.f : 0.f;
 }
-
