@@ -28,3 +28,40 @@ def test_reference_projection_layer_tests_accept_the_b200_render():
     ran = projection_consistency.check(STORED, verbose=False)
     assert ran == ['test_raster_coordinates', 'test_render_projection_consistency',
                    'test_transformation_consistency', 'test_depth_to_world_consistency']
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='needs the reference checkout')
+def test_integration_recipe_repoints_the_reference_callers():
+    """callers bind `render` by name at import, so the drop-in patches the defining module
+    and every module that already imported it.  Exercised here with a recording stand-in (the CUDA renderer cannot
+    run in the build container): after the recipe, the reference's own render_scene() and projection_layer reach the
+    replacement."""
+    sys.path.insert(0, '/root/reference')
+    import diffrend.torch.renderer as ref
+    import diffrend.torch.render as ref_cli
+    import diffrend.torch.projection_layer as ref_proj
+    from oracle import torch_oracle
+    calls = []
+
+    def replacement(scene, **params):
+        calls.append(sorted(params))
+        return torch_oracle.render(scene, **params)
+    replacement.__module__ = 'surf_renderer_b200.renderer'
+    original = ref.render
+    saved = {}
+    try:
+        # ---- the recipe of INTEGRATION.md, with `replacement` standing in for surf_renderer_b200.render
+        ref.render = replacement
+        for name, mod in list(sys.modules.items()):
+            if name.startswith('diffrend') and getattr(mod, 'render', None) is not None and mod is not ref:
+                if getattr(mod.render, '__module__', '') == 'diffrend.torch.renderer':
+                    saved[name] = mod.render
+                    mod.render = replacement
+        # ----
+        assert ref_cli.render is replacement and ref_proj.render is replacement
+        res = ref_cli.render_scene('/root/reference/scenes/basic.json')
+        assert len(calls) == 1 and res['image'].shape[-1] == 3
+    finally:
+        ref.render = original
+        for name, fn in saved.items():
+            sys.modules[name].render = fn
