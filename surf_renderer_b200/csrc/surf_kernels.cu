@@ -136,7 +136,8 @@ static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaS
 }
 
 template <int MODE>
-static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live = nullptr);
+static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live = nullptr,
+                              long long n_rays_cap = 0);
 
 template <int P>
 static int launch_screen(const ScreenParams& prm, int grid, size_t smem, cudaStream_t st) {
@@ -275,15 +276,17 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
 }
 
 template <int MODE>
-static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live) {
+static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live, long long n_rays_cap) {
+    const long long cap = n_rays_cap > 0 ? n_rays_cap : f.n;        // rays stored (row stride of `gray`)
+    if (cap > 0x7fffffffLL) return fail(SURF_ERR_UNSUPPORTED, "more than 2^31 rays in one launch");
     k_prep_rays<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.obound, f.ws.packed);
     SURF_LAUNCHED("k_prep_rays");
     constexpr int P = 4;
     RayParams prm;
-    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.gray = f.ws.gray; prm.zbuf = zbuf; prm.n_pix = f.n;
+    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.gray = f.ws.gray; prm.zbuf = zbuf; prm.n_pix = (int)cap;
     prm.n_live = n_live;
     const int tile = kThreads * P;
-    prm.n_tiles = (f.n + tile - 1) / tile;
+    prm.n_tiles = (int)((cap + tile - 1) / tile);
     const int grid_max = sm_count() * 2;
     int chunk = 1024;
     while (chunk > 64) {
@@ -348,16 +351,17 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
             k_shadow<<<grid, 128, 0, st>>>(sp);
             SURF_LAUNCHED("k_shadow");
         } else {
-            for (int l = 0; l < f.sc.n_lights; ++l) {
-                int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1] = live-ray counter
-                int* slot_of = (int*)(f.ws.gray + (size_t)7 * f.n);
-                SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 8, st));
-                k_rays_shadow<<<(f.n + 255) / 256, 256, 0, st>>>(sp, l, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of);
-                SURF_LAUNCHED("k_rays_shadow");
-                if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live))) return rc;
-                k_shadow_resolve<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, slot_of, f.n, f.ws.vis + (size_t)l * f.n);
-                SURF_LAUNCHED("k_shadow_resolve");
-            }
+            // all lights at once: one ray list of (light, hit pixel) pairs, one intersection launch
+            const int L = f.sc.n_lights;
+            const size_t cap = (size_t)f.n * L;
+            int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1] = live-ray counter
+            int* slot_of = (int*)(f.ws.gray + 7 * cap);
+            SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 8, st));
+            k_rays_shadow<<<dim3((f.n + 255) / 256, L), 256, 0, st>>>(sp, cap, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of);
+            SURF_LAUNCHED("k_rays_shadow");
+            if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live, (long long)cap))) return rc;
+            k_shadow_resolve<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, slot_of, f.n, cap, f.ws.vis);
+            SURF_LAUNCHED("k_shadow_resolve");
         }
     }
     ShadeParams sh;

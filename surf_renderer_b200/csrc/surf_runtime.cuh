@@ -97,9 +97,11 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
     ws->vis = (float*)(p + off);
     if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
-    // generic-ray buffers: always carved (orthographic frames need them too); 36 B per pixel
-    ws->gray = (float*)(p + off); off += align_up((size_t)8 * n_pix * sizeof(float), 256);
-    ws->zbuf2 = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
+    // generic-ray buffers: always carved (orthographic frames need them too); 40 B per ray.  With shadows the rays
+    // of all lights are traced in one launch: n_pix * n_lights rays.
+    const size_t n_rays = (size_t)n_pix * (size_t)(shadow ? (n_lights > 1 ? n_lights : 1) : 1);
+    ws->gray = (float*)(p + off); off += align_up((size_t)8 * n_rays * sizeof(float), 256);
+    ws->zbuf2 = (unsigned long long*)(p + off); off += align_up(n_rays * 8, 256);
     ws->obound = (float*)(p + off); off += 256;
     ws->bytes = off;
 }

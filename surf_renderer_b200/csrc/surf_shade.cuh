@@ -112,15 +112,18 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowPa
     p.vis[(size_t)l * p.n + k] = shadow_visibility(p.sc, f.P, self, l);
 }
 
-// shadow rays of light l (renderer.py:293-299): origin frag_pos + 0.1 L, direction L, t_max = |light - frag_pos|.
-// Only HIT pixels cast a shadow ray (a miss pixel's visibility never reaches an output: its image is masked), and the
-// rays are COMPACTED: pixel k stores its ray in slot j = slot_of[k] of `gray` / `zbuf2` (warp-aggregated atomic
-// counter), so k_intersect_rays only walks *n_live rays - half the work on config E, a quarter on the bunny frame.
-// The order of the slots varies from run to run; every ray's result is independent of its slot.
-__global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, int l, float* __restrict__ gray,
+// Shadow rays (renderer.py:293-299) of ALL lights in one launch (blockIdx.y = light): origin frag_pos + 0.1 L,
+// direction L, t_max = |light - frag_pos|.  Only HIT pixels cast shadow rays (a miss pixel's visibility never reaches
+// an output: its image is masked), and the rays are COMPACTED: ray (light l, pixel k) is stored in slot
+// j = slot_of[l*n + k] of `gray` / `zbuf2` (warp-aggregated atomic counter), so ONE k_intersect_rays launch walks the
+// *n_live rays of every light - half the work on config E, a quarter on the bunny frame, and L times more parallel
+// work per launch on small frames.  The order of the slots varies from run to run; every ray's result is independent
+// of its slot.  `cap` = n * n_lights is the row stride of `gray`.
+__global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, size_t cap, float* __restrict__ gray,
                                                      unsigned long long* __restrict__ zbuf2, float* __restrict__ obound,
                                                      int* __restrict__ n_live, int* __restrict__ slot_of) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
     float len = 0.f;
     Vec3 so = v3(0.f, 0.f, 0.f), L = v3(0.f, 0.f, 0.f);
     float dist = 0.f;
@@ -147,27 +150,28 @@ __global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ Sha
     base = __shfl_sync(0xffffffffu, base, 0);
     if (k < p.n) {
         const int j = live ? base + __popc(ballot & ((1u << lane) - 1u)) : -1;
-        slot_of[k] = j;
+        slot_of[(size_t)l * p.n + k] = j;
         if (live) {
-            const size_t n = (size_t)p.n;
             zbuf2[j] = kMissKey;
-            gray[j] = so.x; gray[n + j] = so.y; gray[2 * n + j] = so.z;
-            gray[3 * n + j] = L.x; gray[4 * n + j] = L.y; gray[5 * n + j] = L.z;
-            gray[6 * n + j] = dist;
+            gray[j] = so.x; gray[cap + j] = so.y; gray[2 * cap + j] = so.z;
+            gray[3 * cap + j] = L.x; gray[4 * cap + j] = L.y; gray[5 * cap + j] = L.z;
+            gray[6 * cap + j] = dist;
         }
     }
     for (int off = 16; off > 0; off >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, off));
     if (lane == 0 && len > 0.f) atomicMax((int*)obound, __float_as_int(len));
 }
 
-// visible iff nothing was hit inside (0, |L|), or the nearest such hit is the fragment's own primitive (:306-309)
+// visible iff nothing was hit inside (0, |L|), or the nearest such hit is the fragment's own primitive (:306-309);
+// one thread per (light, pixel), vis is [L, n]
 __global__ void __launch_bounds__(256) k_shadow_resolve(const unsigned long long* __restrict__ zbuf,
                                                         const unsigned long long* __restrict__ zbuf2,
-                                                        const int* __restrict__ slot_of, int n, float* __restrict__ vis_l) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int j = slot_of[k];
+                                                        const int* __restrict__ slot_of, int n, size_t total, float* __restrict__ vis) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % (size_t)n);
+    const int j = slot_of[idx];
     const unsigned long long self = zbuf[k], hit = j >= 0 ? zbuf2[j] : kMissKey;
     const bool visible = hit == kMissKey || self == kMissKey || (unsigned)(hit & 0xFFFFFFFFull) == (unsigned)(self & 0xFFFFFFFFull);
-    vis_l[k] = visible ? 1.f : 0.f;
+    vis[idx] = visible ? 1.f : 0.f;
 }
