@@ -111,3 +111,42 @@ def test_shadow_visibility_matches_oracle_restatement(seed):
              'normal': (w['normal'].reshape(-1, 3) * hit[:, None]).contiguous()}
     g = emul_driver.backward(m, {'shadow': True}, r2['nearest'].detach().reshape(-1), r2['depth'].detach().reshape(-1), gouts)
     parity.compare_grads(g, ref_g)
+
+
+def _random_case(seed):
+    """shared with tests/test_gpu_parity.py::test_randomized_scenes_and_options_vs_oracle"""
+    from surf_renderer_b200 import scenes as synth
+    rng = np.random.RandomState(seed)
+    with_grads = seed % 2 == 0
+    orders = [('disk', 'sphere', 'triangle', 'plane'), ('triangle', 'plane', 'disk', 'sphere'), ('plane', 'disk', 'triangle', 'sphere')]
+    ortho = (not with_grads) and rng.rand() < 0.3
+    width, height = int(rng.randint(17, 90)), int(rng.randint(9, 70))
+    if ortho:
+        width, height = min(width, 60), min(height, 45)                 # the reference's ortho path: one tile of pixels
+    scene = synth.random_mixed_scene(seed, width=width, height=height, n_disk=int(rng.randint(5, 60)), n_tri=int(rng.randint(3, 40)),
+                                     n_sphere=0 if with_grads else int(rng.randint(1, 6)), n_plane=int(rng.randint(0, 3)),
+                                     n_lights=int(rng.randint(1, 6)), order=orders[seed % 3], homogeneous=bool(rng.rand() < 0.5),
+                                     proj='orthographic' if ortho else 'perspective')
+    params = {'double_sided': bool(rng.rand() < 0.5), 'use_quartic': bool(rng.rand() < 0.3)}
+    if not ortho and rng.rand() < 0.4:
+        params['shadow'] = True
+    mode = int(rng.choice([0, 0, 2, 3, 4])) if not ortho else 0
+    return scene, params, mode, with_grads, ortho
+
+
+@pytest.mark.parametrize('seed', list(range(200, 230)))
+def test_emulated_randomized_scenes_and_options_vs_oracle(seed):
+    """The option-space sweep of the GPU suite on the CPU emulation of the kernel math: random scenes with every
+    primitive kind, random viewport / projection / primitive order / layouts / kwargs, forward against the oracle;
+    the conservative filters never reject an exact hit."""
+    import emul_driver
+    import parity
+    import scene_io
+    from oracle import torch_oracle
+    scene, params, _mode, _with_grads, ortho = _random_case(seed)
+    res, filter_misses, m = emul_driver.forward(scene, **params)
+    assert filter_misses == 0
+    ref = torch_oracle.render(scene_io.clone_scene(scene), **params)
+    origins = torch_oracle.make_rays(scene['camera'])[0] if ortho else None
+    ref_np = {k: v.detach() for k, v in ref.items() if isinstance(v, torch.Tensor)}
+    parity.compare_forward(res, ref_np, scene, ortho_origins=origins)

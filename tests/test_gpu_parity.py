@@ -306,6 +306,35 @@ def test_error_behaviour_matches_reference():
     assert torch.equal(a['image'], b['image'])
 
 
+@pytest.mark.parametrize('seed', list(range(200, 212)))
+def test_randomized_scenes_and_options_vs_oracle(seed):
+    """A sweep over the option space: random scenes with all primitive kinds (or disks + triangles only when gradients
+    are compared - sphere gradients are NaN in the reference), random viewport, projection, primitive order,
+    homogeneous / 3-vector layouts and kwargs (double_sided, use_quartic, shadow, math_mode), forward against the
+    oracle and - for the sphere-free half - gradients against its autograd."""
+    from test_emul_extras import _random_case
+    scene, params, mode, with_grads, _ortho = _random_case(seed)
+    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=with_grads)
+    res = _render(sc, _math_mode=mode, **params)
+    osc = scene_io.clone_scene(scene, requires_grad=with_grads)
+    ref = torch_oracle.render(osc, **params)
+    rep = parity.compare_forward(_cpu(res), _cpu(ref), scene, ortho_origins=_ortho_origins(scene))
+    if with_grads:
+        H, W = ref['depth'].shape
+        w = scene_io.loss_weights((H, W), seed)
+        far = scene['camera']['far']
+        ref_np = {k: v.detach() for k, v in ref.items() if isinstance(v, torch.Tensor)}
+        kink = parity.kink_mask(scene, ref_np, params) & (ref['depth'].detach().reshape(-1).numpy() <= far)
+        good = torch.tensor(rep['good_mask'] & ~kink).view(H, W)           # drop eps-tie and relu-kink pixels (SURVEY A.7)
+        for k in w:
+            w[k] = w[k] * (good[..., None] if w[k].dim() == 3 else good)
+        scene_io.weighted_loss(ref, w, far).backward()
+        scene_io.weighted_loss(res, w, far).backward()
+        lo, lg = scene_io.grad_leaves(osc), scene_io.grad_leaves(sc)
+        names = [k for k in lo if lo[k].grad is not None]
+        parity.compare_grads({k: lg[k].grad.cpu() for k in names}, {k: lo[k].grad for k in names})
+
+
 def test_strided_entry_points_reject_bad_arguments():
     """surf_forward_strided through ctypes: empty batch, misaligned per-scene workspace stride, workspace too small."""
     from surf_renderer_b200 import _abi, scenes as synth
