@@ -141,6 +141,46 @@ def test_gpu_along_ray_gan_shape_vs_oracle():
                           'l': osc['lights']['pos'].grad})
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('seed', list(range(300, 310)))
+def test_gpu_along_ray_randomized_options_vs_oracle(seed):
+    """Option-space sweep of render_splats_along_ray against the oracle restatement (itself bit-exact on the six
+    reference-generated fixtures): random viewport, z as [N] or [N,3], per-light visibility, materials, use_quartic,
+    given normals or estimated ones ('plane' / 'avg_normal' on a smooth depth field), samples 1 or 2; outputs and the
+    gradients of depths, normals and light positions."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_golden_along_ray_scene import along_ray_scene
+    import surf_renderer_b200
+    from oracle import torch_oracle
+    rng = np.random.RandomState(seed)
+    W, H = int(rng.randint(9, 48)), int(rng.randint(7, 40))
+    estimate = rng.rand() < 0.4
+    samples = 2 if rng.rand() < 0.3 else 1
+    scene = along_ray_scene(seed, W, H, with_vis=bool(rng.rand() < 0.4), pos3=bool(rng.rand() < 0.5),
+                            mats=int(rng.randint(1, 5)), smooth_z=estimate or samples > 1)
+    params = {'use_quartic': bool(rng.rand() < 0.3)}
+    if samples > 1:
+        params['samples'] = samples
+    if estimate:
+        del scene['objects']['disk']['normal']
+        params['normal_estimation_method'] = 'plane' if rng.rand() < 0.6 else 'avg_normal'
+    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    osc = scene_io.clone_scene(scene, requires_grad=True)
+    res = surf_renderer_b200.render_splats_along_ray(sc, **params)
+    ref = torch_oracle.render_along_ray(osc, **params)
+    _check_outputs(res, {k: v.detach().numpy() for k, v in ref.items()})
+    ok = torch.tensor(np.linalg.norm(ref['normal'].detach().numpy().astype(np.float64), axis=-1) > 0.5)   # see _check_outputs
+    w = torch.rand(ref['image'].shape, generator=torch.Generator().manual_seed(seed)) * ok[..., None]
+    ((res['image'] * w.cuda()).sum() + (res['depth'] * ok.cuda()).sum()).backward()
+    ((ref['image'] * w).sum() + (ref['depth'] * ok).sum()).backward()
+    cand = {'z': sc['objects']['disk']['pos'].grad.cpu(), 'l': sc['lights']['pos'].grad.cpu()}
+    want = {'z': osc['objects']['disk']['pos'].grad, 'l': osc['lights']['pos'].grad}
+    if not estimate:
+        cand['n'], want['n'] = sc['objects']['disk']['normal'].grad.cpu(), osc['objects']['disk']['normal'].grad
+    parity.compare_grads(cand, want, rtol=1e-4, atol_scale=5e-5)
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='reference tree not present')
 def test_z_to_pcl_cc_matches_live_reference():
     """renderer.py:484-534 (imported by the GAN trainer next to the renderers): pure tensor programs, bit-exact."""
