@@ -213,6 +213,31 @@ def _splat_leaves(sc):
     return [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
 
 
+def test_one_million_splats_sampled_vs_oracle():
+    """Ten times the primitive count of the headline config (1M splats, 256x256: 6.6e10 ray-splat pairs, 980 chunks of
+    1024 records through the TMA ring) - 256 sampled pixels against the oracle, forward and position gradients."""
+    from surf_renderer_b200 import scenes as synth
+    scene = synth.config_e(m=1_000_000, width=256, height=256, radius=0.0015)
+    sc = scene_io.clone_scene(scene, device='cuda')
+    sc['objects']['disk']['pos'].requires_grad_(True)
+    res = _render(sc)
+    g = torch.Generator().manual_seed(3)
+    subset = torch.randperm(256 * 256, generator=g)[:256].sort().values
+    osc = scene_io.clone_scene(scene)
+    osc['objects']['disk']['pos'].requires_grad_(True)
+    ref = torch_oracle.render(osc, pixel_subset=subset, tile_size=64)
+    cand = {k: res[k].detach().cpu().reshape(256 * 256, -1)[subset].reshape(ref[k].shape) for k in ('image', 'depth', 'pos', 'normal', 'nearest')}
+    cand['ray_dir'] = res['ray_dir'].detach().cpu()[:, subset]
+    rep = parity.compare_forward(cand, _cpu(ref), scene)
+    assert rep['hit_pixels'] > 60 and int(cand['nearest'].max()) > 500_000
+    same = torch.tensor(rep['good_mask'])
+    w = (torch.rand(256, 3, generator=g) - 0.3) * same[:, None]
+    (ref['image'].reshape(-1, 3) * w).sum().backward()
+    (res['image'].reshape(-1, 3)[subset.cuda()] * w.cuda()).sum().backward()
+    parity.compare_grads({'pos': sc['objects']['disk']['pos'].grad.cpu()}, {'pos': osc['objects']['disk']['pos'].grad},
+                         rtol=1e-4, atol_scale=2e-5)
+
+
 def test_config_b_bunny_256_gradients_full_size():
     """BASELINE configs[1] backward at full size: bunny.splat 256x256, 7 lights, Phong - gradients of disk positions
     and normals, albedo and light positions against the oracle's autograd on 6000 sampled pixels."""
