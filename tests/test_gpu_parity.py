@@ -238,6 +238,15 @@ def test_one_million_splats_sampled_vs_oracle():
                          rtol=1e-4, atol_scale=2e-5)
 
 
+def test_eight_megapixel_frame_sampled_vs_oracle():
+    """A 4096x2048 frame (8.4M pixels, 4096 pixel tiles; 3*N floats per array) of a mixed scene - 2000 sampled pixels
+    against the oracle."""
+    from surf_renderer_b200 import scenes as synth
+    scene = synth.random_mixed_scene(77, width=4096, height=2048, n_disk=300, n_tri=200, n_sphere=8)
+    rep = _oracle_subset_check(scene, {'double_sided': True}, 2000, 4)
+    assert rep['hit_pixels'] > 500
+
+
 def test_config_b_bunny_256_gradients_full_size():
     """BASELINE configs[1] backward at full size: bunny.splat 256x256, 7 lights, Phong - gradients of disk positions
     and normals, albedo and light positions against the oracle's autograd on 6000 sampled pixels."""
