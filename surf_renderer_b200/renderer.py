@@ -290,6 +290,18 @@ def _render_strided(scene, params):
     mb = MarshalledBatch(scene, dev)
     image, depth, normal, pos, nearest, ray_dir = _RenderStridedFn.apply(mb, dict(params), *mb.fulls)
     B, H, W = mb.batch, mb.m.height, mb.m.width
+    if get_param_value('norm_depth_image_only', params, False):
+        # renderer.py:245-260 per scene of the batch (GAN.get_real_samples passes the flag, gan.py:377-379): depth
+        # normalised to [0, 1] with misses mapped to the scene's minimum; same arithmetic as render()
+        im_depth = depth.view(B, H, W)
+        lo = im_depth.amin(dim=(1, 2), keepdim=True)
+        hi = im_depth.amax(dim=(1, 2), keepdim=True)
+        is_far = (im_depth >= mb.m.far).float()
+        norm = is_far * lo + (1 - is_far) * im_depth
+        norm = (norm - lo) / (hi - lo)
+        return {'image': norm, 'depth': im_depth, 'ray_dist': None, 'obj_dist': None, 'nearest': nearest.view(B, H, W),
+                'ray_dir': ray_dir, 'valid_pixels': None, 'obj_pixel_count': None, 'pixel_obj_count': None,
+                'valid_pixels_mask': None}
     return {'image': image.view(B, H, W, 3), 'depth': depth.view(B, H, W), 'normal': normal.view(B, H, W, 3),
             'pos': pos.view(B, H, W, 3), 'ray_dist': None, 'nearest': nearest.view(B, H, W), 'ray_dir': ray_dir}
 
@@ -376,8 +388,6 @@ def render_batch(scenes, **params):
         normal, pos, nearest [B,H,W], ray_dir [B,3,n]).  This is the cheapest form: no per-scene host work at all."""
     if get_param_value('vis_stat', params, False):
         raise RuntimeError('Removed Support for vis_stat')
-    if get_param_value('norm_depth_image_only', params, False):
-        raise NotImplementedError('norm_depth_image_only is per-frame: call render() for it')
     if isinstance(scenes, dict):
         return _render_strided(scenes, params)
     if len(scenes) == 0:
@@ -385,12 +395,13 @@ def render_batch(scenes, **params):
     stacked = _stack_scenes(scenes) if len(scenes) > 1 else None
     if stacked is not None and batched_scene_size(stacked) != len(scenes):
         stacked = None                   # e.g. the same scene object repeated: nothing to stack along
+    if get_param_value('norm_depth_image_only', params, False) and stacked is None:
+        return [render(sc, **params) for sc in scenes]           # depth-only frames of differently shaped scenes
     if stacked is not None:
         res = _render_strided(stacked, params)
-        cols = {k: torch.unbind(res[k], 0) for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir')}
-        return [{'image': cols['image'][b], 'depth': cols['depth'][b], 'normal': cols['normal'][b], 'pos': cols['pos'][b],
-                 'ray_dist': None, 'nearest': cols['nearest'][b], 'ray_dir': cols['ray_dir'][b]}
-                for b in range(len(scenes))]
+        keys = [k for k in ('image', 'depth', 'normal', 'pos', 'nearest', 'ray_dir') if res.get(k) is not None]
+        cols = {k: torch.unbind(res[k], 0) for k in keys}
+        return [dict({k: None for k in res}, **{k: cols[k][b] for k in keys}) for b in range(len(scenes))]
     dev = _resolve_device(scenes[0])
     ms = [Marshalled(sc, dev) for sc in scenes]
     flat = _RenderBatchFn.apply(ms, dict(params), *[t for m in ms for t in m.floats])

@@ -681,6 +681,21 @@ def test_render_batch_equals_per_scene_render():
     assert surf_renderer_b200.render_batch([]) == []
 
 
+def test_render_batch_norm_depth_image_only():
+    """The flag GAN.get_real_samples passes (gan.py:377-379), for stacked batches and for lists: per scene the same
+    result as render()."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    parts = [scene_io.clone_scene(synth.config_d_scene(i, m=400, width=64, height=40, radius=0.05), device='cuda') for i in range(4)]
+    batch = surf_renderer_b200.render_batch(parts, double_sided=True, norm_depth_image_only=True)
+    odd = parts[:2] + [scene_io.clone_scene(synth.config_d_scene(9, m=300, width=64, height=40, radius=0.05), device='cuda')]
+    listed = surf_renderer_b200.render_batch(odd, double_sided=True, norm_depth_image_only=True)
+    for sc, rb in list(zip(parts, batch)) + list(zip(odd, listed)):
+        r = surf_renderer_b200.render(sc, double_sided=True, norm_depth_image_only=True)
+        assert rb['image'].shape == (40, 64) and torch.equal(r['image'], rb['image']) and torch.equal(r['depth'], rb['depth'])
+        assert float(rb['image'].min()) == 0.0 and 0.0 < float(rb['image'].max()) <= 1.0      # misses keep 1001 in the max (:258)
+
+
 def test_render_batch_of_differently_shaped_scenes_falls_back_to_per_scene_marshalling():
     import surf_renderer_b200
     from surf_renderer_b200 import scenes as synth
