@@ -229,10 +229,11 @@ __device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetVie
 // re-evaluates only the disk that flagged instead of the whole group.  Measured -7.5 % on bunny 256x256 / config D,
 // but -3 % on config E when k_intersect itself is built this way (four more registers, one more FMNMX per group,
 // another ptxas schedule of the packed-FMA loop) - hence a separate copy used by the batch kernel only.
-template <int P>
-__device__ __forceinline__ void chunk_disks_dense(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                                  int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                                  PixelRegs<P>& r) {
+// `nf(local, A, p)` runs the exact test of pixel slot p against disk `local` (A = its record's first float4): the
+// camera-ray narrow phase for k_intersect_batch, the shadow-ray narrow phase for k_intersect_shadow.
+template <int P, class NarrowFn>
+__device__ __forceinline__ void chunk_disks_dense(const float4* __restrict__ s, int local0, int count, PixelRegs<P>& r,
+                                                  NarrowFn&& nf) {
     int i = 0;
     {
         // Software-pipelined: the records of group k+1 are fetched from shared memory while group k computes,
@@ -310,8 +311,8 @@ __device__ __forceinline__ void chunk_disks_dense(const IsectParams& prm, const 
                         for (int q = 0; q < P / 2; ++q) {
                             float e0, e1;
                             unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
-                            if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
-                            if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
+                            if (e0 <= 0.f) nf(local0 + base + g, Ag, 2 * q);
+                            if (e1 <= 0.f) nf(local0 + base + g, Ag, 2 * q + 1);
                         }
                     }
                 }
@@ -328,8 +329,8 @@ __device__ __forceinline__ void chunk_disks_dense(const IsectParams& prm, const 
                     for (int q = 0; q < P / 2; ++q) {
                         float e0, e1;
                         unpack2(disk_margin2<P>(Ag, Bg, r, q), e0, e1);
-                        if (e0 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q);
-                        if (e1 <= 0.f) narrow_one<P>(sv, local0 + base + g, Ag, eye, near_clip, far_clip, r, 2 * q + 1);
+                        if (e0 <= 0.f) nf(local0 + base + g, Ag, 2 * q);
+                        if (e1 <= 0.f) nf(local0 + base + g, Ag, 2 * q + 1);
                     }
                 }
             }
@@ -338,14 +339,13 @@ __device__ __forceinline__ void chunk_disks_dense(const IsectParams& prm, const 
     }
     for (; i < count; ++i) {             // group remainder
         const float4 A = s[2 * i], B = s[2 * i + 1];
-        bool any = false;
 #pragma unroll
         for (int q = 0; q < P / 2; ++q) {
             float e0, e1;
             unpack2(disk_margin2<P>(A, B, r, q), e0, e1);
-            any |= (e0 <= 0.f) | (e1 <= 0.f);
+            if (e0 <= 0.f) nf(local0 + i, A, 2 * q);
+            if (e1 <= 0.f) nf(local0 + i, A, 2 * q + 1);
         }
-        if (any) narrow<P>(prm, sv, local0 + i, A, eye, near_clip, far_clip, r);
     }
 }
 
@@ -671,7 +671,10 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         mbar_wait(&full_bar[stage], parity);
         const float4* s = stage_buf + (size_t)stage * prm0.stage_f4;
         if (sv.kind == KIND_DISK) {
-            if (MODE == 0) chunk_disks_dense<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+            if (MODE == 0)
+                chunk_disks_dense<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
+                    narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
+                });
             else chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         }
         else if (sv.kind == KIND_TRIANGLE) {
@@ -1144,3 +1147,166 @@ __global__ void __launch_bounds__(256) k_intersect_generic(const __grid_constant
     if (best >= 0) zbuf[k] = ((unsigned long long)float_order_key(best_t) << 32) | (unsigned)best;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_intersect_shadow: shadow rays of disk-only (splat) scenes.  All shadow rays of one light lie on lines through that
+// light, so their conservative filter is the CAMERA filter with the light as the common origin: records prepared per
+// light by k_prep_lights (n, n.(c - light) | light - c, -(r+slack)^2), ray directions -L in registers, 10 packed
+// FMA-pipe instr per test in the dense disk loop (instead of 17 for the per-ray-origin filter of k_intersect_rays).
+// The filter tests the whole LINE (no t window), so it also covers the reference's quirk that a hit may lie up to 0.1
+// beyond the light (renderer.py:296-306: t is measured from frag_pos + 0.1 L but compared with |light - frag_pos|).
+// Candidates run the same exact test as k_intersect_rays - forward ray from frag_pos + 0.1 L, window 0 < t < t_max,
+// reference operation order - with the ray read back from `gray`.  Work items: [light][ray tile][primitive chunk];
+// light l's compacted rays sit in slots [l*n, l*n + n_live[l]).
+// ---------------------------------------------------------------------------------------------------
+struct ShadowIsectParams {
+    SceneView sc;
+    const float4* packed;            // [n_lights][packed_stride] records per light origin
+    long long packed_stride;         // float4 units
+    const float* gray;               // [7, cap]: origin xyz, direction xyz, t_max
+    size_t cap;                      // = n * n_lights
+    unsigned long long* zbuf2;       // [cap]
+    const int* n_live;               // [n_lights]
+    int n, n_lights;
+    int tiles_per_light, n_chunks, stage_f4;
+    int chunks_before[kMaxSets + 1];
+};
+
+__global__ void __launch_bounds__(256) k_prep_lights(const __grid_constant__ SceneView sc, float4* __restrict__ packed,
+                                                     long long packed_stride) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (g >= sc.total) return;
+    const int s = find_set(sc, g);
+    const SetView& sv = sc.sets[s];
+    const int i = g - sv.first;
+    const Vec3 o = ld3(sc.light_pos + (size_t)l * sc.light_pos_stride);
+    F4 A, B;
+    prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], o, &A, &B);
+    float4* dst = packed + (size_t)l * packed_stride + sv.rec_off + (size_t)i * 2;
+    dst[0] = make_float4(A.x, A.y, A.z, A.w);
+    dst[1] = make_float4(B.x, B.y, B.z, B.w);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_constant__ ShadowIsectParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    const int tid = threadIdx.x;
+    constexpr int TILE = kThreads * P;
+    // Work grid = the LIVE ray tiles of every light (device-side counts): tile_end[l] = live tiles of lights 0..l.
+    // Every CTA derives the same table, so the contiguous item ranges balance over what actually has to be traced.
+    __shared__ int tile_end[17];
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < prm.n_lights; ++l) { acc += (prm.n_live[l] + TILE - 1) / TILE; tile_end[l] = acc; }
+        tile_end[16] = acc;
+    }
+    __syncthreads();
+    const long long n_items = (long long)tile_end[16] * prm.n_chunks;
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
+    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    if (lo >= hi) return;
+    auto light_of = [&](int tile, int* lt) {
+        int l = 0;
+        while (tile >= tile_end[l]) ++l;
+        *lt = tile - (l ? tile_end[l - 1] : 0);
+        return l;
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int c, int* set, int* local0, int* count) {
+        int s = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxSets; ++k)
+            if (k < prm.sc.n_sets && c >= prm.chunks_before[k]) s = k;
+        const SetView& sv = prm.sc.sets[s];
+        const int ppc = prm.stage_f4 / 2;
+        const int j = c - prm.chunks_before[s];
+        *set = s; *local0 = j * ppc; *count = min(ppc, sv.count - j * ppc);
+    };
+    auto issue = [&](int item, int stage) {
+        int set, local0, count;
+        decode(item % prm.n_chunks, &set, &local0, &count);
+        int lt_unused;
+        const int l = light_of(item / prm.n_chunks, &lt_unused);
+        const SetView& sv = prm.sc.sets[set];
+        const uint32_t bytes = (uint32_t)(count * 2) * 16u;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(stage_buf + (size_t)stage * prm.stage_f4,
+                     prm.packed + (size_t)l * prm.packed_stride + sv.rec_off + (size_t)local0 * 2, bytes, &full_bar[stage]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
+
+    PixelRegs<P> r;
+    int cur_tile = -1;
+    size_t slot0 = 0;            // slot of this thread's pixel slot 0 in the current tile
+    int live_in_tile = 0;        // rays of the current tile that exist (0: the tile is past the light's ray count)
+    auto flush = [&]() {
+        if (cur_tile < 0) return;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            if (r.best_i[p] >= 0)
+                atomicMin(prm.zbuf2 + slot0 + (size_t)p * kThreads,
+                          ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
+    };
+
+    for (int it = lo; it < hi; ++it) {
+        const int kk = it - lo;
+        const int stage = kk % kStages;
+        const uint32_t parity = (uint32_t)((kk / kStages) & 1);
+        __syncthreads();
+        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (kk + kStages - 1) % kStages);
+        const int tile = it / prm.n_chunks;
+        if (tile != cur_tile) {
+            flush();
+            cur_tile = tile;
+            int lt;
+            const int l = light_of(tile, &lt);
+            const int n_l = prm.n_live[l];
+            live_in_tile = max(0, min(TILE, n_l - lt * TILE));
+            slot0 = (size_t)l * prm.n + (size_t)lt * TILE + tid;
+            float d[3][P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const bool ok = p * kThreads + tid < live_in_tile;
+                const size_t sl = slot0 + (size_t)p * kThreads;
+                // direction from the light toward the fragment: -L (a null direction gives NaN margins = no candidate)
+                d[0][p] = ok ? -prm.gray[3 * prm.cap + sl] : 0.f;
+                d[1][p] = ok ? -prm.gray[4 * prm.cap + sl] : 0.f;
+                d[2][p] = ok ? -prm.gray[5 * prm.cap + sl] : 0.f;
+                r.best_t[p] = INFINITY;
+                r.best_i[p] = -1;
+            }
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) {
+                r.dx[q] = pack2(d[0][2 * q], d[0][2 * q + 1]);
+                r.dy[q] = pack2(d[1][2 * q], d[1][2 * q + 1]);
+                r.dz[q] = pack2(d[2][2 * q], d[2][2 * q + 1]);
+            }
+        }
+        int set, local0, count;
+        decode(it % prm.n_chunks, &set, &local0, &count);
+        const SetView& sv = prm.sc.sets[set];
+        mbar_wait(&full_bar[stage], parity);
+        if (live_in_tile == 0) continue;                 // CTA-uniform: nothing to trace in this tile
+        const float4* __restrict__ s = stage_buf + (size_t)stage * prm.stage_f4;
+        chunk_disks_dense<P>(s, local0, count, r, [&](int local, const float4&, int p) {
+            if (p * kThreads + tid >= live_in_tile) return;
+            const size_t sl = slot0 + (size_t)p * kThreads;
+            const Vec3 o = v3(prm.gray[sl], prm.gray[prm.cap + sl], prm.gray[2 * prm.cap + sl]);
+            const Vec3 dir = v3(prm.gray[3 * prm.cap + sl], prm.gray[4 * prm.cap + sl], prm.gray[5 * prm.cap + sl]);
+            const float tmax = prm.gray[6 * prm.cap + sl];
+            Vec3 nn;
+            float numer, t;
+            plane_consts_for_origin(sv, local, o, &nn, &numer);
+            const bool hit = exact_hit(sv, local, nn, numer, o, dir, -INFINITY, INFINITY, &t) && t > 0.f && t < tmax;
+            if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
+        });
+    }
+    flush();
+}

@@ -319,6 +319,45 @@ static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStre
     return SURF_OK;
 }
 
+// shadow rays of splat scenes: per-light records + k_intersect_shadow (see surf_intersect.cuh)
+static int run_intersect_shadow(const Frame& f, const int* n_live, cudaStream_t st) {
+    constexpr int P = 8;
+    const int L = f.sc.n_lights;
+    ShadowIsectParams prm;
+    prm.sc = f.sc; prm.packed = f.ws.packed; prm.packed_stride = packed_f4_total(f.sc);
+    prm.gray = f.ws.gray; prm.cap = (size_t)f.n * L; prm.zbuf2 = f.ws.zbuf2; prm.n_live = n_live;
+    prm.n = f.n; prm.n_lights = L;
+    k_prep_lights<<<dim3((f.sc.total + 255) / 256, L), 256, 0, st>>>(f.sc, f.ws.packed, prm.packed_stride);
+    SURF_LAUNCHED("k_prep_lights");
+    const int tile = kThreads * P;
+    prm.tiles_per_light = (f.n + tile - 1) / tile;
+    const int grid_max = sm_count() * 2;
+    int chunk = 1024;
+    while (chunk > 64) {
+        long long items = 0;
+        for (int s = 0; s < f.sc.n_sets; ++s) items += (f.sc.sets[s].count + chunk - 1) / chunk;
+        if (items * prm.tiles_per_light * L >= 4LL * grid_max) break;
+        chunk /= 2;
+    }
+    prm.stage_f4 = chunk * 2;
+    int nchunks = 0;
+    for (int s = 0; s < kMaxSets; ++s) {
+        prm.chunks_before[s] = nchunks;
+        if (s < f.sc.n_sets) nchunks += (f.sc.sets[s].count + chunk - 1) / chunk;
+    }
+    prm.chunks_before[kMaxSets] = nchunks;
+    prm.n_chunks = nchunks;
+    const long long items = (long long)prm.tiles_per_light * L * nchunks;
+    if (items > 0x7fffffffLL) return fail(SURF_ERR_UNSUPPORTED, "too many shadow work items");
+    const int grid = (int)std::min<long long>(items, grid_max);
+    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
+    auto kern = k_intersect_shadow<P>;
+    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(prm);
+    SURF_LAUNCHED("k_intersect_shadow");
+    return SURF_OK;
+}
+
 static int run_common_prologue(const Frame& f, float* ray_out, cudaStream_t st, bool need_rays_and_zbuf) {
     k_setup<<<1, 32, 0, st>>>(f.cam, f.ws.cam);
     SURF_LAUNCHED("k_setup");
@@ -354,12 +393,18 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
             // all lights at once: one ray list of (light, hit pixel) pairs, one intersection launch
             const int L = f.sc.n_lights;
             const size_t cap = (size_t)f.n * L;
-            int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1] = live-ray counter
+            int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1..] = live-ray counter(s)
             int* slot_of = (int*)(f.ws.gray + 7 * cap);
-            SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 8, st));
-            k_rays_shadow<<<dim3((f.n + 255) / 256, L), 256, 0, st>>>(sp, cap, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of);
+            bool disks_only = true;
+            for (int k = 0; k < f.sc.n_sets; ++k) disks_only &= f.sc.sets[k].kind == KIND_DISK;
+            const int per_light = (disks_only && opt->math_mode != 2) ? 1 : 0;   // math_mode 2 keeps the per-ray-origin filter
+            SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4 * (1 + (size_t)L), st));
+            k_rays_shadow<<<dim3((f.n + 255) / 256, L), 256, 0, st>>>(sp, cap, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of,
+                                                                     per_light);
             SURF_LAUNCHED("k_rays_shadow");
-            if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live, (long long)cap))) return rc;
+            if (per_light) {
+                if ((rc = run_intersect_shadow(f, n_live, st))) return rc;
+            } else if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live, (long long)cap))) return rc;
             k_shadow_resolve<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, slot_of, f.n, cap, f.ws.vis);
             SURF_LAUNCHED("k_shadow_resolve");
         }

@@ -89,7 +89,9 @@ static void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     char* p = (char*)base;
     size_t off = 0;
     ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
-    ws->packed = (float4*)(p + off); off += align_up(packed_bytes_bound(total_prims), 256);
+    // with shadows: one set of disk records per light origin (k_prep_lights), 32 B per primitive and light
+    ws->packed = (float4*)(p + off);
+    off += align_up(packed_bytes_bound(total_prims) * (size_t)(shadow ? (n_lights > 1 ? n_lights : 1) : 1), 256);
     ws->circ = (float4*)(p + off); off += align_up((size_t)total_prims * 16 + 256, 256);
     ws->rays = (float*)(p + off); off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);

@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ ShadowPa
 // of its slot.  `cap` = n * n_lights is the row stride of `gray`.
 __global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ ShadowParams p, size_t cap, float* __restrict__ gray,
                                                      unsigned long long* __restrict__ zbuf2, float* __restrict__ obound,
-                                                     int* __restrict__ n_live, int* __restrict__ slot_of) {
+                                                     int* __restrict__ n_live, int* __restrict__ slot_of, int per_light) {
+    // per_light: light l's rays are compacted into their own range [l*n, l*n + n_live[l]) (k_intersect_shadow walks
+    // the lights one after the other with per-light records); otherwise one list [0, n_live[0]) for all lights
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = blockIdx.y;
     float len = 0.f;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256) k_rays_shadow(const __grid_constant__ Sha
     const unsigned ballot = __ballot_sync(0xffffffffu, live);
     const int lane = threadIdx.x & 31;
     int base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(n_live, __popc(ballot));
+    if (lane == 0 && ballot) base = per_light ? l * p.n + atomicAdd(n_live + l, __popc(ballot)) : atomicAdd(n_live, __popc(ballot));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (k < p.n) {
         const int j = live ? base + __popc(ballot & ((1u << lane) - 1u)) : -1;

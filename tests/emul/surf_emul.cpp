@@ -312,6 +312,14 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
                     plane_consts_for_origin(sv, i, so[pix], &nn, &numer);
                     bool hit = exact_hit(sv, i, nn, numer, so[pix], dir[pix], -INFINITY, INFINITY, &t) && t > 0.f && t < tmax[pix];
                     if (hit && !filter_pass_rays(sv, &pk.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)], so[pix], dir[pix])) ++misses;
+                    // k_intersect_shadow's filter for splat scenes: the camera-style disk filter with the LIGHT as the
+                    // common origin and -L as the ray direction (records as k_prep_lights prepares them)
+                    if (hit && sv.kind == KIND_DISK) {
+                        F4 A, B;
+                        prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride),
+                                  sv.radius[i], ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), &A, &B);
+                        if (!disk_filter(A, B, v3(-dir[pix].x, -dir[pix].y, -dir[pix].z))) ++misses;
+                    }
                 }
             }
         }
