@@ -29,7 +29,7 @@ class GraphedStep:
     """Capture `fn` (no arguments; reads and updates tensors in place) into a CUDA graph after `warmup` eager runs on
     a side stream (torch's capture protocol); calling the object replays it and returns fn's static outputs."""
 
-    def __init__(self, fn, warmup=3):
+    def __init__(self, fn, warmup=3, capture_error_mode='global'):
         if not torch.cuda.is_available():
             raise RuntimeError('GraphedStep needs a CUDA device')
         side = torch.cuda.Stream()
@@ -39,7 +39,8 @@ class GraphedStep:
                 fn()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # 'thread_local' lets other threads (e.g. the NCCL watchdog) keep making CUDA calls while this one captures
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.outputs = fn()
 
     def __call__(self):
