@@ -67,13 +67,12 @@ __global__ void k_setup_batch(CamArgs a, const __grid_constant__ BatchArgs ba, C
                      a.far_clip, ws_at(cs0, ba, b));
 }
 
-__device__ __forceinline__ void prep_body(const SceneView& sc, const CamState* __restrict__ cs, float4* __restrict__ packed,
-                                          int g) {
+// filter records of primitive g for rays from the common origin o (the eye; a light for k_prep_lights)
+__device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* __restrict__ packed, int g) {
     if (g >= sc.total) return;
     const int s = find_set(sc, g);
     const SetView& sv = sc.sets[s];
     const int i = g - sv.first;
-    const Vec3 o = v3(cs->eye[0], cs->eye[1], cs->eye[2]);
     F4 r[4];
     if (sv.kind == KIND_DISK) {
         prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], o,
@@ -94,7 +93,7 @@ __device__ __forceinline__ void prep_body(const SceneView& sc, const CamState* _
 
 __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ SceneView sc, const CamState* __restrict__ cs,
                                               float4* __restrict__ packed) {
-    prep_body(sc, cs, packed, blockIdx.x * blockDim.x + threadIdx.x);
+    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), packed, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256) k_prep_batch(const __grid_constant__ SceneView sc0, const __grid_constant__ BatchArgs ba,
@@ -103,7 +102,8 @@ __global__ void __launch_bounds__(256) k_prep_batch(const __grid_constant__ Scen
     const int b = blockIdx.y;
     if (threadIdx.x == 0) { sc = sc0; scene_at(&sc, ba, b); }
     __syncthreads();
-    prep_body(sc, ws_at(cs0, ba, b), ws_at(packed0, ba, b), blockIdx.x * blockDim.x + threadIdx.x);
+    const CamState* cs = ws_at(cs0, ba, b);
+    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), ws_at(packed0, ba, b), blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __device__ __forceinline__ void raygen_body(const CamState* __restrict__ cs, int pix0, int n, float* __restrict__ rays,

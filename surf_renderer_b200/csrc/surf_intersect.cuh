@@ -401,10 +401,37 @@ __device__ __forceinline__ void chunk_triangles(const IsectParams& prm, const Se
 // one triangle late so that neither the LDS latency of the next record nor the min/max chain is on the critical path.
 // torus 512x512: 0.276 -> 0.241 ms.  (In k_intersect itself the same code moved the register allocation and with it
 // the disk loop's schedule, -1.5 % on config E, so the single-scene splat kernel keeps the scalar version above.)
-template <int P>
-__device__ __forceinline__ void chunk_triangles_packed(const IsectParams& prm, const SetView& sv, const float4* __restrict__ s,
-                                                       int local0, int count, Vec3 eye, float near_clip, float far_clip,
-                                                       PixelRegs<P>& r) {
+// rare path of chunk_triangles_packed: re-evaluate the flagged triangle's filter per pixel pair and run the exact
+// test only on the pixels that pass (instead of on all P pixels of the thread)
+template <int P, class NarrowFn>
+__device__ __forceinline__ void triangle_candidates(const float4* __restrict__ rec, int local, const PixelRegs<P>& r, NarrowFn&& nf) {
+    const float4 A = rec[0], W0 = rec[1], W1 = rec[2], W2 = rec[3];
+#pragma unroll
+    for (int q = 0; q < P / 2; ++q) {
+        const unsigned long long b2 = fma2(pack2(A.z, A.z), r.dz[q], fma2(pack2(A.y, A.y), r.dy[q], mul2(pack2(A.x, A.x), r.dx[q])));
+        float b0, b1;
+        unpack2(b2, b0, b1);
+        const unsigned long long t2 = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
+        float m0 = INFINITY, m1 = INFINITY;
+#define SURF_EDGE1(W)                                                                                                   \
+        {                                                                                                               \
+            const unsigned long long u2 = fma2(pack2(W.z, W.z), r.dz[q], fma2(pack2(W.y, W.y), r.dy[q], mul2(pack2(W.x, W.x), r.dx[q]))); \
+            float c0, c1;                                                                                               \
+            unpack2(fma2(t2, u2, pack2(W.w, W.w)), c0, c1);                                                             \
+            m0 = fminf(m0, c0); m1 = fminf(m1, c1);                                                                     \
+        }
+        SURF_EDGE1(W0)
+        SURF_EDGE1(W1)
+        SURF_EDGE1(W2)
+#undef SURF_EDGE1
+        if (m0 >= 0.f) nf(local, A, 2 * q);
+        if (m1 >= 0.f) nf(local, A, 2 * q + 1);
+    }
+}
+
+template <int P, class NarrowFn>
+__device__ __forceinline__ void chunk_triangles_packed(const float4* __restrict__ s, int local0, int count, PixelRegs<P>& r,
+                                                       NarrowFn&& nf) {
     if (count <= 0) return;
     constexpr int Q = P / 2;
     float4 A = s[0], W0 = s[1], W1 = s[2], W2 = s[3];
@@ -443,11 +470,37 @@ __device__ __forceinline__ void chunk_triangles_packed(const IsectParams& prm, c
             unpack2(c2[q], e0, e1);
             mx = fmaxf(mx, fmaxf(fminf(a0, fminf(b0, e0)), fminf(a1, fminf(b1, e1))));   // NaN-ignoring: conservative
         }
-        if (mx_prev >= 0.f) narrow<P>(prm, sv, local0 + i - 1, s[4 * (i - 1)], eye, near_clip, far_clip, r);
+        if (mx_prev >= 0.f) triangle_candidates<P>(s + 4 * (i - 1), local0 + i - 1, r, nf);
         mx_prev = mx;
         A = An; W0 = W0n; W1 = W1n; W2 = W2n;
     }
-    if (mx_prev >= 0.f) narrow<P>(prm, sv, local0 + count - 1, s[4 * (count - 1)], eye, near_clip, far_clip, r);
+    if (mx_prev >= 0.f) triangle_candidates<P>(s + 4 * (count - 1), local0 + count - 1, r, nf);
+}
+
+// spheres / planes with a caller-supplied narrow phase (k_intersect_shadow); the filters are chunk_spheres' / none
+template <int P, class NarrowFn>
+__device__ __forceinline__ void chunk_spheres_fn(const float4* __restrict__ s, int local0, int count, PixelRegs<P>& r, NarrowFn&& nf) {
+    for (int i = 0; i < count; ++i) {
+        const float4 S = s[i];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            Vec3 d = ray_of<P>(r, p);
+            float hb = fmaf(S.z, d.z, fmaf(S.y, d.y, S.x * d.x));
+            any |= fmaf(hb, hb, -S.w) >= 0.f;
+        }
+        if (any) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) nf(local0 + i, S, p);
+        }
+    }
+}
+template <int P, class NarrowFn>
+__device__ __forceinline__ void chunk_planes_fn(const float4* __restrict__ s, int local0, int count, NarrowFn&& nf) {
+    for (int i = 0; i < count; ++i) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) nf(local0 + i, s[i], p);
+    }
 }
 
 template <int P, int MODE>
@@ -678,7 +731,10 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
             else chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         }
         else if (sv.kind == KIND_TRIANGLE) {
-            if (MODE != 1) chunk_triangles_packed<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
+            if (MODE != 1)
+                chunk_triangles_packed<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
+                    narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
+                });
             else chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
         }
         else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);
@@ -1148,10 +1204,11 @@ __global__ void __launch_bounds__(256) k_intersect_generic(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_intersect_shadow: shadow rays of disk-only (splat) scenes.  All shadow rays of one light lie on lines through that
-// light, so their conservative filter is the CAMERA filter with the light as the common origin: records prepared per
-// light by k_prep_lights (n, n.(c - light) | light - c, -(r+slack)^2), ray directions -L in registers, 10 packed
-// FMA-pipe instr per test in the dense disk loop (instead of 17 for the per-ray-origin filter of k_intersect_rays).
+// k_intersect_shadow: the shadow rays of all lights.  All shadow rays of one light lie on lines through that light, so
+// their conservative filters are the CAMERA filters with the light as the common origin: records prepared per light
+// by k_prep_lights (disk: n, n.(c - light) | light - c, -(r+slack)^2), ray directions -L in registers, 10 packed
+// FMA-pipe instr per ray-disk test in the dense disk loop (instead of 17 for the per-ray-origin filter of
+// k_intersect_rays), the packed triangle filter, the sphere discriminant filter.
 // The filter tests the whole LINE (no t window), so it also covers the reference's quirk that a hit may lie up to 0.1
 // beyond the light (renderer.py:296-306: t is measured from frag_pos + 0.1 L but compared with |light - frag_pos|).
 // Candidates run the same exact test as k_intersect_rays - forward ray from frag_pos + 0.1 L, window 0 < t < t_max,
@@ -1173,18 +1230,9 @@ struct ShadowIsectParams {
 
 __global__ void __launch_bounds__(256) k_prep_lights(const __grid_constant__ SceneView sc, float4* __restrict__ packed,
                                                      long long packed_stride) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = blockIdx.y;
-    if (g >= sc.total) return;
-    const int s = find_set(sc, g);
-    const SetView& sv = sc.sets[s];
-    const int i = g - sv.first;
-    const Vec3 o = ld3(sc.light_pos + (size_t)l * sc.light_pos_stride);
-    F4 A, B;
-    prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride), sv.radius[i], o, &A, &B);
-    float4* dst = packed + (size_t)l * packed_stride + sv.rec_off + (size_t)i * 2;
-    dst[0] = make_float4(A.x, A.y, A.z, A.w);
-    dst[1] = make_float4(B.x, B.y, B.z, B.w);
+    prep_body(sc, ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), packed + (size_t)l * packed_stride,
+              blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 template <int P>
@@ -1224,7 +1272,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
         for (int k = 1; k < kMaxSets; ++k)
             if (k < prm.sc.n_sets && c >= prm.chunks_before[k]) s = k;
         const SetView& sv = prm.sc.sets[s];
-        const int ppc = prm.stage_f4 / 2;
+        const int ppc = prm.stage_f4 / rec_f4(sv.kind);
         const int j = c - prm.chunks_before[s];
         *set = s; *local0 = j * ppc; *count = min(ppc, sv.count - j * ppc);
     };
@@ -1234,10 +1282,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
         int lt_unused;
         const int l = light_of(item / prm.n_chunks, &lt_unused);
         const SetView& sv = prm.sc.sets[set];
-        const uint32_t bytes = (uint32_t)(count * 2) * 16u;
+        const int nf4 = rec_f4(sv.kind);
+        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
         mbar_expect_tx(&full_bar[stage], bytes);
         tma_bulk_g2s(stage_buf + (size_t)stage * prm.stage_f4,
-                     prm.packed + (size_t)l * prm.packed_stride + sv.rec_off + (size_t)local0 * 2, bytes, &full_bar[stage]);
+                     prm.packed + (size_t)l * prm.packed_stride + sv.rec_off + (size_t)local0 * nf4, bytes, &full_bar[stage]);
     };
     if (tid == 0)
         for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
@@ -1295,7 +1344,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
         mbar_wait(&full_bar[stage], parity);
         if (live_in_tile == 0) continue;                 // CTA-uniform: nothing to trace in this tile
         const float4* __restrict__ s = stage_buf + (size_t)stage * prm.stage_f4;
-        chunk_disks_dense<P>(s, local0, count, r, [&](int local, const float4&, int p) {
+        auto nf = [&](int local, const float4&, int p) {     // the exact shadow-ray test of k_intersect_rays<., 1>
             if (p * kThreads + tid >= live_in_tile) return;
             const size_t sl = slot0 + (size_t)p * kThreads;
             const Vec3 o = v3(prm.gray[sl], prm.gray[prm.cap + sl], prm.gray[2 * prm.cap + sl]);
@@ -1306,7 +1355,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
             plane_consts_for_origin(sv, local, o, &nn, &numer);
             const bool hit = exact_hit(sv, local, nn, numer, o, dir, -INFINITY, INFINITY, &t) && t > 0.f && t < tmax;
             if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
-        });
+        };
+        if (sv.kind == KIND_DISK) chunk_disks_dense<P>(s, local0, count, r, nf);
+        else if (sv.kind == KIND_TRIANGLE) chunk_triangles_packed<P>(s, local0, count, r, nf);
+        else if (sv.kind == KIND_SPHERE) chunk_spheres_fn<P>(s, local0, count, r, nf);
+        else chunk_planes_fn<P>(s, local0, count, nf);
     }
     flush();
 }

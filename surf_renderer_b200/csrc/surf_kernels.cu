@@ -319,7 +319,7 @@ static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStre
     return SURF_OK;
 }
 
-// shadow rays of splat scenes: per-light records + k_intersect_shadow (see surf_intersect.cuh)
+// shadow rays: per-light records + k_intersect_shadow (see surf_intersect.cuh)
 static int run_intersect_shadow(const Frame& f, const int* n_live, cudaStream_t st) {
     constexpr int P = 8;
     const int L = f.sc.n_lights;
@@ -335,7 +335,10 @@ static int run_intersect_shadow(const Frame& f, const int* n_live, cudaStream_t 
     int chunk = 1024;
     while (chunk > 64) {
         long long items = 0;
-        for (int s = 0; s < f.sc.n_sets; ++s) items += (f.sc.sets[s].count + chunk - 1) / chunk;
+        for (int s = 0; s < f.sc.n_sets; ++s) {
+            const int ppc = (chunk * 2) / rec_f4(f.sc.sets[s].kind);
+            items += (f.sc.sets[s].count + ppc - 1) / ppc;
+        }
         if (items * prm.tiles_per_light * L >= 4LL * grid_max) break;
         chunk /= 2;
     }
@@ -343,7 +346,10 @@ static int run_intersect_shadow(const Frame& f, const int* n_live, cudaStream_t 
     int nchunks = 0;
     for (int s = 0; s < kMaxSets; ++s) {
         prm.chunks_before[s] = nchunks;
-        if (s < f.sc.n_sets) nchunks += (f.sc.sets[s].count + chunk - 1) / chunk;
+        if (s < f.sc.n_sets) {
+            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
+            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
+        }
     }
     prm.chunks_before[kMaxSets] = nchunks;
     prm.n_chunks = nchunks;
@@ -395,9 +401,7 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
             const size_t cap = (size_t)f.n * L;
             int* n_live = (int*)f.ws.obound + 1;                      // [0] = origin bound, [1..] = live-ray counter(s)
             int* slot_of = (int*)(f.ws.gray + 7 * cap);
-            bool disks_only = true;
-            for (int k = 0; k < f.sc.n_sets; ++k) disks_only &= f.sc.sets[k].kind == KIND_DISK;
-            const int per_light = (disks_only && opt->math_mode != 2) ? 1 : 0;   // math_mode 2 keeps the per-ray-origin filter
+            const int per_light = opt->math_mode != 2 ? 1 : 0;   // math_mode 2 keeps the per-ray-origin filter (cross-check)
             SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4 * (1 + (size_t)L), st));
             k_rays_shadow<<<dim3((f.n + 255) / 256, L), 256, 0, st>>>(sp, cap, f.ws.gray, f.ws.zbuf2, f.ws.obound, n_live, slot_of,
                                                                      per_light);

@@ -301,8 +301,9 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
             tmax[pix] = dist;
             ob = fmaxf(ob, sqrtf(so[pix].x * so[pix].x + so[pix].y * so[pix].y + so[pix].z * so[pix].z));
         }
-        Packed pk;
+        Packed pk, pkl;
         pack_all_rays(sc, ob, &pk);
+        pack_all(sc, ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), &pkl);
         for (int pix = 0; pix < N; ++pix) {
             if (keys[pix] == kMissKey) continue;
             for (int s = 0; s < sc.n_sets; ++s) {
@@ -312,14 +313,10 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
                     plane_consts_for_origin(sv, i, so[pix], &nn, &numer);
                     bool hit = exact_hit(sv, i, nn, numer, so[pix], dir[pix], -INFINITY, INFINITY, &t) && t > 0.f && t < tmax[pix];
                     if (hit && !filter_pass_rays(sv, &pk.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)], so[pix], dir[pix])) ++misses;
-                    // k_intersect_shadow's filter for splat scenes: the camera-style disk filter with the LIGHT as the
-                    // common origin and -L as the ray direction (records as k_prep_lights prepares them)
-                    if (hit && sv.kind == KIND_DISK) {
-                        F4 A, B;
-                        prep_disk(ld3(sv.pos + (size_t)i * sv.pos_stride), ld3(sv.normal + (size_t)i * sv.normal_stride),
-                                  sv.radius[i], ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), &A, &B);
-                        if (!disk_filter(A, B, v3(-dir[pix].x, -dir[pix].y, -dir[pix].z))) ++misses;
-                    }
+                    // k_intersect_shadow's filter: the camera-style filters with the LIGHT as the common origin and -L as
+                    // the ray direction (records as k_prep_lights prepares them)
+                    if (hit && !filter_pass(sv, &pkl.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)],
+                                            v3(-dir[pix].x, -dir[pix].y, -dir[pix].z))) ++misses;
                 }
             }
         }
