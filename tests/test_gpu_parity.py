@@ -765,6 +765,41 @@ def test_render_batch_of_stacked_tensors(width, height):
     assert torch.allclose(albedo.grad, albedo2.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('shadow', [False, True])
+def test_multi_view_batch_of_one_scene(shadow):
+    """The demos' multi-view loop (render_random_camera, full_diff_renderer_demo.py:17-120: one object, many cameras)
+    as a strided batch: the splats are SHARED by all views (stride 0), only the camera eye is batched.  Same bits per
+    view as render(); the shared splats receive the sum of the views' gradients (atomic accumulation across scenes)."""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    base = scene_io.clone_scene(synth.config_d_scene(3, m=700, width=64, height=48, radius=0.05), device='cuda')
+    g = torch.Generator().manual_seed(5)
+    dirs = torch.randn(6, 3, generator=g)
+    eyes = torch.cat((5.0 * dirs / dirs.norm(dim=1, keepdim=True), torch.ones(6, 1)), dim=1).cuda()
+    pos = base['objects']['disk']['pos'].detach().clone().requires_grad_(True)
+    views = scene_io.clone_scene(base, device='cuda')
+    views['objects']['disk']['pos'] = pos
+    views['camera']['eye'] = eyes
+    params = {'double_sided': True, 'shadow': shadow}
+    res = surf_renderer_b200.render_batch(views, **params)
+    assert res['image'].shape == (6, 48, 64, 3)
+    w = torch.linspace(0.5, 1.5, 6, device='cuda')
+    (res['image'] * w[:, None, None, None]).sum().backward()
+    pos2 = pos.detach().clone().requires_grad_(True)
+    total = 0
+    for b in range(6):
+        sc = scene_io.clone_scene(base, device='cuda')
+        sc['objects']['disk']['pos'] = pos2
+        sc['camera']['eye'] = eyes[b]
+        r = surf_renderer_b200.render(sc, **params)
+        for k in ('image', 'depth', 'nearest'):
+            assert torch.equal(r[k], res[k][b]), (k, b)
+        total = total + (r['image'] * w[b]).sum()
+    total.backward()
+    assert torch.allclose(pos.grad, pos2.grad, rtol=1e-4, atol=1e-6)
+    assert float(pos.grad.abs().max()) > 0
+
+
 @pytest.mark.parametrize('variant', ['shadow', 'ortho', 'screen', 'single'])
 def test_strided_batch_fallback_paths(variant):
     """Strided batches outside the fused kernels' envelope (shadow rays, orthographic camera, math_mode 3) run scene
