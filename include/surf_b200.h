@@ -107,7 +107,9 @@ typedef struct SurfOptions {
                                 1 = same, scalar FFMA; 2 = same, packed, one branch per primitive;
                                 3 = fast: per-pair screen-space bounding-circle test (2.25 lane-instr per test);
                                 4 = dense: mode 0's filter with 2-D pixel tiles and per-disk minima (the strided
-                                batch kernel on one scene) for small frames with splats several pixels wide.
+                                batch kernel on one scene) for frames with splats several pixels wide; mode 0
+                                selects it by itself for frames of at most 256x256 pixels and for scenes with
+                                triangle sets (mode 2 never does).
                                 All modes run the same exact narrow phase and give bit-identical results.      */
 } SurfOptions;
 

@@ -199,7 +199,10 @@ static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st
     BatchArgs one_scene;
     bool has_triangles = false;
     for (int k = 0; k < f.sc.n_sets; ++k) has_triangles |= f.sc.sets[k].kind == KIND_TRIANGLE;
-    if (mode == 4 || (mode == 0 && has_triangles)) {
+    // Small frames (<= 256x256 pixels) take it too: a primitive that matters at such a resolution is several pixels
+    // wide, which is the regime the dense body is built for (bunny 256x256: -19 %; with nothing to narrow: +7 %).
+    const bool small_frame = f.n <= 256 * 256;
+    if (mode == 4 || (mode == 0 && (has_triangles || small_frame))) {
         mode = 0;
         if (!ba) {
             std::memset(&one_scene, 0, sizeof(one_scene));
