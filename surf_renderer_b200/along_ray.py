@@ -7,7 +7,8 @@ all autograd-connected to z, normals, lights and materials.  The shading (and, o
 mapping) runs in the CUDA kernels ``k_splat_forward`` / ``k_splat_backward``.  Normal estimation (``normal`` missing;
 ``normal_estimation_method`` 'plane' or 'avg_normal', utils.py:854-923) and supersampling (``samples > 1``,
 renderer.py:603-673) are O(N) device-side tensor programs in front of the same kernels, which then take explicit
-fragment positions.  Not built: ``norm_depth_image_only``, ``orient_splats`` (a no-op in the reference).
+fragment positions.  ``norm_depth_image_only`` (renderer.py:677-686) is honoured; ``orient_splats`` is a no-op in the
+reference and is accepted and ignored.
 """
 from __future__ import annotations
 
