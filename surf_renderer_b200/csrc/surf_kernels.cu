@@ -33,8 +33,9 @@ namespace surf {
 
 #include "surf_runtime.cuh"
 #include "surf_ptx.cuh"
+#include "surf_batch.cuh"
+#include "surf_launch.cuh"
 #include "surf_frame_kernels.cuh"
-#include "surf_intersect.cuh"
 #include "surf_shade.cuh"
 #include "surf_backward.cuh"
 #include "surf_splats.cuh"
@@ -72,26 +73,6 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float* out) {
 // ---------------------------------------------------------------------------------------------------
 // host-side orchestration (device-pointer API)
 // ---------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
-
-struct Frame {           // everything derived from (scene, camera, options) once per call
-    SceneView sc;
-    CamArgs cam;
-    int pix0, n;
-    ShadeFlags fl;
-    bool shadow;
-    Workspace ws;
-};
-
 static int make_frame(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, void* workspace,
                       size_t workspace_bytes, Frame* f) {
     if (!scene || !camera || !opt) return fail(SURF_ERR_BAD_ARG, "null scene/camera/options");
@@ -112,258 +93,6 @@ static int make_frame(const SurfScene* scene, const SurfCamera* camera, const Su
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
     carve(workspace, f->sc.total, f->n, f->sc.n_lights, f->shadow, &f->ws);
     if (f->ws.bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
-    return SURF_OK;
-}
-
-template <int P, int MODE>
-static int launch_intersect(const IsectParams& prm, int grid, size_t smem, cudaStream_t st, const BatchArgs* ba) {
-    if (ba) {
-        auto kern = k_intersect_batch<P, MODE>;
-        SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        timer_mark(0, 0, st);
-        kern<<<grid, kThreads, smem, st>>>(prm, *ba);
-        timer_mark(0, 1, st);
-        SURF_LAUNCHED("k_intersect_batch");
-        return SURF_OK;
-    }
-    auto kern = k_intersect<P, MODE>;
-    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    timer_mark(0, 0, st);
-    kern<<<grid, kThreads, smem, st>>>(prm);
-    timer_mark(0, 1, st);
-    SURF_LAUNCHED("k_intersect");
-    return SURF_OK;
-}
-
-template <int MODE>
-static int run_intersect_rays(const struct Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live = nullptr,
-                              long long n_rays_cap = 0);
-
-template <int P>
-static int launch_screen(const ScreenParams& prm, int grid, size_t smem, cudaStream_t st) {
-    auto kern = k_intersect_screen<P>;
-    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    timer_mark(0, 0, st);
-    kern<<<grid, kThreads, smem, st>>>(prm);
-    timer_mark(0, 1, st);
-    SURF_LAUNCHED("k_intersect_screen");
-    return SURF_OK;
-}
-
-static int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStream_t st) {
-    ScreenParams prm;
-    prm.sc = f.sc; prm.cam = f.ws.cam; prm.circ = f.ws.circ; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
-    prm.pix0 = f.pix0; prm.n_pix = f.n; prm.W = f.cam.W; prm.total = f.sc.total;
-    int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
-    if (P != 4 && P != 8 && P != 16) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 4, 8 or 16 for math_mode 3");
-    const int row0 = f.pix0 / f.cam.W, row1 = (f.pix0 + f.n - 1) / f.cam.W;
-    prm.row0 = row0;
-    prm.tiles_x = (f.cam.W + 8 * P - 1) / (8 * P);
-    const int tiles_y = (row1 - row0 + 1 + 31) / 32;
-    prm.n_tiles = prm.tiles_x * tiles_y;
-    const int occ = P <= 8 ? 3 : 2;
-    const int grid_max = sm_count() * occ;
-    int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
-    if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
-    if (!opt->chunk_prims)
-        while (chunk > 64 && (long long)((f.sc.total + chunk - 1) / chunk) * prm.n_tiles < 4LL * grid_max) chunk /= 2;
-    prm.chunk = chunk;
-    prm.n_chunks = (f.sc.total + chunk - 1) / chunk;
-    const long long items = (long long)prm.n_tiles * prm.n_chunks;
-    const int grid = (int)std::min<long long>(items, grid_max);
-    const size_t smem = (size_t)kStages * chunk * sizeof(float4);
-    if (P == 4) return launch_screen<4>(prm, grid, smem, st);
-    if (P == 8) return launch_screen<8>(prm, grid, smem, st);
-    return launch_screen<16>(prm, grid, smem, st);
-}
-
-// `ba` non-null: strided batch (perspective, plane-filter modes only) - the work grid gets a scene dimension
-static int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const BatchArgs* ba = nullptr) {
-    if (ba && (f.cam.proj != 0 || opt->math_mode == 3)) return fail(SURF_ERR_UNSUPPORTED, "no fused batch for this mode");
-    if (f.cam.proj != 0) {
-        if (opt->math_mode == 1) {       // exact-only fallback kept for cross-checking the filtered kernel
-            k_intersect_generic<<<(f.n + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.pix0, f.n, f.ws.zbuf);
-            SURF_LAUNCHED("k_intersect_generic");
-            return SURF_OK;
-        }
-        SURF_CUDA(cudaMemsetAsync(f.ws.obound, 0, 4, st));
-        k_rays_ortho<<<(f.n + 255) / 256, 256, 0, st>>>(f.ws.cam, f.pix0, f.n, f.ws.gray, f.ws.obound);
-        SURF_LAUNCHED("k_rays_ortho");
-        return run_intersect_rays<0>(f, f.ws.zbuf, st);
-    }
-    if (opt->math_mode == 3) return run_intersect_screen(f, opt, st);
-    // math_mode 4 ("dense"): the batch kernel's body - 2-D pixel tiles, per-disk filter minima - on a single scene,
-    // i.e. a batch of one.  For small frames with splats several pixels wide (bunny 256x256: -11 %).
-    // Scenes with triangle sets take the same body for its packed triangle filter (see chunk_triangles_packed).
-    int mode = opt->math_mode;
-    BatchArgs one_scene;
-    bool has_triangles = false;
-    for (int k = 0; k < f.sc.n_sets; ++k) has_triangles |= f.sc.sets[k].kind == KIND_TRIANGLE;
-    // Small frames (<= 256x256 pixels) take it too: a primitive that matters at such a resolution is several pixels
-    // wide, which is the regime the dense body is built for (bunny 256x256: -19 %; with nothing to narrow: +7 %).
-    const bool small_frame = f.n <= 256 * 256;
-    if (mode == 4 || (mode == 0 && (has_triangles || small_frame))) {
-        mode = 0;
-        if (!ba) {
-            std::memset(&one_scene, 0, sizeof(one_scene));
-            one_scene.n_scenes = 1;
-            ba = &one_scene;
-        }
-    }
-    IsectParams prm;
-    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
-    prm.n_pix = f.n;
-    int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
-    if (P != 2 && P != 4 && P != 8) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 2, 4 or 8");
-    const int tile = kThreads * P;
-    prm.tiles_per_scene = (f.n + tile - 1) / tile;
-    prm.tiles_x = 0; prm.W = f.cam.W; prm.pix0 = f.pix0;
-    if (ba && P == 8 && f.cam.W % 64 == 0) {       // 2-D tiles for the batch kernel (see IsectParams)
-        const int row0 = f.pix0 / f.cam.W, row1 = (f.pix0 + f.n - 1) / f.cam.W;
-        prm.tiles_x = f.cam.W / 64;
-        prm.tiles_per_scene = prm.tiles_x * ((row1 - row0 + 1 + 31) / 32);
-    }
-    prm.n_tiles = prm.tiles_per_scene * (ba ? ba->n_scenes : 1);
-    // stage capacity: chunk_prims disk records (2 float4 each); keep >= 4x grid items for balance on small frames
-    int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
-    if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
-    const int grid_max = sm_count() * 2;
-    if (!opt->chunk_prims) {
-        // pick the largest chunk whose item count splits over the persistent grid with <= 1.5% quantisation loss
-        // (items are dealt as equal contiguous ranges: the slowest CTA runs ceil(items / grid) of them)
-        auto items_for = [&](int ch) {
-            long long items = 0;
-            for (int s = 0; s < f.sc.n_sets; ++s) {
-                const int ppc = (ch * 2) / rec_f4(f.sc.sets[s].kind);
-                items += (f.sc.sets[s].count + ppc - 1) / ppc;
-            }
-            return items * prm.n_tiles;
-        };
-        int best = 64;
-        double best_loss = 1e30;
-        for (int ch = 1024; ch >= 64; ch /= 2) {
-            const long long items = items_for(ch);
-            const long long per = (items + grid_max - 1) / grid_max;
-            const double loss = (double)per * grid_max / (double)items - 1.0;
-            if (loss <= 0.015) { best = ch; best_loss = loss; break; }
-            if (loss < best_loss) { best = ch; best_loss = loss; }
-        }
-        chunk = best;
-    }
-    prm.stage_f4 = chunk * 2;
-    int nchunks = 0;
-    for (int s = 0; s < kMaxSets; ++s) {
-        prm.chunks_before[s] = nchunks;
-        if (s < f.sc.n_sets) {
-            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
-            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
-        }
-    }
-    prm.chunks_before[kMaxSets] = nchunks;
-    prm.n_chunks = nchunks;
-    const long long items = (long long)prm.n_tiles * nchunks;
-    const int grid = (int)std::min<long long>(items, grid_max);
-    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
-#define SURF_DISPATCH(PP)                                                      \
-    if (P == PP) {                                                             \
-        if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st, ba); \
-        if (mode == 1) return launch_intersect<PP, 1>(prm, grid, smem, st, ba); \
-        return launch_intersect<PP, 2>(prm, grid, smem, st, ba);                \
-    }
-    SURF_DISPATCH(2)
-    SURF_DISPATCH(4)
-    SURF_DISPATCH(8)
-#undef SURF_DISPATCH
-    return fail(SURF_ERR_BAD_ARG, "unsupported pixels_per_thread");
-}
-
-template <int MODE>
-static int run_intersect_rays(const Frame& f, unsigned long long* zbuf, cudaStream_t st, const int* n_live, long long n_rays_cap) {
-    const long long cap = n_rays_cap > 0 ? n_rays_cap : f.n;        // rays stored (row stride of `gray`)
-    if (cap > 0x7fffffffLL) return fail(SURF_ERR_UNSUPPORTED, "more than 2^31 rays in one launch");
-    k_prep_rays<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.obound, f.ws.packed);
-    SURF_LAUNCHED("k_prep_rays");
-    constexpr int P = 4;
-    RayParams prm;
-    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.gray = f.ws.gray; prm.zbuf = zbuf; prm.n_pix = (int)cap;
-    prm.n_live = n_live;
-    const int tile = kThreads * P;
-    prm.n_tiles = (int)((cap + tile - 1) / tile);
-    const int grid_max = sm_count() * 2;
-    int chunk = 1024;
-    while (chunk > 64) {
-        long long items = 0;
-        for (int s = 0; s < f.sc.n_sets; ++s) {
-            const int ppc = (chunk * 2) / rec_f4(f.sc.sets[s].kind);
-            items += (f.sc.sets[s].count + ppc - 1) / ppc;
-        }
-        if (items * prm.n_tiles >= 4LL * grid_max) break;
-        chunk /= 2;
-    }
-    prm.stage_f4 = chunk * 2;
-    int nchunks = 0;
-    for (int s = 0; s < kMaxSets; ++s) {
-        prm.chunks_before[s] = nchunks;
-        if (s < f.sc.n_sets) {
-            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
-            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
-        }
-    }
-    prm.chunks_before[kMaxSets] = nchunks;
-    prm.n_chunks = nchunks;
-    const long long items = (long long)prm.n_tiles * nchunks;
-    const int grid = (int)std::min<long long>(items, grid_max);
-    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    auto kern = k_intersect_rays<P, MODE>;
-    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(prm);
-    SURF_LAUNCHED("k_intersect_rays");
-    return SURF_OK;
-}
-
-// shadow rays: per-light records + k_intersect_shadow (see surf_intersect.cuh)
-static int run_intersect_shadow(const Frame& f, const int* n_live, cudaStream_t st) {
-    constexpr int P = 8;
-    const int L = f.sc.n_lights;
-    ShadowIsectParams prm;
-    prm.sc = f.sc; prm.packed = f.ws.packed; prm.packed_stride = packed_f4_total(f.sc);
-    prm.gray = f.ws.gray; prm.cap = (size_t)f.n * L; prm.zbuf2 = f.ws.zbuf2; prm.n_live = n_live;
-    prm.n = f.n; prm.n_lights = L;
-    k_prep_lights<<<dim3((f.sc.total + 255) / 256, L), 256, 0, st>>>(f.sc, f.ws.packed, prm.packed_stride);
-    SURF_LAUNCHED("k_prep_lights");
-    const int tile = kThreads * P;
-    prm.tiles_per_light = (f.n + tile - 1) / tile;
-    const int grid_max = sm_count() * 2;
-    int chunk = 1024;
-    while (chunk > 64) {
-        long long items = 0;
-        for (int s = 0; s < f.sc.n_sets; ++s) {
-            const int ppc = (chunk * 2) / rec_f4(f.sc.sets[s].kind);
-            items += (f.sc.sets[s].count + ppc - 1) / ppc;
-        }
-        if (items * prm.tiles_per_light * L >= 4LL * grid_max) break;
-        chunk /= 2;
-    }
-    prm.stage_f4 = chunk * 2;
-    int nchunks = 0;
-    for (int s = 0; s < kMaxSets; ++s) {
-        prm.chunks_before[s] = nchunks;
-        if (s < f.sc.n_sets) {
-            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
-            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
-        }
-    }
-    prm.chunks_before[kMaxSets] = nchunks;
-    prm.n_chunks = nchunks;
-    const long long items = (long long)prm.tiles_per_light * L * nchunks;
-    if (items > 0x7fffffffLL) return fail(SURF_ERR_UNSUPPORTED, "too many shadow work items");
-    const int grid = (int)std::min<long long>(items, grid_max);
-    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    auto kern = k_intersect_shadow<P>;
-    SURF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(prm);
-    SURF_LAUNCHED("k_intersect_shadow");
     return SURF_OK;
 }
 
@@ -411,7 +140,7 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
             SURF_LAUNCHED("k_rays_shadow");
             if (per_light) {
                 if ((rc = run_intersect_shadow(f, n_live, st))) return rc;
-            } else if ((rc = run_intersect_rays<1>(f, f.ws.zbuf2, st, n_live, (long long)cap))) return rc;
+            } else if ((rc = run_intersect_rays_shadow(f, f.ws.zbuf2, st, n_live, (long long)cap))) return rc;
             k_shadow_resolve<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(f.ws.zbuf, f.ws.zbuf2, slot_of, f.n, cap, f.ws.vis);
             SURF_LAUNCHED("k_shadow_resolve");
         }

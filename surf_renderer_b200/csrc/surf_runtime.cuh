@@ -1,12 +1,13 @@
-// surf_runtime.cuh - part of libsurf_b200.so (single translation unit: included by surf_kernels.cu inside namespace surf).
+// surf_runtime.cuh - part of libsurf_b200.so (included by every translation unit inside namespace surf; the globals are
+// C++17 inline variables, so all translation units of the library share one instance).
 // error handling, launch accounting, kernel timers, workspace layout
 #pragma once
 
 // ---------------------------------------------------------------------------------------------------
 // error handling (thread-local string) / launch accounting and optional timers (process-wide counters)
 // ---------------------------------------------------------------------------------------------------
-static thread_local std::string g_error;
-static std::atomic<int> g_launches{0};   // process-wide: autograd runs backward on its own thread
+inline thread_local std::string g_error;
+inline std::atomic<int> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg): a ring of
 // event pairs per kernel kind so that a whole timed region can be averaged without synchronising inside it
@@ -17,8 +18,8 @@ struct KernelTimers {
     cudaEvent_t ev[3][kTimerRing][2] = {};
     long long count[3] = {0, 0, 0};     // launches recorded since timing was (re-)enabled
 };
-static KernelTimers g_timers;   // process-wide (see g_launches)
-static void timer_mark(int which, int edge, cudaStream_t st) {
+inline KernelTimers g_timers;   // process-wide (see g_launches)
+inline void timer_mark(int which, int edge, cudaStream_t st) {
     if (!g_timers.enabled) return;
     if (!g_timers.created) {
         for (int k = 0; k < 3; ++k)
@@ -30,7 +31,7 @@ static void timer_mark(int which, int edge, cudaStream_t st) {
     cudaEventRecord(g_timers.ev[which][slot][edge], st);
     if (edge == 1) ++g_timers.count[which];
 }
-static double timer_ms(int which, long long index) {
+inline double timer_ms(int which, long long index) {
     const int slot = (int)(index % kTimerRing);
     if (cudaEventSynchronize(g_timers.ev[which][slot][1]) != cudaSuccess) return -1.0;
     float ms = 0.f;
@@ -38,11 +39,11 @@ static double timer_ms(int which, long long index) {
     return (double)ms;
 }
 
-static int fail(int code, const std::string& msg) {
+inline int fail(int code, const std::string& msg) {
     g_error = msg;
     return code;
 }
-static int cuda_fail(cudaError_t e, const char* where) {
+inline int cuda_fail(cudaError_t e, const char* where) {
     g_error = std::string(where) + ": " + cudaGetErrorString(e);
     return SURF_ERR_CUDA;
 }
@@ -78,14 +79,14 @@ struct Workspace {
 };
 constexpr int kMaxAccSlots = 512;
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t packed_bytes_bound(int total_prims) {
+inline size_t packed_bytes_bound(int total_prims) {
     // worst case: all triangles (4 float4 each) + 8 sets x 128-byte padding
     return (size_t)total_prims * 64 + kMaxSets * 128 + 256;
 }
 
-static void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws) {
+inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws) {
     char* p = (char*)base;
     size_t off = 0;
     ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
