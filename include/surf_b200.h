@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SURF_ABI_VERSION 1
+#define SURF_ABI_VERSION 2
 #define SURF_MAX_SETS 8
 
 typedef enum SurfStatus {
@@ -156,6 +156,18 @@ const char* surf_last_error(void);
 /* bytes of device scratch surf_forward / surf_backward need for this problem size
  * (n_lights and shadow only matter when options.shadow is set: + 4*L*n bytes of visibility) */
 size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow);
+/* the exact need of one call: `orthographic` = camera proj 1 (per-pixel ray origins: + 40 B per pixel; shadow frames
+ * carry that list anyway), `step` = the workspace also holds d(loss)/d(image) of surf_step_mse (+ 12 B per pixel).
+ * surf_workspace_bytes() = the bound for orthographic = 1, step = 0. */
+size_t surf_workspace_bytes_ex(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow,
+                               int32_t orthographic, int32_t step);
+
+/* Index arrays (material_idx, light_color_idx) in DEVICE memory cannot be range-checked by the host without a
+ * synchronisation, so the kernels clamp them to the valid range and record the fact in the workspace.  This call
+ * synchronises `cuda_stream` and returns SURF_ERR_BAD_ARG if the last forward that used `workspace` saw an index out of
+ * range - where the reference's index_select (renderer.py:284-286) raises IndexError.  The host-pointer entry points
+ * check their (host) index arrays up front instead. */
+int surf_check_indices(const void* workspace, void* cuda_stream);
 
 /* ---- device-pointer API (what the torch autograd.Function calls) ---- */
 int surf_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
@@ -166,6 +178,24 @@ int surf_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOp
                   void* workspace, size_t workspace_bytes,
                   const int64_t* nearest, const float* depth,
                   const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads, void* cuda_stream);
+
+/* ---- one inverse-rendering step in one call: render -> mean((image - target)^2) -> backward ----
+ * Replaces the loop body of diffrend/torch/test_optimization.py:100-125 (`res = render(scene)`, `loss = mean((im -
+ * target)^2)`, `loss.backward()`): forward of the pixel range, the loss and d(loss)/d(image) fused into the shading
+ * epilogue, then the backward into `scene_grads` - all enqueued by this call.  out->depth and out->nearest are
+ * required (the backward reads them); the other outputs may be NULL.  The workspace must be sized with
+ * surf_workspace_bytes_ex(..., step = 1) unless `grad_image` is provided. */
+typedef struct SurfStepMSE {
+    const float* target_image;   /* [n,3] target of this call's pixel range */
+    float loss_scale;            /* weight of every squared error: 1/(3*W*H) = the mean over the whole frame, also when
+                                    this call renders one band of it (the bands' partial losses then add up) */
+    float* loss;                 /* device [1] or NULL; the library ADDS loss_scale * sum((image-target)^2) to it
+                                    (caller zero-initialises, like the gradient accumulators) */
+    float* grad_image;           /* optional device [n,3] (strided: [B,n,3], required): receives d(loss)/d(image) */
+} SurfStepMSE;
+int surf_step_mse(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options, void* workspace,
+                  size_t workspace_bytes, const SurfOutputs* out, const SurfStepMSE* step,
+                  const SurfSceneGrads* scene_grads, void* cuda_stream);
 
 /* ---- batches of independent scenes: the per-element loop of GAN.get_real_samples (GAN/gan.py:326-377) ----
  * Arrays of n_scenes scenes / cameras / workspaces / outputs (one shared SurfOptions).  All kernels of all scenes are
@@ -199,6 +229,13 @@ int surf_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfC
                           const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
                           size_t workspace_bytes_per_scene, const int64_t* nearest0, const float* depth0,
                           const SurfOutGrads* out_grads0, const SurfSceneGrads* grads0, void* cuda_stream);
+
+/* fused step over a strided batch: target_image / grad_image are [B,n,3]; *loss receives the sum over the scenes
+ * (perspective frames without shadow rays, math_mode != 3 - otherwise SURF_ERR_UNSUPPORTED) */
+int surf_step_mse_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                          const SurfBatchLayout* layout, const SurfOptions* options, void* workspace,
+                          size_t workspace_bytes_per_scene, const SurfOutputs* out0, const SurfStepMSE* step,
+                          const SurfSceneGrads* grads0, void* cuda_stream);
 
 /* ---- one-splat-per-pixel renderer: diffrend/torch/renderer.py:537-751 render_splats_along_ray ----
  * Splat k sits on the ray of flat pixel k at camera-space depth z[k] (negative = in front of the camera,

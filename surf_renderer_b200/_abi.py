@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SURF_ABI_VERSION = 1
+SURF_ABI_VERSION = 2
 SURF_MAX_SETS = 8
 KIND = {'disk': 0, 'plane': 1, 'sphere': 2, 'triangle': 3}
 KIND_NAME = {v: k for k, v in KIND.items()}
@@ -70,6 +70,10 @@ class SurfBatchLayout(C.Structure):
                 ('gamma', C.c_int64), ('eye', C.c_int64), ('at', C.c_int64), ('up', C.c_int64)]
 
 
+class SurfStepMSE(C.Structure):
+    _fields_ = [('target_image', C.c_void_p), ('loss_scale', C.c_float), ('loss', C.c_void_p), ('grad_image', C.c_void_p)]
+
+
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
                 ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p)]
@@ -84,6 +88,13 @@ SYMBOLS = {
     'surf_abi_version': (C.c_int, []),
     'surf_last_error': (C.c_char_p, []),
     'surf_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'surf_workspace_bytes_ex': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'surf_check_indices': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'surf_step_mse': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions), C.c_void_p, C.c_size_t,
+                                C.POINTER(SurfOutputs), C.POINTER(SurfStepMSE), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_step_mse_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfBatchLayout),
+                                        C.POINTER(SurfOptions), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs),
+                                        C.POINTER(SurfStepMSE), C.POINTER(SurfSceneGrads), C.c_void_p]),
     'surf_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
     'surf_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),

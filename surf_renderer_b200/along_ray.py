@@ -92,7 +92,7 @@ class _AlongRayFn(torch.autograd.Function):
         dev = floats[0].device
         n = inp.n
         sc, cam, sp, opt = inp.structs(floats, params)
-        ws_bytes = lib().surf_workspace_bytes(0, n, sc.n_lights, 0)
+        ws_bytes = lib().surf_workspace_bytes_ex(0, n, sc.n_lights, 0, 0, 0)
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         image, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
         pos, normal = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)

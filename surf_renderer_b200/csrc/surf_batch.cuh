@@ -54,8 +54,19 @@ __host__ __device__ inline void scene_at(SceneView* sc, const BatchArgs& ba, int
 }
 
 // filter records of primitive g for rays from the common origin o (the eye; a light for k_prep_lights)
-__device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* __restrict__ packed, int g) {
+// `bad_index` (may be null): set when a material index (every thread checks its primitive) or a light's colour index
+// (thread 0) is out of range - the kernels clamp such indices, surf_check_indices() reports them
+__device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* __restrict__ packed, int g, int* bad_index = nullptr) {
     if (g >= sc.total) return;
+    if (bad_index) {
+        bool bad = false;
+        if (g == 0)
+            for (int l = 0; l < sc.n_lights; ++l) bad |= sc.light_color_idx[l] < 0 || sc.light_color_idx[l] >= sc.n_colors;
+        const int s0 = find_set(sc, g);
+        const int m = sc.sets[s0].mat[g - sc.sets[s0].first];
+        bad |= m < 0 || m >= sc.n_materials;
+        if (bad) atomicOr(bad_index, 1);
+    }
     const int s = find_set(sc, g);
     const SetView& sv = sc.sets[s];
     const int i = g - sv.first;

@@ -17,19 +17,20 @@ __global__ void k_setup_batch(CamArgs a, const __grid_constant__ BatchArgs ba, C
                      a.far_clip, ws_at(cs0, ba, b));
 }
 
-__global__ void __launch_bounds__(256) k_prep(const __grid_constant__ SceneView sc, const CamState* __restrict__ cs,
+__global__ void __launch_bounds__(256) k_prep(const __grid_constant__ SceneView sc, CamState* __restrict__ cs,
                                               float4* __restrict__ packed) {
-    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), packed, blockIdx.x * blockDim.x + threadIdx.x);
+    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), packed, blockIdx.x * blockDim.x + threadIdx.x, &cs->bad_index);
 }
 
 __global__ void __launch_bounds__(256) k_prep_batch(const __grid_constant__ SceneView sc0, const __grid_constant__ BatchArgs ba,
-                                                    const CamState* cs0, float4* packed0) {
+                                                    CamState* cs0, float4* packed0) {
     __shared__ SceneView sc;
     const int b = blockIdx.y;
     if (threadIdx.x == 0) { sc = sc0; scene_at(&sc, ba, b); }
     __syncthreads();
-    const CamState* cs = ws_at(cs0, ba, b);
-    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), ws_at(packed0, ba, b), blockIdx.x * blockDim.x + threadIdx.x);
+    CamState* cs = ws_at(cs0, ba, b);
+    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), ws_at(packed0, ba, b), blockIdx.x * blockDim.x + threadIdx.x,
+              &cs->bad_index);
 }
 
 __device__ __forceinline__ void raygen_body(const CamState* __restrict__ cs, int pix0, int n, float* __restrict__ rays,

@@ -497,14 +497,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
     constexpr int TILE = kThreads * P;
     // Work grid = the LIVE ray tiles of every light (device-side counts): tile_end[l] = live tiles of lights 0..l.
     // Every CTA derives the same table, so the contiguous item ranges balance over what actually has to be traced.
-    __shared__ int tile_end[17];
+    __shared__ int tile_end[kMaxShadowLights + 1];
     if (tid == 0) {
         int acc = 0;
         for (int l = 0; l < prm.n_lights; ++l) { acc += (prm.n_live[l] + TILE - 1) / TILE; tile_end[l] = acc; }
-        tile_end[16] = acc;
+        tile_end[kMaxShadowLights] = acc;
     }
     __syncthreads();
-    const long long n_items = (long long)tile_end[16] * prm.n_chunks;
+    const long long n_items = (long long)tile_end[kMaxShadowLights] * prm.n_chunks;
     const int lo = (int)(n_items * blockIdx.x / gridDim.x);
     const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
     if (lo >= hi) return;

@@ -36,6 +36,7 @@ namespace surf {
 #include "surf_batch.cuh"
 #include "surf_launch.cuh"
 #include "surf_frame_kernels.cuh"
+#include "surf_fast.cuh"
 #include "surf_shade.cuh"
 #include "surf_backward.cuh"
 #include "surf_splats.cuh"
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float* out) {
 // host-side orchestration (device-pointer API)
 // ---------------------------------------------------------------------------------------------------
 static int make_frame(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, void* workspace,
-                      size_t workspace_bytes, Frame* f) {
+                      size_t workspace_bytes, Frame* f, bool step = false) {
     if (!scene || !camera || !opt) return fail(SURF_ERR_BAD_ARG, "null scene/camera/options");
     std::string err;
     if (!build_scene_view(*scene, &f->sc, &err)) return fail(SURF_ERR_BAD_ARG, err);
@@ -89,9 +90,9 @@ static int make_frame(const SurfScene* scene, const SurfCamera* camera, const Su
                      camera->fovy, camera->focal_length, camera->near_clip, camera->far_clip};
     f->fl = ShadeFlags{opt->double_sided, opt->use_quartic};
     f->shadow = opt->shadow != 0;
-    if (f->sc.n_lights > 16 && f->shadow) return fail(SURF_ERR_UNSUPPORTED, "shadow supports at most 16 lights");
+    if (f->sc.n_lights > kMaxShadowLights && f->shadow) return fail(SURF_ERR_UNSUPPORTED, "shadow rays support at most 254 lights");
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
-    carve(workspace, f->sc.total, f->n, f->sc.n_lights, f->shadow, &f->ws);
+    carve(workspace, f->sc.total, f->n, f->sc.n_lights, f->shadow, &f->ws, camera->proj != 0, step);
     if (f->ws.bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
     return SURF_OK;
 }
@@ -106,19 +107,45 @@ static int run_common_prologue(const Frame& f, float* ray_out, cudaStream_t st, 
     return SURF_OK;
 }
 
+// the MSE loss of an inverse-rendering step, fused into the shading epilogue (surf_step_mse)
+struct StepLoss { const float* target; float* g_image; double* loss_acc; float scale; };
+
+// k_shade / k_shade_batch with 4 pixels per thread (all-vector global accesses) on large frames, 1 on small ones
+static int launch_shade(ShadeParams& sh, const StepLoss* loss, const BatchArgs* ba, int n_scenes, cudaStream_t st) {
+    sh.target = loss ? loss->target : nullptr;
+    sh.g_image = loss ? loss->g_image : nullptr;
+    sh.loss_acc = loss ? loss->loss_acc : nullptr;
+    sh.loss_scale = loss ? loss->scale : 0.f;
+    const bool wide = (sh.n % 4 == 0) && (long long)sh.n * n_scenes >= 512 * 1024;
+    const int per_cta = 256 * (wide ? 4 : 1);
+    const dim3 grid((sh.n + per_cta - 1) / per_cta, ba ? n_scenes : 1);
+    timer_mark(1, 0, st);
+    if (ba) {
+        if (wide) k_shade_batch<4><<<grid, 256, 0, st>>>(sh, *ba);
+        else k_shade_batch<1><<<grid, 256, 0, st>>>(sh, *ba);
+    } else {
+        if (wide) k_shade<4><<<grid, 256, 0, st>>>(sh);
+        else k_shade<1><<<grid, 256, 0, st>>>(sh);
+    }
+    timer_mark(1, 1, st);
+    SURF_LAUNCHED(ba ? "k_shade_batch" : "k_shade");
+    return SURF_OK;
+}
+
 static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, void* workspace,
-                        size_t workspace_bytes, const SurfOutputs* out, cudaStream_t st) {
+                        size_t workspace_bytes, const SurfOutputs* out, cudaStream_t st, const StepLoss* loss = nullptr) {
     if (!out) return fail(SURF_ERR_BAD_ARG, "null outputs");
     Frame f;
     int rc = make_frame(scene, camera, opt, workspace, workspace_bytes, &f);
     if (rc) return rc;
     if ((rc = run_common_prologue(f, out->ray_dir, st, true))) return rc;
+    // per-primitive records: the filters of k_intersect, the unit normals k_shade reads back, and the index-range
+    // check.  (Orthographic frames replace them with origin-independent records inside run_intersect_ortho.)
+    k_prep<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.packed);
+    SURF_LAUNCHED("k_prep");
     if (f.cam.proj == 0 && opt->math_mode == 3) {
         k_prep_screen<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.circ);
         SURF_LAUNCHED("k_prep_screen");
-    } else if (f.cam.proj == 0) {
-        k_prep<<<(f.sc.total + 255) / 256, 256, 0, st>>>(f.sc, f.ws.cam, f.ws.packed);
-        SURF_LAUNCHED("k_prep");
     }
     if ((rc = run_intersect(f, opt, st))) return rc;
     if (f.shadow) {
@@ -146,26 +173,22 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
         }
     }
     ShadeParams sh;
-    sh.sc = f.sc; sh.cam = f.ws.cam; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf; sh.vis = f.shadow ? f.ws.vis : nullptr;
+    sh.sc = f.sc; sh.cam = f.ws.cam; sh.packed = f.ws.packed; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf;
+    sh.vis = f.shadow ? f.ws.vis : nullptr;
     sh.pix0 = f.pix0; sh.n = f.n; sh.fl = f.fl;
     sh.image = out->image; sh.depth = out->depth; sh.normal = out->normal; sh.pos = out->pos;
     sh.nearest = (long long*)out->nearest;
-    timer_mark(1, 0, st);
-    k_shade<<<(f.n + 255) / 256, 256, 0, st>>>(sh);
-    timer_mark(1, 1, st);
-    SURF_LAUNCHED("k_shade");
-    return SURF_OK;
+    return launch_shade(sh, loss, nullptr, 1, st);
 }
 
 static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, void* workspace,
                          size_t workspace_bytes, const int64_t* nearest, const float* depth, const SurfOutGrads* og,
-                         const SurfSceneGrads* sg, cudaStream_t st, bool workspace_is_warm) {
+                         const SurfSceneGrads* sg, cudaStream_t st, bool workspace_is_warm, float* step_loss = nullptr) {
     if (!nearest || !depth || !og || !sg) return fail(SURF_ERR_BAD_ARG, "null nearest/depth/out_grads/scene_grads");
     Frame f;
     int rc = make_frame(scene, camera, opt, workspace, workspace_bytes, &f);
     if (rc) return rc;
-    const SlotMap sm = slot_map(f.sc.n_materials, f.sc.n_lights, f.sc.n_colors);
-    if (sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the backward accumulators");
+    const SlotMap sm = slot_map(f.sc.n_materials, f.sc.n_lights, f.sc.n_colors);     // slots past kMaxAccSlots: see BwdAcc
     if (!workspace_is_warm) {
         // recompute camera state and rays (the forward call may have used a different workspace)
         k_setup<<<1, 32, 0, st>>>(f.cam, f.ws.cam);
@@ -191,7 +214,7 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_backward");
     FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
-                      f.sc, f.ws.prim_acc};
+                      f.sc, f.ws.prim_acc, f.ws.loss_acc, step_loss};
     k_backward_finalize<<<(f.sc.total + sm.total + 127) / 128, 128, 0, st>>>(fp);
     SURF_LAUNCHED("k_backward_finalize");
     return SURF_OK;
@@ -213,7 +236,7 @@ static int splat_frame(const SurfScene* scene, const SurfCamera* camera, const S
         return fail(SURF_ERR_BAD_ARG, "z_stride must be 1 or 3, normal_stride 3 or 4");
     if (sc.n_lights > 16 && sp->light_vis) return fail(SURF_ERR_UNSUPPORTED, "light_vis supports at most 16 lights");
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
-    carve(workspace, 0, sp->count, sc.n_lights, false, ws);
+    carve(workspace, 0, sp->count, sc.n_lights, false, ws, false);
     if (ws->bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
     *light_cc = ws->rays;                       // the ray buffer is unused on this path: holds the L x 3 camera-space lights
     *cam = CamArgs{camera->eye, camera->at, camera->up, 0, camera->width, camera->height, camera->fovy,
@@ -319,9 +342,24 @@ double surf_mean_kernel_ms(int32_t which, int32_t* launches) {
 }
 
 size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow) {
+    return surf_workspace_bytes_ex(total_prims, n_pixels, n_lights, shadow, 1, 0);
+}
+size_t surf_workspace_bytes_ex(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow,
+                               int32_t orthographic, int32_t step) {
     Workspace ws;
-    carve(nullptr, total_prims, n_pixels, n_lights, shadow != 0, &ws);
+    carve(nullptr, total_prims, n_pixels, n_lights, shadow != 0, &ws, orthographic != 0, step != 0);
     return ws.bytes;
+}
+
+int surf_check_indices(const void* workspace, void* cuda_stream) {
+    if (!workspace) return fail(SURF_ERR_BAD_ARG, "null workspace");
+    Workspace ws;
+    carve(const_cast<void*>(workspace), 0, 0, 0, false, &ws, false);
+    int flag = 0;
+    SURF_CUDA(cudaMemcpyAsync(&flag, &ws.cam->bad_index, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+    SURF_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    if (flag) return fail(SURF_ERR_BAD_ARG, "material_idx or light color_idx out of range (the reference's index_select raises IndexError)");
+    return SURF_OK;
 }
 
 int surf_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options, void* workspace,
@@ -485,7 +523,8 @@ bool fused_batch_ok(const SurfCamera& c, const SurfOptions& o, int n_scenes) {
 
 // Whole batch in FIVE launches: every kernel gets a scene dimension (blockIdx.y; k_intersect_batch: the work item).
 int forward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfBatchLayout* layout,
-                          const SurfOptions* opt, void* workspace, size_t ws_stride, const SurfOutputs* out0, cudaStream_t st) {
+                          const SurfOptions* opt, void* workspace, size_t ws_stride, const SurfOutputs* out0, cudaStream_t st,
+                          const StepLoss* loss = nullptr) {
     Frame f;
     int rc = make_frame(scene0, camera0, opt, workspace, ws_stride, &f);
     if (rc) return rc;
@@ -500,25 +539,21 @@ int forward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCamer
     SURF_LAUNCHED("k_prep_batch");
     if ((rc = run_intersect(f, opt, st, &ba))) return rc;
     ShadeParams sh;
-    sh.sc = f.sc; sh.cam = f.ws.cam; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf; sh.vis = nullptr;
+    sh.sc = f.sc; sh.cam = f.ws.cam; sh.packed = f.ws.packed; sh.rays = f.ws.rays; sh.zbuf = f.ws.zbuf; sh.vis = nullptr;
     sh.pix0 = f.pix0; sh.n = f.n; sh.fl = f.fl;
     sh.image = out0->image; sh.depth = out0->depth; sh.normal = out0->normal; sh.pos = out0->pos;
     sh.nearest = (long long*)out0->nearest;
-    timer_mark(1, 0, st);
-    k_shade_batch<<<dim3((f.n + 255) / 256, B), 256, 0, st>>>(sh, ba);
-    timer_mark(1, 1, st);
-    SURF_LAUNCHED("k_shade_batch");
-    return SURF_OK;
+    return launch_shade(sh, loss, &ba, n_scenes, st);
 }
 
 int backward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfBatchLayout* layout,
                            const SurfOptions* opt, void* workspace, size_t ws_stride, const int64_t* nearest0,
-                           const float* depth0, const SurfOutGrads* og, const SurfSceneGrads* sg, cudaStream_t st, bool warm) {
+                           const float* depth0, const SurfOutGrads* og, const SurfSceneGrads* sg, cudaStream_t st, bool warm,
+                           float* step_loss = nullptr) {
     Frame f;
     int rc = make_frame(scene0, camera0, opt, workspace, ws_stride, &f);
     if (rc) return rc;
-    const SlotMap sm = slot_map(f.sc.n_materials, f.sc.n_lights, f.sc.n_colors);
-    if (sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the backward accumulators");
+    const SlotMap sm = slot_map(f.sc.n_materials, f.sc.n_lights, f.sc.n_colors);     // slots past kMaxAccSlots: see BwdAcc
     const BatchArgs ba = batch_args(*layout, n_scenes, ws_stride);
     const unsigned B = (unsigned)n_scenes;
     if (!warm) {
@@ -546,7 +581,7 @@ int backward_strided_fused(int n_scenes, const SurfScene* scene0, const SurfCame
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_backward_batch");
     FinalizeParams fp{bp.gp, sm, f.ws.acc, f.sc.n_materials, f.sc.n_lights, f.sc.n_colors, f.sc.light_pos_stride,
-                      f.sc, f.ws.prim_acc};
+                      f.sc, f.ws.prim_acc, f.ws.loss_acc, step_loss};
     k_backward_finalize_batch<<<dim3((f.sc.total + sm.total + 127) / 128, B), 128, 0, st>>>(fp, ba);
     SURF_LAUNCHED("k_backward_finalize_batch");
     return SURF_OK;
@@ -602,6 +637,61 @@ int surf_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfC
         return backward_impl(&s, &c, options, (char*)workspace + (size_t)b * workspace_bytes_per_scene,
                              workspace_bytes_per_scene, nearest0 + b * n, depth0 + b * n, &og, &sg, st, warm);
     });
+}
+
+// ---- fused inverse-rendering step: forward -> MSE loss + d(loss)/d(image) in the shading epilogue -> backward ----
+// One host call, one enqueue (test_optimization.py:100-125).  d(loss)/d(image) and the double loss accumulator live in
+// the (step-sized) workspace; depth / nearest are needed by the backward, so when the caller does not want them as
+// outputs they must still be provided - the Python wrapper always does.
+static int step_frame_check(const SurfOutputs* out, const SurfStepMSE* step, const SurfSceneGrads* grads) {
+    if (!out || !step || !grads) return fail(SURF_ERR_BAD_ARG, "null outputs/step/scene_grads");
+    if (!step->target_image) return fail(SURF_ERR_BAD_ARG, "surf_step_mse needs target_image");
+    if (!out->depth || !out->nearest) return fail(SURF_ERR_BAD_ARG, "surf_step_mse needs out->depth and out->nearest (the backward reads them)");
+    return SURF_OK;
+}
+
+int surf_step_mse(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options, void* workspace,
+                  size_t workspace_bytes, const SurfOutputs* out, const SurfStepMSE* step, const SurfSceneGrads* scene_grads,
+                  void* cuda_stream) {
+    g_launches = 0;
+    int rc = step_frame_check(out, step, scene_grads);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Frame f;
+    if ((rc = make_frame(scene, camera, options, workspace, workspace_bytes, &f, step->grad_image == nullptr))) return rc;
+    SURF_CUDA(cudaMemsetAsync(f.ws.loss_acc, 0, 8, st));
+    float* gimg = step->grad_image ? step->grad_image : f.ws.gimg;
+    const StepLoss loss{step->target_image, gimg, f.ws.loss_acc, step->loss_scale};
+    if ((rc = forward_impl(scene, camera, options, workspace, workspace_bytes, out, st, &loss))) return rc;
+    SurfOutGrads og;
+    og.image = gimg; og.depth = nullptr; og.normal = nullptr; og.pos = nullptr;
+    return backward_impl(scene, camera, options, workspace, workspace_bytes, out->nearest, out->depth, &og, scene_grads, st,
+                         true, step->loss);
+}
+
+int surf_step_mse_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfBatchLayout* layout,
+                          const SurfOptions* options, void* workspace, size_t workspace_bytes_per_scene,
+                          const SurfOutputs* out0, const SurfStepMSE* step, const SurfSceneGrads* grads0, void* cuda_stream) {
+    g_launches = 0;
+    if (!scene0 || !camera0 || !layout || !options || !workspace) return fail(SURF_ERR_BAD_ARG, "null batch argument");
+    int rc = step_frame_check(out0, step, grads0);
+    if (rc) return rc;
+    if (workspace_bytes_per_scene % 256) return fail(SURF_ERR_BAD_ARG, "workspace_bytes_per_scene must be a multiple of 256");
+    if (n_scenes < 1) return fail(SURF_ERR_BAD_ARG, "empty batch");
+    if (!fused_batch_ok(*camera0, *options, n_scenes))
+        return fail(SURF_ERR_UNSUPPORTED, "surf_step_mse_strided: perspective frames without shadow rays and math_mode != 3 only");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Frame f;
+    if ((rc = make_frame(scene0, camera0, options, workspace, workspace_bytes_per_scene, &f))) return rc;
+    SURF_CUDA(cudaMemset2DAsync(f.ws.loss_acc, workspace_bytes_per_scene, 0, 8, (size_t)n_scenes, st));
+    if (!step->grad_image) return fail(SURF_ERR_BAD_ARG, "surf_step_mse_strided needs step->grad_image [B, n, 3]");
+    const StepLoss loss{step->target_image, step->grad_image, f.ws.loss_acc, step->loss_scale};
+    if ((rc = forward_strided_fused(n_scenes, scene0, camera0, layout, options, workspace, workspace_bytes_per_scene, out0, st, &loss)))
+        return rc;
+    SurfOutGrads og;
+    og.image = step->grad_image; og.depth = nullptr; og.normal = nullptr; og.pos = nullptr;
+    return backward_strided_fused(n_scenes, scene0, camera0, layout, options, workspace, workspace_bytes_per_scene,
+                                  out0->nearest, out0->depth, &og, grads0, st, true, step->loss);
 }
 
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
@@ -792,6 +882,14 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
     std::string err;
     if (!build_scene_view(*hs, &probe, &err)) return fail(SURF_ERR_BAD_ARG, err);
     if (!check_camera(*hc, &err)) return fail(SURF_ERR_BAD_ARG, err);
+    // the index arrays are host memory here: range-check them like the reference's index_select would
+    for (int k = 0; k < hs->n_sets; ++k)
+        for (int i = 0; i < hs->sets[k].count; ++i) {
+            const int m = hs->sets[k].material_idx[i];
+            if (m < 0 || m >= hs->n_materials) return fail(SURF_ERR_BAD_ARG, "material_idx out of range");
+        }
+    for (int l = 0; l < hs->n_lights; ++l)
+        if (hs->light_color_idx[l] < 0 || hs->light_color_idx[l] >= hs->n_colors) return fail(SURF_ERR_BAD_ARG, "light color_idx out of range");
     const int N = hc->width * hc->height;
     int p0 = opt->pixel_begin, p1 = opt->pixel_end;
     if (p0 == 0 && p1 == 0) p1 = N;
@@ -833,7 +931,15 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
     if ((rc = h2d(c, pl.dcam.at, hc->at, 12))) return rc;
     if ((rc = h2d(c, pl.dcam.up, hc->up, 12))) return rc;
 
-    if ((rc = forward_impl(&pl.dscene, &pl.dcam, opt, pl.workspace, pl.workspace_bytes, &pl.dout, c->stream))) return rc;
+    // with a target image the loss and d(loss)/d(image) are fused into the shading epilogue (mean over this call's pixels)
+    StepLoss sl{pl.d_target, (float*)pl.dgout.image, pl.d_loss, 1.0f / (3.0f * (float)n)};
+    if (has_target) {
+        if ((rc = h2d(c, pl.d_target, target, (size_t)n * 12))) return rc;
+        SURF_CUDA(cudaMemsetAsync(pl.d_loss, 0, 8, c->stream));
+    }
+    if ((rc = forward_impl(&pl.dscene, &pl.dcam, opt, pl.workspace, pl.workspace_bytes, &pl.dout, c->stream,
+                           has_target ? &sl : nullptr)))
+        return rc;
 
     if (hout) {
         if ((rc = d2h(c, hout->image, pl.dout.image, (size_t)n * 12))) return rc;
@@ -847,10 +953,6 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
         if (!hgrads) return fail(SURF_ERR_BAD_ARG, "null scene_grads");
         SurfOutGrads og = pl.dgout;
         if (has_target) {
-            if ((rc = h2d(c, pl.d_target, target, (size_t)n * 12))) return rc;
-            SURF_CUDA(cudaMemsetAsync(pl.d_loss, 0, 8, c->stream));
-            k_mse_grad<<<(n * 3 + 255) / 256, 256, 0, c->stream>>>(pl.dout.image, pl.d_target, n * 3, (float*)og.image, pl.d_loss);
-            SURF_LAUNCHED("k_mse_grad");
             og.depth = nullptr; og.normal = nullptr; og.pos = nullptr;
         } else {
             if (!hgout) return fail(SURF_ERR_BAD_ARG, "need out_grads or target_image");

@@ -119,6 +119,8 @@ struct CamState {           // produced by camera_setup(); lives in the workspac
     float near_clip, far_clip, far_plus1;
     double step_x, step_y;  // linspace steps 2/(W-1), -2/(H-1)
     int W, H, proj;
+    int bad_index;          // set by k_prep when a material_idx / color_idx is out of range (the kernels clamp; the
+                            // reference's index_select raises IndexError - surf_check_indices reports it)
 };
 
 struct F4 { float x, y, z, w; };
@@ -150,6 +152,7 @@ SURF_HD void camera_setup(const float* eye, const float* at, const float* up, in
     cs->step_x = W > 1 ? 2.0 / (double)(W - 1) : 0.0;
     cs->step_y = H > 1 ? -2.0 / (double)(H - 1) : 0.0;
     cs->W = W; cs->H = H; cs->proj = proj;
+    cs->bad_index = 0;
 }
 
 // screen-plane coordinates of flat pixel `pix` (row-major), np.linspace in float64 then f32 scaling
@@ -534,8 +537,11 @@ SURF_HD float facing_sign(Vec3 V, Vec3 n) {
     return dp > 0.f ? 1.f : (dp < 0.f ? -1.f : (dp == 0.f ? 0.f : dp));
 }
 
+SURF_HD int clamp_index(int v, int count) { return v < 0 ? 0 : (v >= count ? count - 1 : v); }
+
 SURF_HD void shade_pixel(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int mat, ShadeFlags fl,
                          const float* visibility /* [L] or null */, float rgb[3]) {
+    mat = clamp_index(mat, sc.n_materials);
     const float* A = sc.albedo + 3 * mat;
     const float kd = sc.coeffs[3 * mat + 0], ks = sc.coeffs[3 * mat + 1], sh = sc.coeffs[3 * mat + 2];
     Vec3 V = unit_eps(vsub(eye, P), nullptr);
@@ -548,7 +554,7 @@ SURF_HD void shade_pixel(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int mat,
         D = D > 0.f ? D : 0.f;
         S = S > 0.f ? S : 0.f;
         float scal = xadd(xmul(kd, D), xmul(ks, pow_like_torch(S, sh)));
-        const float* col = sc.colors + 3 * sc.light_color_idx[l];
+        const float* col = sc.colors + 3 * clamp_index(sc.light_color_idx[l], sc.n_colors);
         float vis = visibility ? visibility[l] : 1.f;
         for (int c = 0; c < 3; ++c) {
             float tint = xmul(col[c], A[c]);
@@ -591,6 +597,7 @@ SURF_HD void backward_shading(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int
     // reduces across the warp inside end_light()/end_pixel(), so every lane must reach them.  Inactive
     // pixels compute on (finite-or-not) garbage and contribute selected zeros.
     Vec3 gP = *gP_io, gn = *gn_io;
+    m = clamp_index(m, sc.n_materials);
     const float* A = sc.albedo + 3 * m;
     const float kd = sc.coeffs[3 * m + 0], ks = sc.coeffs[3 * m + 1], sh = sc.coeffs[3 * m + 2];
     // forward recompute of the composite to get dLoss/dI (renderer.py:330-340 backwards)
@@ -634,7 +641,7 @@ SURF_HD void backward_shading(const SceneView& sc, Vec3 eye, Vec3 P, Vec3 n, int
         float Sp = Ssg > 0.f ? Ssg : 0.f;
         float spec = powf(Sp, sh);
         float scal = kd * Dp + ks * spec;
-        const int crow = sc.light_color_idx[l];
+        const int crow = clamp_index(sc.light_color_idx[l], sc.n_colors);
         const float* col = sc.colors + 3 * crow;
         float vis = visibility ? visibility[l] : 1.f;
         float g_scal = 0.f;

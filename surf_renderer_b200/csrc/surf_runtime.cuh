@@ -75,9 +75,12 @@ struct Workspace {
                                  // row 7 = int slot_of[n]: where pixel k's compacted shadow ray is stored (-1: none)
     unsigned long long* zbuf2;   // [n] z-buffer keys of the shadow rays
     float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
+    double* loss_acc;            // [1] loss of a fused inverse-rendering step (surf_step_mse)
+    float* gimg;                 // [n, 3] d(loss)/d(image) of a fused step (carved for step calls only)
     size_t bytes;
 };
 constexpr int kMaxAccSlots = 512;
+constexpr int kMaxShadowLights = 254;      // per-light live-ray counters in the workspace / tile table of k_intersect_shadow
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -86,7 +89,10 @@ inline size_t packed_bytes_bound(int total_prims) {
     return (size_t)total_prims * 64 + kMaxSets * 128 + 256;
 }
 
-inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws) {
+// `generic_rays`: the frame traces rays with per-ray origins (orthographic camera, or shadow rays) and needs the
+// generic-ray list + second key buffer (40 B per ray); `step`: a fused step also holds d(loss)/d(image).
+inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws, bool generic_rays = true,
+                  bool step = false) {
     char* p = (char*)base;
     size_t off = 0;
     ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
@@ -98,14 +104,16 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->zbuf = (unsigned long long*)(p + off); off += align_up((size_t)n_pix * 8, 256);
     ws->acc = (double*)(p + off); off += align_up((size_t)kMaxAccSlots * 8, 256);
     ws->prim_acc = (double*)(p + off); off += align_up((size_t)total_prims * 7 * 8, 256);
+    ws->obound = (float*)(p + off); off += 1024;           // [0] origin bound, [1 ..] per-light live-ray counters
+    ws->loss_acc = (double*)(p + off); off += 256;
     ws->vis = (float*)(p + off);
     if (shadow) off += align_up((size_t)n_lights * n_pix * sizeof(float), 256);
-    // generic-ray buffers: always carved (orthographic frames need them too); 40 B per ray.  With shadows the rays
-    // of all lights are traced in one launch: n_pix * n_lights rays.
-    const size_t n_rays = (size_t)n_pix * (size_t)(shadow ? (n_lights > 1 ? n_lights : 1) : 1);
+    // generic-ray buffers, 40 B per ray.  With shadows the rays of all lights are traced in one launch: n_pix * n_lights.
+    const size_t n_rays = (generic_rays || shadow) ? (size_t)n_pix * (size_t)(shadow ? (n_lights > 1 ? n_lights : 1) : 1) : 0;
     ws->gray = (float*)(p + off); off += align_up((size_t)8 * n_rays * sizeof(float), 256);
     ws->zbuf2 = (unsigned long long*)(p + off); off += align_up(n_rays * 8, 256);
-    ws->obound = (float*)(p + off); off += 256;
+    ws->gimg = (float*)(p + off);
+    if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->bytes = off;
 }
 

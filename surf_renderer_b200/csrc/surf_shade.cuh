@@ -1,19 +1,24 @@
-// surf_shade.cuh - part of libsurf_b200.so (single translation unit: included by surf_kernels.cu inside namespace surf).
-// k_shade (resolve + Phong epilogue) and the shadow-ray kernels
+// surf_shade.cuh - part of libsurf_b200.so (included by surf_kernels.cu inside namespace surf).
+// k_shade (resolve + Phong epilogue, optionally fused with the MSE loss of an inverse-rendering step) and the
+// shadow-ray list kernels
 #pragma once
 
 // ---------------------------------------------------------------------------------------------------
-// k_shade: resolve + Phong shading epilogue
+// k_shade: resolve + Phong shading epilogue (renderer.py:183-189, 266-340)
 // ---------------------------------------------------------------------------------------------------
 struct ShadeParams {
     SceneView sc;
     const CamState* cam;
+    const float4* packed;   // per-primitive records of k_prep*: .xyz of a planar primitive's first float4 = unit normal
     const float* rays;
     const unsigned long long* zbuf;
     const float* vis;     // [L, n] or null
     int pix0, n;
     ShadeFlags fl;
     float* image; float* depth; float* normal; float* pos; long long* nearest;
+    // fused loss of an inverse-rendering step (surf_step_mse; test_optimization.py:104): with `target` [n,3] set, the
+    // kernel also writes g_image = 2 loss_scale (image - target) and adds loss_scale * sum((image - target)^2) to *loss_acc
+    const float* target; float* g_image; double* loss_acc; float loss_scale;
 };
 
 __device__ __forceinline__ void pixel_ray(const CamState& cs, const float* rays, int n, int pix0, int k, Vec3* o, Vec3* d) {
@@ -26,7 +31,7 @@ __device__ __forceinline__ void pixel_ray(const CamState& cs, const float* rays,
     }
 }
 
-// cooperative [256,3] -> coalesced store through shared memory
+// cooperative [256,3] -> coalesced store through shared memory (k_splat_forward)
 __device__ __forceinline__ void store3(float* __restrict__ dst, float (*sm)[3], int base, int n, const float v[3]) {
     const int tid = threadIdx.x;
     __syncthreads();
@@ -37,53 +42,184 @@ __device__ __forceinline__ void store3(float* __restrict__ dst, float (*sm)[3], 
     for (int j = tid; j < lim; j += 256) dst[(size_t)base * 3 + j] = flat[j];
 }
 
-__device__ __forceinline__ void shade_body(const ShadeParams& p, float (*sm)[3], int block);
+// winner of pixel k -> outputs.  Hit pixels: depth is the t the exact narrow phase stored in the z-buffer key, the
+// unit normal of a planar primitive comes from its k_prep record (both bit-identical to the reference-order
+// recomputation), shading uses the fast forms of surf_fast.cuh.  Miss pixels report primitive 0 at its unmasked
+// distance (argmin of an all-miss column) through the reference-order path.
+__device__ __forceinline__ PixelOut resolve_fast(const ShadeParams& p, const CamState& cs, const LightS* lights, Vec3 eye,
+                                                 Vec3 o, Vec3 d, unsigned long long key, int k) {
+    PixelOut po;
+    if (key == kMissKey) {
+        const Fragment f = fragment_at(p.sc, 0, o, d);
+        po.nearest = 0;
+        po.depth = cs.far_plus1;
+        po.normal[0] = f.n.x; po.normal[1] = f.n.y; po.normal[2] = f.n.z;
+        po.pos[0] = f.P.x; po.pos[1] = f.P.y; po.pos[2] = f.P.z;
+        po.image[0] = po.image[1] = po.image[2] = 0.f;
+        return po;
+    }
+    const int idx = (int)(key & 0xFFFFFFFFull);
+    const float t = float_from_order_key((uint32_t)(key >> 32));
+    const int set = find_set(p.sc, idx);
+    const SetView& sv = p.sc.sets[set];
+    const int local = idx - sv.first;
+    const Vec3 P = ray_point(o, t, d);
+    Vec3 n;
+    if (sv.kind == KIND_SPHERE) {
+        n = unit_eps(vsub(P, ld3(sv.pos + (size_t)local * sv.pos_stride)), nullptr);          // utils.py:275
+    } else {
+        const float4 A = p.packed[sv.rec_off + (size_t)local * rec_f4(sv.kind)];
+        n = v3(A.x, A.y, A.z);
+    }
+    const MatF mt = load_material(p.sc, clampi(sv.mat[local], 0, p.sc.n_materials - 1));
+    float lit[3];
+    shade_fast(p.sc, lights, eye, P, n, mt, p.fl, p.vis ? p.vis + k : nullptr, (size_t)p.n, lit);
+    composite_fast(lit, true, p.sc.gamma, po.image);
+    po.nearest = idx;
+    po.depth = t;
+    po.normal[0] = n.x; po.normal[1] = n.y; po.normal[2] = n.z;
+    po.pos[0] = P.x; po.pos[1] = P.y; po.pos[2] = P.z;
+    return po;
+}
 
+// PX consecutive pixels per thread: with PX = 4 and n % 4 == 0 every global access of the kernel is a 16-byte
+// vector (rays 3 x LDG.128, keys 2 x LDG.128, image / normal / pos 3 x STG.128 each, depth 1, nearest 2).
+template <int PX>
+__device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights, float* red, int block) {
+    stage_lights(p.sc, lights);
+    const CamState& cs = *p.cam;
+    const Vec3 eye = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
+    const int k0 = (block * 256 + threadIdx.x) * PX;
+    const bool vec = PX == 4 && (p.n & 3) == 0;
+    constexpr int I1 = PX >= 4 ? 1 : 0, I2 = PX >= 4 ? 2 : 0, I3 = PX >= 4 ? 3 : 0;      // (the vector paths only exist for PX = 4)
+    float err = 0.f;
+    if (k0 < p.n) {
+        unsigned long long key[PX];
+        float dx[PX], dy[PX], dz[PX];
+        const bool persp = cs.proj == 0;
+        if (vec) {
+            const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(p.zbuf + k0);
+            const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(p.zbuf + k0 + 2);
+            key[0] = ka.x; key[I1] = ka.y; key[I2] = kb.x; key[I3] = kb.y;
+            if (persp) {
+                const float4 a = *reinterpret_cast<const float4*>(p.rays + k0);
+                const float4 b = *reinterpret_cast<const float4*>(p.rays + (size_t)p.n + k0);
+                const float4 c = *reinterpret_cast<const float4*>(p.rays + 2 * (size_t)p.n + k0);
+                dx[0] = a.x; dx[I1] = a.y; dx[I2] = a.z; dx[I3] = a.w;
+                dy[0] = b.x; dy[I1] = b.y; dy[I2] = b.z; dy[I3] = b.w;
+                dz[0] = c.x; dz[I1] = c.y; dz[I2] = c.z; dz[I3] = c.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const int k = min(k0 + j, p.n - 1);
+                key[j] = p.zbuf[k];
+                if (persp) { dx[j] = p.rays[k]; dy[j] = p.rays[(size_t)p.n + k]; dz[j] = p.rays[2 * (size_t)p.n + k]; }
+            }
+        }
+        PixelOut po[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const int k = min(k0 + j, p.n - 1);
+            Vec3 o = eye, d;
+            if (persp) d = v3(dx[j], dy[j], dz[j]);
+            else { o = pixel_ray_origin_ortho(cs, p.pix0 + k); d = v3(cs.odir[0], cs.odir[1], cs.odir[2]); }
+            po[j] = resolve_fast(p, cs, lights, eye, o, d, key[j], k);
+        }
+        float gi[PX][3];
+        if (p.target) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const int k = min(k0 + j, p.n - 1);
+                const bool live = k0 + j < p.n;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float diff = po[j].image[c] - p.target[(size_t)k * 3 + c];
+                    gi[j][c] = 2.f * p.loss_scale * diff;
+                    if (live) err = fmaf(diff, diff, err);
+                }
+            }
+        }
+        if (vec) {
+            auto store12 = [&](float* dst, int which) {
+                if (!dst) return;
+                float f[12];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        f[3 * j + c] = which == 0 ? po[j % PX].image[c] : (which == 1 ? po[j % PX].normal[c] : (which == 2 ? po[j % PX].pos[c] : gi[j % PX][c]));
+                float4* q = reinterpret_cast<float4*>(dst + (size_t)k0 * 3);
+                q[0] = make_float4(f[0], f[1], f[2], f[3]);
+                q[1] = make_float4(f[4], f[5], f[6], f[7]);
+                q[2] = make_float4(f[8], f[9], f[10], f[11]);
+            };
+            store12(p.image, 0);
+            store12(p.normal, 1);
+            store12(p.pos, 2);
+            if (p.target) store12(p.g_image, 3);
+            if (p.depth) *reinterpret_cast<float4*>(p.depth + k0) = make_float4(po[0].depth, po[I1].depth, po[I2].depth, po[I3].depth);
+            if (p.nearest) {
+                longlong2* q = reinterpret_cast<longlong2*>(p.nearest + k0);
+                q[0] = make_longlong2(po[0].nearest, po[I1].nearest);
+                q[1] = make_longlong2(po[I2].nearest, po[I3].nearest);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                const int k = k0 + j;
+                if (k >= p.n) break;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (p.image) p.image[(size_t)k * 3 + c] = po[j].image[c];
+                    if (p.normal) p.normal[(size_t)k * 3 + c] = po[j].normal[c];
+                    if (p.pos) p.pos[(size_t)k * 3 + c] = po[j].pos[c];
+                    if (p.target && p.g_image) p.g_image[(size_t)k * 3 + c] = gi[j][c];
+                }
+                if (p.depth) p.depth[k] = po[j].depth;
+                if (p.nearest) p.nearest[k] = po[j].nearest;
+            }
+        }
+    }
+    if (p.target) {          // CTA-uniform
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            if (s != 0.f) atomicAdd(p.loss_acc, (double)s * (double)p.loss_scale);
+        }
+    }
+}
+
+template <int PX>
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ShadeParams p) {
-    __shared__ float sm[256][3];
-    shade_body(p, sm, blockIdx.x);
+    __shared__ LightS lights[kLightTable];
+    __shared__ float red[8];
+    shade_body<PX>(p, lights, red, blockIdx.x);
 }
 
 // strided batch: blockIdx.y = scene; outputs are [B, n, ...]
+template <int PX>
 __global__ void __launch_bounds__(256) k_shade_batch(const __grid_constant__ ShadeParams p0, const __grid_constant__ BatchArgs ba) {
-    __shared__ float sm[256][3];
+    __shared__ LightS lights[kLightTable];
+    __shared__ float red[8];
     __shared__ ShadeParams p;
     const int b = blockIdx.y;
     if (threadIdx.x == 0) {
         p = p0;
         scene_at(&p.sc, ba, b);
-        p.cam = ws_at(p0.cam, ba, b); p.rays = ws_at(p0.rays, ba, b); p.zbuf = ws_at(p0.zbuf, ba, b);
+        p.cam = ws_at(p0.cam, ba, b); p.packed = ws_at(p0.packed, ba, b); p.rays = ws_at(p0.rays, ba, b);
+        p.zbuf = ws_at(p0.zbuf, ba, b);
         const long long n = p0.n;
         p.image = adv(p0.image, b * n * 3); p.depth = adv(p0.depth, b * n); p.normal = adv(p0.normal, b * n * 3);
         p.pos = adv(p0.pos, b * n * 3); p.nearest = adv(p0.nearest, b * n);
+        p.target = adv(p0.target, b * n * 3); p.g_image = adv(p0.g_image, b * n * 3);
     }
     __syncthreads();
-    shade_body(p, sm, blockIdx.x);
-}
-
-__device__ __forceinline__ void shade_body(const ShadeParams& p, float (*sm)[3], int block) {
-    const int base = block * 256;
-    const int k = base + threadIdx.x;
-    const bool live = k < p.n;
-    PixelOut po;
-    if (live) {
-        Vec3 o, d;
-        pixel_ray(*p.cam, p.rays, p.n, p.pix0, k, &o, &d);
-        float vis_l[16];
-        const float* vis = nullptr;
-        if (p.vis) {
-            for (int l = 0; l < p.sc.n_lights && l < 16; ++l) vis_l[l] = p.vis[(size_t)l * p.n + k];
-            vis = vis_l;
-        }
-        po = resolve_pixel(p.sc, *p.cam, o, d, p.zbuf[k], p.fl, vis);
-        if (p.depth) p.depth[k] = po.depth;
-        if (p.nearest) p.nearest[k] = po.nearest;
-    } else {
-        po = PixelOut();
-    }
-    if (p.image) store3(p.image, sm, base, p.n, po.image);
-    if (p.normal) store3(p.normal, sm, base, p.n, po.normal);
-    if (p.pos) store3(p.pos, sm, base, p.n, po.pos);
+    shade_body<PX>(p, lights, red, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------

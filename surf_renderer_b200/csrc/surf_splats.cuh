@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_splat_forward(const __grid_constant__ S
         nn[0] = np_[0]; nn[1] = np_[1]; nn[2] = np_[2];
         so = splat_pixel_forward(p.sc, *p.cam, k, p.pos_in ? 0.f : p.z[(size_t)k * p.z_stride],
                                  p.pos_in ? p.pos_in + 3 * (size_t)k : nullptr, v3(nn[0], nn[1], nn[2]),
-                                 p.mat ? p.mat[k] : 0, p.fl, vis);
+                                 p.mat ? clamp_index(p.mat[k], p.sc.n_materials) : 0, p.fl, vis);
         if (p.depth) p.depth[k] = so.depth;
     }
     if (p.image) store3(p.image, sm, base, p.n, so.image);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) k_splat_backward(const __grid_constant__ 
         float gz, gpos[3], gn[3];
         splat_pixel_backward(p.sc, *p.cam, kk, p.pos_in ? 0.f : p.z[(size_t)kk * p.z_stride],
                              p.pos_in ? p.pos_in + 3 * (size_t)kk : nullptr, v3(np_[0], np_[1], np_[2]),
-                             p.mat ? p.mat[kk] : 0, p.fl, vis, g, sink, &gz, gpos, gn);
+                             p.mat ? clamp_index(p.mat[kk], p.sc.n_materials) : 0, p.fl, vis, g, sink, &gz, gpos, gn);
         if (live) {
             if (p.gz && !p.pos_in) p.gz[(size_t)k * p.z_stride] += gz;
             if (p.gpos && p.pos_in)
@@ -127,26 +127,5 @@ __global__ void __launch_bounds__(128) k_splat_finalize(const __grid_constant__ 
     else if (j < p.sm.colors) { if (p.gp.atten) p.gp.atten[j - p.sm.atten] += v; }
     else if (j < p.sm.ambient) { if (p.gp.colors) p.gp.colors[j - p.sm.colors] += v; }
     else if (j < p.sm.gamma) { if (p.gp.ambient) p.gp.ambient[j - p.sm.ambient] += v; }
-}
-
-// d/d(image) of mean((image - target)^2) and the loss itself (inverse-rendering step, test_optimization.py:104)
-__global__ void __launch_bounds__(256) k_mse_grad(const float* __restrict__ image, const float* __restrict__ target,
-                                                  int count, float* __restrict__ g_image, double* __restrict__ loss_acc) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    float e = 0.f;
-    if (j < count) {
-        const float diff = image[j] - target[j];
-        g_image[j] = 2.f * diff / (float)count;
-        e = diff * diff;
-    }
-    e = warp_sum(e);
-    __shared__ float part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = e;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += part[w];
-        atomicAdd(loss_acc, (double)s / (double)count);
-    }
 }
 

@@ -59,6 +59,21 @@ def _as_int_tensor(v, device):
     return t
 
 
+def _host_index_range(v):
+    """(min, max) of an index array held in HOST memory (list / numpy / CPU tensor), None for device tensors - those
+    are range-checked by the kernels (clamped + flagged, see surf_check_indices) without a synchronisation."""
+    if isinstance(v, torch.Tensor):
+        if v.is_cuda or v.numel() == 0:
+            return None
+        t = v.detach().long()
+        return int(t.min()), int(t.max())
+    a = np.asarray(v)
+    if a.size == 0:
+        return None
+    a = a.astype(np.int64)
+    return int(a.min()), int(a.max())
+
+
 def _scalar(v):
     if isinstance(v, torch.Tensor):
         return float(v.detach().cpu().reshape(-1)[0])
@@ -92,6 +107,7 @@ class Marshalled:
 
         self.names, self.floats = [], []      # differentiable float inputs, canonical order
         self.ints = {}
+        self._host_ranges = {}                # index array -> (min, max) when the caller's array is host data
         self.sets = []                        # (kind, count, pos_stride, normal_stride)
 
         def add(name, v):
@@ -112,6 +128,7 @@ class Marshalled:
             count, pstride = int(geo.shape[0]), int(geo.shape[-1])
             nstride = int(self.floats[slots['normal']].shape[-1]) if 'normal' in slots else 0
             self.ints['objects/%s/material_idx' % kind] = _as_int_tensor(prim['material_idx'], device)
+            self._host_ranges['objects/%s/material_idx' % kind] = _host_index_range(prim['material_idx'])
             self.sets.append((kind, count, pstride, nstride, slots))
 
         lights = scene['lights']
@@ -119,6 +136,7 @@ class Marshalled:
         self.i_atten = add('lights/attenuation', lights['attenuation'])
         self.i_ambient = add('lights/ambient', lights['ambient'])
         self.ints['lights/color_idx'] = _as_int_tensor(lights['color_idx'], device)
+        self._host_ranges['lights/color_idx'] = _host_index_range(lights['color_idx'])
         self.i_colors = add('colors', scene['colors'])
         self.i_albedo = add('materials/albedo', scene['materials']['albedo'])
         self.i_coeffs = add('materials/coeffs', scene['materials']['coeffs'])
@@ -142,15 +160,16 @@ class Marshalled:
             mi = self.ints['objects/%s/material_idx' % kind]
             if mi.numel() != count:
                 raise ValueError('%s: material_idx has %d entries for %d primitives' % (kind, mi.numel(), count))
-        # index range checks on the host would force a sync for device tensors; do them only for CPU data
-        if self.device.type == 'cpu':
-            for (kind, _, _, _, _) in self.sets:
-                mi = self.ints['objects/%s/material_idx' % kind]
-                if mi.numel() and (int(mi.min()) < 0 or int(mi.max()) >= n_mat):
-                    raise IndexError('material_idx out of range')
-            ci = self.ints['lights/color_idx']
-            if int(ci.min()) < 0 or int(ci.max()) >= n_col:
-                raise IndexError('color_idx out of range')
+        # Index ranges (the reference's index_select raises IndexError, renderer.py:284-286).  Host data (lists, numpy
+        # arrays, CPU tensors) is checked here; device tensors cannot be read without a synchronisation - the kernels
+        # clamp them and flag the workspace, which render(..., _check_indices=True) / SURF_B200_CHECK_INDICES=1 turns
+        # into the same IndexError.
+        for name, rng in self._host_ranges.items():
+            if rng is None:
+                continue
+            hi = n_col if name == 'lights/color_idx' else n_mat
+            if rng[0] < 0 or rng[1] >= hi:
+                raise IndexError('%s out of range: [%d, %d] for %d rows' % (name, rng[0], rng[1], hi))
 
     # ------------------------------------------------------------------
     def c_scene(self, floats=None):

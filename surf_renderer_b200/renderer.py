@@ -10,6 +10,7 @@ either, utils.py:476).  All compute runs in libsurf_b200.so on the current CUDA 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -28,6 +29,19 @@ def get_param_value(key, dict_var, default_val, required=False):
     return default_val
 
 
+_KEEP_WORKSPACE_BYTES = 32 << 20
+# SURF_B200_CHECK_INDICES=1 (or render(..., _check_indices=True)): after the forward, synchronise and raise IndexError
+# when a material_idx / color_idx held in DEVICE memory was out of range (host-side index arrays are always checked).
+_CHECK_INDICES = os.environ.get('SURF_B200_CHECK_INDICES', '0') not in ('', '0')
+
+
+def _raise_on_bad_indices(workspace_ptr, params):
+    if not params.get('_check_indices', _CHECK_INDICES):
+        return
+    if lib().surf_check_indices(workspace_ptr, _stream_ptr()) != 0:
+        raise IndexError(lib().surf_last_error().decode('utf-8', 'replace'))
+
+
 def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -44,7 +58,7 @@ class _RenderFn(torch.autograd.Function):
         opt = make_options(params, (p0, p1))
         shadow = int(opt.shadow)
         n_lights = int(floats[m.i_light_pos].shape[0])
-        ws_bytes = lib().surf_workspace_bytes(m.total_prims, n, n_lights, shadow)
+        ws_bytes = lib().surf_workspace_bytes_ex(m.total_prims, n, n_lights, shadow, m.proj, 0)
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         image = torch.empty(n, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(n, dtype=torch.float32, device=dev)
@@ -58,8 +72,13 @@ class _RenderFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib().surf_forward(C.byref(sc), C.byref(cam), C.byref(opt), workspace.data_ptr(), ws_bytes,
                                      C.byref(out), _stream_ptr()))
+            _raise_on_bad_indices(workspace.data_ptr(), params)
         ctx.m, ctx.params, ctx.range = m, params, (p0, p1)
-        ctx.workspace = workspace
+        # The backward needs the camera state, the rays and (with shadows) the visibility from the forward workspace.
+        # Small workspaces ride along in the graph (saves two launches in backward); large ones are released now and the
+        # backward recomputes camera + rays into a fresh one (k_setup + k_raygen, a few microseconds per megapixel).
+        ctx.workspace = workspace if (shadow or ws_bytes <= _KEEP_WORKSPACE_BYTES) else None
+        ctx.ws_bytes = ws_bytes
         ctx.save_for_backward(nearest, depth, *floats)
         ctx.mark_non_differentiable(nearest, ray_dir)
         return image, depth, normal, pos, nearest, ray_dir
@@ -71,7 +90,11 @@ class _RenderFn(torch.autograd.Function):
         m = ctx.m
         dev = depth.device
         opt = make_options(ctx.params, ctx.range)
-        opt.forced_nearest = 2          # ctx.workspace still holds this frame's camera state and rays
+        ws = ctx.workspace
+        if ws is not None:
+            opt.forced_nearest = 2      # ctx.workspace still holds this frame's camera state and rays
+        else:
+            ws = torch.empty(ctx.ws_bytes, dtype=torch.uint8, device=dev)
         grads = [torch.zeros_like(t) if ctx.needs_input_grad[3 + i] else None for i, t in enumerate(floats)]
 
         def c(t):
@@ -82,7 +105,6 @@ class _RenderFn(torch.autograd.Function):
                                  for t in (g_image, g_depth, g_normal, g_pos)])
         sg = m.c_grads(grads)
         sc, cam = m.c_scene(floats), m.c_camera()
-        ws = ctx.workspace
         with torch.cuda.device(dev):
             check(lib().surf_backward(C.byref(sc), C.byref(cam), C.byref(opt), ws.data_ptr(), ws.numel(),
                                       nearest.data_ptr(), depth.data_ptr(), C.byref(og), C.byref(sg),
@@ -179,7 +201,7 @@ class _RenderBatchFn(torch.autograd.Function):
             fl = floats[offs[b]:offs[b] + len(m.floats)]
             scenes[b], cams[b] = m.c_scene(fl), m.c_camera()
             npx = m.n_pixels
-            ws_bytes = lib().surf_workspace_bytes(m.total_prims, npx, int(fl[m.i_light_pos].shape[0]), int(opt.shadow))
+            ws_bytes = lib().surf_workspace_bytes_ex(m.total_prims, npx, int(fl[m.i_light_pos].shape[0]), int(opt.shadow), m.proj, 0)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             t = (torch.empty(npx, 3, device=dev), torch.empty(npx, device=dev), torch.empty(npx, 3, device=dev),
                  torch.empty(npx, 3, device=dev), torch.empty(npx, dtype=torch.int64, device=dev),
@@ -243,7 +265,7 @@ class _RenderStridedFn(torch.autograd.Function):
         opt = make_options(params)
         npx = m.n_pixels
         views = mb.views0(fulls)
-        ws_bytes = lib().surf_workspace_bytes(m.total_prims, npx, int(views[m.i_light_pos].shape[0]), int(opt.shadow))
+        ws_bytes = lib().surf_workspace_bytes_ex(m.total_prims, npx, int(views[m.i_light_pos].shape[0]), int(opt.shadow), m.proj, 0)
         ws_bytes = (ws_bytes + 255) // 256 * 256
         workspace = torch.empty(B, ws_bytes, dtype=torch.uint8, device=dev)
         image = torch.empty(B, npx, 3, device=dev)
