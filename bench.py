@@ -1,21 +1,34 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the render hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...       # the reference's own CPU implementation, host cores
+    python bench.py --workload config_d ...                       # BASELINE configs[3]: 64 scenes x 5000 splats at 128x128
 
-Workload (config.workload = "config_e"): BASELINE.json configs[4], the configuration the north-star target is
-quoted on - the inverse-rendering step of 100 000 synthetic disk splats at 1024x1024.
+Workload config_e (default; config.workload = "config_e"): BASELINE.json configs[4], the configuration the north-star
+target is quoted on - the inverse-rendering step of 100 000 synthetic disk splats at 1024x1024.
 One step = render (forward) -> mean((image-target)^2) -> backward to splat positions, normals, albedo and light
-positions -> Adam step.  `value` = ray-primitive tests per second of the whole job = H*W*M per step / step time
-with inputs resident in HBM; `e2e` = the same through the C-ABI host-pointer call (pinned HOST buffers in,
-gradients + loss back in host memory, H2D/D2H inside the timed region).  N>1: the frame is sharded into row
-bands, one per GPU (strong scaling of one frame), image bands all-gathered, packed gradients all-reduced (NCCL).
+positions -> Adam step (the loop body of the reference's test_optimization.py:100-125).
+
+  value   ray-primitive tests per second of the whole job = H*W*M per step / step time, inputs resident in HBM,
+          through surf_renderer_b200.MSEStep (one surf_step_mse call per step) + torch's fused Adam.
+  e2e     the same render -> loss -> backward through the C ABI with HOST buffers (surf_step_host_begin / _end): every
+          step copies the scene and the target from pinned host memory, and the gradients and the loss back to host
+          memory, inside the timed region.  The optimizer of a host-side caller runs on the host and is NOT part of
+          this leg (config.e2e_step says so).
+  N > 1   the frame is sharded into row bands, one per GPU (strong scaling of one frame): no collective in the
+          intersection data path, band-local loss, ONE in-place NCCL all-reduce over the packed [gradients | loss] buffer.
+
+Workload config_d: a stacked batch of 64 scenes (5000 splats each, own camera) at 128x128, scenes sharded over the
+ranks; step = forward, all-gather of the images, a weighted-sum loss on the gathered batch (stand-in for the GAN
+discriminator the reference feeds these frames to, gan.py:326-377), backward; gradients of the light rig shared by all
+scenes all-reduced.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -27,11 +40,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-import numpy as np   # noqa: E402
-import torch         # noqa: E402
-
 FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions)
 N_SM, FP32_LANES = 148, 128
+L2_FLUSH_BYTES = 192 * 1024 * 1024     # > the 126 MB L2
 
 
 def parse_args():
@@ -40,13 +51,18 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='surf', choices=['surf', 'reference'])
-    ap.add_argument('--splats', type=int, default=100_000)
-    ap.add_argument('--size', type=int, default=1024)
+    ap.add_argument('--workload', default='config_e', choices=['config_e', 'config_d'])
+    ap.add_argument('--splats', type=int, default=None)
+    ap.add_argument('--size', type=int, default=None)
     ap.add_argument('--ppt', type=int, default=0, help='pixels per thread of the intersection kernel (0 = default)')
     ap.add_argument('--chunk', type=int, default=0)
     ap.add_argument('--math', type=int, default=0, help='intersection kernel: 0 = default ray-plane FFMA2 filter (10 instr/test), 3 = screen-space fast mode')
+    ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph')
+    ap.add_argument('--ref-size', type=int, default=0, help='reference arm: viewport edge of the bounded sample (0 = auto)')
+    ap.add_argument('--ref-budget', type=float, default=150.0, help='reference arm: seconds of CPU work')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-fast', action='store_true')
     return ap.parse_args()
 
 
@@ -56,6 +72,32 @@ def measured_peaks():
             return json.load(f), 'measured'
     except Exception:
         return {'hbm_gbs': 6650.0, 'sm_max_mhz': 1965.0}, 'fallback'
+
+
+def source_hash():
+    """sha256 over the library sources: ties an ncu capture under profiles/ to the build it was taken on"""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, 'surf_renderer_b200', 'csrc')
+    files = sorted(f for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh', '.h')))
+    for f in files:
+        with open(os.path.join(csrc, f), 'rb') as fh:
+            h.update(f.encode() + b'\0' + fh.read())
+    with open(os.path.join(ROOT, 'include', 'surf_b200.h'), 'rb') as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the ncu --set full capture recorded in
+    profiles/ncu_traffic.json - only when that capture was taken on THIS build (same source hash), workload and N."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            rec = json.load(f)
+        if rec.get('source_hash') != source_hash() or rec.get('workload') != workload or rec.get('n_gpus', 1) != world:
+            return None
+        return rec['kernels'].get(kernel)
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -127,6 +169,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        import numpy as np
         if self.mode == 'nvml':
             self._stop.set()
             self._thread.join(timeout=1.0)
@@ -151,71 +194,152 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle (op-for-op restatement of the reference's torch path) on host cores
+# workload descriptions shared by both arms
 # ----------------------------------------------------------------------------------------------------------
-def cpu_reference_step(scene, target_scene, subset, threads):
-    """One bounded sample of the workload on the CPU: fwd + loss + bwd over `subset` pixels of the frame."""
-    from oracle import torch_oracle
-    from surf_renderer_b200.scenes import clone_scene
+def workload_config(args):
+    if args.workload == 'config_e':
+        M, S = args.splats or 100_000, args.size or 1024
+        return {'workload': 'config_e', 'splats': M, 'width': S, 'height': S, 'lights': 3,
+                'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam',
+                'e2e_step': 'H2D(scene, target) + render fwd + mse + bwd + grad all-reduce + D2H(gradients, loss); the host-side optimizer is not part of this leg',
+                'sharding': 'row-bands x%d' % max(1, args.gpus),
+                'l2': 'flushed between timed steps (%d MiB fill enqueued on the stream, inside the timed region)' % (L2_FLUSH_BYTES >> 20)}, float(M) * S * S
+    M, S, B = args.splats or 5000, args.size or 128, 64
+    return {'workload': 'config_d', 'scenes': B, 'splats': M, 'width': S, 'height': S, 'lights': 7,
+            'step': 'render_batch fwd (stacked scenes) + all-gather(image) + weighted-sum loss + bwd(pos,normal,light_pos) + all-reduce(shared light grads)',
+            'e2e_step': 'H2D(splat positions, normals, camera eyes of the batch) + the same step + D2H(loss)',
+            'sharding': 'scene-blocks x%d' % max(1, args.gpus),
+            'l2': 'flushed between timed steps (%d MiB fill enqueued on the stream, inside the timed region)' % (L2_FLUSH_BYTES >> 20)}, float(B) * M * S * S
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref = the unmodified files; else the oracle port)
+# ----------------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''          # the reference picks CUDA tensors whenever torch sees a GPU
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import torch
+    from oracle import ref_runner, torch_oracle
+    from surf_renderer_b200 import scenes as synth
+    threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sc = clone_scene(scene, requires_grad=False)
-    leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
-    for t in leaves:
-        t.requires_grad_(True)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        tgt = torch_oracle.render(target_scene, pixel_subset=subset, tile_size=512)['image']
-    t_target = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res = torch_oracle.render(sc, pixel_subset=subset, tile_size=512)
-    loss = ((res['image'] - tgt) ** 2).mean()
-    t_fwd = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    loss.backward()
-    t_bwd = time.perf_counter() - t0
-    return t_fwd, t_bwd, t_target
+    config, tests_per_step = workload_config(args)
+    if ref_runner.available():
+        render, _ = ref_runner.load()
+        kind = 'reference'
+        conv = ref_runner.scene_for_reference
+        what = 'UNMODIFIED reference diffrend.torch.renderer.render (oracle/_ref) on CPU tensors'
+    else:
+        render, kind, conv = torch_oracle.render, 'port', synth.clone_scene
+        what = 'torch-CPU op-for-op port of the reference (oracle/torch_oracle.py; oracle/_ref absent)'
 
+    if args.workload == 'config_e':
+        M = config['splats']
+        full = synth.config_e(m=M, width=config['width'], height=config['height'])
 
-def cpu_sample(scene, n_pix_sample, seed=123):
-    vp = scene['camera']['viewport']
-    n = (vp[2] - vp[0]) * (vp[3] - vp[1])
-    g = torch.Generator().manual_seed(seed)
-    return torch.randperm(n, generator=g)[:n_pix_sample].sort().values
+        def make(size):
+            sc = synth.config_e(m=M, width=size, height=size)
+            tg = conv(synth.config_e_target_scene(sc))
+            with torch.no_grad():
+                target = render(tg, tile_size=512)['image']
+            return sc, target
 
+        def one_step(sc, target):
+            s = conv(sc)
+            leaves = [s['objects']['disk']['pos'], s['objects']['disk']['normal'], s['materials']['albedo'], s['lights']['pos']]
+            for t in leaves:
+                t.requires_grad_(True)
+            t0 = time.perf_counter()
+            res = render(s, tile_size=512)
+            loss = ((res['image'] - target) ** 2).mean()
+            t1 = time.perf_counter()
+            loss.backward()
+            return t1 - t0, time.perf_counter() - t1
 
-def run_cpu_baseline(scene, target_scene, budget_s, threads, steps=1, warmup=0):
-    m = int(scene['objects']['disk']['pos'].shape[0])
-    # calibrate on 128 pixels, then size the sample for the time budget
-    sub = cpu_sample(scene, 128)
-    tf, tb, _ = cpu_reference_step(scene, target_scene, sub, threads)
-    per_pix = (tf + tb) / 128
-    vp = scene['camera']['viewport']
-    n_total = (vp[2] - vp[0]) * (vp[3] - vp[1])
-    n_pix = int(max(128, min(8192, n_total, budget_s / max(per_pix, 1e-9) / max(1, steps + warmup))))
-    sub = cpu_sample(scene, n_pix)
-    n_pix = int(sub.numel())
+        # the same scene (all M splats) on a reduced viewport of the same camera: the reference materialises [M, N]
+        # tensors and keeps them for autograd, so the full 1024x1024 frame needs ~2 h and > 1 TB on the CPU
+        size = args.ref_size
+        if not size:
+            sc, tg = make(16)
+            tf, tb = one_step(sc, tg)
+            per_px = (tf + tb) / 256.0
+            want = args.ref_budget / max(1, args.steps + min(args.warmup, 1)) / max(per_px, 1e-9)
+            size = int(max(16, min(48, np.sqrt(want) // 8 * 8)))
+        sc, tg = make(size)
+        n_px = size * size
+        sample = '%dx%d viewport of the same camera x all %d splats, fwd + mse + bwd' % (size, size, M)
+        unit_tests = float(M) * n_px
+        del full
+    else:
+        B = config['scenes']
+        scenes = [synth.config_d_scene(i, m=config['splats'], width=config['width'], height=config['height']) for i in range(2)]
+        g = torch.Generator().manual_seed(1)
+        ws = [torch.rand(config['height'], config['width'], 3, generator=g) for _ in scenes]
+
+        def one_step(scs, _):
+            tf = tb = 0.0
+            for sc, w in zip(scs, ws):
+                s = conv(sc)
+                for t in (s['objects']['disk']['pos'], s['objects']['disk']['normal'], s['lights']['pos']):
+                    t.requires_grad_(True)
+                t0 = time.perf_counter()
+                res = render(s, tile_size=512, double_sided=True)
+                loss = (res['image'] * w).sum()
+                t1 = time.perf_counter()
+                loss.backward()
+                tf += t1 - t0
+                tb += time.perf_counter() - t1
+            return tf, tb
+        sc, tg = scenes, None
+        sample = '2 of the %d scenes (%d splats at %dx%d each), fwd + weighted-sum loss + bwd, one render() per scene like gan.py:326-377' % (
+            B, config['splats'], config['width'], config['height'])
+        unit_tests = 2.0 * config['splats'] * config['width'] * config['height']
+
     times = []
-    for i in range(warmup + steps):
-        tf, tb, _ = cpu_reference_step(scene, target_scene, sub, threads)
-        if i >= warmup:
+    t_start = time.perf_counter()
+    for i in range(min(args.warmup, 1) + max(1, args.steps)):
+        tf, tb = one_step(sc, tg)
+        if i >= min(args.warmup, 1):
             times.append((tf, tb))
+        if time.perf_counter() - t_start > args.ref_budget and times:
+            break
     tf = float(np.mean([t[0] for t in times])); tb = float(np.mean([t[1] for t in times]))
-    tests = float(m) * n_pix
-    return {'value': tests / (tf + tb), 'unit': 'tests/s', 'cores': threads, 'kind': 'port',
-            'sample': '%d random pixels of the %dx%d frame x %d splats, fwd+bwd (fwd %.2fs, bwd %.2fs), torch-CPU '
-                      'op-for-op port of the reference, tile_size=512' % (n_pix, scene['camera']['viewport'][2],
-                                                                          scene['camera']['viewport'][3], m, tf, tb),
-            'fwd_tests_per_s': tests / tf, 'ms_per_sample_step': 1e3 * (tf + tb)}, n_pix, tf + tb
+    value = unit_tests / (tf + tb)
+    cb = {'value': value, 'unit': 'tests/s', 'cores': threads, 'kind': kind,
+          'sample': '%s; %s; %d timed step(s), fwd %.2fs + bwd %.2fs each, tile_size=512, %d torch threads' % (sample, what, len(times), tf, tb, threads),
+          'fwd_tests_per_s': unit_tests / tf, 'ms_per_sample_step': 1e3 * (tf + tb)}
+    line = {'impl': 'reference', 'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)' if args.workload == 'config_e'
+            else 'ray-primitive tests/s (fwd+bwd over a batch of scenes)',
+            'value': value, 'unit': 'tests/s', 'n_gpus': 0, 'steps': len(times), 'warmup': min(args.warmup, 1),
+            'ms_per_step': 1e3 * (tf + tb), 'ms_per_step_is': 'one bounded SAMPLE step (see cpu_baseline.sample), not a full-size step',
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config, 'cpu_baseline': cb,
+            'full_step_s_extrapolated': tests_per_step / value,
+            'e2e': {'value': value, 'unit': 'tests/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    if args.workload == 'config_e':
+        try:
+            line['cpu_baseline_numpy'] = run_numpy_baseline(synth.config_e(m=config['splats'], width=config['width'], height=config['height']))
+        except Exception as e:      # the numpy twin is a side number; never fail the arm on it
+            line['cpu_baseline_numpy'] = {'error': repr(e)}
+    print(json.dumps(line))
+    return 0
 
 
 def run_numpy_baseline(scene, n_pix=96, reps=2):
     """The reference's second CPU renderer (diffrend/numpy/renderer.py, restated in oracle/numpy_oracle.py): forward
     only (it has no gradients), float64, Lambertian, and it materialises the whole [M, N, 4] tensor - so the sample is
     a small pixel subset of the same frame and the same splats."""
+    import torch
     from oracle import numpy_oracle
     hs = numpy_oracle.homogeneous_scene(scene)
     m = int(hs['objects']['disk']['pos'].shape[0])
-    sub = cpu_sample(scene, n_pix).numpy()
+    vp = scene['camera']['viewport']
+    n = (vp[2] - vp[0]) * (vp[3] - vp[1])
+    g = torch.Generator().manual_seed(123)
+    sub = torch.randperm(n, generator=g)[:n_pix].sort().values.numpy()
     best = 1e30
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -227,112 +351,124 @@ def run_numpy_baseline(scene, n_pix=96, reps=2):
                       % (len(sub), m, reps, best)}
 
 
+def cpu_baseline_subprocess(args, budget_s):
+    """The reference arm in a child process with the GPUs hidden (the reference chooses its device at import)."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', args.workload, '--steps', '3',
+           '--warmup', '1', '--ref-budget', str(budget_s)]
+    if args.splats:
+        cmd += ['--splats', str(args.splats)]
+    if args.size:
+        cmd += ['--size', str(args.size)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 4 + 240, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                rec = json.loads(ln)
+                return rec.get('cpu_baseline'), rec.get('cpu_baseline_numpy')
+        return {'error': (out.stderr or out.stdout)[-400:]}, None
+    except Exception as e:
+        return {'error': repr(e)}, None
+
+
 # ----------------------------------------------------------------------------------------------------------
-def main():
-    args = parse_args()
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    from surf_renderer_b200 import scenes as synth
-    scene = synth.config_e(m=args.splats, width=args.size, height=args.size)
-    target_scene = synth.config_e_target_scene(scene)
-    M, H, W = args.splats, args.size, args.size
-    tests_per_step = float(M) * H * W
-    config = {'workload': 'config_e', 'splats': M, 'width': W, 'height': H, 'lights': 3,
-              'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam',
-              'sharding': 'row-bands x%d' % max(1, args.gpus),
-              'l2': 'flushed between timed steps (256 MiB fill enqueued on the stream, inside the timed region)'}
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def timed_region(step, steps, warmup, flush, barrier, world, dev, sampler_rank0):
+    """W warm-up steps, then exactly K steps between barriers, timed with CUDA events on the current stream, max over
+    ranks.  The L2 is flushed between steps by a fill larger than the L2, enqueued on the same stream."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(max(3, warmup)):
+        step()
+    barrier()
+    if sampler_rank0 is not None:
+        sampler_rank0.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    out = None
+    for i in range(steps):
+        flush.fill_(i & 0xff)
+        out = step()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    total_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler_rank0.stop() if sampler_rank0 is not None else None
+    return total_ms / steps, wall, clocks, out
 
-    if args.impl == 'reference':
-        if rank != 0:
-            return 0
-        threads = os.cpu_count() or 1
-        cb, n_pix, step_s = run_cpu_baseline(scene, target_scene, budget_s=150.0, threads=threads,
-                                             steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
-        line = {'impl': 'reference', 'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)',
-                'value': cb['value'], 'unit': 'tests/s', 'n_gpus': 0, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': 1e3 * step_s, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic', 'config': config, 'cpu_baseline': cb,
-                'frames_per_s_extrapolated': cb['value'] / tests_per_step,
-                'cpu_baseline_numpy': run_numpy_baseline(scene),
-                'e2e': {'value': cb['value'], 'unit': 'tests/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        return 0
 
-    # ------------------------------------------------------------------ our arm
+class _DevBlock:
+    """a raw device allocation of the C library as a CUDA-array-interface object (for torch.as_tensor)"""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {'shape': (int(n_floats),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+def run_config_e(args, rank, world, local_rank):
+    import numpy as np   # noqa: F401
+    import torch
     import torch.distributed as dist
     import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
     from surf_renderer_b200.scenes import clone_scene
-    from surf_renderer_b200 import _abi, dist as sdist
+    from surf_renderer_b200 import dist as sdist
     from surf_renderer_b200._lib import check, lib
     from surf_renderer_b200.marshal import Marshalled, make_options
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback'
-    torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    config, tests_per_step = workload_config(args)
+    M, H, W = config['splats'], config['height'], config['width']
+    scene = synth.config_e(m=M, width=W, height=H)
+    target_scene = synth.config_e_target_scene(scene)
     peaks, peak_src = measured_peaks()
     params = {'_pixels_per_thread': args.ppt, '_chunk_prims': args.chunk, '_math_mode': args.math}
-
-    sc = clone_scene(scene, device=dev)
-    leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
-    for t in leaves:
-        t.requires_grad_(True)
-    opt = torch.optim.Adam(leaves, lr=1e-4, fused=True)
-    with torch.no_grad():
-        tgt = surf_renderer_b200.render(clone_scene(target_scene, device=dev), **params)['image']
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    lib().surf_set_kernel_timing(1)
-    launches = []
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        if world > 1:
-            res = sdist.render_bands(sc, gather=('image',), **params)
-        else:
-            res = surf_renderer_b200.render(sc, **params)
-        n_launch = lib().surf_last_launch_count()
-        loss = ((res['image'] - tgt) ** 2).mean()
-        loss.backward()
-        n_launch += lib().surf_last_launch_count()
-        if world > 1:
-            sdist.allreduce_gradients(leaves)
-        opt.step()
-        return loss, n_launch
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    with torch.no_grad():
+        tgt = surf_renderer_b200.render(clone_scene(target_scene, device=dev), **params)['image']
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def build(step_params):
+        sc = clone_scene(scene, device=dev)
+        leaves = [sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']]
+        for t in leaves:
+            t.requires_grad_(True)
+        plan = surf_renderer_b200.MSEStep(sc, tgt, group=(True if world > 1 else None), **step_params)
+        opt = torch.optim.Adam(leaves, lr=1e-4, fused=True, capturable=args.graph)
+
+        def step():
+            loss = plan()
+            opt.step()
+            return loss
+        if args.graph:
+            graphed = surf_renderer_b200.GraphedStep(step, warmup=3, capture_error_mode='thread_local' if world > 1 else 'global')
+            return plan, graphed
+        return plan, step
+
+    plan, step = build(params)
+    lib().surf_set_kernel_timing(0 if args.graph else 1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(2):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    lib().surf_set_kernel_timing(1)                   # reset the library's per-kernel event ring
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)                      # L2 flush between steps (stream-ordered, inside the timed region)
-        loss, n_launch = step()
-        launches.append(n_launch)
-    ev1.record()
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    total_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = total_ms / args.steps
+    lib().surf_set_kernel_timing(0 if args.graph else 1)      # reset the library's per-kernel event ring
+    ms_per_step, wall, clocks, loss = timed_region(step, args.steps, args.warmup, flush, barrier, world, dev, sampler)
     value = tests_per_step / (ms_per_step * 1e-3)
     n_timed = C.c_int32()
     k_mean = {k: lib().surf_mean_kernel_ms(k, C.byref(n_timed)) for k in (0, 1, 2)}
+    lib().surf_set_kernel_timing(0)
 
     # ---- roofline of the dominant kernel (k_intersect), timed live with CUDA events inside the library
     isect_ms = k_mean[0] if k_mean[0] > 0 else None
@@ -345,49 +481,55 @@ def main():
         fma_meas = max(lib().surf_fma_peak(0, 8192, None), lib().surf_fma_peak(1, 8192, None))
         roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
                     'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane,
-                    # dram__bytes_read+write of one k_intersect launch, ncu --set full (profiles/r1_ncu_full_step_kernels.json);
-                    # only meaningful for the default single-GPU config it was captured on
-                    'traffic': 22395904 if (world == 1 and M == 100_000 and H == 1024 and args.math == 0) else None,
+                    # dram bytes of one k_intersect launch from the ncu --set full capture of THIS build, else null
+                    'traffic': ncu_traffic('k_intersect', 'config_e', world), 'source_hash': source_hash(),
                     'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no fp32 entry)' % peak_src,
                     'peak_measured': fma_meas * 2 / 1e12, 'frac_of_measured': ach_lane / fma_meas if fma_meas > 0 else None,
                     'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
                     'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
+                    'step_minus_kernel_ms': ms_per_step - isect_ms,
                     'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
         # the two HBM-side kernels (north star: achieved GB/s against the measured copy bandwidth)
         n_loc = H * W / world
         hbm = float(peaks.get('hbm_gbs', 6650.0))
-        shade_bytes = n_loc * (12 + 8 + 48)            # rays + z-buffer key read; image/depth/normal/pos/nearest written
-        bwd_bytes = n_loc * (12 + 8 + 4 + 12)          # rays, nearest, depth, d(image) read (+ ~28 B per hit pixel of atomics)
+        # k_shade in the step: rays 12 + key 8 + target 12 read; image 12 + depth 4 + nearest 8 + d(image) 12 written
+        shade_bytes = n_loc * (12 + 8 + 12 + 12 + 4 + 8 + 12)
+        # k_backward: rays 12, nearest 8, depth 4, d(image) 12 read (+ ~24 B per hit pixel of atomics, not counted)
+        bwd_bytes = n_loc * (12 + 8 + 4 + 12)
         roofline['hbm_kernels'] = {
             'peak_gbs': hbm, 'peak_source': peak_src + ' MEASURED_PEAKS.json hbm_gbs',
             'k_shade': {'ms': k_mean[1], 'algorithmic_bytes': shade_bytes, 'achieved_gbs': shade_bytes / (k_mean[1] * 1e-3) / 1e9,
-                        'frac': shade_bytes / (k_mean[1] * 1e-3) / 1e9 / hbm} if k_mean[1] > 0 else None,
+                        'frac': shade_bytes / (k_mean[1] * 1e-3) / 1e9 / hbm, 'traffic': ncu_traffic('k_shade', 'config_e', world)} if k_mean[1] > 0 else None,
             'k_backward': {'ms': k_mean[2], 'algorithmic_bytes': bwd_bytes, 'achieved_gbs': bwd_bytes / (k_mean[2] * 1e-3) / 1e9,
-                           'frac': bwd_bytes / (k_mean[2] * 1e-3) / 1e9 / hbm} if k_mean[2] > 0 else None}
+                           'frac': bwd_bytes / (k_mean[2] * 1e-3) / 1e9 / hbm, 'traffic': ncu_traffic('k_backward', 'config_e', world)} if k_mean[2] > 0 else None}
+    launches_per_step = int(plan.launches)
 
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
     fast = None
-    if args.math == 0:
-        params_fast = dict(params, _math_mode=3, _pixels_per_thread=0)
-        params_keep = dict(params)
-        params.clear(); params.update(params_fast)
+    if args.math == 0 and not args.no_fast:
+        plan_f, step_f = build(dict(params, _math_mode=3, _pixels_per_thread=0))
+        lib().surf_set_kernel_timing(1)
         for _ in range(3):
-            step()
+            step_f()
         barrier()
+        lib().surf_set_kernel_timing(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_fast = max(3, min(args.steps, 10))
         e0.record()
-        for _ in range(n_fast):
-            step()
+        for i in range(n_fast):
+            flush.fill_(i & 0xff)
+            step_f()
         e1.record()
         barrier()
         ms_fast = e0.elapsed_time(e1) / n_fast
         fast = {'math_mode': 3, 'ms_per_step': ms_fast, 'tests_per_s': tests_per_step / (ms_fast * 1e-3),
-                'frames_per_s': 1e3 / ms_fast, 'intersect_kernel_ms': lib().surf_last_kernel_ms(0),
-                'note': 'per-pair screen-space bounding-circle level-1 test (2.25 FMA-pipe lane-instr/test); bit-identical outputs'}
-        params.clear(); params.update(params_keep)
+                'frames_per_s': 1e3 / ms_fast, 'intersect_kernel_ms': lib().surf_mean_kernel_ms(0, None),
+                'note': 'per-pair screen-space bounding-circle level-1 test (k_intersect_screen); bit-identical outputs; '
+                        'per-rank time, not max over ranks'}
+        lib().surf_set_kernel_timing(0)
+        del plan_f, step_f
 
-    # ---- e2e: C-ABI host-pointer call, pinned host buffers, H2D + D2H inside the timed region
+    # ---- e2e: the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
         hs = clone_scene(scene)
@@ -404,21 +546,19 @@ def main():
         csg = m.c_grads(grads)
         ctx = lib().surf_context_create(local_rank)
         loss_c = C.c_float()
-
-        want = [i for i, nme in enumerate(m.names) if nme in ('objects/disk/pos', 'objects/disk/normal',
-                                                                'materials/albedo', 'lights/pos')]
-        flat_host = torch.empty(sum(grads[i].numel() for i in want)).pin_memory()
+        ext = torch.cuda.ExternalStream(lib().surf_context_stream(ctx), device=dev)
+        scale = 1.0 / (3.0 * n_total)
+        blk, cnt = C.c_void_p(), C.c_size_t()
 
         def e2e_step():
-            check(lib().surf_render_backward_host(ctx, C.byref(csc), C.byref(ccam), C.byref(copt), None, None,
-                                                  target_host.data_ptr(), C.byref(loss_c), C.byref(csg)))
-            if world > 1:      # sum the per-band partial gradients across ranks (packed buffer, one all-reduce)
-                torch.cat([grads[i].reshape(-1) for i in want], out=flat_host)
-                flat_dev = flat_host.to(dev, non_blocking=True)
-                dist.all_reduce(flat_dev, op=dist.ReduceOp.SUM)
-                flat_host.copy_(flat_dev, non_blocking=True)
-                torch.cuda.synchronize()
-        for _ in range(2):
+            check(lib().surf_step_host_begin(ctx, C.byref(csc), C.byref(ccam), C.byref(copt), target_host.data_ptr(), scale))
+            if world > 1:      # sum the per-band partial gradients (and losses) across ranks on the device block
+                check(lib().surf_context_device_grads(ctx, C.byref(blk), C.byref(cnt)))
+                block = torch.as_tensor(_DevBlock(blk.value, cnt.value), device=dev)
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(block, op=dist.ReduceOp.SUM)
+            check(lib().surf_step_host_end(ctx, C.byref(csg), C.byref(loss_c)))
+        for _ in range(3):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -436,27 +576,124 @@ def main():
         lib().surf_context_destroy(ctx)
         e2e = {'value': tests_per_step / dt, 'unit': 'tests/s', 'h2d_bytes_per_step': int(h2d.value) * world,
                'd2h_bytes_per_step': int(d2h.value) * world, 'ms_per_step': dt * 1e3, 'frames_per_s': 1.0 / dt,
-               'api': 'surf_render_backward_host (C ABI, pinned host buffers)'}
+               'loss': float(loss_c.value), 'timed_with': 'host wall clock around %d steps between barriers, max over ranks' % n_e2e,
+               'api': 'surf_step_host_begin / surf_step_host_end (C ABI, pinned host buffers)'}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
+        return None
     cpu_baseline = cpu_baseline_numpy = None
     if not args.no_cpu_baseline and world == 1:
-        cpu_baseline, _, _ = run_cpu_baseline(scene, target_scene, budget_s=20.0, threads=os.cpu_count() or 1)
-        cpu_baseline_numpy = run_numpy_baseline(scene)
-
-    line = {'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)', 'value': value, 'unit': 'tests/s',
+        cpu_baseline, cpu_baseline_numpy = cpu_baseline_subprocess(args, budget_s=20.0)
+    return {'metric': 'ray-primitive tests/s (fwd+bwd inverse-rendering step)', 'value': value, 'unit': 'tests/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': config, 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
-            'gpu_launches': int(sum(launches)), 'gpu_launches_per_step': int(launches[-1]) if launches else 0,
+            'config': dict(config, graph=bool(args.graph)), 'frames_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
+            'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'cpu_baseline_numpy': cpu_baseline_numpy, 'e2e': e2e,
-            'fast_mode': fast,
-            'wall_s_timed_region': wall}
-    print(json.dumps(line))
+            'fast_mode': fast, 'wall_s_timed_region': wall}
+
+
+def run_config_d(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import surf_renderer_b200
+    from surf_renderer_b200 import dist as sdist, scenes as synth
+    from surf_renderer_b200._lib import lib
+    dev = torch.device('cuda', local_rank)
+    config, tests_per_step = workload_config(args)
+    B, M, S = config['scenes'], config['splats'], config['width']
+    peaks, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = synth.config_d_batch(B, m=M, width=S, height=S, pin=True)      # batched tensors in pinned host memory
+    plan = sdist.ShardedBatchStep(host, device=dev, group=(True if world > 1 else None), double_sided=True)
+    w = torch.rand(B, S, S, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step():
+        return plan.step(lambda image: (image * w).sum())
+
+    lib().surf_set_kernel_timing(1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(2):
+        step()
+    barrier()
+    lib().surf_set_kernel_timing(1)
+    ms_per_step, wall, clocks, loss = timed_region(step, args.steps, args.warmup, flush, barrier, world, dev, sampler)
+    n_timed = C.c_int32()
+    k_mean = {k: lib().surf_mean_kernel_ms(k, C.byref(n_timed)) for k in (0, 1, 2)}
+    lib().surf_set_kernel_timing(0)
+    value = tests_per_step / (ms_per_step * 1e-3)
+    f_clk = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
+    peak_lane = N_SM * FP32_LANES * f_clk
+    roofline = None
+    if k_mean[0] > 0:
+        tests_launch = tests_per_step / world
+        ach_lane = tests_launch * FMA_INSTR_PER_DISK_TEST / (k_mean[0] * 1e-3)
+        roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect_batch', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
+                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane, 'traffic': ncu_traffic('k_intersect_batch', 'config_d', world),
+                    'source_hash': source_hash(),
+                    'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s)' % peak_src,
+                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
+                    'kernel_ms': k_mean[0], 'kernel_share_of_step': k_mean[0] / ms_per_step, 'step_minus_kernel_ms': ms_per_step - k_mean[0],
+                    'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
+    # e2e: the same step with the per-step H2D of the batch inputs (pinned host) and the D2H read of the loss
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            plan.upload()
+            loss = plan.step(lambda image: (image * w).sum())
+            return float(loss)          # D2H read of the result
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': tests_per_step / dt, 'unit': 'tests/s', 'h2d_bytes_per_step': int(plan.upload_bytes) * world,
+               'd2h_bytes_per_step': 4 * world, 'ms_per_step': dt * 1e3,
+               'timed_with': 'host wall clock around %d steps between barriers, max over ranks' % n_e2e,
+               'api': 'surf_renderer_b200.dist.ShardedBatchStep (upload from pinned host arrays + step + loss read-back)'}
+    if rank != 0:
+        return None
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_baseline, _ = cpu_baseline_subprocess(args, budget_s=20.0)
+    return {'metric': 'ray-primitive tests/s (fwd+bwd over a batch of scenes)', 'value': value, 'unit': 'tests/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config, 'batches_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
+            'gpu_launches': int(plan.launches) * args.steps, 'gpu_launches_per_step': int(plan.launches),
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'wall_s_timed_region': wall}
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    line = (run_config_e if args.workload == 'config_e' else run_config_d)(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -281,6 +281,19 @@ int surf_render_backward_host(SurfContext* ctx, const SurfScene* scene, const Su
                               const SurfOptions* options, const SurfOutputs* out,
                               const SurfOutGrads* out_grads, const float* target_image, float* loss,
                               const SurfSceneGrads* scene_grads);
+/* The same step in two halves, for callers that reduce the gradients across devices before reading them (one process
+ * per GPU, each rendering one band of the frame):
+ *   surf_step_host_begin   H2D of the scene and the target band, forward, fused MSE loss (weight `loss_scale` per
+ *                          squared error; <= 0: the mean over this call's pixels), backward - asynchronous on the
+ *                          context's stream;
+ *   surf_context_device_grads  the device block that holds every gradient array of the call, contiguous, with the loss
+ *                          as its last float - run the collective (e.g. ncclAllReduce) over it on surf_context_stream();
+ *   surf_step_host_end     D2H of the gradients and the loss into the caller's host arrays, then synchronise. */
+int surf_step_host_begin(SurfContext* ctx, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                         const float* target_image, float loss_scale);
+int surf_context_device_grads(SurfContext* ctx, float** block, size_t* n_floats);
+void* surf_context_stream(SurfContext* ctx);
+int surf_step_host_end(SurfContext* ctx, const SurfSceneGrads* scene_grads, float* loss);
 /* bytes moved by the last host call */
 int surf_context_last_transfer(const SurfContext* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 

@@ -123,6 +123,11 @@ SYMBOLS = {
                                             C.POINTER(SurfOptions), C.POINTER(SurfOutputs),
                                             C.POINTER(SurfOutGrads), C.c_void_p, C.POINTER(C.c_float),
                                             C.POINTER(SurfSceneGrads)]),
+    'surf_step_host_begin': (C.c_int, [C.c_void_p, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                       C.c_void_p, C.c_float]),
+    'surf_context_device_grads': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    'surf_context_stream': (C.c_void_p, [C.c_void_p]),
+    'surf_step_host_end': (C.c_int, [C.c_void_p, C.POINTER(SurfSceneGrads), C.POINTER(C.c_float)]),
     'surf_context_last_transfer': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     'surf_fma_peak': (C.c_double, [C.c_int32, C.c_int32, C.c_void_p]),
     'surf_last_launch_count': (C.c_int, []),

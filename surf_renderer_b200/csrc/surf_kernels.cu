@@ -306,11 +306,13 @@ static int splats_backward_impl(const SurfScene* scene, const SurfCamera* camera
 // ===================================================================================================
 using namespace surf;
 
+namespace surf { struct HostState; }
 struct SurfContext {
     int device;
     cudaStream_t stream;
     void* arena; size_t arena_bytes;
     uint64_t h2d, d2h;
+    surf::HostState* state;      // the call in flight between surf_step_host_begin and surf_step_host_end
 };
 
 extern "C" {
@@ -733,36 +735,6 @@ double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream) {
     return lane_fma / (ms * 1e-3);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// host-pointer API
-// ---------------------------------------------------------------------------------------------------
-SurfContext* surf_context_create(int32_t device) {
-    if (cudaSetDevice(device) != cudaSuccess) { g_error = "cudaSetDevice failed"; return nullptr; }
-    SurfContext* c = new SurfContext();
-    c->device = device; c->arena = nullptr; c->arena_bytes = 0; c->h2d = c->d2h = 0;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        g_error = "cudaStreamCreate failed";
-        delete c;
-        return nullptr;
-    }
-    return c;
-}
-
-void surf_context_destroy(SurfContext* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->arena) cudaFree(c->arena);
-    cudaStreamDestroy(c->stream);
-    delete c;
-}
-
-int surf_context_last_transfer(const SurfContext* c, uint64_t* h2d, uint64_t* d2h) {
-    if (!c) return fail(SURF_ERR_BAD_ARG, "null context");
-    if (h2d) *h2d = c->h2d;
-    if (d2h) *d2h = c->d2h;
-    return SURF_OK;
-}
-
 }  // extern "C"
 
 namespace surf {
@@ -786,7 +758,14 @@ struct HostPlan {        // device mirrors of every host array of one call
     SurfSceneGrads dgrads;
     void* workspace; size_t workspace_bytes;
     float* d_target; double* d_loss;
-    size_t grads_begin, grads_end;     // arena range holding the gradient accumulators (zeroed per call)
+    size_t grads_begin, grads_end;     // arena range holding the gradient accumulators (zeroed per call); its last
+    float* d_loss_f;                   // float is the loss of a step (so one collective reduces gradients and loss)
+};
+struct HostState {                     // a host call between its begin (H2D + kernels) and end (D2H + synchronise)
+    HostPlan pl;
+    SurfScene hscene;                  // counts / strides of the caller's arrays
+    int n;
+    bool want_bwd, has_target, active;
 };
 
 static size_t set_pos_floats(const SurfPrimSet& s) {
@@ -827,7 +806,8 @@ static void plan_host(const SurfScene& hs, const SurfCamera& hc, const SurfOptio
     pl->dout.ray_dir = (float*)b.take((size_t)(hc.proj == 0 ? n : 1) * 12);
     pl->workspace_bytes = surf_workspace_bytes(total, n, hs.n_lights, opt.shadow);
     pl->workspace = b.take(pl->workspace_bytes);
-    pl->d_target = nullptr; pl->d_loss = nullptr;
+    pl->d_target = nullptr; pl->d_loss = nullptr; pl->d_loss_f = nullptr;
+    pl->grads_begin = pl->grads_end = 0;
     memset(&pl->dgout, 0, sizeof(pl->dgout));
     memset(&pl->dgrads, 0, sizeof(pl->dgrads));
     if (!want_bwd) return;
@@ -854,9 +834,12 @@ static void plan_host(const SurfScene& hs, const SurfCamera& hc, const SurfOptio
     pl->dgrads.albedo = (float*)b.take((size_t)hs.n_materials * 12);
     pl->dgrads.coeffs = (float*)b.take((size_t)hs.n_materials * 12);
     pl->dgrads.gamma = (float*)b.take(4);
+    pl->d_loss_f = (float*)b.take(4);
     pl->grads_end = align_up(b.off, 256);
     b.off = pl->grads_end;
 }
+
+__global__ void k_loss_to_float(const double* __restrict__ acc, float* __restrict__ out) { out[0] = (float)acc[0]; }
 
 static int h2d(SurfContext* c, const void* dst, const void* src, size_t bytes) {
     if (!bytes) return SURF_OK;
@@ -871,11 +854,14 @@ static int d2h(SurfContext* c, void* dst, const void* src, size_t bytes) {
     return SURF_OK;
 }
 
-static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, const SurfOptions* opt,
-                     const SurfOutputs* hout, const SurfOutGrads* hgout, const float* target, float* loss,
-                     const SurfSceneGrads* hgrads, bool want_bwd) {
+// first half of a host call: H2D of the inputs, every kernel of the forward (and backward); asynchronous on c->stream.
+// `loss_scale` <= 0: the mean over this call's pixels.
+static int host_begin(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, const SurfOptions* opt,
+                      const SurfOutputs* hout, const SurfOutGrads* hgout, const float* target, float loss_scale, bool want_bwd) {
     if (!c || !hs || !hc || !opt) return fail(SURF_ERR_BAD_ARG, "null context/scene/camera/options");
     SURF_CUDA(cudaSetDevice(c->device));
+    if (!c->state) c->state = new HostState();
+    c->state->active = false;
     g_launches = 0;
     c->h2d = c->d2h = 0;
     SceneView probe;
@@ -897,7 +883,7 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
     const int n = p1 - p0;
     const bool has_target = want_bwd && target != nullptr;
 
-    HostPlan pl;
+    HostPlan& pl = c->state->pl;
     Bump measure{nullptr, 0, 0};
     plan_host(*hs, *hc, *opt, n, want_bwd, has_target, measure, &pl);
     const size_t need = align_up(measure.off, 256) + 256;
@@ -932,7 +918,7 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
     if ((rc = h2d(c, pl.dcam.up, hc->up, 12))) return rc;
 
     // with a target image the loss and d(loss)/d(image) are fused into the shading epilogue (mean over this call's pixels)
-    StepLoss sl{pl.d_target, (float*)pl.dgout.image, pl.d_loss, 1.0f / (3.0f * (float)n)};
+    StepLoss sl{pl.d_target, (float*)pl.dgout.image, pl.d_loss, loss_scale > 0.f ? loss_scale : 1.0f / (3.0f * (float)n)};
     if (has_target) {
         if ((rc = h2d(c, pl.d_target, target, (size_t)n * 12))) return rc;
         SURF_CUDA(cudaMemsetAsync(pl.d_loss, 0, 8, c->stream));
@@ -950,7 +936,6 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
         if ((rc = d2h(c, hout->ray_dir, pl.dout.ray_dir, (size_t)(hc->proj == 0 ? n : 1) * 12))) return rc;
     }
     if (want_bwd) {
-        if (!hgrads) return fail(SURF_ERR_BAD_ARG, "null scene_grads");
         SurfOutGrads og = pl.dgout;
         if (has_target) {
             og.depth = nullptr; og.normal = nullptr; og.pos = nullptr;
@@ -965,6 +950,31 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
         if ((rc = backward_impl(&pl.dscene, &pl.dcam, opt, pl.workspace, pl.workspace_bytes, pl.dout.nearest,
                                 pl.dout.depth, &og, &pl.dgrads, c->stream, true)))
             return rc;
+        if (has_target) {
+            k_loss_to_float<<<1, 1, 0, c->stream>>>(pl.d_loss, pl.d_loss_f);
+            SURF_LAUNCHED("k_loss_to_float");
+        }
+    }
+    c->state->hscene = *hs;
+    c->state->n = n;
+    c->state->want_bwd = want_bwd;
+    c->state->has_target = has_target;
+    c->state->active = true;
+    return SURF_OK;
+}
+
+// second half: D2H of the gradients and the loss, then synchronise
+static int host_end(SurfContext* c, const SurfSceneGrads* hgrads, float* loss) {
+    if (!c || !c->state || !c->state->active) return fail(SURF_ERR_BAD_ARG, "no host call in flight on this context");
+    SURF_CUDA(cudaSetDevice(c->device));
+    HostState& hsx = *c->state;
+    hsx.active = false;
+    const HostPlan& pl = hsx.pl;
+    const SurfScene* hs = &hsx.hscene;
+    const bool has_target = hsx.has_target;
+    int rc;
+    if (hsx.want_bwd) {
+        if (!hgrads) return fail(SURF_ERR_BAD_ARG, "null scene_grads");
         for (int k = 0; k < hs->n_sets; ++k) {
             const SurfPrimSet& s = hs->sets[k];
             if ((rc = d2h(c, hgrads->sets[k].pos, pl.dgrads.sets[k].pos, set_pos_floats(s) * 4))) return rc;
@@ -979,19 +989,71 @@ static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, 
         if ((rc = d2h(c, hgrads->coeffs, pl.dgrads.coeffs, (size_t)hs->n_materials * 12))) return rc;
         if (hs->gamma && (rc = d2h(c, hgrads->gamma, pl.dgrads.gamma, 4))) return rc;
     }
-    double loss_d = 0.0;
+    float loss_f = 0.f;
     if (has_target && loss) {
-        SURF_CUDA(cudaMemcpyAsync(&loss_d, pl.d_loss, 8, cudaMemcpyDeviceToHost, c->stream));
-        c->d2h += 8;
+        SURF_CUDA(cudaMemcpyAsync(&loss_f, pl.d_loss_f, 4, cudaMemcpyDeviceToHost, c->stream));
+        c->d2h += 4;
     }
     SURF_CUDA(cudaStreamSynchronize(c->stream));
-    if (has_target && loss) *loss = (float)loss_d;
+    if (has_target && loss) *loss = loss_f;
     return SURF_OK;
+}
+
+static int host_call(SurfContext* c, const SurfScene* hs, const SurfCamera* hc, const SurfOptions* opt,
+                     const SurfOutputs* hout, const SurfOutGrads* hgout, const float* target, float* loss,
+                     const SurfSceneGrads* hgrads, bool want_bwd) {
+    if (want_bwd && !hgrads) return fail(SURF_ERR_BAD_ARG, "null scene_grads");
+    int rc = host_begin(c, hs, hc, opt, hout, hgout, target, 0.f, want_bwd);
+    if (rc) return rc;
+    return host_end(c, hgrads, loss);
 }
 
 }  // namespace surf
 
 extern "C" {
+
+SurfContext* surf_context_create(int32_t device) {
+    if (cudaSetDevice(device) != cudaSuccess) { g_error = "cudaSetDevice failed"; return nullptr; }
+    SurfContext* c = new SurfContext();
+    c->device = device; c->arena = nullptr; c->arena_bytes = 0; c->h2d = c->d2h = 0; c->state = nullptr;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_error = "cudaStreamCreate failed";
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void surf_context_destroy(SurfContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->arena) cudaFree(c->arena);
+    cudaStreamDestroy(c->stream);
+    delete c->state;
+    delete c;
+}
+
+int surf_context_last_transfer(const SurfContext* c, uint64_t* h2d, uint64_t* d2h) {
+    if (!c) return fail(SURF_ERR_BAD_ARG, "null context");
+    if (h2d) *h2d = c->h2d;
+    if (d2h) *d2h = c->d2h;
+    return SURF_OK;
+}
+
+int surf_step_host_begin(SurfContext* ctx, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
+                         const float* target_image, float loss_scale) {
+    if (!target_image) return fail(SURF_ERR_BAD_ARG, "surf_step_host_begin needs target_image");
+    return host_begin(ctx, scene, camera, options, nullptr, nullptr, target_image, loss_scale, true);
+}
+int surf_step_host_end(SurfContext* ctx, const SurfSceneGrads* scene_grads, float* loss) { return host_end(ctx, scene_grads, loss); }
+int surf_context_device_grads(SurfContext* ctx, float** block, size_t* n_floats) {
+    if (!ctx || !ctx->state || !ctx->state->active || !ctx->state->want_bwd) return fail(SURF_ERR_BAD_ARG, "no step in flight on this context");
+    const HostPlan& pl = ctx->state->pl;
+    if (block) *block = (float*)((char*)ctx->arena + pl.grads_begin);
+    if (n_floats) *n_floats = (pl.grads_end - pl.grads_begin) / 4;
+    return SURF_OK;
+}
+void* surf_context_stream(SurfContext* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int surf_render_host(SurfContext* ctx, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
                      const SurfOutputs* out) {

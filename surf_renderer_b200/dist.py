@@ -120,6 +120,208 @@ def allreduce_gradients(tensors, group=None):
     return flat.numel() * 4
 
 
+class GradBucket:
+    """The .grad of `tensors` as views of ONE flat fp32 buffer, so that the gradient all-reduce is a single in-place
+    collective with no packing (torch.cat) before it and no copy-back after it.  autograd accumulates into an existing
+    .grad in place, so the views stay attached as long as zero_grad(set_to_none=False) / bucket.zero_() is used."""
+
+    def __init__(self, tensors):
+        self.tensors = [t for t in tensors]
+        dev = self.tensors[0].device
+        self.flat = torch.zeros(sum(t.numel() for t in self.tensors), dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for t in self.tensors:
+            v = self.flat[off:off + t.numel()].view_as(t)
+            t.grad = v
+            self.views.append(v)
+            off += t.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+        for t, v in zip(self.tensors, self.views):
+            if t.grad is not v:
+                t.grad = v
+
+    def all_reduce(self, group=None):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            for t, v in zip(self.tensors, self.views):      # a .grad that was re-created by autograd: fold it back in
+                if t.grad is not v:
+                    if t.grad is not None:
+                        v.copy_(t.grad)
+                    t.grad = v
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self.flat.numel() * 4
+
+
+class ShardedBatchStep:
+    """Scenes-over-GPUs step on a stacked batch (BASELINE configs[3]; the reference renders such a batch in
+    a Python loop of render() calls, GAN/gan.py:326-377, and feeds the frames to a loss network).
+
+    Built ONCE from a batched scene dict (render_batch's stacked form; its batched tensors may live in pinned host
+    memory).  Rank r owns the contiguous block band_range(B, r, G) of scenes: the block's batched tensors are copied to
+    the device and become the plan's leaves (`plan.leaves`: name -> tensor), shared tensors named in `shared_leaves`
+    become leaves whose gradients are all-reduced.  One step is
+
+        forward of the block (surf_forward_strided, five launches)
+        ONE all_gather of the block's images into the full [B, H, W, 3] batch
+        loss = loss_fn(images)                         # the caller's loss on the whole batch (every rank)
+        backward of the block (surf_backward_strided) from d(loss)/d(images)[block]
+        ONE all_reduce over the packed gradients of the shared leaves
+
+    with the marshalling, the workspace, the output and gradient buffers reused by every step.  Per-scene leaves (splat
+    positions, normals) get their gradients locally - no collective touches them."""
+
+    def __init__(self, scene, device=None, group=None, block_leaves=('objects/disk/pos', 'objects/disk/normal'),
+                 shared_leaves=('lights/pos',), **params):
+        from .marshal import MarshalledBatch, batched_scene_size, make_options, select_scenes
+        from .renderer import _resolve_device
+        self.group = None if group in (None, True) else group
+        self.world = dist.get_world_size(self.group) if (group is not None and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(self.group) if self.world > 1 else 0
+        B = batched_scene_size(scene)
+        if B is None:
+            raise ValueError('ShardedBatchStep needs a batched scene dict')
+        if B % self.world:
+            raise ValueError('%d scenes do not split evenly over %d ranks' % (B, self.world))
+        self.B = B
+        self.block = band_range(B, self.rank, self.world)
+        b0, b1 = self.block
+        dev = torch.device(device) if device is not None else _resolve_device(scene)
+        self.device = dev
+        self.params = dict(params)
+        # this rank's block on the device; remember which tensors came from host memory for upload()
+        self._uploads = []
+        local = select_scenes(scene, slice(b0, b1))
+
+        def to_dev(path, v):
+            if not isinstance(v, torch.Tensor):
+                return v
+            src = v
+            t = v.detach().to(dev, non_blocking=True)
+            if t is v.detach() or t.data_ptr() == v.data_ptr():
+                t = t.clone()
+            if not src.is_cuda and src.is_floating_point():
+                self._uploads.append((t, src))
+            return t
+        self.scene = {}
+        for key, val in local.items():
+            if key == 'objects':
+                self.scene[key] = {kind: {f: to_dev('objects/%s/%s' % (kind, f), v) for f, v in prim.items()} for kind, prim in val.items()}
+            elif isinstance(val, dict):
+                self.scene[key] = {f: to_dev('%s/%s' % (key, f), v) for f, v in val.items()}
+            else:
+                self.scene[key] = to_dev(key, val)
+
+        def at(path):
+            node = self.scene
+            for part in path.split('/'):
+                node = node[part]
+            return node
+        self.leaves = {}
+        for path in tuple(block_leaves) + tuple(shared_leaves):
+            t = at(path)
+            t.requires_grad_(True)
+            self.leaves[path] = t
+        self.mb = MarshalledBatch(self.scene, dev)
+        m = self.mb.m
+        self.H, self.W = m.height, m.width
+        n = m.n_pixels
+        nb = b1 - b0
+        self.nb = nb
+        self._opt = make_options(self.params)
+        from ._lib import lib
+        self.ws_bytes = (lib().surf_workspace_bytes_ex(m.total_prims, n, int(m.floats[m.i_light_pos].shape[0]), int(self._opt.shadow), m.proj, 0) + 255) // 256 * 256
+        self.workspace = torch.empty(nb, self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.image_block = torch.empty(nb, n, 3, dtype=torch.float32, device=dev)
+        self.image_full = torch.empty(B, n, 3, dtype=torch.float32, device=dev) if self.world > 1 else self.image_block
+        self.depth = torch.empty(nb, n, dtype=torch.float32, device=dev)
+        self.nearest = torch.empty(nb, n, dtype=torch.int64, device=dev)
+        # gradient buffers: block leaves local, shared leaves in one bucket for the all-reduce
+        fulls = self.mb.fulls
+        self._grads = [None] * len(fulls)
+        shared = [self.leaves[p] for p in shared_leaves]
+        self.bucket = GradBucket(shared) if shared else None
+        self._block_grads = []
+        for i, t in enumerate(fulls):
+            for path, leaf in self.leaves.items():
+                if t is leaf:
+                    if path in shared_leaves:
+                        self._grads[i] = leaf.grad
+                    else:
+                        g = torch.zeros_like(leaf)
+                        leaf.grad = g
+                        self._grads[i] = g
+                        self._block_grads.append(g)
+        missing = [p for p, leaf in self.leaves.items() if not any(t is leaf for t in fulls)]
+        if missing:
+            raise ValueError('ShardedBatchStep: leaves were copied while marshalling: %s' % missing)
+        self.launches = 0
+        self.upload_bytes = sum(t.numel() * t.element_size() for t, _ in self._uploads)
+
+    def upload(self):
+        """copy the block's host-resident inputs to the device again (the per-step H2D of an end-to-end measurement)"""
+        with torch.no_grad():
+            for t, src in self._uploads:
+                t.copy_(src, non_blocking=True)
+
+    def _structs(self):
+        if getattr(self, '_cached', None) is None:          # the leaves are updated in place: pointers never change
+            m, mb = self.mb.m, self.mb
+            self._views = mb.views0(mb.fulls)
+            self._cached = (m.c_scene(self._views), m.c_camera(), mb.c_layout())
+        return self._cached
+
+    def forward(self):
+        import ctypes as C
+        from . import _abi
+        from ._lib import check, lib
+        from .renderer import _stream_ptr
+        sc, cam, lay = self._structs()
+        out = _abi.SurfOutputs(self.image_block.data_ptr(), self.depth.data_ptr(), None, None, self.nearest.data_ptr(), None)
+        with torch.cuda.device(self.device):
+            check(lib().surf_forward_strided(self.nb, C.byref(sc), C.byref(cam), C.byref(lay), C.byref(self._opt),
+                                             self.workspace.data_ptr(), self.ws_bytes, C.byref(out), _stream_ptr()))
+        self.launches = lib().surf_last_launch_count()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.image_full, self.image_block, group=self.group)
+        return self.image_full.view(self.B, self.H, self.W, 3)
+
+    def backward(self, g_image_full):
+        import ctypes as C
+        from . import _abi
+        from ._lib import check, lib
+        from .renderer import _stream_ptr
+        b0, b1 = self.block
+        g = g_image_full.reshape(self.B, -1, 3)[b0:b1]
+        if not g.is_contiguous():
+            g = g.contiguous()
+        for gb in self._block_grads:
+            gb.zero_()
+        if self.bucket is not None:
+            self.bucket.zero_()
+        sc, cam, lay = self._structs()
+        og = _abi.SurfOutGrads(g.data_ptr(), None, None, None)
+        sg = self.mb.m.c_grads(self._grads)
+        opt = self._opt
+        opt.forced_nearest = 2
+        with torch.cuda.device(self.device):
+            check(lib().surf_backward_strided(self.nb, C.byref(sc), C.byref(cam), C.byref(lay), C.byref(opt),
+                                              self.workspace.data_ptr(), self.ws_bytes, self.nearest.data_ptr(),
+                                              self.depth.data_ptr(), C.byref(og), C.byref(sg), _stream_ptr()))
+        opt.forced_nearest = 0
+        self.launches += lib().surf_last_launch_count()
+        if self.bucket is not None:
+            self.bucket.all_reduce(self.group)
+
+    def step(self, loss_fn):
+        """forward -> all_gather -> loss_fn(images [B,H,W,3]) -> backward -> all_reduce; returns the loss tensor"""
+        images = self.forward().detach().requires_grad_(True)
+        loss = loss_fn(images)
+        (g,) = torch.autograd.grad(loss, images)
+        self.backward(g)
+        return loss.detach()
+
+
 def shard_scenes(n_scenes, rank, world):
     """Scenes-over-GPUs (GAN batch, gan.py:326-377): scene b -> rank b mod world."""
     return list(range(rank, n_scenes, world))

@@ -140,6 +140,22 @@ def config_d_scene(index, m=5000, width=128, height=128, radius=0.025, cam_dist=
                        n_lights=7, coeffs=(1.0, 0.0, 0.0), gamma=1.0)
 
 
+def config_d_batch(n_scenes=64, m=5000, width=128, height=128, radius=0.025, pin=False):
+    """BASELINE configs[3] as ONE batched scene dict (render_batch's stacked form): splat positions / normals [B,M,3]
+    and camera eyes [B,4] carry the batch dimension, everything else (radius, lights, materials) is shared.
+    pin=True: the batched tensors live in pinned host memory (the per-step upload of an end-to-end measurement)."""
+    parts = [config_d_scene(i, m=m, width=width, height=height, radius=radius) for i in range(n_scenes)]
+    s = parts[0]
+    disk = s['objects']['disk']
+    disk['pos'] = torch.stack([p['objects']['disk']['pos'] for p in parts], 0).contiguous()
+    disk['normal'] = torch.stack([p['objects']['disk']['normal'] for p in parts], 0).contiguous()
+    s['camera']['eye'] = torch.stack([torch.as_tensor(p['camera']['eye'], dtype=torch.float32) for p in parts], 0).contiguous()
+    if pin:
+        disk['pos'], disk['normal'] = disk['pos'].pin_memory(), disk['normal'].pin_memory()
+        s['camera']['eye'] = s['camera']['eye'].pin_memory()
+    return s
+
+
 def random_mixed_scene(seed, width=48, height=40, n_disk=12, n_plane=1, n_sphere=3, n_tri=10,
                        n_lights=3, n_mat=5, order=('disk', 'sphere', 'triangle', 'plane'),
                        homogeneous=False, proj='perspective'):

@@ -63,6 +63,25 @@ def _check_scene_sharding(rank, world):
     return bool(ok)
 
 
+def _check_grad_bucket(rank, world):
+    """GradBucket: the leaves' .grad are views of one flat buffer; autograd accumulates into them in place and ONE
+    in-place all-reduce sums them over ranks - same numbers as allreduce_gradients' pack / reduce / copy-back"""
+    from surf_renderer_b200 import dist as sdist
+    g = torch.Generator().manual_seed(7)
+    a0, b0 = torch.rand(5, 3, generator=g), torch.rand(4, generator=g)
+    a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    bucket = sdist.GradBucket([a, b])
+    ((a * (rank + 1)).sum() + (b ** 2).sum() * (rank + 2)).backward()
+    ok = a.grad.data_ptr() == bucket.views[0].data_ptr() and b.grad.data_ptr() == bucket.views[1].data_ptr()
+    bucket.all_reduce()
+    exp_a = torch.full((5, 3), float(sum(r + 1 for r in range(world))))
+    exp_b = 2 * b0 * float(sum(r + 2 for r in range(world)))
+    ok = ok and torch.allclose(a.grad, exp_a) and torch.allclose(b.grad, exp_b)
+    bucket.zero_()
+    ok = ok and float(a.grad.abs().sum()) == 0.0 and a.grad.data_ptr() == bucket.views[0].data_ptr()
+    return bool(ok)
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -99,6 +118,7 @@ def _worker(rank, world, port, tmp):
     full = sdist.gather_scene_outputs(stack, 5)
     ok = ok and torch.equal(full.reshape(-1), torch.arange(5.0)) and nbytes > 0
     ok = ok and _check_scene_sharding(rank, world)
+    ok = ok and _check_grad_bucket(rank, world)
     open(os.path.join(tmp, 'ok%d' % rank), 'w').write('1' if ok else '0')
     dist.destroy_process_group()
 

@@ -66,7 +66,7 @@ def test_mse_step_matches_oracle_autograd(which):
     assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
     for k in ref_grads:
         assert torch.allclose(lv[k].grad, g0[k], rtol=1e-4, atol=1e-6 * float(g0[k].abs().max()))
-    assert plan.launches >= 8
+    assert plan.launches >= 6          # setup, raygen, prep, intersect, shade, backward, finalize (memsets not counted)
 
 
 def test_mse_step_equals_the_autograd_path_of_this_library():
