@@ -112,6 +112,7 @@ try:
     vals = [float(graphed()) for _ in range(3)]
     torch.cuda.synchronize()
     report['graph_with_nccl'] = {'captured': True, 'losses': vals}
+    del graphed
 except Exception as e:      # noqa: BLE001
     report['graph_with_nccl'] = {'captured': False, 'error': repr(e)[:300]}
     torch.cuda.synchronize()
@@ -126,5 +127,10 @@ if rank == 0:
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, 'dist_worker_n%d.json' % world), 'w') as f:
         f.write(json.dumps(report))
-dist.destroy_process_group()
-sys.exit(0 if flag.item() else 1)
+code = 0 if flag.item() else 1
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+# A process group whose collectives were captured into a CUDA graph can hang in destroy_process_group(); every rank has
+# passed the barrier above, so leave without the teardown.
+os._exit(code)

@@ -25,7 +25,7 @@ def test_two_rank_sharded_paths_equal_the_single_gpu_results():
         pytest.skip('needs at least two GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dist_worker.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
     rep = json.loads(lines[-1])
