@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 
 FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions)
 N_SM, FP32_LANES = 148, 128
-L2_FLUSH_BYTES = 192 * 1024 * 1024     # > the 126 MB L2
+L2_FLUSH_BYTES = 144 * 1024 * 1024     # > the 126 MB L2
 
 
 def parse_args():
@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument('--chunk', type=int, default=0)
     ap.add_argument('--math', type=int, default=0, help='intersection kernel: 0 = default ray-plane FFMA2 filter (10 instr/test), 3 = screen-space fast mode')
     ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph')
+    ap.add_argument('--torch-adam', action='store_true', help="torch.optim.Adam(fused=True) instead of the library's packed Adam kernel")
     ap.add_argument('--ref-size', type=int, default=0, help='reference arm: viewport edge of the bounded sample (0 = auto)')
     ap.add_argument('--ref-budget', type=float, default=150.0, help='reference arm: seconds of CPU work')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -200,7 +201,7 @@ def workload_config(args):
     if args.workload == 'config_e':
         M, S = args.splats or 100_000, args.size or 1024
         return {'workload': 'config_e', 'splats': M, 'width': S, 'height': S, 'lights': 3,
-                'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam',
+                'step': 'render fwd + mse(image,target) + bwd(pos,normal,albedo,light_pos) + Adam (%s)' % ('torch fused' if args.torch_adam else 'surf_adam_step'),
                 'e2e_step': 'H2D(scene, target) + render fwd + mse + bwd + grad all-reduce + D2H(gradients, loss); the host-side optimizer is not part of this leg',
                 'sharding': 'row-bands x%d' % max(1, args.gpus),
                 'l2': 'flushed between timed steps (%d MiB fill enqueued on the stream, inside the timed region)' % (L2_FLUSH_BYTES >> 20)}, float(M) * S * S
@@ -446,7 +447,10 @@ def run_config_e(args, rank, world, local_rank):
         for t in leaves:
             t.requires_grad_(True)
         plan = surf_renderer_b200.MSEStep(sc, tgt, group=(True if world > 1 else None), **step_params)
-        opt = torch.optim.Adam(leaves, lr=1e-4, fused=True, capturable=args.graph)
+        if args.torch_adam:
+            opt = torch.optim.Adam(leaves, lr=1e-4, fused=True, capturable=args.graph)
+        else:
+            opt = surf_renderer_b200.PackedAdam(plan, lr=1e-4)          # one kernel over the packed gradient buffer
 
         def step():
             loss = plan()
@@ -502,7 +506,7 @@ def run_config_e(args, rank, world, local_rank):
                         'frac': shade_bytes / (k_mean[1] * 1e-3) / 1e9 / hbm, 'traffic': ncu_traffic('k_shade', 'config_e', world)} if k_mean[1] > 0 else None,
             'k_backward': {'ms': k_mean[2], 'algorithmic_bytes': bwd_bytes, 'achieved_gbs': bwd_bytes / (k_mean[2] * 1e-3) / 1e9,
                            'frac': bwd_bytes / (k_mean[2] * 1e-3) / 1e9 / hbm, 'traffic': ncu_traffic('k_backward', 'config_e', world)} if k_mean[2] > 0 else None}
-    launches_per_step = int(plan.launches)
+    launches_per_step = int(plan.launches) + (0 if args.torch_adam else 2)      # + k_adam_advance, k_adam_packed
 
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
     fast = None

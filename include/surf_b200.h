@@ -197,6 +197,20 @@ int surf_step_mse(const SurfScene* scene, const SurfCamera* camera, const SurfOp
                   size_t workspace_bytes, const SurfOutputs* out, const SurfStepMSE* step,
                   const SurfSceneGrads* scene_grads, void* cuda_stream);
 
+/* ---- the optimizer of that loop: `optimizer.step()` (test_optimization.py:122; torch.optim.Adam, no amsgrad, no weight
+ * decay) for parameter tensors whose gradients are packed back to back in ONE flat buffer (the layout MSEStep gives
+ * them for the single all-reduce).  exp_avg / exp_avg_sq have the gradients' packed layout; `state` is three device
+ * floats (step count, 1 - beta1^t, sqrt(1 - beta2^t)), all zero-initialised by the caller and advanced on the device,
+ * so the call replays from a CUDA graph. */
+#define SURF_ADAM_MAX_TENSORS 16
+typedef struct SurfAdamTensors {
+    int32_t count;
+    float* param[SURF_ADAM_MAX_TENSORS];     /* device pointers of the parameter tensors, in packed order */
+    int64_t size[SURF_ADAM_MAX_TENSORS];     /* their element counts */
+} SurfAdamTensors;
+int surf_adam_step(const SurfAdamTensors* tensors, const float* grads_packed, float* exp_avg, float* exp_avg_sq,
+                   float* state, float lr, float beta1, float beta2, float eps, void* cuda_stream);
+
 /* ---- batches of independent scenes: the per-element loop of GAN.get_real_samples (GAN/gan.py:326-377) ----
  * Arrays of n_scenes scenes / cameras / workspaces / outputs (one shared SurfOptions).  All kernels of all scenes are
  * launched by this one call, fanned out over internal streams that fork from and join to `cuda_stream`; gradients of

@@ -74,6 +74,13 @@ class SurfStepMSE(C.Structure):
     _fields_ = [('target_image', C.c_void_p), ('loss_scale', C.c_float), ('loss', C.c_void_p), ('grad_image', C.c_void_p)]
 
 
+SURF_ADAM_MAX_TENSORS = 16
+
+
+class SurfAdamTensors(C.Structure):
+    _fields_ = [('count', C.c_int32), ('param', C.c_void_p * SURF_ADAM_MAX_TENSORS), ('size', C.c_int64 * SURF_ADAM_MAX_TENSORS)]
+
+
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
                 ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p)]
@@ -89,6 +96,8 @@ SYMBOLS = {
     'surf_last_error': (C.c_char_p, []),
     'surf_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'surf_workspace_bytes_ex': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'surf_adam_step': (C.c_int, [C.POINTER(SurfAdamTensors), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_void_p]),
     'surf_check_indices': (C.c_int, [C.c_void_p, C.c_void_p]),
     'surf_step_mse': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions), C.c_void_p, C.c_size_t,
                                 C.POINTER(SurfOutputs), C.POINTER(SurfStepMSE), C.POINTER(SurfSceneGrads), C.c_void_p]),

@@ -72,6 +72,43 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float* out) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// packed Adam: optimizer.step() of the inverse-rendering loop (test_optimization.py:122, torch.optim.Adam without
+// amsgrad / weight decay) for leaves whose gradients sit in ONE flat buffer (MSEStep).  torch's fused multi-tensor Adam
+// spends ~80 us on config E's four leaves (two of 300 000 floats, two tiny ones: ten thread blocks); this is one
+// grid-wide launch plus a one-thread launch that advances the step counter and the bias corrections on the device
+// (graph-capturable: nothing step-dependent is a launch parameter).
+// ---------------------------------------------------------------------------------------------------
+struct AdamTensors { int count; float* param[SURF_ADAM_MAX_TENSORS]; long long begin[SURF_ADAM_MAX_TENSORS + 1]; };
+
+__global__ void k_adam_advance(float* __restrict__ state, float beta1, float beta2) {
+    // state[0] = step count, [1] = 1 - beta1^t, [2] = sqrt(1 - beta2^t)
+    const float t = state[0] + 1.f;
+    state[0] = t;
+    state[1] = 1.f - powf(beta1, t);
+    state[2] = sqrtf(1.f - powf(beta2, t));
+}
+
+__global__ void __launch_bounds__(256) k_adam_packed(const __grid_constant__ AdamTensors tn, const float* __restrict__ grads,
+                                                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                     const float* __restrict__ state, float lr, float beta1, float beta2, float eps) {
+    const long long total = tn.begin[tn.count];
+    const float bc1 = state[1], bc2_sqrt = state[2];
+    const float step_size = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (i >= tn.begin[j + 1]) ++j;
+        const float g = grads[i];
+        const float m = beta1 * exp_avg[i] + (1.f - beta1) * g;
+        const float v = beta2 * exp_avg_sq[i] + (1.f - beta2) * g * g;
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        float* p = tn.param[j] + (i - tn.begin[j]);
+        *p = *p - step_size * (m / denom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host-side orchestration (device-pointer API)
 // ---------------------------------------------------------------------------------------------------
 static int make_frame(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, void* workspace,
@@ -694,6 +731,30 @@ int surf_step_mse_strided(int32_t n_scenes, const SurfScene* scene0, const SurfC
     og.image = step->grad_image; og.depth = nullptr; og.normal = nullptr; og.pos = nullptr;
     return backward_strided_fused(n_scenes, scene0, camera0, layout, options, workspace, workspace_bytes_per_scene,
                                   out0->nearest, out0->depth, &og, grads0, st, true, step->loss);
+}
+
+int surf_adam_step(const SurfAdamTensors* tensors, const float* grads_packed, float* exp_avg, float* exp_avg_sq, float* state,
+                   float lr, float beta1, float beta2, float eps, void* cuda_stream) {
+    g_launches = 0;
+    if (!tensors || !grads_packed || !exp_avg || !exp_avg_sq || !state) return fail(SURF_ERR_BAD_ARG, "null adam argument");
+    if (tensors->count < 1 || tensors->count > SURF_ADAM_MAX_TENSORS) return fail(SURF_ERR_BAD_ARG, "surf_adam_step: 1..16 tensors");
+    AdamTensors tn;
+    tn.count = tensors->count;
+    long long off = 0;
+    for (int j = 0; j < tensors->count; ++j) {
+        if (!tensors->param[j] || tensors->size[j] < 0) return fail(SURF_ERR_BAD_ARG, "surf_adam_step: bad tensor");
+        tn.param[j] = tensors->param[j];
+        tn.begin[j] = off;
+        off += tensors->size[j];
+    }
+    tn.begin[tensors->count] = off;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    k_adam_advance<<<1, 1, 0, st>>>(state, beta1, beta2);
+    SURF_LAUNCHED("k_adam_advance");
+    const int grid = (int)std::max<long long>(1, std::min<long long>((off + 255) / 256, (long long)sm_count() * 8));
+    k_adam_packed<<<grid, 256, 0, st>>>(tn, grads_packed, exp_avg, exp_avg_sq, state, lr, beta1, beta2, eps);
+    SURF_LAUNCHED("k_adam_packed");
+    return SURF_OK;
 }
 
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,

@@ -154,6 +154,41 @@ class MSEStep:
         return torch.cat([parts[r, :b - a] for r, (a, b) in enumerate(sizes)], dim=0).view(self.H, self.W, 3)
 
 
+class PackedAdam:
+    """optimizer.step() of the reference loop (test_optimization.py:122: torch.optim.Adam, no amsgrad / weight decay) for
+    the leaves of an MSEStep, whose gradients are views of the plan's packed buffer: ONE kernel over the packed layout
+    (surf_adam_step) instead of torch's multi-tensor launch.  Step count and bias corrections live on the device, so
+    plan() + opt.step() captures into a CUDA graph.
+
+        plan = MSEStep(scene, target);  opt = PackedAdam(plan, lr=1e-3)
+        for it in range(300):  loss = plan();  opt.step()
+    """
+
+    def __init__(self, plan, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if len(plan.leaves) > _abi.SURF_ADAM_MAX_TENSORS:
+            raise ValueError('PackedAdam handles at most %d leaves' % _abi.SURF_ADAM_MAX_TENSORS)
+        self.plan = plan
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        n = plan.packed.numel() - 1                              # (the last float of the packed buffer is the loss)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=plan.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=plan.device)
+        self.state = torch.zeros(4, dtype=torch.float32, device=plan.device)
+        self._tn = _abi.SurfAdamTensors()
+        self._tn.count = len(plan.leaves)
+        for j, t in enumerate(plan.leaves):
+            self._tn.param[j] = t.data_ptr()
+            self._tn.size[j] = t.numel()
+
+    def step(self):
+        with torch.cuda.device(self.plan.device):
+            check(lib().surf_adam_step(C.byref(self._tn), self.plan.packed.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.state.data_ptr(), self.lr, self.betas[0],
+                                       self.betas[1], self.eps, _stream_ptr()))
+
+    def zero_grad(self, set_to_none=False):
+        self.plan.packed.zero_()
+
+
 def render_mse_step(scene, target, group=None, **params):
     """One-off form of MSEStep: builds the plan, runs one step, returns (loss, plan).  Prefer keeping the plan."""
     plan = MSEStep(scene, target, group=group, **params)
