@@ -55,6 +55,25 @@ def is_fresh():
     return os.path.exists(SO) and all(_unit_fresh(u) and os.path.getmtime(SO) >= os.path.getmtime(_obj(u)) for u in UNITS)
 
 
+def build_variant(out_so, defines, units=('surf_kernels.cu',)):
+    """A/B build: recompile `units` with extra -D defines into a separate object directory and link `out_so` from
+    them plus the regular objects of the other units (load it with SURF_B200_LIB=<out_so>)."""
+    build()
+    nvcc = nvcc_path()
+    vdir = out_so + '.obj'
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for u in UNITS:
+        if u in units:
+            o = os.path.join(vdir, u.replace('.cu', '.o'))
+            subprocess.check_call([nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + ['-c', os.path.join(CSRC, u), '-o', o])
+            objs.append(o)
+        else:
+            objs.append(_obj(u))
+    subprocess.check_call([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', out_so])
+    return out_so
+
+
 def build(force=False, verbose=False):
     if not force and is_fresh():
         return SO

@@ -153,15 +153,19 @@ static int launch_shade(ShadeParams& sh, const StepLoss* loss, const BatchArgs* 
     sh.g_image = loss ? loss->g_image : nullptr;
     sh.loss_acc = loss ? loss->loss_acc : nullptr;
     sh.loss_scale = loss ? loss->scale : 0.f;
-    const bool wide = (sh.n % 4 == 0) && (long long)sh.n * n_scenes >= 512 * 1024;
-    const int per_cta = 256 * (wide ? 4 : 1);
-    const dim3 grid((sh.n + per_cta - 1) / per_cta, ba ? n_scenes : 1);
+    // PX pixels per thread: 2 (vector accesses) on frames large enough to fill the machine that way, else 1
+    const int px = ((sh.n % 2 == 0) && (long long)sh.n * n_scenes >= 256 * 1024) ? kShadePX : 1;
+    const int per_cta = 256 * px;
+    const int tiles = (sh.n + per_cta - 1) / per_cta;
+    const int wave = sm_count() * kShadeBlocksPerSM;                 // resident CTAs: persistent, one wave
+    const int ns = ba ? n_scenes : 1;
+    const dim3 grid(std::max(1, std::min(tiles, (wave + ns - 1) / ns)), ns);
     timer_mark(1, 0, st);
     if (ba) {
-        if (wide) k_shade_batch<4><<<grid, 256, 0, st>>>(sh, *ba);
+        if (px > 1) k_shade_batch<kShadePX><<<grid, 256, 0, st>>>(sh, *ba);
         else k_shade_batch<1><<<grid, 256, 0, st>>>(sh, *ba);
     } else {
-        if (wide) k_shade<4><<<grid, 256, 0, st>>>(sh);
+        if (px > 1) k_shade<kShadePX><<<grid, 256, 0, st>>>(sh);
         else k_shade<1><<<grid, 256, 0, st>>>(sh);
     }
     timer_mark(1, 1, st);

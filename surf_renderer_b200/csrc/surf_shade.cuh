@@ -6,6 +6,15 @@
 // ---------------------------------------------------------------------------------------------------
 // k_shade: resolve + Phong shading epilogue (renderer.py:183-189, 266-340)
 // ---------------------------------------------------------------------------------------------------
+#ifndef SURF_SHADE_BLOCKS
+#define SURF_SHADE_BLOCKS 4        // resident CTAs per SM k_shade is compiled for (4 -> 64 registers)
+#endif
+#ifndef SURF_SHADE_PX
+#define SURF_SHADE_PX 2            // pixels per thread on large frames
+#endif
+constexpr int kShadeBlocksPerSM = SURF_SHADE_BLOCKS;
+constexpr int kShadePX = SURF_SHADE_PX;
+
 struct ShadeParams {
     SceneView sc;
     const CamState* cam;
@@ -82,32 +91,67 @@ __device__ __forceinline__ PixelOut resolve_fast(const ShadeParams& p, const Cam
     return po;
 }
 
-// PX consecutive pixels per thread: with PX = 4 and n % 4 == 0 every global access of the kernel is a 16-byte
-// vector (rays 3 x LDG.128, keys 2 x LDG.128, image / normal / pos 3 x STG.128 each, depth 1, nearest 2).
+// PX consecutive pixels per thread.  With n % PX == 0 every global access of the kernel is a vector: PX = 2 -> rays
+// 3 x LDG.64, keys 1 x LDG.128, image / normal / pos / d(image) 3 x STG.64 each, depth STG.64, nearest STG.128.
+// (PX = 4 doubles the widths but needs 4 x 11 output registers live at once; it spills at the 80 registers three
+// resident CTAs allow, and this kernel is latency-bound - dependent key -> record -> material gathers - so
+// occupancy wins.)
+// Persistent CTAs: the grid is sized to one wave (launch_shade) and every CTA strides over the 256*PX-pixel tiles, so the
+// light table is staged (and its barrier paid) once per CTA and no partial last wave is left idle.
+template <int PX> struct VecF;
+template <> struct VecF<1> { typedef float T; };
+template <> struct VecF<2> { typedef float2 T; };
+template <> struct VecF<4> { typedef float4 T; };
+
 template <int PX>
-__device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights, float* red, int block) {
+__device__ __forceinline__ void load_px(const float* __restrict__ src, float out[PX]) {
+    const typename VecF<PX>::T v = *reinterpret_cast<const typename VecF<PX>::T*>(src);
+    const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+    for (int j = 0; j < PX; ++j) out[j] = f[j];
+}
+// 3*PX contiguous floats at dst (12*PX-byte aligned): three vector stores
+template <int PX>
+__device__ __forceinline__ void store_3px(float* __restrict__ dst, const float f[3 * PX]) {
+    typedef typename VecF<PX>::T V;
+    V* q = reinterpret_cast<V*>(dst);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        V v;
+        float* w = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) w[j] = f[i * PX + j];
+        q[i] = v;
+    }
+}
+
+template <int PX>
+__device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights, float* red, int block, int n_blocks) {
     stage_lights(p.sc, lights);
     const CamState& cs = *p.cam;
     const Vec3 eye = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
-    const int k0 = (block * 256 + threadIdx.x) * PX;
-    const bool vec = PX == 4 && (p.n & 3) == 0;
-    constexpr int I1 = PX >= 4 ? 1 : 0, I2 = PX >= 4 ? 2 : 0, I3 = PX >= 4 ? 3 : 0;      // (the vector paths only exist for PX = 4)
+    const bool vec = PX > 1 && (p.n % PX) == 0;
+    const bool persp = cs.proj == 0;
     float err = 0.f;
-    if (k0 < p.n) {
+    const int n_tiles = (p.n + 256 * PX - 1) / (256 * PX);
+    for (int tile = block; tile < n_tiles; tile += n_blocks) {
+        const int k0 = (tile * 256 + threadIdx.x) * PX;
+        if (k0 >= p.n) continue;
         unsigned long long key[PX];
         float dx[PX], dy[PX], dz[PX];
-        const bool persp = cs.proj == 0;
         if (vec) {
-            const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(p.zbuf + k0);
-            const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(p.zbuf + k0 + 2);
-            key[0] = ka.x; key[I1] = ka.y; key[I2] = kb.x; key[I3] = kb.y;
+            if (PX == 1) key[0] = p.zbuf[k0];
+            else {
+#pragma unroll
+                for (int j = 0; j < PX; j += 2) {
+                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(p.zbuf + k0 + j);
+                    key[j] = kk.x; key[j + (PX > 1 ? 1 : 0)] = kk.y;
+                }
+            }
             if (persp) {
-                const float4 a = *reinterpret_cast<const float4*>(p.rays + k0);
-                const float4 b = *reinterpret_cast<const float4*>(p.rays + (size_t)p.n + k0);
-                const float4 c = *reinterpret_cast<const float4*>(p.rays + 2 * (size_t)p.n + k0);
-                dx[0] = a.x; dx[I1] = a.y; dx[I2] = a.z; dx[I3] = a.w;
-                dy[0] = b.x; dy[I1] = b.y; dy[I2] = b.z; dy[I3] = b.w;
-                dz[0] = c.x; dz[I1] = c.y; dz[I2] = c.z; dz[I3] = c.w;
+                load_px<PX>(p.rays + k0, dx);
+                load_px<PX>(p.rays + (size_t)p.n + k0, dy);
+                load_px<PX>(p.rays + 2 * (size_t)p.n + k0, dz);
             }
         } else {
 #pragma unroll
@@ -117,52 +161,48 @@ __device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights,
                 if (persp) { dx[j] = p.rays[k]; dy[j] = p.rays[(size_t)p.n + k]; dz[j] = p.rays[2 * (size_t)p.n + k]; }
             }
         }
-        PixelOut po[PX];
+        float img[3 * PX], nrm[3 * PX], pos[3 * PX], gi[3 * PX], dep[PX];
+        long long nea[PX];
 #pragma unroll
         for (int j = 0; j < PX; ++j) {
             const int k = min(k0 + j, p.n - 1);
             Vec3 o = eye, d;
             if (persp) d = v3(dx[j], dy[j], dz[j]);
             else { o = pixel_ray_origin_ortho(cs, p.pix0 + k); d = v3(cs.odir[0], cs.odir[1], cs.odir[2]); }
-            po[j] = resolve_fast(p, cs, lights, eye, o, d, key[j], k);
-        }
-        float gi[PX][3];
-        if (p.target) {
+            const PixelOut po = resolve_fast(p, cs, lights, eye, o, d, key[j], k);
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const int k = min(k0 + j, p.n - 1);
+            for (int c = 0; c < 3; ++c) { img[3 * j + c] = po.image[c]; nrm[3 * j + c] = po.normal[c]; pos[3 * j + c] = po.pos[c]; }
+            dep[j] = po.depth;
+            nea[j] = po.nearest;
+            if (p.target) {
                 const bool live = k0 + j < p.n;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float diff = po[j].image[c] - p.target[(size_t)k * 3 + c];
-                    gi[j][c] = 2.f * p.loss_scale * diff;
+                    const float diff = po.image[c] - p.target[(size_t)k * 3 + c];
+                    gi[3 * j + c] = 2.f * p.loss_scale * diff;
                     if (live) err = fmaf(diff, diff, err);
                 }
             }
         }
         if (vec) {
-            auto store12 = [&](float* dst, int which) {
-                if (!dst) return;
-                float f[12];
+            if (p.image) store_3px<PX>(p.image + (size_t)k0 * 3, img);
+            if (p.normal) store_3px<PX>(p.normal + (size_t)k0 * 3, nrm);
+            if (p.pos) store_3px<PX>(p.pos + (size_t)k0 * 3, pos);
+            if (p.target && p.g_image) store_3px<PX>(p.g_image + (size_t)k0 * 3, gi);
+            if (p.depth) {
+                typename VecF<PX>::T v;
+                float* w = reinterpret_cast<float*>(&v);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        f[3 * j + c] = which == 0 ? po[j % PX].image[c] : (which == 1 ? po[j % PX].normal[c] : (which == 2 ? po[j % PX].pos[c] : gi[j % PX][c]));
-                float4* q = reinterpret_cast<float4*>(dst + (size_t)k0 * 3);
-                q[0] = make_float4(f[0], f[1], f[2], f[3]);
-                q[1] = make_float4(f[4], f[5], f[6], f[7]);
-                q[2] = make_float4(f[8], f[9], f[10], f[11]);
-            };
-            store12(p.image, 0);
-            store12(p.normal, 1);
-            store12(p.pos, 2);
-            if (p.target) store12(p.g_image, 3);
-            if (p.depth) *reinterpret_cast<float4*>(p.depth + k0) = make_float4(po[0].depth, po[I1].depth, po[I2].depth, po[I3].depth);
+                for (int j = 0; j < PX; ++j) w[j] = dep[j];
+                *reinterpret_cast<typename VecF<PX>::T*>(p.depth + k0) = v;
+            }
             if (p.nearest) {
-                longlong2* q = reinterpret_cast<longlong2*>(p.nearest + k0);
-                q[0] = make_longlong2(po[0].nearest, po[I1].nearest);
-                q[1] = make_longlong2(po[I2].nearest, po[I3].nearest);
+                if (PX == 1) p.nearest[k0] = nea[0];
+                else {
+#pragma unroll
+                    for (int j = 0; j < PX; j += 2)
+                        *reinterpret_cast<longlong2*>(p.nearest + k0 + j) = make_longlong2(nea[j], nea[j + (PX > 1 ? 1 : 0)]);
+                }
             }
         } else {
 #pragma unroll
@@ -171,13 +211,13 @@ __device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights,
                 if (k >= p.n) break;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (p.image) p.image[(size_t)k * 3 + c] = po[j].image[c];
-                    if (p.normal) p.normal[(size_t)k * 3 + c] = po[j].normal[c];
-                    if (p.pos) p.pos[(size_t)k * 3 + c] = po[j].pos[c];
-                    if (p.target && p.g_image) p.g_image[(size_t)k * 3 + c] = gi[j][c];
+                    if (p.image) p.image[(size_t)k * 3 + c] = img[3 * j + c];
+                    if (p.normal) p.normal[(size_t)k * 3 + c] = nrm[3 * j + c];
+                    if (p.pos) p.pos[(size_t)k * 3 + c] = pos[3 * j + c];
+                    if (p.target && p.g_image) p.g_image[(size_t)k * 3 + c] = gi[3 * j + c];
                 }
-                if (p.depth) p.depth[k] = po[j].depth;
-                if (p.nearest) p.nearest[k] = po[j].nearest;
+                if (p.depth) p.depth[k] = dep[j];
+                if (p.nearest) p.nearest[k] = nea[j];
             }
         }
     }
@@ -195,15 +235,15 @@ __device__ __forceinline__ void shade_body(const ShadeParams& p, LightS* lights,
 }
 
 template <int PX>
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ShadeParams p) {
+__global__ void __launch_bounds__(256, kShadeBlocksPerSM) k_shade(const __grid_constant__ ShadeParams p) {
     __shared__ LightS lights[kLightTable];
     __shared__ float red[8];
-    shade_body<PX>(p, lights, red, blockIdx.x);
+    shade_body<PX>(p, lights, red, blockIdx.x, gridDim.x);
 }
 
 // strided batch: blockIdx.y = scene; outputs are [B, n, ...]
 template <int PX>
-__global__ void __launch_bounds__(256) k_shade_batch(const __grid_constant__ ShadeParams p0, const __grid_constant__ BatchArgs ba) {
+__global__ void __launch_bounds__(256, kShadeBlocksPerSM) k_shade_batch(const __grid_constant__ ShadeParams p0, const __grid_constant__ BatchArgs ba) {
     __shared__ LightS lights[kLightTable];
     __shared__ float red[8];
     __shared__ ShadeParams p;
@@ -219,7 +259,7 @@ __global__ void __launch_bounds__(256) k_shade_batch(const __grid_constant__ Sha
         p.target = adv(p0.target, b * n * 3); p.g_image = adv(p0.g_image, b * n * 3);
     }
     __syncthreads();
-    shade_body<PX>(p, lights, red, blockIdx.x);
+    shade_body<PX>(p, lights, red, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------

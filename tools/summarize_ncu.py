@@ -73,5 +73,30 @@ def full(path, out):
         print(json.dumps(r, indent=1))
 
 
+def traffic(path, out, workload='config_e', n_gpus='1'):
+    """profiles/ncu_traffic.json for bench.py's roofline.traffic: DRAM bytes (read + write) per launch of each captured
+    kernel, stamped with the hash of the library sources the capture was taken on (bench.py only reports it when the
+    hash matches the build it is running)."""
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    import bench
+    recs = json.load(open(path))
+    kernels = {}
+    for r in recs:
+        name = r['Kernel Name'].split('(')[0].split('<')[0].replace('void ', '').replace('surf::', '').strip()
+        rd = wr = None
+        for k, v in r.items():
+            if k.startswith('dram__bytes_read.sum'):
+                rd = float(v.replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[k.split('[')[1].rstrip(']')]
+            if k.startswith('dram__bytes_write.sum'):
+                wr = float(v.replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[k.split('[')[1].rstrip(']')]
+        if rd is not None and wr is not None:
+            kernels[name] = int(rd + wr)
+    json.dump({'source_hash': bench.source_hash(), 'workload': workload, 'n_gpus': int(n_gpus), 'kernels': kernels,
+               'from': os.path.basename(path), 'what': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full'},
+              open(out, 'w'), indent=1)
+    print(open(out).read())
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
