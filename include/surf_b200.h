@@ -261,18 +261,28 @@ typedef struct SurfSplats {
     int32_t count;            /* must equal width * height */
     const float* z;           /* [count] depths, or column 2 of a [count,3] position array (z_stride = 3) */
     int32_t z_stride;         /* 1 or 3 */
-    const float* normal;      /* [count, normal_stride] camera-space normals (used as given, not normalised) */
+    const float* normal;      /* [count, normal_stride] camera-space normals (used as given, not normalised); ignored
+                                 when estimate_normals != 0 */
     int32_t normal_stride;    /* 3 or 4 */
     const int32_t* material_idx; /* [count], or NULL = material 0 */
     const float* light_vis;   /* [L, count] per-light visibility (constant), or NULL */
-    const float* pos;         /* optional [count,3] explicit camera-space positions (supersampled fragments,
-                                 renderer.py:603-673); when non-NULL `z` is ignored and count need not equal W*H */
+    const float* pos;         /* optional [count,3] explicit camera-space fragment positions; when non-NULL `z` is ignored,
+                                 count need not equal W*H, and samples / estimate_normals must be 1 / 0 */
+    int32_t samples;          /* supersampling K (renderer.py:603-673): every pixel's splat plane is intersected with its
+                                 K x K sub-pixel rays; outputs are [(H K) (W K), ...].  0 or 1 = off */
+    int32_t estimate_normals; /* 0 = `normal` is given; 1 = 3x3 constrained plane fit (utils.py:886-923, the GAN's
+                                 normal_estimation_method='plane'); 2 = average neighbour cross product (utils.py:854-883) */
+    float* norm_depth;        /* optional [n] output: norm_depth_image_only (renderer.py:677-686): depth normalised to
+                                 [0, 1] over the frame, fragments at or beyond the camera's far plane mapped to 0 */
 } SurfSplats;
 typedef struct SurfSplatGrads {
     float* z;                 /* same stride as SurfSplats.z; caller zero-initialises, the library adds */
-    float* normal;            /* same stride as SurfSplats.normal */
+    float* normal;            /* same stride as SurfSplats.normal (given normals only) */
     float* pos;               /* [count,3], only with explicit positions */
 } SurfSplatGrads;
+/* bytes of device scratch per scene (camera, camera-space lights, accumulators, estimated normals, per-splat gradient
+ * accumulators); n_splats = width * height (or `count` with explicit positions) */
+size_t surf_splats_workspace_bytes(int32_t n_splats, int32_t n_lights);
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
                         const SurfSplats* splats, void* workspace, size_t workspace_bytes,
                         const SurfOutputs* out, void* cuda_stream);
@@ -280,6 +290,26 @@ int surf_splats_backward(const SurfScene* scene, const SurfCamera* camera, const
                          const SurfSplats* splats, void* workspace, size_t workspace_bytes,
                          const SurfOutGrads* out_grads, const SurfSceneGrads* scene_grads,
                          const SurfSplatGrads* splat_grads, void* cuda_stream);
+
+/* ---- a batch of along-ray frames in one call: the per-element loop of the GAN generator step, GAN/gan.py:563-597
+ * (each element: its own depths / normals, camera eye and light positions; shared materials and camera scalars).
+ * Scene b reads the pointers of `splats0` / `scene0->light_pos` / `camera0->eye` advanced by b * stride ELEMENTS
+ * (0 = shared); outputs and incoming gradients are [B, n, ...]; `workspace` holds B slices of
+ * workspace_bytes_per_scene (>= surf_splats_workspace_bytes, a multiple of 256).  Gradients of shared arrays receive
+ * the sum over the batch. */
+typedef struct SurfSplatBatch {
+    int64_t z, normal, material_idx, light_vis;   /* strides of the SurfSplats arrays */
+    int64_t light_pos;                            /* stride of scene0->light_pos ([B, L, 4] -> 4 L) */
+    int64_t eye;                                  /* stride of camera0->eye */
+} SurfSplatBatch;
+int surf_splats_forward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                                const SurfOptions* options, const SurfSplats* splats0, const SurfSplatBatch* batch,
+                                void* workspace, size_t workspace_bytes_per_scene, const SurfOutputs* out0,
+                                void* cuda_stream);
+int surf_splats_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0,
+                                 const SurfOptions* options, const SurfSplats* splats0, const SurfSplatBatch* batch,
+                                 void* workspace, size_t workspace_bytes_per_scene, const SurfOutGrads* out_grads0,
+                                 const SurfSceneGrads* scene_grads, const SurfSplatGrads* splat_grads0, void* cuda_stream);
 
 /* ---- host-pointer API (self-contained: H2D, kernels, D2H) ---- */
 typedef struct SurfContext SurfContext;

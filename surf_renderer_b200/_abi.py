@@ -83,7 +83,13 @@ class SurfAdamTensors(C.Structure):
 
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
-                ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p)]
+                ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p),
+                ('samples', C.c_int32), ('estimate_normals', C.c_int32), ('norm_depth', C.c_void_p)]
+
+
+class SurfSplatBatch(C.Structure):
+    _fields_ = [('z', C.c_int64), ('normal', C.c_int64), ('material_idx', C.c_int64), ('light_vis', C.c_int64),
+                ('light_pos', C.c_int64), ('eye', C.c_int64)]
 
 
 class SurfSplatGrads(C.Structure):
@@ -119,6 +125,14 @@ SYMBOLS = {
     'surf_backward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfBatchLayout),
                                         C.POINTER(SurfOptions), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_splats_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'surf_splats_forward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                              C.POINTER(SurfSplats), C.POINTER(SurfSplatBatch), C.c_void_p, C.c_size_t,
+                                              C.POINTER(SurfOutputs), C.c_void_p]),
+    'surf_splats_backward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
+                                               C.POINTER(SurfSplats), C.POINTER(SurfSplatBatch), C.c_void_p, C.c_size_t,
+                                               C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.POINTER(SurfSplatGrads),
+                                               C.c_void_p]),
     'surf_splats_forward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                       C.POINTER(SurfSplats), C.c_void_p, C.c_size_t, C.POINTER(SurfOutputs), C.c_void_p]),
     'surf_splats_backward': (C.c_int, [C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),

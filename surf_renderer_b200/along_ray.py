@@ -1,14 +1,23 @@
 """Drop-in for ``diffrend.torch.renderer.render_splats_along_ray`` (reference: renderer.py:537-751): one splat per
 pixel at camera-space depth z along the pixel's ray - the differentiable path the GAN generator renders through
 (GAN/gan.py:563-597).  Same scene dict; ``scene['objects']['disk']`` holds ``pos`` ([N] depths or [N,3] whose z
-column is used), ``normal`` [N,3|4] in camera coordinates, ``material_idx`` [N] and optionally ``light_vis`` [L,N].
-Returned keys: ``image [H,W,3]`` (no tonemap, like the reference), ``depth [H,W]``, ``pos [H,W,3]``, ``normal [H,W,3]``;
-all autograd-connected to z, normals, lights and materials.  The shading (and, on the default path, the z -> position
-mapping) runs in the CUDA kernels ``k_splat_forward`` / ``k_splat_backward``.  Normal estimation (``normal`` missing;
-``normal_estimation_method`` 'plane' or 'avg_normal', utils.py:854-923) and supersampling (``samples > 1``,
-renderer.py:603-673) are O(N) device-side tensor programs in front of the same kernels, which then take explicit
-fragment positions.  ``norm_depth_image_only`` (renderer.py:677-686) is honoured; ``orient_splats`` is a no-op in the
-reference and is accepted and ignored.
+column is used), optionally ``normal`` [N,3|4] in camera coordinates, ``material_idx`` [N] and optionally
+``light_vis`` [L,N].  Returned keys: ``image [H,W,3]`` (no tonemap, like the reference), ``depth [H,W]``,
+``pos [H,W,3]``, ``normal [H,W,3]``, all autograd-connected to z, normals, lights and materials.
+
+Everything between the caller's tensors and the outputs runs in the CUDA kernels of csrc/surf_splats.cuh - nothing is
+computed with torch ops here:
+
+  * ``normal`` missing -> 3x3 stencil normal estimation in ``k_splat_normals`` (``normal_estimation_method`` 'plane',
+    utils.py:886-923, or 'avg_normal', utils.py:854-883) with an analytic backward (``k_splat_normals_backward``);
+  * ``samples`` K > 1 -> the K x K sub-pixel plane intersections of renderer.py:603-673 inside ``k_splat_forward``
+    (outputs are [H K, W K, ...]);
+  * ``norm_depth_image_only`` (renderer.py:677-686) -> depth min / max reduced in ``k_splat_forward``, normalised by
+    ``k_splat_normdepth``;  ``orient_splats`` is a no-op in the reference and is accepted and ignored.
+
+``render_splats_along_ray_batch`` renders a whole generator batch - depths [B,N], normals [B,N,3], camera eyes [B,3|4],
+light positions [B,L,4] - in ONE call per direction (``surf_splats_forward_strided``), replacing the per-element Python
+loop of gan.py:563-597.
 """
 from __future__ import annotations
 
@@ -22,51 +31,91 @@ from ._lib import check, lib
 from .marshal import _as_float_tensor, _as_int_tensor, _scalar, make_options
 from .renderer import _resolve_device, _stream_ptr, get_param_value
 
+_METHODS = {'plane': 1, 'avg_normal': 2}
 
-class _SplatInputs:
-    """Flat inputs of one call.  `explicit` = (pos [n,3], normal [n,3], material_idx [n] | None, light_vis [L,n] | None,
-    H, W) when the fragments were prepared by the tensor program (estimated normals / supersampling)."""
 
-    def __init__(self, scene, device, explicit=None):
+def _host_viewport(cam):
+    vp = cam['viewport']
+    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
+    return int(vp[2] - vp[0]), int(vp[3] - vp[1])
+
+
+class _SplatCall:
+    """Flat inputs of one call (single frame: batch = None, or a batch of B frames)."""
+
+    def __init__(self, scene, params, device, batch=None):
         cam = scene['camera']
-        vp = cam['viewport']
-        vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
-        self.width, self.height = int(vp[2] - vp[0]), int(vp[3] - vp[1])
-        self.n = self.width * self.height
+        self.width, self.height = _host_viewport(cam)
+        self.n_src = self.width * self.height
         self.fovy, self.focal = _scalar(cam['fovy']), _scalar(cam['focal_length'])
         self.near, self.far = _scalar(cam.get('near', 0.1)), _scalar(cam.get('far', 1000.0))
-        self.cam_vecs = {k: _as_float_tensor(cam[k], device).detach().reshape(-1)[:3].contiguous() for k in ('eye', 'at', 'up')}
+        self.batch = batch
+        B = batch
         disk = scene['objects']['disk']
-        self.explicit = explicit is not None
-        if self.explicit:
-            e_pos, e_normal, e_mat, e_vis, self.height, self.width = explicit
-            self.n = self.width * self.height
-            disk = {'pos': e_pos, 'normal': e_normal, 'material_idx': e_mat, 'light_vis': e_vis}
         lights = scene['lights']
+        normal = get_param_value('normal', disk, None)
+        self.estimate = 0
+        if normal is None:
+            method = get_param_value('normal_estimation_method', params, 'plane')
+            if method not in _METHODS:
+                raise ValueError("normal_estimation_method must be 'plane' or 'avg_normal'")   # 'quadric' maps to None upstream
+            self.estimate = _METHODS[method]
+        self.samples = int(get_param_value('samples', params, 1))
+        self.norm_depth = bool(get_param_value('norm_depth_image_only', params, False))
+        z = _as_float_tensor(disk['pos'], device)
+        base = 1 if B is None else 2
+        if z.dim() not in (base, base + 1) or (z.dim() == base + 1 and z.shape[-1] != 3):
+            raise ValueError('disk.pos must be [N] or [N,3]' if B is None else 'disk.pos must be [B,N] or [B,N,3]')
+        self.z_stride = 1 if z.dim() == base else 3
+        if z.shape[base - 1] != self.n_src or (B is not None and z.shape[0] != B):
+            raise ValueError('render_splats_along_ray needs one splat per pixel: %s splats for %dx%d'
+                             % (tuple(z.shape), self.width, self.height))
+        lp = _as_float_tensor(lights['pos'], device)
+        if lp.shape[-1] != 4:
+            raise ValueError('lights.pos must be homogeneous [L,4] (it is multiplied by the 4x4 view matrix, renderer.py:709)')
+        self.n_lights = int(lp.shape[-2])
         self.names = ['objects/disk/pos', 'objects/disk/normal', 'lights/pos', 'lights/attenuation', 'lights/ambient',
                       'colors', 'materials/albedo', 'materials/coeffs']
-        self.floats = [_as_float_tensor(v, device) for v in (disk['pos'], disk['normal'], lights['pos'], lights['attenuation'],
-                                                             lights['ambient'], scene['colors'], scene['materials']['albedo'],
-                                                             scene['materials']['coeffs'])]
-        z = self.floats[0]
-        if z.shape[0] != self.n:
-            raise ValueError('render_splats_along_ray needs one splat per pixel: %d splats for %dx%d' % (z.shape[0], self.width, self.height))
-        self.z_stride = 1 if z.dim() == 1 else int(z.shape[-1])
-        if self.z_stride not in (1, 3) or (self.explicit and self.z_stride != 3):
-            raise ValueError('disk.pos must be [N] or [N,3]')
-        if self.floats[2].shape[-1] != 4:
-            raise ValueError('lights.pos must be homogeneous [L,4] (it is multiplied by the 4x4 view matrix, renderer.py:709)')
+        nrm = _as_float_tensor(normal, device) if normal is not None else None
+        self.floats = [z, nrm, lp, _as_float_tensor(lights['attenuation'], device), _as_float_tensor(lights['ambient'], device),
+                       _as_float_tensor(scene['colors'], device), _as_float_tensor(scene['materials']['albedo'], device),
+                       _as_float_tensor(scene['materials']['coeffs'], device)]
         mi = disk.get('material_idx', None)
         self.mat = _as_int_tensor(mi, device) if mi is not None else None
+        if self.samples > 1 and self.mat is None:
+            raise AssertionError('supersampling needs material_idx (renderer.py:605)')
         self.color_idx = _as_int_tensor(lights['color_idx'], device)
         lv = disk.get('light_vis', None)
         self.vis = _as_float_tensor(lv, device).detach() if lv is not None else None
+        eye = _as_float_tensor(cam['eye'], device).detach()
+        self.eye_stride = 0
+        if B is not None and eye.dim() == 2:
+            if eye.shape[0] != B:
+                raise ValueError('camera.eye batch dimension disagrees with disk.pos')
+            eye = eye[:, :3].contiguous()
+            self.eye_stride = 3
+        else:
+            eye = eye.reshape(-1)[:3].contiguous()
+        self.cam_vecs = {'eye': eye}
+        for k in ('at', 'up'):
+            self.cam_vecs[k] = _as_float_tensor(cam[k], device).detach().reshape(-1)[:3].contiguous()
+        K = max(1, self.samples)
+        self.out_h, self.out_w = self.height * K, self.width * K
+        self.n_out = self.n_src * K * K
 
-    def structs(self, fl, params):
+    def _bstride(self, t, base_dim):
+        """element stride between scenes of tensor t (0 when it carries no batch dimension)"""
+        if self.batch is None or t is None or t.dim() == base_dim:
+            return 0
+        if t.shape[0] != self.batch:
+            raise ValueError('batched along-ray scene: leading dimensions disagree')
+        return int(t.stride(0))
+
+    def structs(self, fl, params, norm_depth_ptr=None):
         z, nrm, lpos, att, amb, col, alb, cof = fl
         sc = _abi.SurfScene()
         sc.n_sets = 0
-        sc.n_lights, sc.light_pos, sc.light_pos_stride = int(lpos.shape[0]), lpos.data_ptr(), 4
+        sc.n_lights, sc.light_pos, sc.light_pos_stride = self.n_lights, lpos.data_ptr(), 4
         sc.light_color_idx, sc.light_attenuation, sc.ambient = self.color_idx.data_ptr(), att.data_ptr(), amb.data_ptr()
         sc.n_colors, sc.colors = int(col.shape[0]), col.data_ptr()
         sc.n_materials = min(int(alb.shape[0]), int(cof.shape[0]))
@@ -76,40 +125,63 @@ class _SplatInputs:
         cam.eye, cam.at, cam.up = (self.cam_vecs[k].data_ptr() for k in ('eye', 'at', 'up'))
         cam.near_clip, cam.far_clip = self.near, self.far
         sp = _abi.SurfSplats()
-        sp.count = self.n
-        if self.explicit:
-            sp.pos = z.data_ptr()
+        sp.count = self.n_src
         sp.z = z.data_ptr() + (8 if self.z_stride == 3 else 0)          # column 2 of a [N,3] position array
-        sp.z_stride, sp.normal, sp.normal_stride = self.z_stride, nrm.data_ptr(), int(nrm.shape[-1])
+        sp.z_stride = self.z_stride
+        if nrm is not None:
+            sp.normal, sp.normal_stride = nrm.data_ptr(), int(nrm.shape[-1])
         sp.material_idx = self.mat.data_ptr() if self.mat is not None else None
         sp.light_vis = self.vis.data_ptr() if self.vis is not None else None
-        return sc, cam, sp, make_options(params)
+        sp.samples, sp.estimate_normals = self.samples, self.estimate
+        sp.norm_depth = norm_depth_ptr
+        lay = _abi.SurfSplatBatch()
+        if self.batch is not None:
+            lay.z = self._bstride(z, 1 if self.z_stride == 1 else 2)
+            lay.normal = self._bstride(nrm, 2)
+            lay.material_idx = self._bstride(self.mat, 1)
+            lay.light_vis = self._bstride(self.vis, 2)
+            lay.light_pos = self._bstride(lpos, 2)
+            lay.eye = self.eye_stride
+        return sc, cam, sp, lay, make_options(params)
 
 
 class _AlongRayFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, inp, params, *floats):
+    def forward(ctx, call, params, *floats):
         dev = floats[0].device
-        n = inp.n
-        sc, cam, sp, opt = inp.structs(floats, params)
-        ws_bytes = lib().surf_workspace_bytes_ex(0, n, sc.n_lights, 0, 0, 0)
-        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        image, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
-        pos, normal = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+        B = call.batch or 1
+        n = call.n_out
+        ws_bytes = lib().surf_splats_workspace_bytes(call.n_src, call.n_lights)
+        workspace = torch.empty(B, ws_bytes, dtype=torch.uint8, device=dev)
+        lead = (B,) if call.batch is not None else ()
+        image, depth = torch.empty(lead + (n, 3), device=dev), torch.empty(lead + (n,), device=dev)
+        pos, normal = torch.empty(lead + (n, 3), device=dev), torch.empty(lead + (n, 3), device=dev)
+        norm_depth = torch.empty(lead + (n,), device=dev) if call.norm_depth else None
+        sc, cam, sp, lay, opt = call.structs(floats, params, norm_depth.data_ptr() if norm_depth is not None else None)
         out = _abi.SurfOutputs(image.data_ptr(), depth.data_ptr(), normal.data_ptr(), pos.data_ptr(), None, None)
         with torch.cuda.device(dev):
-            check(lib().surf_splats_forward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), workspace.data_ptr(),
-                                            ws_bytes, C.byref(out), _stream_ptr()))
-        ctx.inp, ctx.params, ctx.workspace = inp, params, workspace
-        ctx.save_for_backward(*floats)
-        return image, depth, pos, normal
+            if call.batch is None:
+                check(lib().surf_splats_forward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), workspace.data_ptr(),
+                                                ws_bytes, C.byref(out), _stream_ptr()))
+            else:
+                check(lib().surf_splats_forward_strided(B, C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), C.byref(lay),
+                                                        workspace.data_ptr(), ws_bytes, C.byref(out), _stream_ptr()))
+        ctx.call, ctx.params, ctx.workspace = call, params, workspace
+        ctx.save_for_backward(*[t for t in floats if t is not None])
+        ctx.has = [t is not None for t in floats]
+        if norm_depth is None:
+            norm_depth = depth.new_empty(0)
+        ctx.mark_non_differentiable(norm_depth)
+        return image, depth, pos, normal, norm_depth
 
     @staticmethod
-    def backward(ctx, g_image, g_depth, g_pos, g_normal):
-        floats = ctx.saved_tensors
-        inp = ctx.inp
-        sc, cam, sp, opt = inp.structs(floats, ctx.params)
-        grads = [torch.zeros_like(t) if ctx.needs_input_grad[2 + i] else None for i, t in enumerate(floats)]
+    def backward(ctx, g_image, g_depth, g_pos, g_normal, _g_nd):
+        saved = list(ctx.saved_tensors)
+        floats = [saved.pop(0) if h else None for h in ctx.has]
+        call = ctx.call
+        B = call.batch or 1
+        sc, cam, sp, lay, opt = call.structs(floats, ctx.params)
+        grads = [torch.zeros_like(t) if (t is not None and ctx.needs_input_grad[2 + i]) else None for i, t in enumerate(floats)]
 
         def ptr(t):
             return None if t is None else t.data_ptr()
@@ -119,124 +191,26 @@ class _AlongRayFn(torch.autograd.Function):
         sg.light_pos, sg.light_attenuation, sg.ambient = ptr(grads[2]), ptr(grads[3]), ptr(grads[4])
         sg.colors, sg.albedo, sg.coeffs = ptr(grads[5]), ptr(grads[6]), ptr(grads[7])
         spg = _abi.SurfSplatGrads()
-        if grads[0] is not None and inp.explicit:
-            spg.pos = grads[0].data_ptr()
-        elif grads[0] is not None:
-            spg.z = grads[0].data_ptr() + (8 if inp.z_stride == 3 else 0)
+        if grads[0] is not None:
+            spg.z = grads[0].data_ptr() + (8 if call.z_stride == 3 else 0)
         spg.normal = ptr(grads[1])
         ws = ctx.workspace
         with torch.cuda.device(floats[0].device):
-            check(lib().surf_splats_backward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), ws.data_ptr(), ws.numel(),
-                                             C.byref(og), C.byref(sg), C.byref(spg), _stream_ptr()))
+            if call.batch is None:
+                check(lib().surf_splats_backward(C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), ws.data_ptr(), ws.shape[1],
+                                                 C.byref(og), C.byref(sg), C.byref(spg), _stream_ptr()))
+            else:
+                check(lib().surf_splats_backward_strided(B, C.byref(sc), C.byref(cam), C.byref(opt), C.byref(sp), C.byref(lay),
+                                                         ws.data_ptr(), ws.shape[1], C.byref(og), C.byref(sg), C.byref(spg),
+                                                         _stream_ptr()))
         return (None, None) + tuple(grads)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# device-side tensor programs in front of the shading kernels (all differentiable torch ops on the scene's device)
-# ---------------------------------------------------------------------------------------------------------------
-def _unit(u, eps=1e-10):
-    """utils.py:135-139 normalize: eps inside the sum, zero lengths divide by one."""
-    length = torch.sqrt(torch.sum(u * u + eps, dim=-1, keepdim=True))
-    return u / torch.where(length > 0, length, torch.ones_like(length))
-
-
-def _image_plane(inp, device):
-    """image-plane coordinates of the pixel grid: float64 linspace -> f32 -> scaled in f32 (renderer.py:570-577)"""
-    h = np.tan(inp.fovy / 2) * 2 * inp.focal
-    w = h * (inp.width / inp.height)
-    gx, gy = np.meshgrid(np.linspace(-1, 1, inp.width), np.linspace(1, -1, inp.height))
-    x = torch.tensor(gx.ravel(), dtype=torch.float32, device=device) * (w / 2)
-    y = torch.tensor(gy.ravel(), dtype=torch.float32, device=device) * (h / 2)
-    return x, y, w, h
-
-
-def _neighbour_diffs(pos_hw):
-    """utils.py:772-792 grad_spatial2d: differences to the 8 neighbours with reflect padding -> [8, H, W, 3]"""
-    xp = torch.nn.functional.pad(pos_hw.permute(2, 0, 1)[None], (1, 1, 1, 1), mode='reflect')[0].permute(1, 2, 0)
-    Hp, Wp = xp.shape[:2]
-    centre = xp[1:-1, 1:-1, :]
-    return torch.stack([xp[1 + dy:Hp + dy - 1, 1 + dx:Wp + dx - 1, :] - centre
-                        for dy in (-1, 0, 1) for dx in (-1, 0, 1) if not (dx == 0 and dy == 0)], dim=0)
-
-
-def _normals_plane_fit(pos_hw):
-    """utils.py:886-923: least-squares plane through each splat and its 8 neighbours with n_z fixed to 1."""
-    nd = _unit(_neighbour_diffs(pos_hw)).reshape(8, -1, 3)
-    m = nd[:, :, :2].transpose(0, 1)                                    # [N, 8, 2]
-    mtm = m.transpose(1, 2) @ m                                         # [N, 2, 2]
-    a, b, c, d = mtm[:, 0, 0], mtm[:, 0, 1], mtm[:, 1, 0], mtm[:, 1, 1]
-    det = a * d - b * c + 1e-12
-    rhs = (m.transpose(1, 2) @ (-nd[:, :, 2].transpose(0, 1)[:, :, None]))[:, :, 0]        # [N, 2]
-    nx = (d * rhs[:, 0] - b * rhs[:, 1]) / det
-    ny = (-c * rhs[:, 0] + a * rhs[:, 1]) / det
-    return _unit(torch.stack((nx, ny, torch.ones_like(nx)), dim=1))
-
-
-def _normals_average(pos_hw):
-    """utils.py:854-883 find_average_normal: mean of the 8 neighbour-difference cross products, clamped to [0, 1]."""
-    nd = _unit(_neighbour_diffs(pos_hw))
-    ring = ((4, 2), (2, 1), (1, 0), (0, 3), (3, 5), (5, 6), (6, 7), (7, 4))
-    n = torch.stack([torch.linalg.cross(nd[i], nd[j], dim=-1) for i, j in ring], dim=0).mean(dim=0)
-    return torch.clamp(_unit(n), 0.0, 1.0).reshape(-1, 3)
-
-
-def _upsampled(x, H, W, C, K):
-    """renderer.py:476-481 reshape_upsampled_data: [N, C, K*K] (sub-column major) -> [H*K * W*K, C] row-major"""
-    return x.view(H, W, C, K, K).permute(0, 3, 1, 4, 2).contiguous().view(H * W * K * K, C)
-
-
-def _prepare_fragments(scene, inp0, params, device):
-    """positions / normals / materials / visibility of the (possibly supersampled) fragments, as tensors"""
-    disk = scene['objects']['disk']
-    z_in = _as_float_tensor(disk['pos'], device)
-    x, y, w, h = _image_plane(inp0, device)
-    H, W, focal = inp0.height, inp0.width, inp0.focal
-    Z = -torch.relu(-(z_in if z_in.dim() == 1 else z_in[:, 2]))
-    pos = torch.stack((-Z * x / focal, -Z * y / focal, Z), dim=1)
-    normals = get_param_value('normal', disk, None)
-    if normals is None:
-        method = get_param_value('normal_estimation_method', params, 'plane')
-        if method not in ('plane', 'avg_normal'):
-            raise ValueError("normal_estimation_method must be 'plane' or 'avg_normal'")       # 'quadric' maps to None upstream
-        normals = (_normals_plane_fit if method == 'plane' else _normals_average)(pos.view(H, W, 3))
-    else:
-        normals = _as_float_tensor(normals, device)[:, :3]
-    mat = disk.get('material_idx', None)
-    mat = _as_int_tensor(mat, device) if mat is not None else None
-    vis = disk.get('light_vis', None)
-    vis = _as_float_tensor(vis, device).detach() if vis is not None else None
-    K = int(get_param_value('samples', params, 1))
-    if K > 1:
-        if mat is None:
-            raise AssertionError('supersampling needs material_idx (renderer.py:605)')
-        plane_d = torch.sum(pos * normals, dim=1)
-        zz = torch.full_like(x, -focal)
-        sub_w, sub_h = w / (K * W - 1), h / (K * H - 1)
-        p_ss = []
-        for deltax in np.linspace(-1, 1, K):
-            xx = x + float(deltax * sub_w / 2)
-            for deltay in np.linspace(1, -1, K):
-                yy = y + float(deltay * sub_h / 2)
-                ray = _unit(torch.stack((xx, yy, zz), dim=1))
-                t = plane_d / torch.sum(ray * normals, dim=1)
-                p_ss.append(t[:, None] * ray)
-        pos = _upsampled(torch.stack(p_ss, dim=2), H, W, 3, K)
-        normals = _upsampled(normals[:, :, None].expand(-1, -1, K * K).contiguous(), H, W, 3, K)
-        mat = _upsampled(mat[:, None, None].expand(-1, 1, K * K).contiguous(), H, W, 1, K).view(-1).contiguous()
-        if vis is not None:
-            L = vis.shape[0]
-            vis = _upsampled(vis.transpose(0, 1)[:, :, None].expand(-1, -1, K * K).contiguous(), H, W, L, K).transpose(0, 1).contiguous()
-        H, W = H * K, W * K
-    return pos.contiguous(), normals.contiguous(), mat, vis, H, W
 
 
 def z_to_pcl_CC(z, camera):
     """Reference: diffrend/torch/renderer.py:484-507.  Camera-space point cloud [N,3] of one depth per pixel
     (z negative in front of the camera, clamped with -relu(-z)); differentiable in z, runs on z's device.  The GAN
     trainer imports it next to render / render_splats_along_ray (GAN/gan.py:28-29, :446)."""
-    vp = camera['viewport']
-    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
-    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    W, H = _host_viewport(camera)
     focal = _scalar(camera['focal_length'])
     h = np.tan(_scalar(camera['fovy']) / 2) * 2 * focal
     w = h * (W / H)
@@ -251,9 +225,7 @@ def z_to_pcl_CC(z, camera):
 
 def z_to_pcl_CC_batched(z, camera):
     """Reference: diffrend/torch/renderer.py:510-534, z is [B, H*W]; returns [B, H*W, 3]."""
-    vp = camera['viewport']
-    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
-    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    W, H = _host_viewport(camera)
     focal = _scalar(camera['focal_length'])
     h = np.tan(_scalar(camera['fovy']) / 2) * 2 * focal
     w = h * (W / H)
@@ -264,34 +236,34 @@ def z_to_pcl_CC_batched(z, camera):
     return torch.stack((-Z * x / focal, -Z * y / focal, Z), dim=-1)
 
 
-def build_inputs(scene, params, device):
-    """_SplatInputs of a call: the plain z-per-pixel form, or explicit fragments when normals are estimated / samples > 1"""
-    disk = scene['objects']['disk']
-    if get_param_value('normal', disk, None) is None or get_param_value('samples', params, 1) > 1:
-        probe = _SplatInputs.__new__(_SplatInputs)          # camera-only view for the tensor program
-        cam = scene['camera']
-        vp = cam['viewport']
-        vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
-        probe.width, probe.height = int(vp[2] - vp[0]), int(vp[3] - vp[1])
-        probe.fovy, probe.focal = _scalar(cam['fovy']), _scalar(cam['focal_length'])
-        return _SplatInputs(scene, device, explicit=_prepare_fragments(scene, probe, params, device))
-    return _SplatInputs(scene, device)
+def _result(call, image, depth, pos, normal, norm_depth):
+    H, W = call.out_h, call.out_w
+    lead = (call.batch,) if call.batch is not None else ()
+    if call.norm_depth:
+        # renderer.py:677-686 returns pos / normal flat ([N,3]) in this branch
+        return {'image': norm_depth.view(lead + (H, W)), 'depth': depth.view(lead + (H, W)), 'pos': pos, 'normal': normal}
+    return {'image': image.view(lead + (H, W, 3)), 'depth': depth.view(lead + (H, W)), 'pos': pos.view(lead + (H, W, 3)),
+            'normal': normal.view(lead + (H, W, 3))}
 
 
 def render_splats_along_ray(scene, **params):
     """Reference: diffrend/torch/renderer.py:537 ``render_splats_along_ray(scene, **params)``."""
     dev = _resolve_device(scene)
-    inp = build_inputs(scene, params, dev)
-    image, depth, pos, normal = _AlongRayFn.apply(inp, dict(params), *inp.floats)
-    H, W = inp.height, inp.width
-    if get_param_value('norm_depth_image_only', params, False):
-        # renderer.py:677-686: depth normalised to [0, 1], fragments at or beyond `far` mapped to the minimum; `pos`
-        # and `normal` are returned flat ([N,3]) like the reference's pos_CC / normals_CC.  Same arithmetic as `where`
-        # (utils.py:58-60): blend, subtract, divide.
-        im_depth = depth.view(H, W)
-        min_depth = torch.min(im_depth)
-        is_far = (im_depth >= float(_scalar(scene['camera'].get('far', 1000.0)))).float()
-        norm = is_far * min_depth + (1 - is_far) * im_depth
-        norm = (norm - min_depth) / (torch.max(im_depth) - min_depth)
-        return {'image': norm, 'depth': im_depth, 'pos': pos, 'normal': normal}
-    return {'image': image.view(H, W, 3), 'depth': depth.view(H, W), 'pos': pos.view(H, W, 3), 'normal': normal.view(H, W, 3)}
+    call = _SplatCall(scene, params, dev)
+    return _result(call, *_AlongRayFn.apply(call, dict(params), *call.floats))
+
+
+def render_splats_along_ray_batch(scene, **params):
+    """A batch of along-ray frames in one call per direction (the loop body of GAN/gan.py:563-597 for every element):
+    ``disk.pos`` [B,N] or [B,N,3]; optionally batched ``disk.normal`` [B,N,3|4], ``disk.material_idx`` [B,N],
+    ``disk.light_vis`` [B,L,N], ``camera.eye`` [B,3|4], ``lights.pos`` [B,L,4]; everything else shared.  Returns the
+    reference's keys with a leading batch dimension."""
+    dev = _resolve_device(scene)
+    pos = scene['objects']['disk']['pos']
+    if not isinstance(pos, torch.Tensor) or pos.dim() < 2:
+        raise ValueError('render_splats_along_ray_batch needs disk.pos of shape [B,N] or [B,N,3]')
+    n_src = (lambda wh: wh[0] * wh[1])(_host_viewport(scene['camera']))
+    if pos.dim() == 2 and pos.shape[0] == n_src and pos.shape[1] == 3:
+        raise ValueError('disk.pos [N,3] is a single frame: use render_splats_along_ray')
+    call = _SplatCall(scene, params, dev, batch=int(pos.shape[0]))
+    return _result(call, *_AlongRayFn.apply(call, dict(params), *call.floats))

@@ -41,103 +41,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-struct DeviceSink {
-    const BackwardParams& p;
-    double* cta_acc;           // shared, [sm.total]
-    float alb[3], cf[3], amb[3], gam;
-    float lp[3], at[3], col[3];
-    __device__ DeviceSink(const BackwardParams& prm, double* shared_acc) : p(prm), cta_acc(shared_acc) {
-        for (int c = 0; c < 3; ++c) alb[c] = cf[c] = amb[c] = lp[c] = at[c] = col[c] = 0.f;
-        gam = 0.f;
-    }
-    __device__ void albedo(int, int c, float v) { alb[c] += v; }
-    __device__ void coeff(int, int c, float v) { cf[c] += v; }
-    __device__ void ambient(int c, float v) { amb[c] += v; }
-    __device__ void gamma(float v) { gam += v; }
-    __device__ void light_pos(int, int c, float v) { lp[c] += v; }
-    __device__ void atten(int, int c, float v) { at[c] += v; }
-    __device__ void color(int, int c, float v) { col[c] += v; }
-    __device__ void add_cta(int slot, float warp_total) { atomicAdd(&cta_acc[slot], (double)warp_total); }
-    __device__ void end_light(int l, int crow) {
-        const int lane = threadIdx.x & 31;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = warp_sum(lp[c]), b = warp_sum(at[c]), e = warp_sum(col[c]);
-            if (lane == 0) {
-                if (a != 0.f) add_cta(p.sm.light_pos + l * 3 + c, a);
-                if (b != 0.f) add_cta(p.sm.atten + l * 3 + c, b);
-                if (e != 0.f) add_cta(p.sm.colors + crow * 3 + c, e);
-            }
-            lp[c] = at[c] = col[c] = 0.f;
-        }
-    }
-    __device__ void end_splat(int m) { flush_scalars(m); }
-    __device__ void end_pixel(int set, int local, int idx, int m, const float* g7) {
-        flush_scalars(m);
-        flush_primitive(set, local, idx, g7);
-    }
-    __device__ void flush_scalars(int m) {
-        const int lane = threadIdx.x & 31;
-        // global scalars
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = warp_sum(amb[c]);
-            if (lane == 0 && a != 0.f) add_cta(p.sm.ambient + c, a);
-        }
-        float gsum = warp_sum(gam);
-        if (lane == 0 && gsum != 0.f) add_cta(p.sm.gamma, gsum);
-        // per-material rows: warp-uniform material is the common case (splat scenes use one material)
-        const int m0 = __shfl_sync(0xffffffffu, m, 0);
-        if (__all_sync(0xffffffffu, m == m0)) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float a = warp_sum(alb[c]), b = warp_sum(cf[c]);
-                if (lane == 0) {
-                    if (a != 0.f) add_cta(p.sm.albedo + m0 * 3 + c, a);
-                    if (b != 0.f) add_cta(p.sm.coeffs + m0 * 3 + c, b);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (alb[c] != 0.f) atomicAdd(&cta_acc[p.sm.albedo + m * 3 + c], (double)alb[c]);
-                if (cf[c] != 0.f) atomicAdd(&cta_acc[p.sm.coeffs + m * 3 + c], (double)cf[c]);
-            }
-        }
-    }
-    __device__ void flush_primitive(int set, int local, int idx, const float* g7) {
-        const int lane = threadIdx.x & 31;
-        // per-primitive gradients: warp-segmented reduction keyed by the winner index, then one
-        // red.global.add per component from the segment leader
-        const unsigned peers = __match_any_sync(0xffffffffu, idx);
-        const int leader = __ffs(peers) - 1;
-        float v[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) v[c] = g7[c];
-        unsigned rest = peers & ~(1u << leader);
-        // every lane walks the union of peer sets in lock-step (max 31 steps, usually 0-3)
-        const unsigned any_rest = __reduce_or_sync(0xffffffffu, rest);
-        if (any_rest) {
-            for (int src = 0; src < 32; ++src) {
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    float o = __shfl_sync(0xffffffffu, g7[c], src);
-                    if (lane == leader && ((rest >> src) & 1u)) v[c] += o;
-                }
-            }
-        }
-        if (lane == leader) {
-            // double accumulation: per-pixel contributions of a grazing primitive cancel heavily, and a
-            // sequential fp32 atomic sum would carry ~1e-4 relative noise (the reference sums pairwise)
-            double* dst = p.prim_acc + (size_t)idx * 7;
-#pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (v[c] != 0.f) atomicAdd(dst + c, (double)v[c]);
-        }
-        (void)set; (void)local;
-    }
-};
-
 // ---------------------------------------------------------------------------------------------------
 // k_backward (fast forms, surf_fast.cuh): thread per pixel, persistent grid-stride CTAs.
 //   * one pass over the lights for the composite (dL/dI needs the sum over lights), one for the gradients; both use

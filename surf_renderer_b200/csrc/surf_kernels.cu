@@ -261,81 +261,148 @@ static int backward_impl(const SurfScene* scene, const SurfCamera* camera, const
     return SURF_OK;
 }
 
-static int splat_frame(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
-                       void* workspace, size_t workspace_bytes, SplatParams* p, CamArgs* cam, Workspace* ws, float** light_cc) {
+// ---------------------------------------------------------------------------------------------------
+// render_splats_along_ray: host orchestration (single scene = a batch of one)
+// ---------------------------------------------------------------------------------------------------
+static int splat_frame(int n_scenes, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
+                       const SurfSplatBatch* batch, void* workspace, size_t ws_stride, SplatParams* p, CamArgs* cam,
+                       SplatWorkspace* ws) {
     if (!scene || !camera || !opt || !sp) return fail(SURF_ERR_BAD_ARG, "null scene/camera/options/splats");
+    if (n_scenes < 1 || n_scenes > 65535) return fail(SURF_ERR_BAD_ARG, "batch of 1..65535 scenes");
     std::string err;
     SceneView sc;
     if (!build_scene_view(*scene, &sc, &err, true)) return fail(SURF_ERR_BAD_ARG, err);
     if (!check_camera(*camera, &err)) return fail(SURF_ERR_BAD_ARG, err);
     if (camera->proj != 0) return fail(SURF_ERR_UNSUPPORTED, "render_splats_along_ray is defined for the perspective frustum");
     if (scene->light_pos_stride != 4) return fail(SURF_ERR_BAD_ARG, "along-ray lights must be homogeneous [L,4] (torch.mm with the 4x4 view matrix)");
-    if (!sp->pos && sp->count != camera->width * camera->height) return fail(SURF_ERR_BAD_ARG, "one splat per pixel: count must equal width*height");
-    if (sp->count < 1) return fail(SURF_ERR_BAD_ARG, "no splats");
-    if ((!sp->z && !sp->pos) || !sp->normal) return fail(SURF_ERR_BAD_ARG, "splat depths (or positions) and normals are required");
-    if ((!sp->pos && sp->z_stride != 1 && sp->z_stride != 3) || (sp->normal_stride != 3 && sp->normal_stride != 4))
-        return fail(SURF_ERR_BAD_ARG, "z_stride must be 1 or 3, normal_stride 3 or 4");
-    if (sc.n_lights > 16 && sp->light_vis) return fail(SURF_ERR_UNSUPPORTED, "light_vis supports at most 16 lights");
+    const int K = sp->samples > 1 ? sp->samples : 1;
+    const int n_src = camera->width * camera->height;
+    if (sp->pos) {
+        if (K != 1 || sp->estimate_normals) return fail(SURF_ERR_BAD_ARG, "explicit fragment positions exclude samples > 1 and normal estimation");
+        if (sp->count < 1) return fail(SURF_ERR_BAD_ARG, "no splats");
+    } else {
+        if (sp->count != n_src) return fail(SURF_ERR_BAD_ARG, "one splat per pixel: count must equal width*height");
+        if (!sp->z) return fail(SURF_ERR_BAD_ARG, "splat depths are required");
+        if (sp->z_stride != 1 && sp->z_stride != 3) return fail(SURF_ERR_BAD_ARG, "z_stride must be 1 or 3");
+    }
+    if (sp->estimate_normals < 0 || sp->estimate_normals > 2) return fail(SURF_ERR_BAD_ARG, "estimate_normals: 0 (given), 1 (plane), 2 (avg_normal)");
+    if (!sp->estimate_normals) {
+        if (!sp->normal) return fail(SURF_ERR_BAD_ARG, "splat normals are required unless they are estimated");
+        if (sp->normal_stride != 3 && sp->normal_stride != 4) return fail(SURF_ERR_BAD_ARG, "normal_stride must be 3 or 4");
+    }
+    if (K > 1 && !sp->material_idx) return fail(SURF_ERR_BAD_ARG, "supersampling needs material_idx (renderer.py:605)");
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
-    carve(workspace, 0, sp->count, sc.n_lights, false, ws, false);
-    if (ws->bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
-    *light_cc = ws->rays;                       // the ray buffer is unused on this path: holds the L x 3 camera-space lights
+    const int n_in = sp->pos ? sp->count : n_src;
+    carve_splats(workspace, n_in, sc.n_lights, ws);
+    if (ws->bytes > ws_stride) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_splats_workspace_bytes");
     *cam = CamArgs{camera->eye, camera->at, camera->up, 0, camera->width, camera->height, camera->fovy,
                    camera->focal_length, camera->near_clip, camera->far_clip};
+    std::memset(p, 0, sizeof(*p));
     p->sc = sc;
-    p->sc.light_pos = *light_cc; p->sc.light_pos_stride = 3; p->sc.gamma = nullptr;
+    p->sc.light_pos = ws->light_cc; p->sc.light_pos_stride = 3; p->sc.gamma = nullptr;
     p->cam = ws->cam;
-    p->z = sp->z; p->z_stride = sp->z_stride; p->normal = sp->normal; p->normal_stride = sp->normal_stride;
-    p->mat = sp->material_idx; p->vis = sp->light_vis; p->n = sp->count;
-    p->pos_in = sp->pos; p->gpos = nullptr;
+    p->z = sp->z; p->z_stride = sp->z_stride ? sp->z_stride : 1;
+    p->estimate = sp->estimate_normals;
+    p->normal = p->estimate ? ws->nest : sp->normal;
+    p->normal_stride = p->estimate ? 3 : sp->normal_stride;
+    p->mat = sp->material_idx; p->vis = sp->light_vis;
+    p->pos_in = sp->pos;
+    p->W = camera->width; p->H = camera->height; p->K = K;
+    p->n_src = n_in;
+    p->n = sp->pos ? sp->count : n_src * K * K;
     p->fl = ShadeFlags{0, opt->use_quartic};
-    p->image = p->depth = p->normal_out = p->pos = nullptr;
-    p->g_image = p->g_depth = p->g_normal = p->g_pos = nullptr;
-    p->gz = p->gnormal = nullptr;
+    p->nest = ws->nest; p->gpos_src = ws->gpos_src; p->gn_src = ws->gn_src; p->minmax = ws->minmax;
+    p->far_clip = camera->far_clip;
     p->sm = slot_map(sc.n_materials, sc.n_lights, sc.n_colors);
     p->acc = ws->acc;
-    if (p->sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the backward accumulators");
+    if (p->sm.total > kMaxAccSlots) return fail(SURF_ERR_UNSUPPORTED, "too many materials/lights/colours for the along-ray backward accumulators");
+    SplatBatchArgs& ba = p->ba;
+    std::memset(&ba, 0, sizeof(ba));
+    if (batch) {
+        ba.z = batch->z; ba.normal = batch->normal; ba.mat = batch->material_idx; ba.vis = batch->light_vis;
+        ba.light_pos = batch->light_pos; ba.eye = batch->eye;
+    }
+    ba.ws_stride = n_scenes > 1 ? (long long)ws_stride : 0;
+    ba.out_stride = p->n;
     return SURF_OK;
 }
 
-static int splats_forward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
-                               void* workspace, size_t bytes, const SurfOutputs* out, cudaStream_t st) {
+static int splats_forward_impl(int n_scenes, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt,
+                               const SurfSplats* sp, const SurfSplatBatch* batch, void* workspace, size_t ws_stride,
+                               const SurfOutputs* out, cudaStream_t st) {
     if (!out) return fail(SURF_ERR_BAD_ARG, "null outputs");
-    SplatParams p; CamArgs cam; Workspace ws; float* lcc;
-    int rc = splat_frame(scene, camera, opt, sp, workspace, bytes, &p, &cam, &ws, &lcc);
+    SplatParams p; CamArgs cam; SplatWorkspace ws;
+    int rc = splat_frame(n_scenes, scene, camera, opt, sp, batch, workspace, ws_stride, &p, &cam, &ws);
     if (rc) return rc;
-    k_splat_setup<<<1, 64, 0, st>>>(cam, ws.cam, scene->light_pos, scene->n_lights, lcc);
+    if (sp->norm_depth && !out->depth) return fail(SURF_ERR_BAD_ARG, "norm_depth needs out->depth");
+    const unsigned B = (unsigned)n_scenes;
+    k_splat_setup<<<B, 64, 0, st>>>(cam, p.ba.eye, ws.cam, scene->light_pos, p.ba.light_pos, scene->n_lights, ws.light_cc,
+                                    ws.minmax, p.ba.ws_stride);
     SURF_LAUNCHED("k_splat_setup");
+    if (p.estimate) {
+        k_splat_normals<<<dim3((p.n_src + 255) / 256, B), 256, 0, st>>>(p);
+        SURF_LAUNCHED("k_splat_normals");
+    }
     p.image = out->image; p.depth = out->depth; p.normal_out = out->normal; p.pos = out->pos;
+    p.norm_depth = sp->norm_depth;
     timer_mark(1, 0, st);
-    k_splat_forward<<<(p.n + 255) / 256, 256, 0, st>>>(p);
+    k_splat_forward<<<dim3((p.n + 255) / 256, B), 256, 0, st>>>(p);
     timer_mark(1, 1, st);
     SURF_LAUNCHED("k_splat_forward");
+    if (p.norm_depth) {
+        k_splat_normdepth<<<dim3((p.n + 255) / 256, B), 256, 0, st>>>(p);
+        SURF_LAUNCHED("k_splat_normdepth");
+    }
     return SURF_OK;
 }
 
-static int splats_backward_impl(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt, const SurfSplats* sp,
-                                void* workspace, size_t bytes, const SurfOutGrads* og, const SurfSceneGrads* sg,
-                                const SurfSplatGrads* spg, cudaStream_t st) {
+static int splats_backward_impl(int n_scenes, const SurfScene* scene, const SurfCamera* camera, const SurfOptions* opt,
+                                const SurfSplats* sp, const SurfSplatBatch* batch, void* workspace, size_t ws_stride,
+                                const SurfOutGrads* og, const SurfSceneGrads* sg, const SurfSplatGrads* spg, cudaStream_t st) {
     if (!og || !sg || !spg) return fail(SURF_ERR_BAD_ARG, "null out_grads/scene_grads/splat_grads");
-    SplatParams p; CamArgs cam; Workspace ws; float* lcc;
-    int rc = splat_frame(scene, camera, opt, sp, workspace, bytes, &p, &cam, &ws, &lcc);
+    SplatParams p; CamArgs cam; SplatWorkspace ws;
+    int rc = splat_frame(n_scenes, scene, camera, opt, sp, batch, workspace, ws_stride, &p, &cam, &ws);
     if (rc) return rc;
-    k_splat_setup<<<1, 64, 0, st>>>(cam, ws.cam, scene->light_pos, scene->n_lights, lcc);
+    const unsigned B = (unsigned)n_scenes;
+    // the workspace may be a fresh one: recompute camera, lights and (if estimated) the normals
+    k_splat_setup<<<B, 64, 0, st>>>(cam, p.ba.eye, ws.cam, scene->light_pos, p.ba.light_pos, scene->n_lights, ws.light_cc,
+                                    ws.minmax, p.ba.ws_stride);
     SURF_LAUNCHED("k_splat_setup");
-    SURF_CUDA(cudaMemsetAsync(ws.acc, 0, sizeof(double) * kMaxAccSlots, st));
+    if (p.estimate) {
+        k_splat_normals<<<dim3((p.n_src + 255) / 256, B), 256, 0, st>>>(p);
+        SURF_LAUNCHED("k_splat_normals");
+    }
+    const size_t stride = n_scenes > 1 ? ws_stride : 0;
+    SURF_CUDA(cudaMemset2DAsync(ws.acc, stride ? stride : sizeof(double) * kMaxAccSlots, 0, sizeof(double) * kMaxAccSlots, B, st));
+    const bool scatter = p.K > 1 || p.estimate != 0;
+    if (scatter) {     // gpos_src and gn_src are adjacent: one memset per scene
+        const size_t bytes = (size_t)((char*)ws.gn_src - (char*)ws.gpos_src) + (size_t)p.n_src * 12;
+        SURF_CUDA(cudaMemset2DAsync(ws.gpos_src, stride ? stride : bytes, 0, bytes, B, st));
+    }
     p.g_image = og->image; p.g_depth = og->depth; p.g_normal = og->normal; p.g_pos = og->pos;
     p.gz = spg->z; p.gnormal = spg->normal; p.gpos = spg->pos;
+    for (int s = 0; s < kMaxSets; ++s) p.gp.prim_pos[s] = p.gp.prim_normal[s] = p.gp.prim_radius[s] = nullptr;
+    p.gp.light_pos = nullptr; p.gp.atten = sg->light_attenuation; p.gp.ambient = sg->ambient;
+    p.gp.colors = sg->colors; p.gp.albedo = sg->albedo; p.gp.coeffs = sg->coeffs; p.gp.gamma = nullptr;
+    const int gx = std::max(1, std::min((p.n + kBwdThreads - 1) / kBwdThreads, (sm_count() * 8 + n_scenes - 1) / n_scenes));
     timer_mark(2, 0, st);
-    k_splat_backward<<<std::min((p.n + 127) / 128, sm_count() * 8), 128, 0, st>>>(p);
+    k_splat_backward<<<dim3(gx, B), kBwdThreads, 0, st>>>(p);
     timer_mark(2, 1, st);
     SURF_LAUNCHED("k_splat_backward");
+    if (p.estimate) {
+        k_splat_normals_backward<<<dim3((p.n_src + 255) / 256, B), 256, 0, st>>>(p);
+        SURF_LAUNCHED("k_splat_normals_backward");
+    }
+    if (scatter) {
+        k_splat_src_finalize<<<dim3((p.n_src + 255) / 256, B), 256, 0, st>>>(p);
+        SURF_LAUNCHED("k_splat_src_finalize");
+    }
     SplatFinalizeParams fp;
-    for (int s = 0; s < kMaxSets; ++s) fp.gp.prim_pos[s] = fp.gp.prim_normal[s] = fp.gp.prim_radius[s] = nullptr;
-    fp.gp.light_pos = sg->light_pos; fp.gp.atten = sg->light_attenuation; fp.gp.ambient = sg->ambient;
-    fp.gp.colors = sg->colors; fp.gp.albedo = sg->albedo; fp.gp.coeffs = sg->coeffs; fp.gp.gamma = nullptr;
+    fp.gp = p.gp;
+    fp.gp.light_pos = sg->light_pos;
     fp.sm = p.sm; fp.acc = ws.acc; fp.cam = ws.cam; fp.L = scene->n_lights;
-    k_splat_finalize<<<(p.sm.total + 127) / 128, 128, 0, st>>>(fp);
+    fp.ws_stride = p.ba.ws_stride; fp.light_stride = p.ba.light_pos;
+    k_splat_finalize<<<dim3((p.sm.total + 127) / 128, B), 128, 0, st>>>(fp);
     SURF_LAUNCHED("k_splat_finalize");
     return SURF_OK;
 }
@@ -761,19 +828,46 @@ int surf_adam_step(const SurfAdamTensors* tensors, const float* grads_packed, fl
     return SURF_OK;
 }
 
+size_t surf_splats_workspace_bytes(int32_t n_splats, int32_t n_lights) {
+    SplatWorkspace ws;
+    carve_splats(nullptr, n_splats, n_lights, &ws);
+    return align_up(ws.bytes, 256);
+}
+
 int surf_splats_forward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
                         const SurfSplats* splats, void* workspace, size_t workspace_bytes, const SurfOutputs* out,
                         void* cuda_stream) {
     g_launches = 0;
-    return splats_forward_impl(scene, camera, options, splats, workspace, workspace_bytes, out, (cudaStream_t)cuda_stream);
+    return splats_forward_impl(1, scene, camera, options, splats, nullptr, workspace, workspace_bytes, out, (cudaStream_t)cuda_stream);
 }
 
 int surf_splats_backward(const SurfScene* scene, const SurfCamera* camera, const SurfOptions* options,
                          const SurfSplats* splats, void* workspace, size_t workspace_bytes, const SurfOutGrads* out_grads,
                          const SurfSceneGrads* scene_grads, const SurfSplatGrads* splat_grads, void* cuda_stream) {
     g_launches = 0;
-    return splats_backward_impl(scene, camera, options, splats, workspace, workspace_bytes, out_grads, scene_grads,
+    return splats_backward_impl(1, scene, camera, options, splats, nullptr, workspace, workspace_bytes, out_grads, scene_grads,
                                 splat_grads, (cudaStream_t)cuda_stream);
+}
+
+int surf_splats_forward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfOptions* options,
+                                const SurfSplats* splats0, const SurfSplatBatch* batch, void* workspace,
+                                size_t workspace_bytes_per_scene, const SurfOutputs* out0, void* cuda_stream) {
+    g_launches = 0;
+    if (!batch) return fail(SURF_ERR_BAD_ARG, "null batch layout");
+    if (workspace_bytes_per_scene % 256) return fail(SURF_ERR_BAD_ARG, "workspace_bytes_per_scene must be a multiple of 256");
+    return splats_forward_impl(n_scenes, scene0, camera0, options, splats0, batch, workspace, workspace_bytes_per_scene, out0,
+                               (cudaStream_t)cuda_stream);
+}
+
+int surf_splats_backward_strided(int32_t n_scenes, const SurfScene* scene0, const SurfCamera* camera0, const SurfOptions* options,
+                                 const SurfSplats* splats0, const SurfSplatBatch* batch, void* workspace,
+                                 size_t workspace_bytes_per_scene, const SurfOutGrads* out_grads0, const SurfSceneGrads* scene_grads,
+                                 const SurfSplatGrads* splat_grads0, void* cuda_stream) {
+    g_launches = 0;
+    if (!batch) return fail(SURF_ERR_BAD_ARG, "null batch layout");
+    if (workspace_bytes_per_scene % 256) return fail(SURF_ERR_BAD_ARG, "workspace_bytes_per_scene must be a multiple of 256");
+    return splats_backward_impl(n_scenes, scene0, camera0, options, splats0, batch, workspace, workspace_bytes_per_scene,
+                                out_grads0, scene_grads, splat_grads0, (cudaStream_t)cuda_stream);
 }
 
 double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream) {

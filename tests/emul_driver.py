@@ -77,7 +77,7 @@ class _EmulSplats(C.Structure):
 
 
 def _splat_setup(scene, params, inp=None):
-    from surf_renderer_b200.along_ray import build_inputs
+    from along_ray_program import build_inputs
     if inp is None:
         inp = build_inputs(scene, params, torch.device('cpu'))
     sc, cam, sp, opt = inp.structs(inp.floats, params)

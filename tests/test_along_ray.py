@@ -63,7 +63,7 @@ def _prepared(scene, requires_grad=False, device='cpu'):
 def test_emulated_along_ray_matches_reference_golden(name):
     """kernel math through the emulation; for estimated normals / supersampling the fragments come from the package's
     tensor program (run on CPU tensors here) and the emulated kernel gradients are chained through it with autograd."""
-    from surf_renderer_b200 import along_ray
+    import along_ray_program as along_ray
     scene, params, outs, grads, extra = _load(name)
     sc = _prepared(scene, requires_grad=True)
     inp = along_ray.build_inputs(sc, params, torch.device('cpu'))
@@ -179,6 +179,91 @@ def test_gpu_along_ray_randomized_options_vs_oracle(seed):
     if not estimate:
         cand['n'], want['n'] = sc['objects']['disk']['normal'].grad.cpu(), osc['objects']['disk']['normal'].grad
     parity.compare_grads(cand, want, rtol=1e-4, atol_scale=5e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('variant', ['given_normals', 'plane_samples2', 'avg_normal'])
+def test_gpu_along_ray_batch_equals_the_per_element_loop(variant):
+    """render_splats_along_ray_batch (one call per direction) against the loop of gan.py:563-597: per element its own
+    depths, normals, camera eye and light positions; outputs and gradients - also of the shared material table, which
+    receives the sum over the batch."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_golden_along_ray_scene import along_ray_scene
+    import surf_renderer_b200
+    B, W, H = 5, 24, 20
+    g = torch.Generator().manual_seed(9)
+    elems = [along_ray_scene(400 + b, W, H, mats=2, smooth_z=True) for b in range(B)]
+    params = {}
+    if variant == 'plane_samples2':
+        params = {'samples': 2, 'normal_estimation_method': 'plane'}
+    elif variant == 'avg_normal':
+        params = {'normal_estimation_method': 'avg_normal'}
+    estimate = variant != 'given_normals'
+    eyes = torch.stack([torch.tensor([0.3 * b, 0.1 * b, 4.0 + 0.2 * b, 1.0]) for b in range(B)])
+    lights = torch.stack([elems[b]['lights']['pos'] + 0.1 * b for b in range(B)])
+    zs = torch.stack([elems[b]['objects']['disk']['pos'] for b in range(B)])
+    ns = torch.stack([elems[b]['objects']['disk']['normal'] for b in range(B)])
+
+    def scene_of(z, n, eye, lp, albedo):
+        sc = scene_io.clone_scene(elems[0], device='cuda')
+        sc['objects']['disk']['pos'] = z
+        if estimate:
+            sc['objects']['disk'].pop('normal', None)
+        else:
+            sc['objects']['disk']['normal'] = n
+        sc['camera']['eye'] = eye
+        sc['lights']['pos'] = lp
+        sc['materials']['albedo'] = albedo
+        return sc
+
+    w = torch.rand(B, H * (2 if 'samples' in params else 1), W * (2 if 'samples' in params else 1), 3, generator=g).cuda()
+    # batched call
+    zb, nb = zs.cuda().requires_grad_(True), ns.cuda().requires_grad_(True)
+    lb = lights.cuda().requires_grad_(True)
+    alb_b = elems[0]['materials']['albedo'].cuda().requires_grad_(True)
+    res = surf_renderer_b200.render_splats_along_ray_batch(scene_of(zb, nb, eyes.cuda(), lb, alb_b), **params)
+    ((res['image'] * w).sum() + res['depth'].sum()).backward()
+    # loop
+    zl, nl = zs.cuda().requires_grad_(True), ns.cuda().requires_grad_(True)
+    ll = lights.cuda().requires_grad_(True)
+    alb_l = elems[0]['materials']['albedo'].cuda().requires_grad_(True)
+    loss = 0
+    outs = []
+    for b in range(B):
+        r = surf_renderer_b200.render_splats_along_ray(scene_of(zl[b], nl[b], eyes[b].cuda(), ll[b], alb_l), **params)
+        outs.append(r)
+        loss = loss + (r['image'] * w[b]).sum() + r['depth'].sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    for k in ('image', 'depth', 'pos', 'normal'):
+        assert torch.equal(res[k], torch.stack([o[k] for o in outs])), k
+    assert torch.allclose(zb.grad, zl.grad, rtol=1e-4, atol=1e-6 * float(zl.grad.abs().max()))
+    assert torch.allclose(lb.grad, ll.grad, rtol=1e-4, atol=1e-6 * float(ll.grad.abs().max()))
+    assert torch.allclose(alb_b.grad, alb_l.grad, rtol=1e-4, atol=1e-6 * float(alb_l.grad.abs().max()))
+    if not estimate:
+        assert torch.allclose(nb.grad, nl.grad, rtol=1e-4, atol=1e-6 * float(nl.grad.abs().max()))
+
+
+@pytest.mark.gpu
+def test_gpu_along_ray_is_kernels_only():
+    """no torch op sits between the caller's z and the kernels: forward + backward of an estimated-normal,
+    supersampled frame launch only the library's kernels (counted by the library) and exactly the autograd glue's
+    allocations / fills"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_golden_along_ray_scene import along_ray_scene
+    import surf_renderer_b200
+    from surf_renderer_b200._lib import lib
+    scene = along_ray_scene(5, 32, 32, mats=1, smooth_z=True)
+    del scene['objects']['disk']['normal']
+    sc = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    res = surf_renderer_b200.render_splats_along_ray(sc, samples=2, normal_estimation_method='plane')
+    assert lib().surf_last_launch_count() == 3          # k_splat_setup, k_splat_normals, k_splat_forward
+    res['image'].sum().backward()
+    torch.cuda.synchronize()
+    assert lib().surf_last_launch_count() == 6          # setup, normals, backward, normals_backward, src_finalize, finalize
+    assert res['image'].shape == (64, 64, 3)
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/diffrend'), reason='reference tree not present')
