@@ -311,6 +311,40 @@ int surf_splats_backward_strided(int32_t n_scenes, const SurfScene* scene0, cons
                                  void* workspace, size_t workspace_bytes_per_scene, const SurfOutGrads* out_grads0,
                                  const SurfSceneGrads* scene_grads, const SurfSplatGrads* splat_grads0, void* cuda_stream);
 
+/* ---- projection layer: surfels of one view projected into another camera and scattered onto its pixel grid ----
+ * surf_project_surfels       <- diffrend/torch/projection_layer.py:20-86  project_surfels + project_image_coordinates:
+ *                               world -> camera (lookat) -> image plane (x = f X / Z, nonzero_divide) -> pixel
+ *                               coordinates px_coord [B,N,3] = (pixel x, pixel y, depth -Z) and the destination index
+ *                               px_idx [B,N] = round(py - 0.5) * W + round(px - 0.5), or W*H ("dump") outside the frame
+ * surf_scatter_forward       <- diffrend/torch/utils.py:146-175 scatter_mean_dim0 (mode 0: out = mean of the surfels
+ *                               that land on a pixel, mask = pixel received nothing) and utils.py:178-215
+ *                               scatter_weighted_blended_oit (mode 1: weights alpha(center_dist_2) * exp(-z_scale z),
+ *                               out = sum(x a w) / (sum(a w) + 1e-8))
+ * Camera vectors are [B,3] with element strides (0 = shared).  `out` [B,n_dst,C] and `denom` [B,n_dst] are written by
+ * the library (zeroed first); gradients are ADDED to caller-zeroed arrays like everywhere else in this ABI. */
+typedef struct SurfProjection {
+    int32_t batch, n_surfels, pos_stride;   /* positions [B, N, 3|4] */
+    int32_t width, height;
+    double fovy, focal_length;
+    const float* eye; const float* at; const float* up;
+    int64_t eye_stride, at_stride, up_stride;
+} SurfProjection;
+int surf_project_surfels(const SurfProjection* proj, const float* pos_wc, float* px_coord, int64_t* px_idx, void* cuda_stream);
+int surf_project_surfels_backward(const SurfProjection* proj, const float* pos_wc, const float* g_px_coord, float* g_pos,
+                                  void* cuda_stream);
+typedef struct SurfScatter {
+    int32_t batch, n, channels;   /* x [B, n, C], idx [B, n] */
+    int32_t n_dst;                /* destinations per batch element; an index outside [0, n_dst) is dropped */
+    int32_t mode;                 /* 0 = scatter_mean_dim0, 1 = scatter_weighted_blended_oit */
+    float sigma, z_scale;         /* OIT: Gaussian sigma of the pixel-centre weight, Beer-Lambert extinction */
+    int32_t use_depth, use_center_dist;
+} SurfScatter;
+int surf_scatter_forward(const SurfScatter* scatter, const float* x, const int64_t* idx, const float* z,
+                         const float* center_dist_2, float* out, float* denom, uint8_t* mask, void* cuda_stream);
+int surf_scatter_backward(const SurfScatter* scatter, const float* x, const int64_t* idx, const float* z,
+                          const float* center_dist_2, const float* out, const float* denom, const float* g_out,
+                          float* g_x, float* g_z, float* g_center_dist_2, void* cuda_stream);
+
 /* ---- host-pointer API (self-contained: H2D, kernels, D2H) ---- */
 typedef struct SurfContext SurfContext;
 SurfContext* surf_context_create(int32_t device);

@@ -74,6 +74,17 @@ class SurfStepMSE(C.Structure):
     _fields_ = [('target_image', C.c_void_p), ('loss_scale', C.c_float), ('loss', C.c_void_p), ('grad_image', C.c_void_p)]
 
 
+class SurfProjection(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('n_surfels', C.c_int32), ('pos_stride', C.c_int32), ('width', C.c_int32), ('height', C.c_int32),
+                ('fovy', C.c_double), ('focal_length', C.c_double), ('eye', C.c_void_p), ('at', C.c_void_p), ('up', C.c_void_p),
+                ('eye_stride', C.c_int64), ('at_stride', C.c_int64), ('up_stride', C.c_int64)]
+
+
+class SurfScatter(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('n', C.c_int32), ('channels', C.c_int32), ('n_dst', C.c_int32), ('mode', C.c_int32),
+                ('sigma', C.c_float), ('z_scale', C.c_float), ('use_depth', C.c_int32), ('use_center_dist', C.c_int32)]
+
+
 SURF_ADAM_MAX_TENSORS = 16
 
 
@@ -125,6 +136,12 @@ SYMBOLS = {
     'surf_backward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfBatchLayout),
                                         C.POINTER(SurfOptions), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.POINTER(SurfOutGrads), C.POINTER(SurfSceneGrads), C.c_void_p]),
+    'surf_project_surfels': (C.c_int, [C.POINTER(SurfProjection), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'surf_project_surfels_backward': (C.c_int, [C.POINTER(SurfProjection), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'surf_scatter_forward': (C.c_int, [C.POINTER(SurfScatter), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    'surf_scatter_backward': (C.c_int, [C.POINTER(SurfScatter), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'surf_splats_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'surf_splats_forward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                               C.POINTER(SurfSplats), C.POINTER(SurfSplatBatch), C.c_void_p, C.c_size_t,

@@ -19,7 +19,8 @@ COMMON = ['surf_view.h', 'surf_math.cuh', 'surf_runtime.cuh', 'surf_ptx.cuh', 's
 ISECT = COMMON + ['surf_intersect.cuh']
 # translation unit -> headers it includes (csrc-relative)
 UNITS = {
-    'surf_kernels.cu': COMMON + ['surf_frame_kernels.cuh', 'surf_shade.cuh', 'surf_backward.cuh', 'surf_splats.cuh'],
+    'surf_kernels.cu': COMMON + ['surf_frame_kernels.cuh', 'surf_shade.cuh', 'surf_backward.cuh', 'surf_splats.cuh',
+                                 'surf_fast.cuh', 'surf_scatter.cuh'],
     'surf_isect_main.cu': ISECT,
     'surf_isect_batch.cu': ISECT,
     'surf_isect_rays.cu': ISECT + ['surf_intersect_rays.cuh'],

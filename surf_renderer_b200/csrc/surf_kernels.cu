@@ -40,6 +40,7 @@ namespace surf {
 #include "surf_shade.cuh"
 #include "surf_backward.cuh"
 #include "surf_splats.cuh"
+#include "surf_scatter.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // FP32 FMA-pipe microbenchmark (roofline denominator check)
@@ -825,6 +826,99 @@ int surf_adam_step(const SurfAdamTensors* tensors, const float* grads_packed, fl
     const int grid = (int)std::max<long long>(1, std::min<long long>((off + 255) / 256, (long long)sm_count() * 8));
     k_adam_packed<<<grid, 256, 0, st>>>(tn, grads_packed, exp_avg, exp_avg_sq, state, lr, beta1, beta2, eps);
     SURF_LAUNCHED("k_adam_packed");
+    return SURF_OK;
+}
+
+// ---- projection layer: surfel projection + scatter renderers (projection_layer.py:20-106, utils.py:146-215) ----
+static int project_params(const SurfProjection* pr, ProjectParams* p) {
+    if (!pr || !pr->eye || !pr->at || !pr->up) return fail(SURF_ERR_BAD_ARG, "null projection / camera vectors");
+    if (pr->batch < 1 || pr->batch > 65535 || pr->n_surfels < 1) return fail(SURF_ERR_BAD_ARG, "empty projection batch");
+    if (pr->pos_stride != 3 && pr->pos_stride != 4) return fail(SURF_ERR_BAD_ARG, "pos_stride must be 3 or 4");
+    if (pr->width < 1 || pr->height < 1) return fail(SURF_ERR_BAD_ARG, "empty viewport");
+    const double h = tan(pr->fovy / 2) * 2 * pr->focal_length;
+    const double w = h * ((double)pr->width / (double)pr->height);
+    std::memset(p, 0, sizeof(*p));
+    p->batch = pr->batch; p->n = pr->n_surfels; p->pos_stride = pr->pos_stride; p->W = pr->width; p->H = pr->height;
+    p->f = (float)pr->focal_length;
+    p->sx_px = (float)(-(pr->width - 1) / w); p->sy_px = (float)((pr->height - 1) / h);
+    p->cx = (float)(pr->width / 2.0); p->cy = (float)(pr->height / 2.0);
+    p->eye = pr->eye; p->at = pr->at; p->up = pr->up;
+    p->eye_stride = pr->eye_stride; p->at_stride = pr->at_stride; p->up_stride = pr->up_stride;
+    return SURF_OK;
+}
+
+int surf_project_surfels(const SurfProjection* proj, const float* pos_wc, float* px_coord, int64_t* px_idx, void* cuda_stream) {
+    g_launches = 0;
+    ProjectParams p;
+    int rc = project_params(proj, &p);
+    if (rc) return rc;
+    if (!pos_wc || !px_coord) return fail(SURF_ERR_BAD_ARG, "null positions / px_coord");
+    p.pos = pos_wc; p.px_coord = px_coord; p.px_idx = (long long*)px_idx;
+    k_project_surfels<<<dim3((p.n + 255) / 256, p.batch), 256, 0, (cudaStream_t)cuda_stream>>>(p);
+    SURF_LAUNCHED("k_project_surfels");
+    return SURF_OK;
+}
+
+int surf_project_surfels_backward(const SurfProjection* proj, const float* pos_wc, const float* g_px_coord, float* g_pos,
+                                  void* cuda_stream) {
+    g_launches = 0;
+    ProjectParams p;
+    int rc = project_params(proj, &p);
+    if (rc) return rc;
+    if (!pos_wc || !g_px_coord || !g_pos) return fail(SURF_ERR_BAD_ARG, "null positions / gradients");
+    p.pos = pos_wc; p.g_px = g_px_coord; p.g_pos = g_pos;
+    k_project_surfels_backward<<<dim3((p.n + 255) / 256, p.batch), 256, 0, (cudaStream_t)cuda_stream>>>(p);
+    SURF_LAUNCHED("k_project_surfels_backward");
+    return SURF_OK;
+}
+
+static int scatter_params(const SurfScatter* sc, ScatterParams* p) {
+    if (!sc) return fail(SURF_ERR_BAD_ARG, "null scatter description");
+    if (sc->batch < 1 || sc->batch > 65535 || sc->n < 1 || sc->channels < 1 || sc->n_dst < 1) return fail(SURF_ERR_BAD_ARG, "empty scatter");
+    if (sc->mode != 0 && sc->mode != 1) return fail(SURF_ERR_BAD_ARG, "scatter mode: 0 (mean) or 1 (weighted blended OIT)");
+    std::memset(p, 0, sizeof(*p));
+    p->batch = sc->batch; p->n = sc->n; p->channels = sc->channels; p->n_dst = sc->n_dst; p->mode = sc->mode;
+    p->use_depth = sc->use_depth; p->use_center_dist = sc->use_center_dist;
+    const double s2 = (double)sc->sigma * sc->sigma;
+    p->alpha0 = (float)(1.0 / (2.0 * 3.14159265358979323846 * s2));
+    p->inv_2s2 = (float)(1.0 / (2.0 * s2));
+    p->z_scale = sc->z_scale;
+    p->eps = sc->mode == 1 ? 1e-8f : 0.f;
+    return SURF_OK;
+}
+
+int surf_scatter_forward(const SurfScatter* scatter, const float* x, const int64_t* idx, const float* z, const float* center_dist_2,
+                         float* out, float* denom, uint8_t* mask, void* cuda_stream) {
+    g_launches = 0;
+    ScatterParams p;
+    int rc = scatter_params(scatter, &p);
+    if (rc) return rc;
+    if (!x || !idx || !out || !denom) return fail(SURF_ERR_BAD_ARG, "null scatter operand");
+    if (p.mode == 1 && ((p.use_depth && !z) || (p.use_center_dist && !center_dist_2))) return fail(SURF_ERR_BAD_ARG, "OIT scatter needs z / center_dist_2");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    p.x = x; p.idx = (const long long*)idx; p.z = z; p.cd2 = center_dist_2; p.out = out; p.denom = denom; p.mask = mask;
+    SURF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)p.batch * p.n_dst * p.channels, st));
+    SURF_CUDA(cudaMemsetAsync(denom, 0, sizeof(float) * (size_t)p.batch * p.n_dst, st));
+    k_scatter_accum<<<dim3((p.n + 255) / 256, p.batch), 256, 0, st>>>(p);
+    SURF_LAUNCHED("k_scatter_accum");
+    const size_t total = (size_t)p.batch * p.n_dst;
+    k_scatter_normalize<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    SURF_LAUNCHED("k_scatter_normalize");
+    return SURF_OK;
+}
+
+int surf_scatter_backward(const SurfScatter* scatter, const float* x, const int64_t* idx, const float* z, const float* center_dist_2,
+                          const float* out, const float* denom, const float* g_out, float* g_x, float* g_z, float* g_center_dist_2,
+                          void* cuda_stream) {
+    g_launches = 0;
+    ScatterParams p;
+    int rc = scatter_params(scatter, &p);
+    if (rc) return rc;
+    if (!x || !idx || !out || !denom || !g_out) return fail(SURF_ERR_BAD_ARG, "null scatter operand");
+    p.x = x; p.idx = (const long long*)idx; p.z = z; p.cd2 = center_dist_2; p.out = (float*)out; p.denom = (float*)denom;
+    p.g_out = g_out; p.g_x = g_x; p.g_z = g_z; p.g_cd2 = g_center_dist_2;
+    k_scatter_backward<<<dim3((p.n + 255) / 256, p.batch), 256, 0, (cudaStream_t)cuda_stream>>>(p);
+    SURF_LAUNCHED("k_scatter_backward");
     return SURF_OK;
 }
 
