@@ -19,7 +19,7 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 def golden_cases():
     """fixtures of render() (make_golden.py)"""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith('.npz') and not f.startswith(('ar_', 'np_', 'b200_')))
+                  if f.endswith('.npz') and not f.startswith(('ar_', 'np_', 'b200_', 'pl_')))
 
 
 def along_ray_cases():
