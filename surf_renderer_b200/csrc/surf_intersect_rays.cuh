@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen
         if (cur_tile < 0) return;
 #pragma unroll
         for (int p = 0; p < P; ++p)
-            if (best_i[p] >= 0) {
+            if (best_i[p] >= 0 && ((valid >> p) & 1u)) {
                 unsigned long long key = ((unsigned long long)float_order_key(best_t[p]) << 32) | (unsigned)best_i[p];
                 atomicMin(prm.zbuf + kbase + p, key);
             }
@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen
                         float lo_, hi_;
                         unpack2(x2[p >> 1], lo_, hi_);
                         const float dx = ((p & 1) ? hi_ : lo_) + C.x;
-                        if (fmaf(dx, dx, sy) <= 0.f) {
+                        // slots outside the frame are skipped explicitly: an always-flag record (-rho^2 = -inf: planes,
+                        // primitives reaching the camera plane) also "contains" their far-away stand-in coordinate
+                        if (((valid >> p) & 1u) && fmaf(dx, dx, sy) <= 0.f) {
                             float t;
                             if (exact_pair(prm, first + i + g, kbase + p, &t) && t < best_t[p]) {
                                 best_t[p] = t;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, (P <= 8 ? 3 : 2)) k_intersect_screen
                 float lo_, hi_;
                 unpack2(x2[p >> 1], lo_, hi_);
                 const float dx = ((p & 1) ? hi_ : lo_) + C.x;
-                if (fmaf(dx, dx, sy) <= 0.f) {
+                if (((valid >> p) & 1u) && fmaf(dx, dx, sy) <= 0.f) {
                     float t;
                     if (exact_pair(prm, first + i, kbase + p, &t) && t < best_t[p]) {
                         best_t[p] = t;
