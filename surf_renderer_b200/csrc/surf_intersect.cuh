@@ -25,6 +25,13 @@ struct IsectParams {
     // candidates into one or two warps instead of every warp that owns one of its rows.  tiles_x = 0: flat tiles
     // of kThreads * P consecutive pixels (the single-scene kernel's mapping; any width, no masked-out lanes).
     int tiles_x, W, pix0;
+    // k_intersect_batch: hybrid work distribution.  Every CTA first walks a contiguous static share of `static_per`
+    // items (consecutive items share the pixel tile: rays and running best stay in registers), then the CTAs draw
+    // runs of `run_len` items of the remaining pool [dyn_begin, n_items) from *work_counter (zeroed by the host before
+    // the launch).  Dense frames have a data-dependent narrow phase, so purely static equal shares finish unevenly
+    // (ncu on bunny 256x256: the SMs were busy 78 % of the kernel's duration).
+    int* work_counter;
+    int static_per, dyn_begin, run_len;
 };
 
 // surf_isect_batch.cu: launches k_intersect_batch<P, mode> (run_intersect in surf_isect_main.cu picks P, mode and the grid)
@@ -611,21 +618,36 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ int item_of[kStages];          // the item whose records fill each stage; -1 = no more work
     const IsectParams& prm = BATCH ? *sprm : prm0;
 
     const int tid = threadIdx.x;
-    const long long n_items = (long long)prm0.n_tiles * prm0.n_chunks;
-    const int lo = (int)(n_items * blockIdx.x / gridDim.x);
-    const int hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
-    if (lo >= hi) return;
-
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int item, int stage) {      // chunking (prm0) is the same for every scene of a batch
+    // producer state (thread 0 only): the run it is walking through - first the static share, then runs of the pool
+    const int n_items = prm0.n_tiles * prm0.n_chunks;
+    int run_next = (int)blockIdx.x * prm0.static_per, run_end = run_next + prm0.static_per;
+    auto next_item = [&]() -> int {
+        if (run_next >= run_end) {
+            const int u = atomicAdd(prm0.work_counter, 1);
+            const long long a = (long long)prm0.dyn_begin + (long long)u * prm0.run_len;
+            if (a >= n_items) return -1;
+            run_next = (int)a;
+            run_end = (int)min((long long)n_items, a + prm0.run_len);
+        }
+        return run_next++;
+    };
+    auto issue = [&](int stage) {      // chunking (prm0) is the same for every scene of a batch
+        const int item = next_item();
+        item_of[stage] = item;
+        if (item < 0) {                // sentinel: complete the phase without a copy
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+            return;
+        }
         int set, local0, count;
         decode_chunk(prm0, item % prm0.n_chunks, &set, &local0, &count);
         const SetView& sv = prm0.sc.sets[set];
@@ -637,7 +659,7 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         tma_bulk_g2s(stage_buf + (size_t)stage * prm0.stage_f4, src, bytes, &full_bar[stage]);
     };
     if (tid == 0)
-        for (int k = 0; k < kStages - 1 && lo + k < hi; ++k) issue(lo + k, k);
+        for (int k = 0; k < kStages - 1; ++k) issue(k);
 
     Vec3 eye = v3(prm0.cam->eye[0], prm0.cam->eye[1], prm0.cam->eye[2]);
     const float near_clip = prm0.cam->near_clip, far_clip = prm0.cam->far_clip;    // camera scalars are batch-wide
@@ -675,12 +697,14 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         }
     };
 
-    for (int it = lo; it < hi; ++it) {
-        const int k = it - lo;
+    for (int k = 0;; ++k) {
         const int stage = k % kStages;
         const uint32_t parity = (uint32_t)((k / kStages) & 1);
-        __syncthreads();   // every thread is done with item it-1, whose stage is the one refilled below
-        if (tid == 0 && it + kStages - 1 < hi) issue(it + kStages - 1, (k + kStages - 1) % kStages);
+        __syncthreads();   // every thread is done with step k-1, whose stage is the one refilled below
+        if (tid == 0) issue((k + kStages - 1) % kStages);
+        mbar_wait(&full_bar[stage], parity);
+        const int it = item_of[stage];
+        if (it < 0) break;             // CTA-uniform: the sentinel reaches every thread through the same stage
 
         const int tile = it / prm0.n_chunks;
         if (tile != cur_tile) {
@@ -726,7 +750,6 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         int set, local0, count;
         decode_chunk(prm0, it % prm0.n_chunks, &set, &local0, &count);
         const SetView& sv = prm.sc.sets[set];
-        mbar_wait(&full_bar[stage], parity);
         const float4* s = stage_buf + (size_t)stage * prm0.stage_f4;
         if (sv.kind == KIND_DISK) {
             if (MODE == 0)

@@ -111,7 +111,15 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
     if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
-    if (ba) return launch_intersect_batch(prm, *ba, P, mode, grid, smem, st);
+    if (ba) {
+        // hybrid distribution: 3/4 of the items as contiguous static shares, the rest drawn dynamically in short runs
+        prm.static_per = (int)((items * 3 / 4) / grid);
+        prm.dyn_begin = prm.static_per * grid;
+        prm.run_len = (int)std::max<long long>(1, (items - prm.dyn_begin) / (12LL * grid));
+        prm.work_counter = (int*)f.ws.obound + 255;          // last cell of the 1 KB counter block
+        SURF_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(int), st));
+        return launch_intersect_batch(prm, *ba, P, mode, grid, smem, st);
+    }
 #define SURF_DISPATCH(PP)                                                  \
     if (P == PP) {                                                         \
         if (mode == 0) return launch_intersect<PP, 0>(prm, grid, smem, st); \

@@ -13,6 +13,10 @@ from surf_renderer_b200._lib import lib           # noqa: E402
 which = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 extra = {'_math_mode': int(sys.argv[3])} if len(sys.argv) > 3 else {}
+if len(sys.argv) > 4:
+    extra['_chunk_prims'] = int(sys.argv[4])
+if len(sys.argv) > 5:
+    extra['_pixels_per_thread'] = int(sys.argv[5])
 
 
 def fixture(name, size):
@@ -35,4 +39,4 @@ with torch.no_grad():
     for _ in range(reps):
         call(sc)
 torch.cuda.synchronize()
-print(which, 'intersect kernel ms (mean of %d): %.4f' % (reps, lib().surf_mean_kernel_ms(0, None)))
+print(which, extra, 'intersect kernel ms (mean of %d): %.4f' % (reps, lib().surf_mean_kernel_ms(0, None)))
