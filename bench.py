@@ -618,18 +618,28 @@ def run_config_d(args, rank, world, local_rank):
     w = torch.rand(B, S, S, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def step():
+    def eager_step():
         return plan.step(lambda image: (image * w).sum())
 
-    lib().surf_set_kernel_timing(1)
+    step = eager_step
+    if args.graph:      # the whole step incl. its two NCCL collectives replays from one CUDA graph
+        step = surf_renderer_b200.GraphedStep(eager_step, warmup=3, capture_error_mode='thread_local' if world > 1 else 'global')
+
+    lib().surf_set_kernel_timing(0 if args.graph else 1)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(2):
         step()
     barrier()
-    lib().surf_set_kernel_timing(1)
+    lib().surf_set_kernel_timing(0 if args.graph else 1)
     ms_per_step, wall, clocks, loss = timed_region(step, args.steps, args.warmup, flush, barrier, world, dev, sampler)
     n_timed = C.c_int32()
     k_mean = {k: lib().surf_mean_kernel_ms(k, C.byref(n_timed)) for k in (0, 1, 2)}
+    if args.graph:      # kernel durations from a few eager steps after the timed region (events cannot be read inside a graph)
+        lib().surf_set_kernel_timing(1)
+        for _ in range(3):
+            eager_step()
+        barrier()
+        k_mean = {k: lib().surf_mean_kernel_ms(k, C.byref(n_timed)) for k in (0, 1, 2)}
     lib().surf_set_kernel_timing(0)
     value = tests_per_step / (ms_per_step * 1e-3)
     f_clk = float(peaks.get('sm_max_mhz', 1965.0)) * 1e6
@@ -650,7 +660,7 @@ def run_config_d(args, rank, world, local_rank):
     if not args.no_e2e:
         def e2e_step():
             plan.upload()
-            loss = plan.step(lambda image: (image * w).sum())
+            loss = step()
             return float(loss)          # D2H read of the result
         for _ in range(3):
             e2e_step()
@@ -677,7 +687,7 @@ def run_config_d(args, rank, world, local_rank):
     return {'metric': 'ray-primitive tests/s (fwd+bwd over a batch of scenes)', 'value': value, 'unit': 'tests/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': config, 'batches_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
+            'config': dict(config, graph=bool(args.graph)), 'batches_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
             'gpu_launches': int(plan.launches) * args.steps, 'gpu_launches_per_step': int(plan.launches),
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'wall_s_timed_region': wall}
 

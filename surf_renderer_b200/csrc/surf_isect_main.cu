@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -113,9 +114,14 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
     if (ba) {
         // hybrid distribution: 3/4 of the items as contiguous static shares, the rest drawn dynamically in short runs
-        prm.static_per = (int)((items * 3 / 4) / grid);
+        // measured (B200): splat batches / dense splat frames are fastest with 12/16 static (config D 2.45 -> 2.28 ms,
+        // bunny 256x256 0.189 -> 0.184 ms), triangle meshes with 14/16 (their items are 4x heavier per record)
+        static const int s16_env = getenv("SURF_DYN_STATIC16") ? atoi(getenv("SURF_DYN_STATIC16")) : -1;     // tuning knobs
+        const int s16 = s16_env >= 0 ? s16_env : (has_triangles ? 14 : 12);
+        static const int rpc = getenv("SURF_DYN_RUNS") ? atoi(getenv("SURF_DYN_RUNS")) : 12;
+        prm.static_per = (int)((items * s16 / 16) / grid);
         prm.dyn_begin = prm.static_per * grid;
-        prm.run_len = (int)std::max<long long>(1, (items - prm.dyn_begin) / (12LL * grid));
+        prm.run_len = (int)std::max<long long>(1, (items - prm.dyn_begin) / ((long long)rpc * grid));
         prm.work_counter = (int*)f.ws.obound + 255;          // last cell of the 1 KB counter block
         SURF_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(int), st));
         return launch_intersect_batch(prm, *ba, P, mode, grid, smem, st);

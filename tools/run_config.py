@@ -34,6 +34,27 @@ elif which == 'D':
     call = lambda s: surf_renderer_b200.render_batch(s, double_sided=True, **extra)      # noqa: E731
 else:
     sc, call = scene_io.clone_scene(synth.config_e(), device='cuda'), lambda s: surf_renderer_b200.render(s, **extra)
+if os.environ.get('RUN_GRAPH'):
+    # back-to-back replays from a CUDA graph: the GPU never idles between launches (clocks stay up)
+    with torch.no_grad():
+        for _ in range(3):
+            call(sc)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10):
+                call(sc)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    print(which, extra, 'graph replay: %.4f ms per forward (all kernels)' % (e0.elapsed_time(e1) / (10 * reps)))
+    sys.exit(0)
 lib().surf_set_kernel_timing(1)
 with torch.no_grad():
     for _ in range(reps):
