@@ -501,6 +501,7 @@ struct StreamPool {
     int device = -1;
     cudaStream_t st[kBatchStreams] = {};
     cudaEvent_t fork = nullptr, join[kBatchStreams] = {};
+    std::mutex in_use;       // one fork / launch / join sequence at a time: the events are shared by all callers
 };
 static std::mutex g_pool_mutex;
 static std::vector<StreamPool*> g_pools;
@@ -528,6 +529,9 @@ static int run_batch(int32_t n_scenes, cudaStream_t caller, PerScene&& per_scene
     StreamPool* pool = stream_pool();
     if (!pool) return fail(SURF_ERR_CUDA, "could not create the batch stream pool");
     const int lanes = std::min<int>(kBatchStreams, n_scenes);
+    // Two threads in surf_*_batch on one device (forward on the main thread, backward on autograd's) would otherwise
+    // re-record `fork` / `join[k]` between the other's record and wait.
+    std::lock_guard<std::mutex> busy(pool->in_use);
     SURF_CUDA(cudaEventRecord(pool->fork, caller));
     for (int k = 0; k < lanes; ++k) SURF_CUDA(cudaStreamWaitEvent(pool->st[k], pool->fork, 0));
     int rc = SURF_OK;

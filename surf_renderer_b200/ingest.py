@@ -175,6 +175,10 @@ def make_torch_var(var_dict, device=None):
     for key, value in var_dict.items():
         if isinstance(value, dict):
             make_torch_var(value, device)
+        elif key == 'viewport' and isinstance(value, (list, np.ndarray)):
+            # the frame size is host-side control data: as a CPU tensor, render() reads it without a device
+            # synchronisation (and a step that uses this scene stays CUDA-graph capturable)
+            var_dict[key] = torch.tensor(np.asarray(value).tolist(), dtype=torch.int64)
         elif isinstance(value, list):
             var_dict[key] = tensor_of(value)
         elif isinstance(value, np.ndarray):

@@ -106,6 +106,18 @@ def test_kernel_variants_are_bit_identical(ppt, chunk, mode):
         assert torch.equal(base[k], var[k]), k
 
 
+def test_mode3_is_bit_identical_to_mode0_on_the_full_config_e_frame():
+    """every output of the screen-space kernel (math_mode 3) equals the default ray-plane kernel's bit for bit on ALL
+    1024 x 1024 pixels of config E (100 000 splats) - not a sample"""
+    from surf_renderer_b200 import scenes as synth
+    scene = scene_io.clone_scene(synth.config_e(), device='cuda')
+    a = _render(scene, _math_mode=0)
+    b = _render(scene, _math_mode=3)
+    for k in ('nearest', 'depth', 'image', 'pos', 'normal', 'ray_dir'):
+        assert torch.equal(a[k], b[k]), k
+    assert int((a['depth'] <= scene['camera']['far']).sum()) > 400_000
+
+
 def test_row_bands_equal_full_frame():
     """pixels are independent (renderer.py:170-198): any flat pixel range reproduces the full frame's bits."""
     import surf_renderer_b200

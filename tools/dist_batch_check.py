@@ -1,6 +1,7 @@
 """Scenes-over-GPUs (BASELINE configs[3]: 64 scenes x 5000 splats at 128x128, fwd+bwd): run under torchrun, one rank
-per GPU.  Checks render_batch_sharded against a single-GPU render_batch of the whole batch and times the step with
-CUDA events (max over ranks).
+per GPU.  Checks dist.ShardedBatchStep at full size against a single-GPU render_batch of the whole batch (images
+bit-identical, block gradients and the all-reduced light gradients within atomics tolerance) and times the step with
+CUDA events (max over ranks), eager and replayed from a CUDA graph.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_batch_check.py
 """
@@ -11,69 +12,64 @@ import torch
 import torch.distributed as dist
 import scene_io, surf_renderer_b200
 from surf_renderer_b200 import dist as sdist, scenes as synth
-from surf_renderer_b200.renderer import _stack_scenes
 
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
 if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dist.init_process_group('nccl', device_id=dev)
 B = 64
+batch = synth.config_d_batch(B)
+w = torch.rand(B, 128, 128, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+plan = sdist.ShardedBatchStep(batch, device=dev, group=(True if world > 1 else None), double_sided=True)
+loss_fn = lambda im: (im * w).sum()      # noqa: E731
 
 
-def build():
-    st = _stack_scenes([scene_io.clone_scene(synth.config_d_scene(i), device='cuda') for i in range(B)])
-    lights = st['lights']['pos'][0].detach().clone().requires_grad_(True)      # one light rig shared by all scenes
-    st['lights']['pos'] = lights
-    for f in ('pos', 'normal'):
-        st['objects']['disk'][f] = st['objects']['disk'][f].detach().requires_grad_(True)
-    return st, lights
+def timed(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
 
 
-st, lights = build()
-w = torch.rand(B, 128, 128, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
-
-
-def step():
-    for t in (st['objects']['disk']['pos'], st['objects']['disk']['normal'], lights):
-        t.grad = None
-    res = sdist.render_batch_sharded(st, double_sided=True)
-    (res['image'] * w).sum().backward()
-    sdist.allreduce_gradients([st['objects']['disk']['pos'], st['objects']['disk']['normal'], lights])
-    return res
-
-
-for _ in range(3):
-    res = step()
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 10
-e0.record()
-for _ in range(reps):
-    res = step()
-e1.record()
-torch.cuda.synchronize()
-ms = torch.tensor([e0.elapsed_time(e1) / reps], device='cuda')
-if world > 1:
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-
+ms_eager = timed(lambda: plan.step(loss_fn))
 # parity against the whole batch on one GPU
-st1, lights1 = build()
-ref = surf_renderer_b200.render_batch(st1, double_sided=True)
+plan.step(loss_fn)
+ref_sc = scene_io.clone_scene(batch, device=dev)
+for t in (ref_sc['objects']['disk']['pos'], ref_sc['objects']['disk']['normal'], ref_sc['lights']['pos']):
+    t.requires_grad_(True)
+ref = surf_renderer_b200.render_batch(ref_sc, double_sided=True)
 (ref['image'] * w).sum().backward()
-ok = torch.equal(res['image'], ref['image']) and torch.equal(res['nearest'], ref['nearest'])
-ok = ok and torch.allclose(st['objects']['disk']['pos'].grad, st1['objects']['disk']['pos'].grad, rtol=1e-4, atol=1e-6)
-ok = ok and torch.allclose(lights.grad, lights1.grad, rtol=1e-3, atol=1e-4)
-flag = torch.tensor([1 if ok else 0], device='cuda')
+b0, b1 = plan.block
+ok = torch.equal(plan.image_full.view(B, 128, 128, 3), ref['image'])
+gp, gr = plan.leaves['objects/disk/pos'].grad, ref_sc['objects']['disk']['pos'].grad[b0:b1]
+ok = ok and torch.allclose(gp, gr, rtol=1e-4, atol=2e-6 * float(gr.abs().max()))
+gl, glr = plan.leaves['lights/pos'].grad, ref_sc['lights']['pos'].grad
+ok = ok and torch.allclose(gl, glr, rtol=1e-3, atol=1e-5 * float(glr.abs().max()))
+graphed = surf_renderer_b200.GraphedStep(lambda: plan.step(loss_fn), warmup=3, capture_error_mode='thread_local' if world > 1 else 'global')
+ms_graph = timed(graphed)
+flag = torch.tensor([1 if ok else 0], device=dev)
 if world > 1:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    out = {'n_gpus': world, 'scenes': B, 'splats': 5000, 'size': 128, 'fwd_bwd_ms': float(ms), 'parity_all_ranks': bool(flag.item()),
-           'tests_per_s': B * 5000 * 128 * 128 / (float(ms) * 1e-3)}
+    out = {'n_gpus': world, 'scenes': B, 'splats': 5000, 'size': 128, 'fwd_bwd_ms_eager': ms_eager, 'fwd_bwd_ms_graph': ms_graph,
+           'parity_all_ranks': bool(flag.item()), 'tests_per_s_graph': B * 5000 * 128 * 128 / (ms_graph * 1e-3)}
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     open(os.path.join(ROOT, 'gpurun_out', 'dist_batch_n%d.json' % world), 'w').write(json.dumps(out))
+torch.cuda.synchronize()
 if world > 1:
-    dist.destroy_process_group()
-sys.exit(0 if flag.item() else 1)
+    dist.barrier()
+sys.stdout.flush()
+os._exit(0 if flag.item() else 1)
