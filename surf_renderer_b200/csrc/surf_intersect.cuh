@@ -515,8 +515,13 @@ __device__ __forceinline__ void chunk_planes_fn(const float4* __restrict__ s, in
     }
 }
 
+// resident CTAs per SM the single-scene kernel is compiled for with P = 4 pixels per thread (2 = the shipped
+// configuration; 3 caps the kernel at 84 registers - an A/B knob, see profiles/)
+#ifndef SURF_ISECT_P4_BLOCKS
+#define SURF_ISECT_P4_BLOCKS 2
+#endif
 template <int P, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) k_intersect(const __grid_constant__ IsectParams prm) {
+__global__ void __launch_bounds__(kThreads, (P == 4 ? SURF_ISECT_P4_BLOCKS : 2)) k_intersect(const __grid_constant__ IsectParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* stage_buf = reinterpret_cast<float4*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[kStages];

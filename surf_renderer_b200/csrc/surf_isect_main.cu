@@ -74,7 +74,7 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     // stage capacity: chunk_prims disk records (2 float4 each); keep >= 4x grid items for balance on small frames
     int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
     if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
-    const int grid_max = sm_count() * 2;
+    const int grid_max = sm_count() * ((P == 4 && !ba) ? SURF_ISECT_P4_BLOCKS : 2);
     if (!opt->chunk_prims) {
         // pick the largest chunk whose item count splits over the persistent grid with <= 1.5% quantisation loss
         // (items are dealt as equal contiguous ranges: the slowest CTA runs ceil(items / grid) of them)

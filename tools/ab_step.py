@@ -25,7 +25,12 @@ if which == 'e':
     sc = clone_scene(scene, device=dev)
     for t in (sc['objects']['disk']['pos'], sc['objects']['disk']['normal'], sc['materials']['albedo'], sc['lights']['pos']):
         t.requires_grad_(True)
-    plan = surf_renderer_b200.MSEStep(sc, tgt)
+    extra = {}
+    if os.environ.get('AB_PPT'):
+        extra['_pixels_per_thread'] = int(os.environ['AB_PPT'])
+    if os.environ.get('AB_CHUNK'):
+        extra['_chunk_prims'] = int(os.environ['AB_CHUNK'])
+    plan = surf_renderer_b200.MSEStep(sc, tgt, **extra)
     step = plan
 else:
     host = synth.config_d_batch(64)
@@ -44,7 +49,7 @@ for i in range(reps):
 e1.record()
 torch.cuda.synchronize()
 n = C.c_int32()
-out = {'lib': os.path.basename(LIB_PATH), 'workload': which, 'ms_per_step': e0.elapsed_time(e1) / reps,
+out = {'lib': os.path.basename(LIB_PATH), 'workload': which, 'ppt': os.environ.get('AB_PPT'), 'chunk': os.environ.get('AB_CHUNK'), 'ms_per_step': e0.elapsed_time(e1) / reps,
        'intersect_ms': lib().surf_mean_kernel_ms(0, C.byref(n)), 'shade_ms': lib().surf_mean_kernel_ms(1, C.byref(n)),
        'backward_ms': lib().surf_mean_kernel_ms(2, C.byref(n)), 'launches_timed': n.value}
 print(json.dumps(out))
