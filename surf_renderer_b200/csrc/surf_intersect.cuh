@@ -776,188 +776,10 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
     flush();
 }
 
-// ---------------------------------------------------------------------------------------------------
-// k_intersect_batch, warp-private pipelines.  ncu on the CTA-wide version (profiles/): 12-13 % of the stall samples
-// of configs B / D sat on the ~170 per-item instructions around __syncthreads + mbarrier wait - every item made eight
-// warps wait for the slowest one, and in dense frames the narrow phase makes warps finish unevenly.  Here every WARP
-// owns its ring of shared-memory stages, its mbarriers and its work items [warp tile of 256 pixels][chunk]: lane 0
-// issues the TMA bulk copies, the warp synchronises only with itself (__syncwarp), and draws its items from a
-// static share + a dynamic pool like the CTA version did.  Each warp fetches its own copy of a chunk's records
-// (8x the L2 -> shared traffic of the CTA version: ~0.13 B per test, a few hundred GB/s - far below the L2's rate).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kWarps = kThreads / 32;
-struct WarpScene {             // what one warp needs of its current scene (strided batches)
-    SetView sets[kMaxSets];
-    const float* rays;
-    unsigned long long* zbuf;
-    float eye[3];
-};
-
-template <int P, int MODE, bool BATCH>
-__device__ __forceinline__ void intersect_body_warp(const IsectParams& prm0, const BatchArgs* ba) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
-    __shared__ int item_of[kWarps][kStages];
-    __shared__ WarpScene wscene[kWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float4* stage_buf = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * kStages * prm0.stage_f4;
-    WarpScene& ws = wscene[warp];
-
-    if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[warp][s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    // producer state (lane 0): static share first, then runs of the dynamic pool.  Items: [warp tile][chunk].
-    const int n_wtiles = prm0.n_tiles * kWarps;
-    const long long n_items = (long long)n_wtiles * prm0.n_chunks;
-    const long long gw = (long long)blockIdx.x * kWarps + warp;
-    long long run_next = gw * prm0.static_per, run_end = run_next + prm0.static_per;
-    auto next_item = [&]() -> long long {
-        if (run_next >= run_end) {
-            const int u = atomicAdd(prm0.work_counter, 1);
-            const long long a = (long long)prm0.dyn_begin + (long long)u * prm0.run_len;
-            if (a >= n_items) return -1;
-            run_next = a;
-            run_end = min(n_items, a + (long long)prm0.run_len);
-        }
-        return run_next++;
-    };
-    auto issue = [&](int stage) {
-        const long long item = next_item();
-        item_of[warp][stage] = (int)item;
-        if (item < 0) {                // sentinel: complete the phase without a copy
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[warp][stage])) : "memory");
-            return;
-        }
-        int set, local0, count;
-        decode_chunk(prm0, (int)(item % prm0.n_chunks), &set, &local0, &count);
-        const SetView& sv = prm0.sc.sets[set];
-        const int nf4 = rec_f4(sv.kind);
-        const int tile = (int)(item / prm0.n_chunks) / kWarps;
-        const float4* packed = BATCH ? ws_at(prm0.packed, *ba, tile / prm0.tiles_per_scene) : prm0.packed;
-        const float4* src = packed + sv.rec_off + (size_t)local0 * nf4;
-        const uint32_t bytes = (uint32_t)(count * nf4) * 16u;
-        mbar_expect_tx(&full_bar[warp][stage], bytes);
-        tma_bulk_g2s(stage_buf + (size_t)stage * prm0.stage_f4, src, bytes, &full_bar[warp][stage]);
-    };
-    if (lane == 0)
-        for (int k = 0; k < kStages - 1; ++k) issue(k);
-
-    const float near_clip = prm0.cam->near_clip, far_clip = prm0.cam->far_clip;    // camera scalars are batch-wide
-    constexpr int TILE = kThreads * P;
-    PixelRegs<P> r;
-    int cur_wtile = -1, cur_lt = 0, cur_w = 0, cur_b = -1;
-    Vec3 eye = v3(0.f, 0.f, 0.f);
-    const bool tiles2d = prm0.tiles_x > 0;
-    // flat pixel (relative to pix0) of this lane's slot p in warp tile (cur_lt, cur_w), or -1 outside the frame
-    auto pix_of = [&](int p) -> int {
-        if (!tiles2d) {
-            const int pix = cur_lt * TILE + p * kThreads + cur_w * 32 + lane;
-            return pix < prm0.n_pix ? pix : -1;
-        }
-        const int ty = cur_lt / prm0.tiles_x, tx = cur_lt - ty * prm0.tiles_x;
-        const int col = tx * 64 + (cur_w & 3) * 16 + (lane & 15);
-        const int row = prm0.pix0 / prm0.W + ty * 32 + (cur_w >> 2) * 16 + (lane >> 4) + 2 * p;
-        const int pix = row * prm0.W + col - prm0.pix0;
-        return (col < prm0.W && pix >= 0 && pix < prm0.n_pix) ? pix : -1;
-    };
-    auto flush = [&]() {
-        if (cur_wtile < 0) return;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int pix = pix_of(p);
-            if (r.best_i[p] >= 0 && pix >= 0) {
-                unsigned long long key = ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p];
-                atomicMin(ws.zbuf + pix, key);
-            }
-        }
-    };
-
-    for (int k = 0;; ++k) {
-        const int stage = k % kStages;
-        const uint32_t parity = (uint32_t)((k / kStages) & 1);
-        __syncwarp();      // every lane is done with step k-1, whose stage is the one refilled below
-        if (lane == 0) issue((k + kStages - 1) % kStages);
-        mbar_wait(&full_bar[warp][stage], parity);
-        const int it = item_of[warp][stage];
-        if (it < 0) break;             // warp-uniform
-
-        const int wtile = it / prm0.n_chunks;
-        if (wtile != cur_wtile) {
-            flush();
-            cur_wtile = wtile;
-            const int tile = wtile / kWarps;
-            cur_w = wtile - tile * kWarps;
-            const int b = BATCH ? tile / prm0.tiles_per_scene : 0;
-            cur_lt = tile - b * prm0.tiles_per_scene;
-            if (b != cur_b) {          // warp-uniform: re-point this warp's scene block
-                __syncwarp();
-                if (lane == 0) {
-                    SceneView sc = prm0.sc;
-                    if (BATCH) scene_at(&sc, *ba, b);
-                    for (int s = 0; s < kMaxSets; ++s) ws.sets[s] = sc.sets[s];
-                    ws.rays = BATCH ? ws_at(prm0.rays, *ba, b) : prm0.rays;
-                    ws.zbuf = BATCH ? ws_at(prm0.zbuf, *ba, b) : prm0.zbuf;
-                    const CamState* cam = BATCH ? ws_at(prm0.cam, *ba, b) : prm0.cam;
-                    ws.eye[0] = cam->eye[0]; ws.eye[1] = cam->eye[1]; ws.eye[2] = cam->eye[2];
-                }
-                __syncwarp();
-                cur_b = b;
-                eye = v3(ws.eye[0], ws.eye[1], ws.eye[2]);
-            }
-            float d[3][P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int pix = pix_of(p);
-                const bool ok = pix >= 0;
-                d[0][p] = ok ? ws.rays[pix] : 0.f;
-                d[1][p] = ok ? ws.rays[(size_t)prm0.n_pix + pix] : 0.f;
-                d[2][p] = ok ? ws.rays[2 * (size_t)prm0.n_pix + pix] : 0.f;
-                r.best_t[p] = INFINITY;
-                r.best_i[p] = -1;
-            }
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                r.dx[q] = pack2(d[0][2 * q], d[0][2 * q + 1]);
-                r.dy[q] = pack2(d[1][2 * q], d[1][2 * q + 1]);
-                r.dz[q] = pack2(d[2][2 * q], d[2][2 * q + 1]);
-            }
-        }
-
-        int set, local0, count;
-        decode_chunk(prm0, it % prm0.n_chunks, &set, &local0, &count);
-        const SetView& sv = ws.sets[set];
-        const float4* s = stage_buf + (size_t)stage * prm0.stage_f4;
-        if (sv.kind == KIND_DISK) {
-            if (MODE == 0)
-                chunk_disks_dense<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
-                    narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
-                });
-            else chunk_disks<P, MODE>(prm0, sv, s, local0, count, eye, near_clip, far_clip, r);
-        }
-        else if (sv.kind == KIND_TRIANGLE) {
-            if (MODE != 1)
-                chunk_triangles_packed<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
-                    narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
-                });
-            else chunk_triangles<P>(prm0, sv, s, local0, count, eye, near_clip, far_clip, r);
-        }
-        else if (sv.kind == KIND_SPHERE) chunk_spheres<P>(prm0, sv, s, local0, count, eye, near_clip, far_clip, r);
-        else chunk_planes<P>(prm0, sv, s, local0, count, eye, near_clip, far_clip, r);
-    }
-    flush();
-}
-
 template <int P, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_intersect_batch(const __grid_constant__ IsectParams prm0,
                                                                  const __grid_constant__ BatchArgs ba) {
-#ifdef SURF_BATCH_CTA_PIPELINE
     __shared__ IsectParams sprm;
     intersect_body<P, MODE, true>(prm0, &ba, &sprm);
-#else
-    intersect_body_warp<P, MODE, true>(prm0, &ba);
-#endif
 }
 

@@ -75,11 +75,7 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     int chunk = opt->chunk_prims ? opt->chunk_prims : 1024;
     if (chunk < 32 || chunk > 2048 || chunk % 32) return fail(SURF_ERR_BAD_ARG, "chunk_prims must be a multiple of 32 in [32, 2048]");
     const int grid_max = sm_count() * ((P == 4 && !ba) ? SURF_ISECT_P4_BLOCKS : 2);
-    if (ba) {
-        // k_intersect_batch: warp-private pipelines (kWarps x kStages stages per CTA in shared memory), dynamic shares
-        if (!opt->chunk_prims) chunk = 128;
-        chunk = std::min(chunk, 128);
-    } else if (!opt->chunk_prims) {
+    if (!opt->chunk_prims) {
         // pick the largest chunk whose item count splits over the persistent grid with <= 1.5% quantisation loss
         // (items are dealt as equal contiguous ranges: the slowest CTA runs ceil(items / grid) of them)
         auto items_for = [&](int ch) {
@@ -112,23 +108,20 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     }
     prm.chunks_before[kMaxSets] = nchunks;
     prm.n_chunks = nchunks;
-    const long long items = (long long)prm.n_tiles * nchunks * (ba ? kWarps : 1);      // batch kernel: per-warp items
-    const int grid = (int)std::min<long long>(ba ? std::max<long long>(1, (items + kWarps - 1) / kWarps) : items, grid_max);
-    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4) * (ba ? kWarps : 1);
+    const long long items = (long long)prm.n_tiles * nchunks;
+    const int grid = (int)std::min<long long>(items, grid_max);
+    const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
     if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
     if (ba) {
         // hybrid distribution: 3/4 of the items as contiguous static shares, the rest drawn dynamically in short runs
-        // hybrid distribution over the grid's warps: s16/16 of the items as contiguous static shares, the rest drawn
-        // dynamically in short runs
+        // measured (B200): splat batches / dense splat frames are fastest with 12/16 static (config D 2.45 -> 2.28 ms,
+        // bunny 256x256 0.189 -> 0.184 ms), triangle meshes with 14/16 (their items are 4x heavier per record)
         static const int s16_env = getenv("SURF_DYN_STATIC16") ? atoi(getenv("SURF_DYN_STATIC16")) : -1;     // tuning knobs
-        static const int rpc = getenv("SURF_DYN_RUNS") ? atoi(getenv("SURF_DYN_RUNS")) : 8;
-        const int s16 = s16_env >= 0 ? s16_env : 12;
-        const long long n_warps = (long long)grid * kWarps;
-        prm.static_per = (int)((items * s16 / 16) / n_warps);
-        const long long dyn_begin = (long long)prm.static_per * n_warps;
-        if (items > 0x7fffffffLL) return fail(SURF_ERR_UNSUPPORTED, "too many batch work items");
-        prm.dyn_begin = (int)dyn_begin;
-        prm.run_len = (int)std::max<long long>(1, (items - dyn_begin) / ((long long)rpc * n_warps));
+        const int s16 = s16_env >= 0 ? s16_env : (has_triangles ? 14 : 12);
+        static const int rpc = getenv("SURF_DYN_RUNS") ? atoi(getenv("SURF_DYN_RUNS")) : 12;
+        prm.static_per = (int)((items * s16 / 16) / grid);
+        prm.dyn_begin = prm.static_per * grid;
+        prm.run_len = (int)std::max<long long>(1, (items - prm.dyn_begin) / ((long long)rpc * grid));
         prm.work_counter = (int*)f.ws.obound + 255;          // last cell of the 1 KB counter block
         SURF_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(int), st));
         return launch_intersect_batch(prm, *ba, P, mode, grid, smem, st);
