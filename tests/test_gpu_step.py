@@ -93,6 +93,46 @@ def test_mse_step_equals_the_autograd_path_of_this_library():
         assert torch.allclose(lb[k].grad, la[k].grad, rtol=1e-4, atol=2e-6 * scale), k
 
 
+@pytest.mark.parametrize('variant', ['shadow', 'ortho', 'mode3', 'spheres'])
+def test_mse_step_option_space_equals_the_autograd_path(variant):
+    """the fused step honours the same options as render(): shadow rays (visibility from the forward workspace),
+    orthographic frames, the screen-space intersection kernel, sphere primitives"""
+    import surf_renderer_b200
+    from surf_renderer_b200 import scenes as synth
+    params = {'double_sided': True}
+    if variant == 'shadow':
+        scene = synth.random_mixed_scene(31, width=64, height=48, n_disk=40, n_tri=20, n_sphere=0)
+        params['shadow'] = True
+    elif variant == 'ortho':
+        scene = synth.random_mixed_scene(32, width=56, height=40, n_disk=30, n_tri=20, n_sphere=0, proj='orthographic')
+    elif variant == 'mode3':
+        scene = synth.random_mixed_scene(33, width=130, height=17, n_disk=40, n_tri=20, n_sphere=0)
+        params['_math_mode'] = 3
+    else:
+        scene = synth.random_mixed_scene(34, width=64, height=48, n_disk=20, n_tri=10, n_sphere=4)
+    H, W = scene['camera']['viewport'][3], scene['camera']['viewport'][2]
+    target = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    a = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    res = surf_renderer_b200.render(a, **params)
+    loss_a = ((res['image'] - target) ** 2).mean()
+    loss_a.backward()
+    b = scene_io.clone_scene(scene, device='cuda', requires_grad=True)
+    plan = surf_renderer_b200.MSEStep(b, target, **params)
+    loss_b = plan()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.image.view(H, W, 3), res['image'])
+    assert abs(float(loss_a) - float(loss_b)) <= 2e-6 * abs(float(loss_a))
+    la, lb = _leaves(a), _leaves(b)
+    checked = 0
+    for k in la:
+        if la[k].grad is None:
+            continue
+        scale = float(la[k].grad.abs().max())
+        assert torch.allclose(lb[k].grad, la[k].grad, rtol=1e-4, atol=3e-6 * max(scale, 1e-30)), k
+        checked += 1
+    assert checked >= 5
+
+
 def test_mse_step_with_adam_replays_from_a_cuda_graph():
     import surf_renderer_b200
     from surf_renderer_b200 import scenes as synth
