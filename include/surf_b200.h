@@ -345,6 +345,28 @@ int surf_scatter_backward(const SurfScatter* scatter, const float* x, const int6
                           const float* center_dist_2, const float* out, const float* denom, const float* g_out,
                           float* g_x, float* g_z, float* g_center_dist_2, void* cuda_stream);
 
+/* surf_bilinear_oit_*      <- projection_layer.py:170-240, the scatter stage of projection_renderer_differentiable_fast:
+ *                            every surfel goes to the four pixels around px_coord with bilinear weights, each corner
+ *                            scatter blended like scatter_weighted_blended_oit (sigma 0.5, z_scale 2 in the reference's
+ *                            call), the four normalised results summed: out [B,P,C], soft mask [B,P], optionally the
+ *                            new depth [B,P].  `acc` (surf_bilinear_acc_floats floats, written by the forward) carries
+ *                            the per-corner accumulators to the backward, which ADDS d/dx and d/d(px_coord).
+ * surf_gaussian_blur      <- projection_layer.py:156-168 blur(): separable, zero-padded, taps within 3 sigma; the
+ *                            operation is its own adjoint, so the backward is the same call on the gradient. */
+typedef struct SurfBilinear {
+    int32_t batch, n, channels, width, height;
+    float sigma, z_scale;
+    int32_t use_depth, use_center_dist, compute_depth;
+} SurfBilinear;
+size_t surf_bilinear_acc_floats(const SurfBilinear* bl);
+int surf_bilinear_oit_forward(const SurfBilinear* bl, const float* px_coord, const float* x, float* acc, float* out,
+                              float* mask, float* depth, void* cuda_stream);
+int surf_bilinear_oit_backward(const SurfBilinear* bl, const float* px_coord, const float* x, const float* acc,
+                               const float* g_out, const float* g_mask, const float* g_depth, float* g_x,
+                               float* g_px_coord, void* cuda_stream);
+int surf_gaussian_blur(const float* image, float* scratch, float* out, int32_t batch, int32_t height, int32_t width,
+                       int32_t channels, float sigma, void* cuda_stream);
+
 /* ---- host-pointer API (self-contained: H2D, kernels, D2H) ---- */
 typedef struct SurfContext SurfContext;
 SurfContext* surf_context_create(int32_t device);

@@ -85,6 +85,12 @@ class SurfScatter(C.Structure):
                 ('sigma', C.c_float), ('z_scale', C.c_float), ('use_depth', C.c_int32), ('use_center_dist', C.c_int32)]
 
 
+class SurfBilinear(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('n', C.c_int32), ('channels', C.c_int32), ('width', C.c_int32), ('height', C.c_int32),
+                ('sigma', C.c_float), ('z_scale', C.c_float), ('use_depth', C.c_int32), ('use_center_dist', C.c_int32),
+                ('compute_depth', C.c_int32)]
+
+
 SURF_ADAM_MAX_TENSORS = 16
 
 
@@ -142,6 +148,11 @@ SYMBOLS = {
                                        C.c_void_p, C.c_void_p]),
     'surf_scatter_backward': (C.c_int, [C.POINTER(SurfScatter), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'surf_bilinear_acc_floats': (C.c_size_t, [C.POINTER(SurfBilinear)]),
+    'surf_bilinear_oit_forward': (C.c_int, [C.POINTER(SurfBilinear), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'surf_bilinear_oit_backward': (C.c_int, [C.POINTER(SurfBilinear), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    'surf_gaussian_blur': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     'surf_splats_workspace_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
     'surf_splats_forward_strided': (C.c_int, [C.c_int32, C.POINTER(SurfScene), C.POINTER(SurfCamera), C.POINTER(SurfOptions),
                                               C.POINTER(SurfSplats), C.POINTER(SurfSplatBatch), C.c_void_p, C.c_size_t,

@@ -926,6 +926,76 @@ int surf_scatter_backward(const SurfScatter* scatter, const float* x, const int6
     return SURF_OK;
 }
 
+static int bilinear_params(const SurfBilinear* bl, BilinearParams* p) {
+    if (!bl) return fail(SURF_ERR_BAD_ARG, "null bilinear description");
+    if (bl->batch < 1 || bl->batch > 65535 || bl->n < 1 || bl->channels < 1 || bl->width < 1 || bl->height < 1)
+        return fail(SURF_ERR_BAD_ARG, "empty bilinear scatter");
+    std::memset(p, 0, sizeof(*p));
+    p->batch = bl->batch; p->n = bl->n; p->channels = bl->channels; p->W = bl->width; p->H = bl->height;
+    p->use_depth = bl->use_depth; p->use_center_dist = bl->use_center_dist; p->want_depth = bl->compute_depth;
+    const double s2 = (double)bl->sigma * bl->sigma;
+    p->alpha0 = (float)(1.0 / (2.0 * 3.14159265358979323846 * s2));
+    p->inv_2s2 = (float)(1.0 / (2.0 * s2));
+    p->z_scale = bl->z_scale;
+    p->eps = 1e-8f;
+    return SURF_OK;
+}
+
+size_t surf_bilinear_acc_floats(const SurfBilinear* bl) {
+    return bl ? (size_t)bl->batch * 4 * (size_t)bl->width * bl->height * (size_t)(bl->channels + 3) : 0;
+}
+
+int surf_bilinear_oit_forward(const SurfBilinear* bl, const float* px_coord, const float* x, float* acc, float* out, float* mask,
+                              float* depth, void* cuda_stream) {
+    g_launches = 0;
+    BilinearParams p;
+    int rc = bilinear_params(bl, &p);
+    if (rc) return rc;
+    if (!px_coord || !x || !acc || !out || !mask) return fail(SURF_ERR_BAD_ARG, "null bilinear operand");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    p.px = px_coord; p.x = x; p.acc = acc; p.out = out; p.mask = mask; p.depth = bl->compute_depth ? depth : nullptr;
+    SURF_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * surf_bilinear_acc_floats(bl), st));
+    k_bilinear_accum<<<dim3((p.n + 255) / 256, p.batch), 256, 0, st>>>(p);
+    SURF_LAUNCHED("k_bilinear_accum");
+    const size_t total = (size_t)p.batch * p.W * p.H;
+    k_bilinear_normalize<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    SURF_LAUNCHED("k_bilinear_normalize");
+    return SURF_OK;
+}
+
+int surf_bilinear_oit_backward(const SurfBilinear* bl, const float* px_coord, const float* x, const float* acc, const float* g_out,
+                               const float* g_mask, const float* g_depth, float* g_x, float* g_px_coord, void* cuda_stream) {
+    g_launches = 0;
+    BilinearParams p;
+    int rc = bilinear_params(bl, &p);
+    if (rc) return rc;
+    if (!px_coord || !x || !acc) return fail(SURF_ERR_BAD_ARG, "null bilinear operand");
+    p.px = px_coord; p.x = x; p.acc = (float*)acc;
+    p.g_out = g_out; p.g_mask = g_mask; p.g_depth = g_depth; p.g_x = g_x; p.g_px = g_px_coord;
+    k_bilinear_backward<<<dim3((p.n + 255) / 256, p.batch), 256, 0, (cudaStream_t)cuda_stream>>>(p);
+    SURF_LAUNCHED("k_bilinear_backward");
+    return SURF_OK;
+}
+
+int surf_gaussian_blur(const float* image, float* scratch, float* out, int32_t batch, int32_t height, int32_t width, int32_t channels,
+                       float sigma, void* cuda_stream) {
+    g_launches = 0;
+    if (!image || !scratch || !out || batch < 1 || height < 1 || width < 1 || channels < 1 || !(sigma > 0.f))
+        return fail(SURF_ERR_BAD_ARG, "bad blur argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int half = (int)floor((double)sigma * 3.0);
+    double sum = 0.0;
+    for (int d = -half; d <= half; ++d) sum += exp(-(double)(d * d) / (2.0 * (double)sigma * sigma));
+    const float inv_2s2 = (float)(1.0 / (2.0 * (double)sigma * sigma)), norm = (float)(1.0 / sum);
+    const size_t total = (size_t)batch * height * width * channels;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    k_blur_pass<<<grid, 256, 0, st>>>(image, scratch, batch, height, width, channels, 0, half, inv_2s2, norm);
+    SURF_LAUNCHED("k_blur_pass");
+    k_blur_pass<<<grid, 256, 0, st>>>(scratch, out, batch, height, width, channels, 1, half, inv_2s2, norm);
+    SURF_LAUNCHED("k_blur_pass");
+    return SURF_OK;
+}
+
 size_t surf_splats_workspace_bytes(int32_t n_splats, int32_t n_lights) {
     SplatWorkspace ws;
     carve_splats(nullptr, n_splats, n_lights, &ws);

@@ -151,3 +151,158 @@ __global__ void __launch_bounds__(256) k_scatter_backward(const __grid_constant_
         if (p.g_cd2 && p.use_center_dist) p.g_cd2[e] += g_w * w * (-p.inv_2s2);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// projection_renderer_differentiable_fast (projection_layer.py:170-279): every surfel is splatted onto the four pixels
+// around its projection with bilinear weights, each of the four corner scatters blended with Weighted Blended OIT
+// (weights alpha(centre distance) * exp(-z_scale depth)), the four normalised results summed; then a separable
+// Gaussian blur.  The reference runs scatter_weighted_blended_oit eight to twelve times (rgb, soft mask, depth x four
+// corners) over padded copies; here one kernel accumulates all of it, one normalises, one gather-form kernel does the
+// backward w.r.t. the surfel data AND the pixel coordinates (x, y, depth), and the blur is its own adjoint.
+//   accumulators per corner k and pixel: A_k (sum of weights), C_k[ch] (data), M_k (soft mask), D_k (depth)
+// ---------------------------------------------------------------------------------------------------
+struct BilinearParams {
+    int batch, n, channels, W, H;
+    int use_depth, use_center_dist, want_depth;
+    float alpha0, inv_2s2, z_scale, eps;
+    const float* px;          // [B, n, 3] pixel x, pixel y, depth
+    const float* x;           // [B, n, ch]
+    float* acc;               // [B, 4, P, ch + 3]: C_k[ch], A_k, M_k, D_k
+    float* out;               // [B, P, ch]
+    float* mask;              // [B, P]
+    float* depth;             // [B, P] or null
+    const float* g_out; const float* g_mask; const float* g_depth;     // backward inputs
+    float* g_x; float* g_px;                                            // backward outputs (added)
+};
+
+struct BilinearSurfel { int ix, iy; float fx, fy, depth, s; };
+__device__ __forceinline__ BilinearSurfel bilinear_surfel(const BilinearParams& p, size_t e) {
+    BilinearSurfel b;
+    const float* q = p.px + e * 3;
+    const float ax = q[0] - 0.5f, ay = q[1] - 0.5f;
+    const float flx = floorf(ax), fly = floorf(ay);
+    b.ix = (int)flx; b.iy = (int)fly;
+    b.fx = ax - flx; b.fy = ay - fly;
+    b.depth = q[2];
+    float s = 1.f;
+    if (p.use_center_dist) s *= p.alpha0 * expf(-(b.fx * b.fx + b.fy * b.fy) * p.inv_2s2);
+    if (p.use_depth) s *= expf(-p.z_scale * b.depth);
+    b.s = s;
+    return b;
+}
+// corner k = (dx, dy) in the reference's order (0,0), (0,1), (1,0), (1,1); weight and destination pixel (-1: outside)
+__device__ __forceinline__ void bilinear_corner(const BilinearParams& p, const BilinearSurfel& b, int k, float* w, int* dst) {
+    const int dx = k >> 1, dy = k & 1;
+    *w = (dx ? b.fx : 1.f - b.fx) * (dy ? b.fy : 1.f - b.fy);
+    const int cx = b.ix + dx, cy = b.iy + dy;
+    *dst = (cx < 0 || cy < 0 || cx >= p.W || cy >= p.H) ? -1 : cy * p.W + cx;
+}
+
+__global__ void __launch_bounds__(256) k_bilinear_accum(const __grid_constant__ BilinearParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+    if (i >= p.n) return;
+    const size_t e = (size_t)bi * p.n + i;
+    const BilinearSurfel b = bilinear_surfel(p, e);
+    const int P = p.W * p.H, stride = p.channels + 3;
+    const float* x = p.x + e * p.channels;
+    for (int k = 0; k < 4; ++k) {
+        float w; int dst;
+        bilinear_corner(p, b, k, &w, &dst);
+        if (dst < 0) continue;
+        float* a = p.acc + (((size_t)bi * 4 + k) * P + dst) * stride;
+        const float ws = w * b.s;
+        for (int c = 0; c < p.channels; ++c) atomicAdd(a + c, x[c] * ws);
+        atomicAdd(a + p.channels, b.s);
+        atomicAdd(a + p.channels + 1, ws);
+        if (p.want_depth) atomicAdd(a + p.channels + 2, b.depth * ws);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bilinear_normalize(const __grid_constant__ BilinearParams p) {
+    const int P = p.W * p.H, stride = p.channels + 3;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)p.batch * P) return;
+    const int bi = (int)(j / P), pix = (int)(j - (size_t)bi * P);
+    float m = 0.f, d = 0.f;
+    for (int c = 0; c < p.channels; ++c) p.out[j * p.channels + c] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        const float* a = p.acc + (((size_t)bi * 4 + k) * P + pix) * stride;
+        const float A = a[p.channels];
+        const float inv = 1.f / ((fabsf(A) > 0.f ? A : 1.f) + p.eps);
+        for (int c = 0; c < p.channels; ++c) p.out[j * p.channels + c] += a[c] * inv;
+        m += a[p.channels + 1] * inv;
+        d += a[p.channels + 2] * inv;
+    }
+    p.mask[j] = m;
+    if (p.depth) p.depth[j] = d;
+}
+
+__global__ void __launch_bounds__(256) k_bilinear_backward(const __grid_constant__ BilinearParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y;
+    if (i >= p.n) return;
+    const size_t e = (size_t)bi * p.n + i;
+    const BilinearSurfel b = bilinear_surfel(p, e);
+    const int P = p.W * p.H, stride = p.channels + 3;
+    const float* x = p.x + e * p.channels;
+    float g_s = 0.f, g_fx = 0.f, g_fy = 0.f, g_depth = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        float w; int dst;
+        bilinear_corner(p, b, k, &w, &dst);
+        if (dst < 0) continue;
+        const float* a = p.acc + (((size_t)bi * 4 + k) * P + dst) * stride;
+        const float A = a[p.channels];
+        if (!(fabsf(A) > 0.f)) continue;
+        const float inv = 1.f / (A + p.eps);
+        const size_t j = (size_t)bi * P + dst;
+        float g_w = 0.f, g_sk = 0.f;        // d/d(bilinear weight), d/d(s) through this corner
+        for (int c = 0; c < p.channels; ++c) {
+            const float go = p.g_out ? p.g_out[j * p.channels + c] : 0.f;
+            if (p.g_x) p.g_x[e * p.channels + c] += go * w * b.s * inv;
+            g_w += go * x[c];
+            g_sk += go * (x[c] * w - a[c] * inv);
+        }
+        const float gm = p.g_mask ? p.g_mask[j] : 0.f;
+        g_w += gm;
+        g_sk += gm * (w - a[p.channels + 1] * inv);
+        if (p.want_depth && p.g_depth) {
+            const float gd = p.g_depth[j];
+            g_w += gd * b.depth;
+            g_sk += gd * (b.depth * w - a[p.channels + 2] * inv);
+            g_depth += gd * w * b.s * inv;
+        }
+        g_w *= b.s * inv;
+        g_s += g_sk * inv;
+        const int dx = k >> 1, dy = k & 1;
+        g_fx += g_w * (dx ? 1.f : -1.f) * (dy ? b.fy : 1.f - b.fy);
+        g_fy += g_w * (dy ? 1.f : -1.f) * (dx ? b.fx : 1.f - b.fx);
+    }
+    if (p.use_center_dist) {
+        const float g_cd2 = g_s * b.s * (-p.inv_2s2);
+        g_fx += 2.f * b.fx * g_cd2;
+        g_fy += 2.f * b.fy * g_cd2;
+    }
+    if (p.use_depth) g_depth += g_s * b.s * (-p.z_scale);
+    if (p.g_px) {
+        float* g = p.g_px + e * 3;
+        g[0] += g_fx; g[1] += g_fy; g[2] += g_depth;
+    }
+}
+
+// one pass of the separable Gaussian blur of projection_layer.py:156-168 (zero padding): along W (axis 0) or H (axis 1)
+// of a [B, H, W, C] image; taps [-half, half], weights exp(-d^2 / (2 sigma^2)) normalised to sum 1
+__global__ void __launch_bounds__(256) k_blur_pass(const float* __restrict__ in, float* __restrict__ out, int batch, int H, int W,
+                                                   int C, int axis, int half, float inv_2s2, float norm) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)batch * H * W * C;
+    if (j >= total) return;
+    const int c = (int)(j % C);
+    const int xq = (int)((j / C) % W), yq = (int)((j / ((size_t)C * W)) % H);
+    const size_t base = j - ((size_t)yq * W + xq) * C - c;          // start of this batch element's image
+    float acc = 0.f;
+    for (int d = -half; d <= half; ++d) {
+        const int xx = axis == 0 ? xq + d : xq, yy = axis == 0 ? yq : yq + d;
+        if (xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
+        acc = fmaf(expf(-(float)(d * d) * inv_2s2) * norm, in[base + ((size_t)yy * W + xx) * C + c], acc);
+    }
+    out[j] = acc;
+}

@@ -166,3 +166,110 @@ def projection_renderer(surfels, rgb, camera):
     flat = rgb.reshape(rgb.size(0), -1, rgb.size(-1))
     out, mask = scatter_mean_dim0(flat, px_idx)
     return out.reshape(rgb.shape), mask.reshape(rgb.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# projection_renderer_differentiable_fast (projection_layer.py:170-279)
+# ---------------------------------------------------------------------------------------------------------------
+class _BilinearOITFn(torch.autograd.Function):
+    """the scatter stage: four bilinear corner scatters blended with Weighted Blended OIT, summed (one kernel)"""
+
+    @staticmethod
+    def forward(ctx, px_coord, x, W, H, use_depth, use_center_dist, compute_depth):
+        _need_cuda(x)
+        px_coord, x = _f32c(px_coord), _f32c(x)
+        B, n, ch = x.shape
+        desc = _abi.SurfBilinear(B, n, ch, W, H, 0.5, 2.0, int(bool(use_depth)), int(bool(use_center_dist)), int(bool(compute_depth)))
+        acc = torch.empty(lib().surf_bilinear_acc_floats(C.byref(desc)), dtype=torch.float32, device=x.device)
+        out = torch.empty(B, W * H, ch, dtype=torch.float32, device=x.device)
+        mask = torch.empty(B, W * H, dtype=torch.float32, device=x.device)
+        depth = torch.empty(B, W * H, dtype=torch.float32, device=x.device) if compute_depth else None
+        with torch.cuda.device(x.device):
+            check(lib().surf_bilinear_oit_forward(C.byref(desc), px_coord.data_ptr(), x.data_ptr(), acc.data_ptr(), out.data_ptr(),
+                                                  mask.data_ptr(), depth.data_ptr() if depth is not None else None, _stream_ptr()))
+        ctx.desc = desc
+        ctx.save_for_backward(px_coord, x, acc)
+        if depth is None:
+            depth = out.new_empty(0)
+        return out, mask, depth
+
+    @staticmethod
+    def backward(ctx, g_out, g_mask, g_depth):
+        px_coord, x, acc = ctx.saved_tensors
+        g_x = torch.zeros_like(x) if ctx.needs_input_grad[1] else None
+        g_px = torch.zeros_like(px_coord) if ctx.needs_input_grad[0] else None
+        ptr = lambda t: None if t is None else t.data_ptr()      # noqa: E731
+        go = _f32c(g_out) if g_out is not None else None
+        gm = _f32c(g_mask) if g_mask is not None else None
+        gd = _f32c(g_depth) if (g_depth is not None and ctx.desc.compute_depth and g_depth.numel()) else None
+        with torch.cuda.device(x.device):
+            check(lib().surf_bilinear_oit_backward(C.byref(ctx.desc), px_coord.data_ptr(), x.data_ptr(), acc.data_ptr(), ptr(go), ptr(gm),
+                                                   ptr(gd), ptr(g_x), ptr(g_px), _stream_ptr()))
+        return g_px, g_x, None, None, None, None, None
+
+
+class _BlurFn(torch.autograd.Function):
+    """projection_layer.py:156-168 blur(): separable zero-padded Gaussian over a [B, H, W, C] image; self-adjoint"""
+
+    @staticmethod
+    def _run(img, sigma):
+        img = _f32c(img)
+        B, H, W, ch = img.shape
+        scratch, out = torch.empty_like(img), torch.empty_like(img)
+        with torch.cuda.device(img.device):
+            check(lib().surf_gaussian_blur(img.data_ptr(), scratch.data_ptr(), out.data_ptr(), B, H, W, ch, float(sigma), _stream_ptr()))
+        return out
+
+    @staticmethod
+    def forward(ctx, img, sigma):
+        _need_cuda(img)
+        ctx.sigma = sigma
+        return _BlurFn._run(img, sigma)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _BlurFn._run(g, ctx.sigma), None
+
+
+def blur(image_bhwc, blur_size):
+    """Gaussian blur of a [B, H, W, C] image with sigma = blur_size * H / 6 (the reference's blur() takes the image as
+    [B, C, H, W] and reads the size of its second-to-last axis, i.e. H)."""
+    return _BlurFn.apply(image_bhwc, blur_size * image_bhwc.size(1) / 6)
+
+
+def projection_renderer_differentiable_fast(surfels, rgb, camera, rotated_image=None, blur_size=0.15, use_depth=True,
+                                            use_center_dist=True, compute_new_depth=False, blur_rotated_image=True,
+                                            detach_mask=False, detach_mask2=False, detach_depth_merge=False):
+    """projection_layer.py:170-279: project the surfels, splat them bilinearly with Weighted Blended OIT, blur, and merge
+    with `rotated_image` through the soft mask.  Differentiable w.r.t. `rgb`, `rotated_image` and - through the pixel
+    coordinates and the depth - the surfel positions.  Returns (out [B,H,W,C], {'mask', 'image1'[, 'depth']})."""
+    _, px_coord = project_image_coordinates(surfels, camera)
+    vp = camera['viewport']
+    vp = vp.detach().cpu().numpy() if isinstance(vp, torch.Tensor) else np.asarray(vp)
+    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    rgb_in = rgb.reshape(rgb.size(0), -1, rgb.size(-1))
+    if detach_depth_merge:
+        px_coord = torch.cat((px_coord[..., :2], px_coord[..., 2:].detach()), dim=-1)
+    rgb_out, soft_mask, depth_out = _BilinearOITFn.apply(px_coord, rgb_in, W, H, use_depth, use_center_dist, compute_new_depth)
+    rgb_out = blur(rgb_out.view(*rgb.size()), blur_size)
+    soft_mask = blur(soft_mask.view(*rgb.size()[:-1], 1), blur_size)
+    # merge (projection_layer.py:247-279; elementwise, the reference's own formulation)
+    soft_mask_nonzero = torch.where(soft_mask > 0, soft_mask, torch.ones_like(soft_mask)) + 1e-20
+    rgb_out_normalized = torch.where(soft_mask > 0, rgb_out / soft_mask_nonzero, rgb_out)
+    if rotated_image is not None:
+        if blur_rotated_image:
+            rotated_image = blur(rotated_image, blur_size)
+        if detach_mask:
+            out = torch.where(soft_mask > 1, rgb_out / soft_mask_nonzero.detach(), rgb_out + rotated_image * (1 - soft_mask.detach()))
+        elif detach_mask2:
+            soft_mask_detached = soft_mask.detach()
+            out = soft_mask_detached * rgb_out_normalized + (1 - soft_mask_detached) * rotated_image
+        else:
+            out = torch.where(soft_mask > 1, rgb_out / soft_mask_nonzero, rgb_out + rotated_image * (1 - soft_mask))
+    else:
+        out = rgb_out_normalized
+    proj_out = {'mask': soft_mask, 'image1': rgb_out_normalized}
+    if compute_new_depth:
+        depth_img = depth_out.view(*rgb.size()[:-1], 1)
+        proj_out['depth'] = torch.where(soft_mask > 0, depth_img / soft_mask_nonzero, depth_img)
+    return out, proj_out
