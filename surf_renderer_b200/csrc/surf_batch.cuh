@@ -56,7 +56,8 @@ __host__ __device__ inline void scene_at(SceneView* sc, const BatchArgs& ba, int
 // filter records of primitive g for rays from the common origin o (the eye; a light for k_prep_lights)
 // `bad_index` (may be null): set when a material index (every thread checks its primitive) or a light's colour index
 // (thread 0) is out of range - the kernels clamp such indices, surf_check_indices() reports them
-__device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* __restrict__ packed, int g, int* bad_index = nullptr) {
+__device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* __restrict__ packed, int g, int* bad_index = nullptr,
+                                          int tri_form = 0 /* 0: line form (shadow rays); 1: edge functions; 2: always pass */) {
     if (g >= sc.total) return;
     if (bad_index) {
         bool bad = false;
@@ -80,8 +81,12 @@ __device__ __forceinline__ void prep_body(const SceneView& sc, Vec3 o, float4* _
         prep_sphere(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], o, &r[0]);
     } else {
         const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
-        prep_triangle(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
-                      ld3(sv.normal + (size_t)i * sv.normal_stride), o, &r[0], &r[1], &r[2], &r[3]);
+        if (tri_form == 0)
+            prep_triangle_line(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                               ld3(sv.normal + (size_t)i * sv.normal_stride), o, &r[0], &r[1], &r[2], &r[3]);
+        else
+            prep_triangle(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                          ld3(sv.normal + (size_t)i * sv.normal_stride), o, &r[0], &r[1], &r[2], &r[3], tri_form == 1);
     }
     const int nf4 = rec_f4(sv.kind);
     float4* dst = packed + sv.rec_off + (size_t)i * nf4;

@@ -19,7 +19,9 @@ __global__ void k_setup_batch(CamArgs a, const __grid_constant__ BatchArgs ba, C
 
 __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ SceneView sc, CamState* __restrict__ cs,
                                               float4* __restrict__ packed) {
-    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), packed, blockIdx.x * blockDim.x + threadIdx.x, &cs->bad_index);
+    // camera rays: the edge-function triangle filter assumes hits at t >= 0, i.e. a non-negative near plane
+    prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), packed, blockIdx.x * blockDim.x + threadIdx.x, &cs->bad_index,
+              cs->near_clip >= 0.f ? 1 : 2);
 }
 
 __global__ void __launch_bounds__(256) k_prep_batch(const __grid_constant__ SceneView sc0, const __grid_constant__ BatchArgs ba,
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256) k_prep_batch(const __grid_constant__ Scen
     __syncthreads();
     CamState* cs = ws_at(cs0, ba, b);
     prep_body(sc, v3(cs->eye[0], cs->eye[1], cs->eye[2]), ws_at(packed0, ba, b), blockIdx.x * blockDim.x + threadIdx.x,
-              &cs->bad_index);
+              &cs->bad_index, cs->near_clip >= 0.f ? 1 : 2);
 }
 
 __device__ __forceinline__ void raygen_body(const CamState* __restrict__ cs, int pix0, int n, float* __restrict__ rays,

@@ -394,12 +394,10 @@ __device__ __forceinline__ void chunk_triangles(const IsectParams& prm, const Se
         bool any = false;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            Vec3 d = ray_of<P>(r, p);
-            float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
-            float t = A.w * rcp_approx(b);
-            float c0 = fmaf(t, fmaf(W0.z, d.z, fmaf(W0.y, d.y, W0.x * d.x)), W0.w);
-            float c1 = fmaf(t, fmaf(W1.z, d.z, fmaf(W1.y, d.y, W1.x * d.x)), W1.w);
-            float c2 = fmaf(t, fmaf(W2.z, d.z, fmaf(W2.y, d.y, W2.x * d.x)), W2.w);
+            Vec3 d = ray_of<P>(r, p);          // edge-function form (prep_triangle): three dot products
+            float c0 = fmaf(W0.z, d.z, fmaf(W0.y, d.y, fmaf(W0.x, d.x, W0.w)));
+            float c1 = fmaf(W1.z, d.z, fmaf(W1.y, d.y, fmaf(W1.x, d.x, W1.w)));
+            float c2 = fmaf(W2.z, d.z, fmaf(W2.y, d.y, fmaf(W2.x, d.x, W2.w)));
             any |= (c0 >= 0.f) & (c1 >= 0.f) & (c2 >= 0.f);
         }
         if (any) narrow<P>(prm, sv, local0 + i, A, eye, near_clip, far_clip, r);
@@ -415,21 +413,31 @@ __device__ __forceinline__ void chunk_triangles(const IsectParams& prm, const Se
 // the disk loop's schedule, -1.5 % on config E, so the single-scene splat kernel keeps the scalar version above.)
 // rare path of chunk_triangles_packed: re-evaluate the flagged triangle's filter per pixel pair and run the exact
 // test only on the pixels that pass (instead of on all P pixels of the thread)
-template <int P, class NarrowFn>
+// EDGE = true: records of prep_triangle (edge functions G_i . d + slack >= 0: 9 packed FMAs per triangle and pixel
+// pair, no reciprocal) - camera rays.  EDGE = false: records of prep_triangle_line (t (d.W_i) + w_i >= 0 with
+// t ~ numer rcp(n.d): 16 packed FMAs + 2 MUFU) - the shadow rays of a light, where t may have either sign.
+template <int P, bool EDGE, class NarrowFn>
 __device__ __forceinline__ void triangle_candidates(const float4* __restrict__ rec, int local, const PixelRegs<P>& r, NarrowFn&& nf) {
     const float4 A = rec[0], W0 = rec[1], W1 = rec[2], W2 = rec[3];
 #pragma unroll
     for (int q = 0; q < P / 2; ++q) {
-        const unsigned long long b2 = fma2(pack2(A.z, A.z), r.dz[q], fma2(pack2(A.y, A.y), r.dy[q], mul2(pack2(A.x, A.x), r.dx[q])));
-        float b0, b1;
-        unpack2(b2, b0, b1);
-        const unsigned long long t2 = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
+        unsigned long long t2 = 0;
+        if (!EDGE) {
+            const unsigned long long b2 = fma2(pack2(A.z, A.z), r.dz[q], fma2(pack2(A.y, A.y), r.dy[q], mul2(pack2(A.x, A.x), r.dx[q])));
+            float b0, b1;
+            unpack2(b2, b0, b1);
+            t2 = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
+        }
         float m0 = INFINITY, m1 = INFINITY;
 #define SURF_EDGE1(W)                                                                                                   \
         {                                                                                                               \
-            const unsigned long long u2 = fma2(pack2(W.z, W.z), r.dz[q], fma2(pack2(W.y, W.y), r.dy[q], mul2(pack2(W.x, W.x), r.dx[q]))); \
             float c0, c1;                                                                                               \
-            unpack2(fma2(t2, u2, pack2(W.w, W.w)), c0, c1);                                                             \
+            if (EDGE) {                                                                                                 \
+                unpack2(fma2(pack2(W.z, W.z), r.dz[q], fma2(pack2(W.y, W.y), r.dy[q], fma2(pack2(W.x, W.x), r.dx[q], pack2(W.w, W.w)))), c0, c1); \
+            } else {                                                                                                    \
+                const unsigned long long u2 = fma2(pack2(W.z, W.z), r.dz[q], fma2(pack2(W.y, W.y), r.dy[q], mul2(pack2(W.x, W.x), r.dx[q]))); \
+                unpack2(fma2(t2, u2, pack2(W.w, W.w)), c0, c1);                                                         \
+            }                                                                                                           \
             m0 = fminf(m0, c0); m1 = fminf(m1, c1);                                                                     \
         }
         SURF_EDGE1(W0)
@@ -441,7 +449,7 @@ __device__ __forceinline__ void triangle_candidates(const float4* __restrict__ r
     }
 }
 
-template <int P, class NarrowFn>
+template <int P, bool EDGE, class NarrowFn>
 __device__ __forceinline__ void chunk_triangles_packed(const float4* __restrict__ s, int local0, int count, PixelRegs<P>& r,
                                                        NarrowFn&& nf) {
     if (count <= 0) return;
@@ -451,28 +459,41 @@ __device__ __forceinline__ void chunk_triangles_packed(const float4* __restrict_
     for (int i = 0; i < count; ++i) {
         const int nxt = (i + 1 < count ? i + 1 : i) * 4;
         const float4 An = s[nxt], W0n = s[nxt + 1], W1n = s[nxt + 2], W2n = s[nxt + 3];
-        unsigned long long b2[Q], t2[Q], u2[Q], c0[Q], c1[Q], c2[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) b2[q] = mul2(pack2(A.x, A.x), r.dx[q]);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) b2[q] = fma2(pack2(A.y, A.y), r.dy[q], b2[q]);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) b2[q] = fma2(pack2(A.z, A.z), r.dz[q], b2[q]);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            float b0, b1;
-            unpack2(b2[q], b0, b1);
-            t2[q] = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
-        }
+        unsigned long long c0[Q], c1[Q], c2[Q];
+        if (EDGE) {
+            // stage-major over the Q pixel pairs: each warp-uniform record scalar feeds Q consecutive instructions
 #define SURF_EDGE(W, c)                                                                                  \
-        _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = mul2(pack2(W.x, W.x), r.dx[q]);            \
-        _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = fma2(pack2(W.y, W.y), r.dy[q], u2[q]);     \
-        _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = fma2(pack2(W.z, W.z), r.dz[q], u2[q]);     \
-        _Pragma("unroll") for (int q = 0; q < Q; ++q) c[q] = fma2(t2[q], u2[q], pack2(W.w, W.w));
-        SURF_EDGE(W0, c0)
-        SURF_EDGE(W1, c1)
-        SURF_EDGE(W2, c2)
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) c[q] = fma2(pack2(W.x, W.x), r.dx[q], pack2(W.w, W.w)); \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) c[q] = fma2(pack2(W.y, W.y), r.dy[q], c[q]);            \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) c[q] = fma2(pack2(W.z, W.z), r.dz[q], c[q]);
+            SURF_EDGE(W0, c0)
+            SURF_EDGE(W1, c1)
+            SURF_EDGE(W2, c2)
 #undef SURF_EDGE
+        } else {
+            unsigned long long b2[Q], t2[Q], u2[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) b2[q] = mul2(pack2(A.x, A.x), r.dx[q]);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) b2[q] = fma2(pack2(A.y, A.y), r.dy[q], b2[q]);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) b2[q] = fma2(pack2(A.z, A.z), r.dz[q], b2[q]);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                float b0, b1;
+                unpack2(b2[q], b0, b1);
+                t2[q] = mul2(pack2(A.w, A.w), pack2(rcp_approx(b0), rcp_approx(b1)));
+            }
+#define SURF_EDGE(W, c)                                                                                  \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = mul2(pack2(W.x, W.x), r.dx[q]);            \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = fma2(pack2(W.y, W.y), r.dy[q], u2[q]);     \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) u2[q] = fma2(pack2(W.z, W.z), r.dz[q], u2[q]);     \
+            _Pragma("unroll") for (int q = 0; q < Q; ++q) c[q] = fma2(t2[q], u2[q], pack2(W.w, W.w));
+            SURF_EDGE(W0, c0)
+            SURF_EDGE(W1, c1)
+            SURF_EDGE(W2, c2)
+#undef SURF_EDGE
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -482,11 +503,11 @@ __device__ __forceinline__ void chunk_triangles_packed(const float4* __restrict_
             unpack2(c2[q], e0, e1);
             mx = fmaxf(mx, fmaxf(fminf(a0, fminf(b0, e0)), fminf(a1, fminf(b1, e1))));   // NaN-ignoring: conservative
         }
-        if (mx_prev >= 0.f) triangle_candidates<P>(s + 4 * (i - 1), local0 + i - 1, r, nf);
+        if (mx_prev >= 0.f) triangle_candidates<P, EDGE>(s + 4 * (i - 1), local0 + i - 1, r, nf);
         mx_prev = mx;
         A = An; W0 = W0n; W1 = W1n; W2 = W2n;
     }
-    if (mx_prev >= 0.f) triangle_candidates<P>(s + 4 * (count - 1), local0 + count - 1, r, nf);
+    if (mx_prev >= 0.f) triangle_candidates<P, EDGE>(s + 4 * (count - 1), local0 + count - 1, r, nf);
 }
 
 // spheres / planes with a caller-supplied narrow phase (k_intersect_shadow); the filters are chunk_spheres' / none
@@ -765,7 +786,7 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         }
         else if (sv.kind == KIND_TRIANGLE) {
             if (MODE != 1)
-                chunk_triangles_packed<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
+                chunk_triangles_packed<P, true>(s, local0, count, r, [&](int local, const float4& A, int p) {
                     narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
                 });
             else chunk_triangles<P>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);

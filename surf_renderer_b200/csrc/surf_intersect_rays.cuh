@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
             if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
         };
         if (sv.kind == KIND_DISK) chunk_disks_dense<P>(s, local0, count, r, nf);
-        else if (sv.kind == KIND_TRIANGLE) chunk_triangles_packed<P>(s, local0, count, r, nf);
+        else if (sv.kind == KIND_TRIANGLE) chunk_triangles_packed<P, false>(s, local0, count, r, nf);
         else if (sv.kind == KIND_SPHERE) chunk_spheres_fn<P>(s, local0, count, r, nf);
         else chunk_planes_fn<P>(s, local0, count, nf);
     }

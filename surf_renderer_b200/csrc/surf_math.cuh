@@ -232,8 +232,9 @@ SURF_HD void prep_sphere(Vec3 c, float r, Vec3 o, F4* S) {
     if ((double)w > cc - slack) w = nextafterf(w, -INFINITY);
     *S = f4((float)ocx, (float)ocy, (float)ocz, w);
 }
-// TRIANGLE: A = (n, numer); W_i = (n x e_i, (o - v_i).(n x e_i) + slack).  Filter: t (d.W_i) + W_i.w >= 0
-SURF_HD void prep_triangle(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, Vec3 o, F4* A, F4* W0, F4* W1, F4* W2) {
+// TRIANGLE, line form (rays on lines through o, any sign of t - the shadow rays of a light):
+// A = (n, numer); W_i = (n x e_i, (o - v_i).(n x e_i) + slack).  Filter: t (d.W_i) + W_i.w >= 0, t ~ numer * rcp(n.d)
+SURF_HD void prep_triangle_line(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, Vec3 o, F4* A, F4* W0, F4* W1, F4* W2) {
     PlaneConst pc = plane_const(v0, nraw);
     *A = f4(pc.n.x, pc.n.y, pc.n.z, plane_numer(pc, o));
     const Vec3 vs[3] = {v0, v1, v2};
@@ -260,7 +261,50 @@ SURF_HD void prep_triangle(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, Vec3 o, F4* A, 
         *outs[i] = f4((float)wx, (float)wy, (float)wz, f_round_up(k + slack));
     }
 }
-
+// TRIANGLE, edge-function form (camera rays from the common origin o, hits at t >= 0).  With P = o + t d and
+// t = numer / (n.d), the edge function (P - v_i).(n x e_i) = k_i + t (d.W_i) times (n.d) is LINEAR in d:
+//   c_i (n.d) = (numer W_i + k_i n) . d,   and sign(n.d) = sign(numer) =: sg for every hit with t > 0,
+// so the inside test of edge i is ONE dot product, no division:  G_i . d + slack >= 0,  G_i = sg (numer W_i + k_i n).
+// Record: A = (n, numer) (exact narrow phase, shading), G_i = (G_i.xyz, slack_i).  3 x 3 FMAs per test instead of
+// 16 + a reciprocal.  `t_nonneg` false (a negative near plane admits hits behind the origin): always-pass records.
+SURF_HD void prep_triangle(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 nraw, Vec3 o, F4* A, F4* W0, F4* W1, F4* W2, bool t_nonneg = true) {
+    PlaneConst pc = plane_const(v0, nraw);
+    const float numer_f = plane_numer(pc, o);
+    *A = f4(pc.n.x, pc.n.y, pc.n.z, numer_f);
+    F4* outs[3] = {W0, W1, W2};
+    if (!t_nonneg) {
+        for (int i = 0; i < 3; ++i) *outs[i] = f4(0.f, 0.f, 0.f, 1.f);
+        return;
+    }
+    const Vec3 vs[3] = {v0, v1, v2};
+    double emax = 0.0, el[3];
+    double e[3][3];
+    for (int i = 0; i < 3; ++i) {
+        const Vec3& a = vs[i];
+        const Vec3& b = vs[(i + 1) % 3];
+        e[i][0] = (double)b.x - a.x; e[i][1] = (double)b.y - a.y; e[i][2] = (double)b.z - a.z;
+        el[i] = dlen(e[i][0], e[i][1], e[i][2]);
+        emax = el[i] > emax ? el[i] : emax;
+    }
+    const double nx = pc.n.x, ny = pc.n.y, nz = pc.n.z;
+    // numer in double from the same rounded normal (the fp32 numer of the exact path differs by rounding: covered by the slack)
+    const double numer = ((double)v0.x - o.x) * nx + ((double)v0.y - o.y) * ny + ((double)v0.z - o.z) * nz;
+    const double sg = numer > 0.0 ? 1.0 : (numer < 0.0 ? -1.0 : 0.0);
+    for (int i = 0; i < 3; ++i) {
+        const double wx = ny * e[i][2] - nz * e[i][1];
+        const double wy = nz * e[i][0] - nx * e[i][2];
+        const double wz = nx * e[i][1] - ny * e[i][0];
+        const Vec3& v = vs[i];
+        const double ovx = (double)o.x - v.x, ovy = (double)o.y - v.y, ovz = (double)o.z - v.z;
+        const double k = ovx * wx + ovy * wy + ovz * wz;
+        const double gx = sg * (numer * wx + k * nx), gy = sg * (numer * wy + k * ny), gz = sg * (numer * wz + k * nz);
+        const double scale = dlen(o.x, o.y, o.z) + dlen(v.x, v.y, v.z) + dlen(ovx, ovy, ovz) + emax;
+        // slack of the line form (in units of the edge function, |n.d| <= 1) + rounding of G and of the fp32 dot
+        // product + the fp32 rounding of the exact path's own plane constants relative to these double ones
+        const double slack = 4e-6 * el[i] * scale + 2e-6 * (fabs(numer) * el[i] + fabs(k)) + 1e-6 * dlen(gx, gy, gz) + 1e-30;
+        *outs[i] = f4((float)gx, (float)gy, (float)gz, f_round_up(slack));
+    }
+}
 // ---------------------------------------------------------------------------------------------------
 // level-1 screen-space record (perspective camera): a circle on the image plane z = -focal that contains the
 // projection of the primitive's bounding sphere.  Any exact hit point P of the primitive lies inside that
@@ -397,7 +441,15 @@ SURF_HD bool sphere_filter(const F4& S, Vec3 d) {
     float hb = fmaf(S.z, d.z, fmaf(S.y, d.y, S.x * d.x));
     return fmaf(hb, hb, -S.w) >= 0.f;
 }
-SURF_HD bool triangle_filter(const F4& A, const F4& W0, const F4& W1, const F4& W2, Vec3 d) {
+// edge-function form (prep_triangle): three dot products
+SURF_HD bool triangle_filter(const F4&, const F4& W0, const F4& W1, const F4& W2, Vec3 d) {
+    float c0 = fmaf(W0.z, d.z, fmaf(W0.y, d.y, fmaf(W0.x, d.x, W0.w)));
+    float c1 = fmaf(W1.z, d.z, fmaf(W1.y, d.y, fmaf(W1.x, d.x, W1.w)));
+    float c2 = fmaf(W2.z, d.z, fmaf(W2.y, d.y, fmaf(W2.x, d.x, W2.w)));
+    return (c0 >= 0.f) & (c1 >= 0.f) & (c2 >= 0.f);
+}
+// line form (prep_triangle_line)
+SURF_HD bool triangle_filter_line(const F4& A, const F4& W0, const F4& W1, const F4& W2, Vec3 d) {
     float b = fmaf(A.z, d.z, fmaf(A.y, d.y, A.x * d.x));
     float t = A.w * approx_rcp(b);
     float c0 = fmaf(t, fmaf(W0.z, d.z, fmaf(W0.y, d.y, W0.x * d.x)), W0.w);
