@@ -21,7 +21,8 @@ struct Packed {
     std::vector<F4> rec;
 };
 
-void pack_all(const SceneView& sc, Vec3 o, Packed* pk) {
+// line_form: the records of a light origin (shadow rays: t of either sign), like k_prep_lights; else the camera's
+void pack_all(const SceneView& sc, Vec3 o, Packed* pk, bool line_form = false, bool t_nonneg = true) {
     pk->rec.assign(packed_f4_total(sc), f4(0, 0, 0, 0));
     for (int s = 0; s < sc.n_sets; ++s) {
         const SetView& sv = sc.sets[s];
@@ -36,8 +37,12 @@ void pack_all(const SceneView& sc, Vec3 o, Packed* pk) {
                 prep_sphere(ld3(sv.pos + (size_t)i * sv.pos_stride), sv.radius[i], o, r);
             } else {
                 const float* f = sv.pos + (size_t)i * 3 * sv.pos_stride;
-                prep_triangle(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
-                              ld3(sv.normal + (size_t)i * sv.normal_stride), o, r, r + 1, r + 2, r + 3);
+                if (line_form)
+                    prep_triangle_line(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                                       ld3(sv.normal + (size_t)i * sv.normal_stride), o, r, r + 1, r + 2, r + 3);
+                else
+                    prep_triangle(ld3(f), ld3(f + sv.pos_stride), ld3(f + 2 * sv.pos_stride),
+                                  ld3(sv.normal + (size_t)i * sv.normal_stride), o, r, r + 1, r + 2, r + 3, t_nonneg);
             }
         }
     }
@@ -73,12 +78,12 @@ bool filter_pass_rays(const SetView& sv, const F4* r, Vec3 o, Vec3 d) {
     }
 }
 
-bool filter_pass(const SetView& sv, const F4* r, Vec3 d) {
+bool filter_pass(const SetView& sv, const F4* r, Vec3 d, bool line_form = false) {
     switch (sv.kind) {
         case KIND_DISK: return disk_filter(r[0], r[1], d);
         case KIND_PLANE: return true;
         case KIND_SPHERE: return sphere_filter(r[0], d);
-        default: return triangle_filter(r[0], r[1], r[2], r[3], d);
+        default: return line_form ? triangle_filter_line(r[0], r[1], r[2], r[3], d) : triangle_filter(r[0], r[1], r[2], r[3], d);
     }
 }
 
@@ -141,7 +146,7 @@ long long emul_forward(const SurfScene* scene, const SurfCamera* cam, const Surf
     ShadeFlags fl = {opt->double_sided, opt->use_quartic};
     Packed pk;
     const Vec3 eye = v3(cs.eye[0], cs.eye[1], cs.eye[2]);
-    if (cs.proj == 0) pack_all(sc, eye, &pk);
+    if (cs.proj == 0) pack_all(sc, eye, &pk, false, cs.near_clip >= 0.f);
     else {
         float ob = 0.f;
         for (int pix = p0; pix < p1; ++pix) {
@@ -303,7 +308,7 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
         }
         Packed pk, pkl;
         pack_all_rays(sc, ob, &pk);
-        pack_all(sc, ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), &pkl);
+        pack_all(sc, ld3(sc.light_pos + (size_t)l * sc.light_pos_stride), &pkl, true);
         for (int pix = 0; pix < N; ++pix) {
             if (keys[pix] == kMissKey) continue;
             for (int s = 0; s < sc.n_sets; ++s) {
@@ -316,7 +321,7 @@ long long emul_shadow_filter_misses(const SurfScene* scene, const SurfCamera* ca
                     // k_intersect_shadow's filter: the camera-style filters with the LIGHT as the common origin and -L as
                     // the ray direction (records as k_prep_lights prepares them)
                     if (hit && !filter_pass(sv, &pkl.rec[sv.rec_off + (size_t)i * rec_f4(sv.kind)],
-                                            v3(-dir[pix].x, -dir[pix].y, -dir[pix].z))) ++misses;
+                                            v3(-dir[pix].x, -dir[pix].y, -dir[pix].z), true)) ++misses;
                 }
             }
         }
