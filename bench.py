@@ -655,6 +655,27 @@ def run_config_d(args, rank, world, local_rank):
                     'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
                     'kernel_ms': k_mean[0], 'kernel_share_of_step': k_mean[0] / ms_per_step, 'step_minus_kernel_ms': ms_per_step - k_mean[0],
                     'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
+    # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
+    fast = None
+    if not args.no_fast:
+        plan_f = sdist.ShardedBatchStep(host, device=dev, group=(True if world > 1 else None), double_sided=True, _math_mode=3)
+        for _ in range(3):
+            plan_f.step(lambda image: (image * w).sum())
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_fast = max(3, min(args.steps, 10))
+        e0.record()
+        for i in range(n_fast):
+            flush.fill_(i & 0xff)
+            loss_f = plan_f.step(lambda image: (image * w).sum())
+        e1.record()
+        barrier()
+        ms_fast = e0.elapsed_time(e1) / n_fast
+        fast = {'math_mode': 3, 'ms_per_step': ms_fast, 'tests_per_s': tests_per_step / (ms_fast * 1e-3), 'loss': float(loss_f),
+                'note': 'k_intersect_screen per scene over the internal stream pool (no fused batch kernel for this mode); '
+                        'bit-identical outputs; per-rank time, not max over ranks'}
+        del plan_f
+
     # e2e: the same step with the per-step H2D of the batch inputs (pinned host) and the D2H read of the loss
     e2e = None
     if not args.no_e2e:
@@ -689,7 +710,8 @@ def run_config_d(args, rank, world, local_rank):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(config, graph=bool(args.graph)), 'batches_per_s': 1e3 / ms_per_step, 'loss': float(loss.detach()),
             'gpu_launches': int(plan.launches) * args.steps, 'gpu_launches_per_step': int(plan.launches),
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'wall_s_timed_region': wall}
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'fast_mode': fast,
+            'wall_s_timed_region': wall}
 
 
 def main():
