@@ -272,6 +272,11 @@ typedef struct SurfSplats {
                                  K x K sub-pixel rays; outputs are [(H K) (W K), ...].  0 or 1 = off */
     int32_t estimate_normals; /* 0 = `normal` is given; 1 = 3x3 constrained plane fit (utils.py:886-923, the GAN's
                                  normal_estimation_method='plane'); 2 = average neighbour cross product (utils.py:854-883) */
+    int32_t ndc_stride;       /* 0, or 3 | 4: `pos` holds NDC coordinates [count, ndc_stride] - render_splats_NDC
+                                 (renderer.py:358-474): unprojected with the inverse perspective of the camera's
+                                 fovy / near / far (ops.py:61-68), shaded with the UNNORMALISED view vector -pos like the
+                                 reference (:437) and with options.double_sided honoured; gradients go to
+                                 SurfSplatGrads.pos in the same layout */
     float* norm_depth;        /* optional [n] output: norm_depth_image_only (renderer.py:677-686): depth normalised to
                                  [0, 1] over the frame, fragments at or beyond the camera's far plane mapped to 0 */
 } SurfSplats;

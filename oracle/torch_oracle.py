@@ -445,8 +445,8 @@ def _shadow_visibility(light_pos, frag_p, winner, objects, params, n_pix):
 
 # --------------------------------------------------------------------------
 # render_splats_along_ray (renderer.py:537-751): one splat per pixel at depth z along the pixel's ray, shaded in
-# camera coordinates.  Restated for samples == 1 with caller-provided normals (the GAN generator path,
-# GAN/gan.py:563-597); normal estimation (utils.py:886-972) and supersampling are not restated.
+# camera coordinates (the GAN generator path, GAN/gan.py:563-597), with the 3x3-stencil normal estimation
+# (utils.py:772-923) and the K x K supersampling (renderer.py:603-673).
 # --------------------------------------------------------------------------
 def view_matrix(eye, at, up):
     """utils.py:376-382 ``lookat``: world -> camera, the inverse of camera_pose."""
@@ -586,3 +586,48 @@ def render_along_ray(scene, **params):
     im = torch.nn.functional.relu(torch.sum(per_light, dim=0).view(H, W, 3))
     return {'image': im, 'depth': depth, 'pos': pos_cc[..., :3].view(H, W, 3),
             'normal': normals_cc[..., :3].contiguous().view(H, W, 3)}
+
+
+# --------------------------------------------------------------------------
+# render_splats_NDC (renderer.py:358-474): one splat per pixel given in normalised device coordinates, unprojected
+# with the inverse right-handed [-1, 1] perspective matrix (ops.py:7-68) and shaded in camera coordinates with the
+# UNNORMALISED view vector -pos (renderer.py:437) - unlike render_along_ray, which normalises it.
+# --------------------------------------------------------------------------
+def unproject_matrix(fovy, aspect, near, far):
+    """ops.py:50-58 ``inv_perspective_RH_NO``."""
+    t = np.tan(fovy / 2.)
+    m00, m11 = 1 / (aspect * t), 1 / t
+    m22, m23 = (near + far) / (far - near), -2 * near * far / (far - near)
+    return _f32([[1 / m00, 0, 0, 0], [0, 1 / m11, 0, 0], [0, 0, 0, -1], [0, 0, 1 / m23, -m22 / m23]])
+
+
+def render_splats_ndc(scene, **params):
+    camera = scene['camera']
+    vp = np.array(camera['viewport'])
+    W, H = int(vp[2] - vp[0]), int(vp[3] - vp[1])
+    mcam = view_matrix(eye=camera['eye'][:3], at=camera['at'][:3], up=camera['up'][:3])
+    minv = unproject_matrix(camera['fovy'], W / H, camera['near'], camera['far'])
+    splats = scene['objects']['disk']
+    pos_ndc, normals = splats['pos'], splats['normal']
+    if pos_ndc.size()[-1] == 3:
+        pos_ndc = torch.cat((pos_ndc, _f32(np.ones((pos_ndc.size()[0], 1)))), dim=1)
+    pos_cc = torch.matmul(pos_ndc, minv.transpose(1, 0))
+    pos_cc = pos_cc / pos_cc[..., 3][:, None]
+    depth = lp_norm(pos_cc[..., :3]).view(H, W)
+    if params.get('norm_depth_image_only', False):                       # renderer.py:392-401
+        lo = torch.min(depth)
+        norm = blend(depth >= camera['far'], lo, depth)
+        norm = (norm - lo) / (torch.max(depth) - lo)
+        return {'image': norm, 'depth': depth, 'pos': pos_cc, 'normal': normals}
+    lights = scene['lights']
+    light_rgb = scene['colors'][lights['color_idx']]
+    light_cc = torch.mm(lights['pos'], mcam.transpose(1, 0))
+    frag_n, frag_p = normals[:, :3], pos_cc[:, :3]
+    albedo = torch.index_select(scene['materials']['albedo'], 0, splats['material_idx'])
+    coeffs = torch.index_select(scene['materials']['coeffs'], 0, splats['material_idx'])
+    per_light = phong(frag_normals=frag_n, to_light=light_cc[:, None, :3] - frag_p[:, :3], to_eye=-frag_p[:, :3],
+                      atten=lights['attenuation'], coeffs=coeffs, light_rgb=light_rgb, ambient=lights['ambient'],
+                      albedo=albedo, double_sided=params.get('double_sided', False),
+                      use_quartic=params.get('use_quartic', False), visibility=None)
+    im = torch.nn.functional.relu(torch.sum(per_light, dim=0).view(H, W, 3))
+    return {'image': im, 'depth': depth, 'pos': pos_cc[:, :3].view(H, W, 3), 'normal': normals[:, :3].view(H, W, 3)}

@@ -101,7 +101,7 @@ class SurfAdamTensors(C.Structure):
 class SurfSplats(C.Structure):
     _fields_ = [('count', C.c_int32), ('z', C.c_void_p), ('z_stride', C.c_int32), ('normal', C.c_void_p),
                 ('normal_stride', C.c_int32), ('material_idx', C.c_void_p), ('light_vis', C.c_void_p), ('pos', C.c_void_p),
-                ('samples', C.c_int32), ('estimate_normals', C.c_int32), ('norm_depth', C.c_void_p)]
+                ('samples', C.c_int32), ('estimate_normals', C.c_int32), ('ndc_stride', C.c_int32), ('norm_depth', C.c_void_p)]
 
 
 class SurfSplatBatch(C.Structure):

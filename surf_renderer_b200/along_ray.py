@@ -43,6 +43,8 @@ def _host_viewport(cam):
 class _SplatCall:
     """Flat inputs of one call (single frame: batch = None, or a batch of B frames)."""
 
+    ndc_stride = 0
+
     def __init__(self, scene, params, device, batch=None):
         cam = scene['camera']
         self.width, self.height = _host_viewport(cam)
@@ -191,7 +193,9 @@ class _AlongRayFn(torch.autograd.Function):
         sg.light_pos, sg.light_attenuation, sg.ambient = ptr(grads[2]), ptr(grads[3]), ptr(grads[4])
         sg.colors, sg.albedo, sg.coeffs = ptr(grads[5]), ptr(grads[6]), ptr(grads[7])
         spg = _abi.SurfSplatGrads()
-        if grads[0] is not None:
+        if grads[0] is not None and call.ndc_stride:
+            spg.pos = grads[0].data_ptr()
+        elif grads[0] is not None:
             spg.z = grads[0].data_ptr() + (8 if call.z_stride == 3 else 0)
         spg.normal = ptr(grads[1])
         ws = ctx.workspace
@@ -267,3 +271,64 @@ def render_splats_along_ray_batch(scene, **params):
         raise ValueError('disk.pos [N,3] is a single frame: use render_splats_along_ray')
     call = _SplatCall(scene, params, dev, batch=int(pos.shape[0]))
     return _result(call, *_AlongRayFn.apply(call, dict(params), *call.floats))
+
+
+class _NDCCall(_SplatCall):
+    """Flat inputs of render_splats_NDC: explicit fragment positions in normalised device coordinates."""
+
+    def __init__(self, scene, params, device):
+        cam = scene['camera']
+        self.width, self.height = _host_viewport(cam)
+        self.fovy, self.focal = _scalar(cam['fovy']), _scalar(cam.get('focal_length', 1.0))
+        self.near, self.far = _scalar(cam['near']), _scalar(cam['far'])
+        self.batch = None
+        disk, lights = scene['objects']['disk'], scene['lights']
+        pos = _as_float_tensor(disk['pos'], device)
+        if pos.dim() != 2 or pos.shape[1] not in (3, 4):
+            raise ValueError('render_splats_NDC: disk.pos must be [N,3] or [N,4] (normalised device coordinates)')
+        self.n_src = self.n_out = int(pos.shape[0])
+        if self.n_src != self.width * self.height:
+            raise RuntimeError('render_splats_NDC needs one splat per pixel: %d splats for %dx%d (renderer.py:389)'
+                               % (self.n_src, self.width, self.height))
+        self.ndc_stride = int(pos.shape[1])
+        self.z_stride, self.estimate, self.samples = 1, 0, 1
+        self.norm_depth = bool(get_param_value('norm_depth_image_only', params, False))
+        nrm = _as_float_tensor(disk['normal'], device)
+        lp = _as_float_tensor(lights['pos'], device)
+        if lp.shape[-1] != 4:
+            raise ValueError('lights.pos must be homogeneous [L,4] (it is multiplied by the 4x4 view matrix, renderer.py:424)')
+        self.n_lights = int(lp.shape[0])
+        self.names = ['objects/disk/pos', 'objects/disk/normal', 'lights/pos', 'lights/attenuation', 'lights/ambient',
+                      'colors', 'materials/albedo', 'materials/coeffs']
+        self.floats = [pos, nrm, lp, _as_float_tensor(lights['attenuation'], device), _as_float_tensor(lights['ambient'], device),
+                       _as_float_tensor(scene['colors'], device), _as_float_tensor(scene['materials']['albedo'], device),
+                       _as_float_tensor(scene['materials']['coeffs'], device)]
+        self.mat = _as_int_tensor(disk['material_idx'], device)
+        self.color_idx = _as_int_tensor(lights['color_idx'], device)
+        self.vis = None
+        self.eye_stride = 0
+        self.cam_vecs = {k: _as_float_tensor(cam[k], device).detach().reshape(-1)[:3].contiguous() for k in ('eye', 'at', 'up')}
+        self.out_h, self.out_w = self.height, self.width
+
+    def structs(self, fl, params, norm_depth_ptr=None):
+        sc, cam, sp, lay, opt = super().structs(fl, params, norm_depth_ptr)
+        sp.z, sp.z_stride = None, 1
+        sp.pos, sp.ndc_stride = fl[0].data_ptr(), self.ndc_stride
+        return sc, cam, sp, lay, opt
+
+
+def render_splats_NDC(scene, **params):
+    """Reference: diffrend/torch/renderer.py:358 ``render_splats_NDC(scene, **params)`` - one splat per pixel given in
+    the camera's normalised device coordinates (``disk.pos`` [N,3|4]), unprojected with the inverse perspective of
+    camera fovy / near / far (ops.py:50-68) and shaded in camera coordinates with the unnormalised view vector
+    (renderer.py:437); ``double_sided``, ``use_quartic`` and ``norm_depth_image_only`` honoured.  Runs in the kernels of
+    ``render_splats_along_ray`` (``SurfSplats.ndc_stride``); gradients reach pos, normals, lights and materials."""
+    dev = _resolve_device(scene)
+    call = _NDCCall(scene, params, dev)
+    image, depth, pos, normal, norm_depth = _AlongRayFn.apply(call, dict(params), *call.floats)
+    H, W = call.height, call.width
+    if call.norm_depth:
+        # renderer.py:392-401 returns the homogeneous [N,4] positions (w = 1 after the division) and the caller's normals
+        return {'image': norm_depth.view(H, W), 'depth': depth.view(H, W),
+                'pos': torch.cat((pos, torch.ones_like(pos[:, :1])), dim=1), 'normal': call.floats[1]}
+    return {'image': image.view(H, W, 3), 'depth': depth.view(H, W), 'pos': pos.view(H, W, 3), 'normal': normal.view(H, W, 3)}

@@ -115,8 +115,8 @@ __device__ __forceinline__ void backward_shading_fast(const SceneView& sc, const
                                                       const float g_image[3], const BwdAcc& acc, const SlotMap& sm, int lane,
                                                       Vec3* gP_io, Vec3* gn_io) {
     const MatF mt = load_material(sc, m);
-    float inv_len;
-    const Vec3 V = view_vector(eye, P, &inv_len);
+    float inv_len = 1.f;
+    const Vec3 V = fl.raw_view ? v3(eye.x - P.x, eye.y - P.y, eye.z - P.z) : view_vector(eye, P, &inv_len);
     const float Vn = f_dot(V, n);
     const float sg = fl.double_sided ? sign_or_zero(Vn) : 1.f;
     const float amb[3] = {sc.ambient[0], sc.ambient[1], sc.ambient[2]};
@@ -216,7 +216,8 @@ __device__ __forceinline__ void backward_shading_fast(const SceneView& sc, const
         }
         if (lane == 1) acc.add(sm.colors + crow * 3 + 2, tot2);
     }
-    if (active) {   // V = Vv / |Vv|
+    if (active && fl.raw_view) gP = v3(gP.x - gV.x, gP.y - gV.y, gP.z - gV.z);       // V = eye - P
+    else if (active) {   // V = Vv / |Vv|
         const float gv_dot = f_dot(gV, V);
         gP = v3(gP.x - (gV.x - gv_dot * V.x) * inv_len, gP.y - (gV.y - gv_dot * V.y) * inv_len,
                 gP.z - (gV.z - gv_dot * V.z) * inv_len);

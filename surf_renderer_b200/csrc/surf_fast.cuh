@@ -106,7 +106,7 @@ __device__ __forceinline__ float sign_or_zero(float dp) { return dp > 0.f ? 1.f 
 __device__ __forceinline__ void shade_fast(const SceneView& sc, const LightS* table, Vec3 eye, Vec3 P, Vec3 n, const MatF& mt,
                                            ShadeFlags fl, const float* __restrict__ vis, size_t vis_stride, float rgb[3]) {
     float inv_len;
-    const Vec3 V = view_vector(eye, P, &inv_len);
+    const Vec3 V = fl.raw_view ? v3(eye.x - P.x, eye.y - P.y, eye.z - P.z) : view_vector(eye, P, &inv_len);
     const float Vn = f_dot(V, n);
     const float sg = fl.double_sided ? sign_or_zero(Vn) : 1.f;
     float acc[3] = {0.f, 0.f, 0.f};

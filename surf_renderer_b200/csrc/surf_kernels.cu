@@ -311,7 +311,16 @@ static int splat_frame(int n_scenes, const SurfScene* scene, const SurfCamera* c
     p->W = camera->width; p->H = camera->height; p->K = K;
     p->n_src = n_in;
     p->n = sp->pos ? sp->count : n_src * K * K;
-    p->fl = ShadeFlags{0, opt->use_quartic};
+    p->fl = ShadeFlags{sp->ndc_stride ? opt->double_sided : 0, opt->use_quartic, sp->ndc_stride ? 1 : 0};
+    if (sp->ndc_stride) {
+        if (!sp->pos || (sp->ndc_stride != 3 && sp->ndc_stride != 4)) return fail(SURF_ERR_BAD_ARG, "NDC splats: pos [count, 3|4] required");
+        // inverse of the right-handed [-1, 1] perspective matrix (diffrend/torch/ops.py:19-68)
+        const double th = tan(camera->fovy / 2.0), aspect = (double)camera->width / (double)camera->height;
+        const double m22 = ((double)camera->near_clip + camera->far_clip) / ((double)camera->far_clip - camera->near_clip);
+        const double m23 = -2.0 * camera->near_clip * camera->far_clip / ((double)camera->far_clip - camera->near_clip);
+        p->ndc_stride = sp->ndc_stride;
+        p->ndc_a0 = (float)(aspect * th); p->ndc_a1 = (float)th; p->ndc_b = (float)(1.0 / m23); p->ndc_c = (float)(-m22 / m23);
+    }
     p->nest = ws->nest; p->gpos_src = ws->gpos_src; p->gn_src = ws->gn_src; p->minmax = ws->minmax;
     p->far_clip = camera->far_clip;
     p->sm = slot_map(sc.n_materials, sc.n_lights, sc.n_colors);

@@ -553,7 +553,8 @@ SURF_HD Fragment fragment_at(const SceneView& sc, int idx, Vec3 o, Vec3 d) {
 // shading (renderer.py:82-125).  Returns sum over lights of the per-light colour (ambient included per
 // light) before masking / relu / tonemap.
 // ---------------------------------------------------------------------------------------------------
-struct ShadeFlags { int double_sided, use_quartic; };
+struct ShadeFlags { int double_sided, use_quartic; int raw_view; };   // raw_view: the view vector is used unnormalised
+                                                                     // (render_splats_NDC passes cam_dir = -frag_pos, renderer.py:437)
 
 SURF_HD float pow_like_torch(float base, float e) { return powf(base, e); }
 

@@ -53,6 +53,8 @@ struct SplatParams {
     const int* mat;
     const float* vis;             // [L, n_src] or null
     const float* pos_in;          // [n, 3] explicit fragment positions (K = 1 only) or null
+    int ndc_stride;               // 3 | 4: pos_in holds NDC coordinates [n, ndc_stride] (render_splats_NDC); 0: camera space
+    float ndc_a0, ndc_a1, ndc_b, ndc_c;    // inverse perspective (ops.py:61-68): X = a0 x / w', Y = a1 y / w', Z = -w / w', w' = b z + c w
     int W, H, K;                  // source grid and samples per pixel edge; output grid is (H K) x (W K)
     int n_src, n;                 // W H source splats, n output fragments
     int estimate;                 // 0: `normal` is the caller's; 1 / 2: estimated (plane fit / average normal)
@@ -79,14 +81,14 @@ __device__ __forceinline__ void splat_scene(SplatParams& p, int b) {
     else p.normal = adv(p.normal, b * ba.normal);
     p.mat = adv(p.mat, b * ba.mat);
     p.vis = adv(p.vis, b * ba.vis);
-    p.pos_in = adv(p.pos_in, (long long)b * ba.out_stride * 3);
+    p.pos_in = adv(p.pos_in, (long long)b * ba.out_stride * (p.ndc_stride ? p.ndc_stride : 3));
     p.image = adv(p.image, (long long)b * ba.out_stride * 3); p.depth = adv(p.depth, (long long)b * ba.out_stride);
     p.normal_out = adv(p.normal_out, (long long)b * ba.out_stride * 3); p.pos = adv(p.pos, (long long)b * ba.out_stride * 3);
     p.norm_depth = adv(p.norm_depth, (long long)b * ba.out_stride);
     p.g_image = adv(p.g_image, (long long)b * ba.out_stride * 3); p.g_depth = adv(p.g_depth, (long long)b * ba.out_stride);
     p.g_normal = adv(p.g_normal, (long long)b * ba.out_stride * 3); p.g_pos = adv(p.g_pos, (long long)b * ba.out_stride * 3);
     p.gz = adv(p.gz, b * ba.z); p.gnormal = adv(p.gnormal, b * ba.normal);
-    p.gpos = adv(p.gpos, (long long)b * ba.out_stride * 3);
+    p.gpos = adv(p.gpos, (long long)b * ba.out_stride * (p.ndc_stride ? p.ndc_stride : 3));
     p.gp.light_pos = adv(p.gp.light_pos, b * ba.light_pos);
 }
 
@@ -282,14 +284,23 @@ __device__ __forceinline__ Fragment2 splat_fragment2(const SplatParams& p, const
     f.src = row * p.W + col;
     const float* np_ = p.normal + (size_t)f.src * p.normal_stride;
     f.n = v3(np_[0], np_[1], np_[2]);
-    if (p.pos_in) {
+    if (p.pos_in && p.ndc_stride) {
+        // renderer.py:384-387: pos_CC = Minv [x y z w]^T, divided by its w
+        const float* q = p.pos_in + (size_t)p.ndc_stride * k;
+        const float w = p.ndc_stride == 4 ? q[3] : 1.f;
+        const float iw = 1.f / fmaf(p.ndc_b, q[2], p.ndc_c * w);
+        f.P = v3(p.ndc_a0 * q[0] * iw, p.ndc_a1 * q[1] * iw, -w * iw);
+        f.P0 = f.P; f.x = f.y = 0.f;
+        f.inv_ray_len = iw;           // (reused as 1 / w' by the backward)
+    } else if (p.pos_in) {
         f.P = ld3(p.pos_in + 3 * (size_t)k);
         f.P0 = f.P; f.x = f.y = 0.f;
     } else {
         f.P0 = splat_position(p, cs, row, col, &f.x, &f.y);
         f.P = f.P0;
     }
-    f.inv_rn = 0.f; f.d = 0.f; f.inv_ray_len = 0.f; f.ray = v3(0.f, 0.f, 0.f);
+    f.inv_rn = 0.f; f.d = 0.f; f.ray = v3(0.f, 0.f, 0.f);
+    if (!(p.pos_in && p.ndc_stride)) f.inv_ray_len = 0.f;
     if (K > 1) {
         // sub-pixel ray through (x + deltax dx / 2, y + deltay dy / 2, -focal); deltax = linspace(-1, 1, K)[a] etc.
         const float h_img = 2.f * cs.sy, w_img = 2.f * cs.sx;
@@ -396,7 +407,23 @@ __global__ void __launch_bounds__(kBwdThreads) k_splat_backward(const __grid_con
             gn = f_axpy(g_rn, f.ray, gn);
             gP0 = v3(g_d * f.n.x, g_d * f.n.y, g_d * f.n.z);
         }
-        if (p.pos_in) {
+        if (p.pos_in && p.ndc_stride) {
+            if (p.gpos) {       // P = (a0 x, a1 y, -w) / w',  w' = b z + c w
+                const float* q = p.pos_in + (size_t)p.ndc_stride * k;
+                const float iw = f.inv_ray_len;
+                const float g_wp = -f_dot(gP0, f.P) * iw;
+                float* g = p.gpos + (size_t)p.ndc_stride * k;
+                g[0] += gP0.x * p.ndc_a0 * iw;
+                g[1] += gP0.y * p.ndc_a1 * iw;
+                g[2] += g_wp * p.ndc_b;
+                if (p.ndc_stride == 4) g[3] += -gP0.z * iw + g_wp * p.ndc_c;
+                (void)q;
+            }
+            if (p.gnormal) {
+                float* dst = p.gnormal + (size_t)f.src * p.normal_stride;
+                dst[0] += gn.x; dst[1] += gn.y; dst[2] += gn.z;
+            }
+        } else if (p.pos_in) {
             if (p.gpos) { p.gpos[3 * (size_t)k] += gP0.x; p.gpos[3 * (size_t)k + 1] += gP0.y; p.gpos[3 * (size_t)k + 2] += gP0.z; }
             if (p.gnormal) {
                 float* dst = p.gnormal + (size_t)f.src * p.normal_stride;

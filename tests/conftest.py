@@ -19,7 +19,7 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 def golden_cases():
     """fixtures of render() (make_golden.py)"""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith('.npz') and not f.startswith(('ar_', 'np_', 'b200_', 'pl_')))
+                  if f.endswith('.npz') and not f.startswith(('ar_', 'np_', 'b200_', 'pl_', 'ndc_')))
 
 
 def along_ray_cases():
@@ -30,3 +30,8 @@ def along_ray_cases():
 def numpy_twin_cases():
     """fixtures of the reference's numpy twin renderer (make_golden_numpy.py)"""
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('np_'))
+
+
+def ndc_cases():
+    """fixtures of render_splats_NDC() (make_golden_ndc.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('ndc_'))
