@@ -1,6 +1,6 @@
 """Build libsurf_b200.so (sm_100a) in-tree with nvcc.  `python -m surf_renderer_b200.build [--force] [-v]`.
 
-The library is four translation units (csrc/surf_launch.cuh lists them) compiled in parallel to objects under
+The library is five translation units (csrc/surf_launch.cuh lists them) compiled in parallel to objects under
 csrc/_obj/ and linked into one shared library; only the units whose sources changed are recompiled."""
 from __future__ import annotations
 
@@ -23,6 +23,7 @@ UNITS = {
                                  'surf_fast.cuh', 'surf_scatter.cuh'],
     'surf_isect_main.cu': ISECT,
     'surf_isect_batch.cu': ISECT,
+    'surf_isect_const.cu': ISECT,
     'surf_isect_rays.cu': ISECT + ['surf_intersect_rays.cuh'],
 }
 SOURCES = [os.path.join(CSRC, u) for u in UNITS]

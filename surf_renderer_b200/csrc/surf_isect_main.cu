@@ -58,7 +58,25 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
         }
     }
     IsectParams prm;
-    prm.sc = f.sc; prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
+    prm.sc = f.sc;
+    // Disk sets of large single frames go through k_intersect_const (records via the constant bank / uniform registers,
+    // surf_isect_const.cu); the staged kernel below then handles the scene's other sets.  math_mode 5 keeps the staged
+    // kernel for everything (A/B, and the cross-check of the GPU suite).
+    if (mode == 0 && !ba && (opt->pixels_per_thread == 0 || opt->pixels_per_thread == 8)) {
+        int kept = 0;
+        for (int k = 0; k < f.sc.n_sets; ++k) {
+            const SetView& sv = f.sc.sets[k];
+            if (sv.kind == KIND_DISK && sv.count >= 256 && const_path_fits(f, sv)) {
+                const int rc = run_intersect_const(f, sv, st);
+                if (rc) return rc;
+            } else prm.sc.sets[kept++] = sv;
+        }
+        if (kept == 0) return SURF_OK;
+        prm.sc.n_sets = kept;
+    }
+    if (mode == 5) mode = 0;
+    const SceneView& scv = prm.sc;
+    prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.n_pix = f.n;
     int P = opt->pixels_per_thread ? opt->pixels_per_thread : 8;
     if (P != 2 && P != 4 && P != 8) return fail(SURF_ERR_BAD_ARG, "pixels_per_thread must be 2, 4 or 8");
@@ -80,9 +98,9 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
         // (items are dealt as equal contiguous ranges: the slowest CTA runs ceil(items / grid) of them)
         auto items_for = [&](int ch) {
             long long items = 0;
-            for (int s = 0; s < f.sc.n_sets; ++s) {
-                const int ppc = (ch * 2) / rec_f4(f.sc.sets[s].kind);
-                items += (f.sc.sets[s].count + ppc - 1) / ppc;
+            for (int s = 0; s < scv.n_sets; ++s) {
+                const int ppc = (ch * 2) / rec_f4(scv.sets[s].kind);
+                items += (scv.sets[s].count + ppc - 1) / ppc;
             }
             return items * prm.n_tiles;
         };
@@ -101,9 +119,9 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     int nchunks = 0;
     for (int s = 0; s < kMaxSets; ++s) {
         prm.chunks_before[s] = nchunks;
-        if (s < f.sc.n_sets) {
-            const int ppc = prm.stage_f4 / rec_f4(f.sc.sets[s].kind);
-            nchunks += (f.sc.sets[s].count + ppc - 1) / ppc;
+        if (s < scv.n_sets) {
+            const int ppc = prm.stage_f4 / rec_f4(scv.sets[s].kind);
+            nchunks += (scv.sets[s].count + ppc - 1) / ppc;
         }
     }
     prm.chunks_before[kMaxSets] = nchunks;
@@ -111,7 +129,7 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     const long long items = (long long)prm.n_tiles * nchunks;
     const int grid = (int)std::min<long long>(items, grid_max);
     const size_t smem = (size_t)kStages * prm.stage_f4 * sizeof(float4);
-    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..4");
+    if (mode < 0 || mode > 2) return fail(SURF_ERR_BAD_ARG, "math_mode must be 0..5");
     if (ba) {
         // hybrid distribution: 3/4 of the items as contiguous static shares, the rest drawn dynamically in short runs
         // measured (B200): splat batches / dense splat frames are fastest with 12/16 static (config D 2.45 -> 2.28 ms,

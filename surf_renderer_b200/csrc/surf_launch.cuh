@@ -1,9 +1,11 @@
 // surf_launch.cuh - part of libsurf_b200.so (included by every translation unit inside namespace surf).
 // The per-call frame description and the host-side launch functions that cross translation units.  The library is
-// built from four translation units so that they compile in parallel and a change to the shading / backward code
+// built from five translation units so that they compile in parallel and a change to the shading / backward code
 // does not recompile the intersection templates:
 //   surf_kernels.cu      C ABI, frame / shade / backward / splat kernels, host orchestration
 //   surf_isect_main.cu   k_intersect<P, MODE> (single scene) + run_intersect (chunking, dispatch)
+//   surf_isect_const.cu  k_filter_const / k_narrow_queue / k_const_fallback (disk sets of large single frames: records
+//                        through the constant bank into uniform registers - config E's hot kernel)
 //   surf_isect_batch.cu  k_intersect_batch<P, MODE> (strided batches, dense frames, triangle scenes)
 //   surf_isect_rays.cu   k_intersect_screen, k_intersect_rays, k_intersect_generic, k_intersect_shadow + prep kernels
 #pragma once
@@ -30,6 +32,9 @@ struct Frame {           // everything derived from (scene, camera, options) onc
 
 // surf_isect_main.cu.  `ba` non-null: strided batch (perspective, plane-filter modes only)
 int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const BatchArgs* ba = nullptr);
+// surf_isect_const.cu: one disk set of a perspective frame, records streamed through the constant bank
+int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st);
+bool const_path_fits(const Frame& f, const SetView& sv);       // the workspace carries a candidate queue for this frame
 // surf_isect_rays.cu
 int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStream_t st);                 // math_mode 3
 int run_intersect_ortho(const Frame& f, const SurfOptions* opt, cudaStream_t st);                  // per-pixel origins

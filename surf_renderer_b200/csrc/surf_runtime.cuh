@@ -77,6 +77,12 @@ struct Workspace {
     float* obound;               // [1] max |origin| over the generic rays of the launch (as float bits, atomicMax)
     double* loss_acc;            // [1] loss of a fused inverse-rendering step (surf_step_mse)
     float* gimg;                 // [n, 3] d(loss)/d(image) of a fused step (carved for step calls only)
+    // candidate queue of the constant-bank intersection path (surf_isect_const.cu), frames above 256x256 pixels only:
+    uint2* cq;                   // [cq_capacity] (thread slot, record group) pairs that passed the conservative filter
+    int* cq_ctl;                 // [0] entries appended; 256 bytes, followed directly by
+    unsigned char* cq_flags;     // [launch][tile] overflow map, cq_flag_bytes
+    int cq_capacity;
+    size_t cq_flag_bytes;
     size_t bytes;
 };
 constexpr int kMaxAccSlots = 512;
@@ -114,6 +120,15 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->zbuf2 = (unsigned long long*)(p + off); off += align_up(n_rays * 8, 256);
     ws->gimg = (float*)(p + off);
     if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
+    ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
+    if (n_pix > 256 * 256 && !generic_rays) {
+        // 2 candidates per pixel (config E appends about 1.1 per pixel); one flag byte per (2042-disk launch, 2048-pixel tile)
+        ws->cq_capacity = 2 * n_pix;
+        ws->cq = (uint2*)(p + off); off += align_up((size_t)ws->cq_capacity * sizeof(uint2), 256);
+        ws->cq_ctl = (int*)(p + off); off += 256;
+        ws->cq_flag_bytes = align_up((size_t)(total_prims / 2042 + 1) * (size_t)(n_pix / 2048 + 1), 256);
+        ws->cq_flags = (unsigned char*)(p + off); off += ws->cq_flag_bytes;
+    }
     ws->bytes = off;
 }
 
