@@ -45,19 +45,23 @@ namespace surf {
 #include "surf_launch.cuh"
 #include "surf_intersect.cuh"
 
-constexpr int kConstRecs = 2042;                      // 32-byte disk records per launch: the 64 KB constant bank less three groups
-                                                      // that the filter loop may read (and ignore) behind a segment's last group
+constexpr int kBankGroups = 1024;                     // the 64 KB constant bank holds 1024 groups of two 32-byte disk records
+constexpr int kSlackGroups = 3;                       // the filter loop may read (and ignore) this many groups behind a segment's last
+// records per launch: the whole bank, or one half of it - then consecutive launches alternate between the halves and
+// between two streams, so that the copy into one half and the ramp of the next kernel overlap the kernel on the other
+constexpr int const_groups(int halves) { return kBankGroups / halves - kSlackGroups; }
 constexpr int kConstGrid = 3 * 160;                   // persistent grid: at most 3 CTAs per SM, 160 SMs
 constexpr int kConstP = 8;                            // pixels per thread
-__constant__ float4 c_recs[2 * (kConstRecs + 6)];
-// pads an odd record count: n = (0, 0, 1), numer = 0, o - c = 0, -(r + slack)^2 = +inf - the margin is +inf (or NaN) for every ray
-__device__ float4 g_pad_record[2] = {{0.f, 0.f, 1.f, 0.f}, {0.f, 0.f, 0.f, __builtin_huge_valf()}};
+__constant__ float4 c_recs[4 * kBankGroups];
+// records that never pass, to fill the last group of a launch.  Plane filter: n = (0, 0, 1), numer = 0, o - c = 0,
+// -(r + slack)^2 = +inf (the margin is +inf or NaN for every ray); then three sphere records: oc = 0, -(|oc|^2 - r^2) = -inf
+__device__ float4 g_pad_record[5] = {{0.f, 0.f, 1.f, 0.f}, {0.f, 0.f, 0.f, __builtin_huge_valf()}, {0.f, 0.f, 0.f, -__builtin_huge_valf()},
+                                     {0.f, 0.f, 0.f, -__builtin_huge_valf()}, {0.f, 0.f, 0.f, -__builtin_huge_valf()}};
 
 struct ConstParams {
     const float* rays;               // [3, n]
     int n_pix, n_tiles;
-    int group0, n_groups;            // the records of this launch: set-local index / 2 of c_recs[0]; pairs of records in the
-                                     // bank (an odd count is padded with a record that never passes)
+    int group0;                      // set-local group index of bank group 0 (the segments count bank groups)
     uint2* queue;                    // candidates: x = thread slot (tile * kThreads + tid), y = set-local group index
     int* ctl;                        // [0] entries appended (may exceed capacity), [1] flagged (launch, tile) pairs
     int capacity;
@@ -111,6 +115,44 @@ __device__ __forceinline__ float const_margin_min(const float4 A, const float4 B
     return m;
 }
 
+// FILTER 1 - bounding sphere of the disk (centre c, radius r): the ray passes within r of c iff (oc . d)^2 - (|oc|^2 - r^2) >= 0
+// for a unit d.  Four FMA-pipe lane-instructions per ray-disk test (3 for oc . d, 1 for the square-and-subtract) instead of
+// the plane filter's 10 + a reciprocal; what passes is re-filtered per pixel by the plane filter in k_narrow_queue before
+// the exact test.  S = (oc, -(|oc|^2 - (r + slack)^2)) comes from k_sphere_records, the slack covering every rounding of
+// this evaluation and of the reference-order hit test.  Running maximum over the thread's pixels (NaN-ignoring).
+template <int P>
+__device__ __forceinline__ float sphere_margin_max(const float4 S, const PixelRegs<P>& r, float m) {
+    constexpr int Q = P / 2;
+    const unsigned long long ox = pack2(S.x, S.x), oy = pack2(S.y, S.y), oz = pack2(S.z, S.z), nc = pack2(S.w, S.w);
+    unsigned long long s2[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s2[q] = mul2(ox, r.dx[q]);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s2[q] = fma2(oy, r.dy[q], s2[q]);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s2[q] = fma2(oz, r.dz[q], s2[q]);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s2[q] = fma2(s2[q], s2[q], nc);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        float e0, e1;
+        unpack2(s2[q], e0, e1);
+        m = fmaxf(m, fmaxf(e0, e1));
+    }
+    return m;
+}
+
+// one group of the bank = 64 bytes: two plane-filter records (FILTER 0) or four sphere records (FILTER 1).  Returns a value
+// that is <= 0 iff some (pixel, disk) pair of the group passed.
+template <int P, int FILTER>
+__device__ __forceinline__ float group_margin(const float4 a, const float4 b, const float4 c, const float4 d, const PixelRegs<P>& r) {
+    if (FILTER == 0) return const_margin_min<P>(c, d, r, const_margin_min<P>(a, b, r, INFINITY));
+    float m = sphere_margin_max<P>(a, r, -INFINITY);
+    m = sphere_margin_max<P>(b, r, m);
+    m = sphere_margin_max<P>(c, r, m);
+    return -sphere_margin_max<P>(d, r, m);
+}
+
 template <int P>
 __device__ __forceinline__ void load_tile_rays(const float* __restrict__ rays, int n_pix, int tile, int tid, PixelRegs<P>& r) {
     float d[3][P];
@@ -138,7 +180,7 @@ __device__ __forceinline__ void push_candidate(const ConstParams& prm, int tile,
     else prm.flags[tile] = 1;           // k_const_fallback redoes this tile against this launch's records
 }
 
-template <int P>
+template <int P, int FILTER>
 __global__ void __launch_bounds__(kThreads, 2) k_filter_const(const __grid_constant__ ConstParams prm) {
     const int tid = threadIdx.x;
     for (int sgi = 0; sgi < 3; ++sgi) {
@@ -146,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_filter_const(const __grid_const
         for (int tile = sg.x; tile < sg.y; ++tile) {
             PixelRegs<P> r;
             load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
-            // Groups of two disks, two groups per iteration with the records of the next group fetched (LDCU) while the
+            // Groups of two (plane filter) or four (sphere filter) disks, two groups per iteration with the records of the next group fetched (LDCU) while the
             // current one computes - the constant cache is cold at every launch.  The branch taken for group k tests a
             // filter minimum that finished long ago, so neither the FMNMX3 chain nor the branch resolution sits on the
             // critical path.  The host makes every segment an even number of groups and ends it one group past its last
@@ -156,12 +198,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_filter_const(const __grid_const
 #pragma unroll 1
             for (int k = sg.z; k < sg.w; k += 2) {
                 const float4 c0 = c_recs[4 * k + 4], d0 = c_recs[4 * k + 5], c1 = c_recs[4 * k + 6], d1 = c_recs[4 * k + 7];
-                float m = const_margin_min<P>(a0, b0, r, INFINITY);
-                m = const_margin_min<P>(a1, b1, r, m);
+                const float m = group_margin<P, FILTER>(a0, b0, a1, b1, r);
                 if (m_prev <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k - 1);
                 a0 = c_recs[4 * k + 8]; b0 = c_recs[4 * k + 9]; a1 = c_recs[4 * k + 10]; b1 = c_recs[4 * k + 11];
-                float m2 = const_margin_min<P>(c0, d0, r, INFINITY);
-                m2 = const_margin_min<P>(c1, d1, r, m2);
+                const float m2 = group_margin<P, FILTER>(c0, d0, c1, d1, r);
                 if (m <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k);
                 m_prev = m2;
             }
@@ -179,6 +219,8 @@ struct NarrowParams {
     const uint2* queue;
     const int* ctl;
     int capacity;
+    int group_size;                  // disks per queue entry: 2 (plane filter) or 4 (sphere filter)
+    const float4* spheres;           // sphere filter: the set's sphere records (the pairs that passed are found again first)
 };
 
 // one thread per candidate: per-pixel filter of the group's disks, exact narrow phase for the pairs that pass
@@ -194,8 +236,11 @@ __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ Na
         load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
 #pragma unroll
         for (int p = 0; p < P; ++p) { r.best_t[p] = INFINITY; r.best_i[p] = -1; }
-        const int first = (int)c.y * 2, last = min(first + 2, prm.sv.count);
+        const int first = (int)c.y * prm.group_size, last = min(first + prm.group_size, prm.sv.count);
         for (int i = first; i < last; ++i) {
+            if (prm.spheres) {
+                if (!(sphere_margin_max<P>(prm.spheres[i], r, -INFINITY) >= 0.f)) continue;
+            }
             const float4 A = prm.recs[2 * i], B = prm.recs[2 * i + 1];
 #pragma unroll
             for (int q = 0; q < P / 2; ++q) {
@@ -219,7 +264,7 @@ __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ Na
 struct FallbackParams {
     NarrowParams np;
     const unsigned char* flags;      // [n_launches][n_tiles]
-    int n_launches, n_tiles;
+    int n_launches, n_tiles, recs_per_launch;
 };
 template <int P>
 __global__ void __launch_bounds__(kThreads, 2) k_const_fallback(const __grid_constant__ FallbackParams fp) {
@@ -235,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_const_fallback(const __grid_con
         load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
 #pragma unroll
         for (int p = 0; p < P; ++p) { r.best_t[p] = INFINITY; r.best_i[p] = -1; }
-        const int local0 = launch * kConstRecs, count = min(kConstRecs, prm.sv.count - local0);
+        const int local0 = launch * fp.recs_per_launch, count = min(fp.recs_per_launch, prm.sv.count - local0);
         IsectParams unused;
         chunk_disks<P, 2>(unused, prm.sv, prm.recs + 2 * (size_t)local0, local0, count, eye, near_clip, far_clip, r);
 #pragma unroll
@@ -247,18 +292,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_const_fallback(const __grid_con
     }
 }
 
+// sphere-filter records of a disk set, S_i = (o - c_i, -(|o - c_i|^2 - rs^2) + slack) in global primitive order.  rs is the
+// plane filter's inflated radius (prep_disk: r + 2e-6 * scale bounds what the reference-order fp32 hit test can accept);
+// the distance from c to the ray's line is at most the in-plane distance the hit test measures, so a hit implies
+// |oc|^2 - (oc . d^)^2 <= rs^2.  slack = 16 u |oc|^2 (u = 2^-24) covers the fp32 evaluation: rounding of oc (<= 2 u |oc|^2 on the
+// square of the dot product), of the three-term dot product (<= 6 u |oc|^2), |d|^2 = 1 +- 4 u, and the final rounding up.
+__global__ void __launch_bounds__(256) k_sphere_records(SetView sv, const CamState* __restrict__ cam, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.count) return;
+    const float* c = sv.pos + (size_t)i * sv.pos_stride;
+    const double ox = cam->eye[0], oy = cam->eye[1], oz = cam->eye[2];
+    const double x = ox - (double)c[0], y = oy - (double)c[1], z = oz - (double)c[2], r = fabs((double)sv.radius[i]);
+    const double oc2 = x * x + y * y + z * z;
+    const double scale = sqrt(ox * ox + oy * oy + oz * oz) + sqrt((double)c[0] * c[0] + (double)c[1] * c[1] + (double)c[2] * c[2]) + sqrt(oc2) + r;
+    const double rs = r + 2e-6 * scale;
+    const double w = -(oc2 - rs * rs * (1.0 + 1e-6)) + 16.0 * 5.9604644775390625e-8 * oc2 + 1e-30;
+    out[sv.first + i] = make_float4((float)x, (float)y, (float)z, f_round_up(w));
+}
+
 // The constant bank is one per device: launches that use it are serialised across streams with an event (a stream
 // under graph capture skips that: the captured work is ordered inside its graph).
-struct ConstBankState { std::mutex mu; cudaEvent_t done[64] = {}; bool used[64] = {}; };
+struct ConstBankState {
+    std::mutex mu;
+    cudaEvent_t done[64] = {}, fork[64] = {}, join[64][3] = {};
+    cudaStream_t side[64][3] = {};
+    bool used[64] = {};
+};
 static ConstBankState g_bank;
 
 bool const_path_fits(const Frame& f, const SetView& sv) {
     const int n_tiles = (f.n + kThreads * kConstP - 1) / (kThreads * kConstP);
-    const long long n_launches = (sv.count + kConstRecs - 1) / kConstRecs;
+    const long long n_launches = (sv.count + 2 * const_groups(4) - 1) / (2 * const_groups(4));
     return f.ws.cq != nullptr && n_launches * n_tiles <= (long long)f.ws.cq_flag_bytes;
 }
 
-int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st) {
+int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStream_t st) {
     if (sv.kind != KIND_DISK) return fail(SURF_ERR_BAD_ARG, "the constant-bank kernel takes disk sets");
     constexpr int P = kConstP;
     if (!const_path_fits(f, sv)) return fail(SURF_ERR_WORKSPACE, "workspace holds no candidate queue for this frame");
@@ -266,7 +334,15 @@ int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st) {
     prm.rays = f.ws.rays; prm.n_pix = f.n;
     prm.n_tiles = (f.n + kThreads * P - 1) / (kThreads * P);
     prm.queue = f.ws.cq; prm.ctl = f.ws.cq_ctl; prm.capacity = f.ws.cq_capacity;
-    const int n_launches = (sv.count + kConstRecs - 1) / kConstRecs;
+    // small frames (row bands of a multi-GPU step): half-bank launches alternating between two streams hide the
+    // kernel -> copy -> kernel bubbles (about 8 us per launch, 8 % of a 1/8-frame launch); large frames: whole-bank launches
+    static const int halves_env = getenv("SURF_CONST_HALVES") ? atoi(getenv("SURF_CONST_HALVES")) : 0;      // tuning knob
+    const int halves = halves_env == 1 || halves_env == 2 || halves_env == 4 ? halves_env : 2;
+    // filter 0: 32-byte plane records, two per group; filter 1: 16-byte sphere records (computed here), four per group
+    const int group_size = filter == 1 ? 4 : 2;
+    const size_t rec_bytes = 64 / group_size;
+    const int per_launch = const_groups(halves) * group_size;
+    const int n_launches = (sv.count + per_launch - 1) / per_launch;
     int dev = 0;
     SURF_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(SURF_ERR_UNSUPPORTED, "device ordinal beyond 63");
@@ -274,11 +350,22 @@ int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st) {
     SURF_CUDA(cudaStreamIsCapturing(st, &cap));
     const bool ordered = cap == cudaStreamCaptureStatusNone;
     std::lock_guard<std::mutex> lock(g_bank.mu);
-    if (ordered) {
-        if (!g_bank.done[dev]) SURF_CUDA(cudaEventCreateWithFlags(&g_bank.done[dev], cudaEventDisableTiming));
-        if (g_bank.used[dev]) SURF_CUDA(cudaStreamWaitEvent(st, g_bank.done[dev], 0));
+    if (!g_bank.done[dev]) {
+        SURF_CUDA(cudaEventCreateWithFlags(&g_bank.done[dev], cudaEventDisableTiming));
+        SURF_CUDA(cudaEventCreateWithFlags(&g_bank.fork[dev], cudaEventDisableTiming));
+        for (int k = 0; k < 3; ++k) {
+            SURF_CUDA(cudaEventCreateWithFlags(&g_bank.join[dev][k], cudaEventDisableTiming));
+            SURF_CUDA(cudaStreamCreateWithFlags(&g_bank.side[dev][k], cudaStreamNonBlocking));
+        }
     }
+    if (ordered && g_bank.used[dev]) SURF_CUDA(cudaStreamWaitEvent(st, g_bank.done[dev], 0));
     const float4* recs = f.ws.packed + sv.rec_off;
+    const char* bank_src = (const char*)recs;
+    if (filter == 1) {
+        k_sphere_records<<<(sv.count + 255) / 256, 256, 0, st>>>(sv, f.ws.cam, f.ws.circ);
+        SURF_LAUNCHED("k_sphere_records");
+        bank_src = (const char*)(f.ws.circ + sv.first);
+    }
     void* pad = nullptr;
     SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_record));
     static const int per_sm = getenv("SURF_CONST_CTAS") ? atoi(getenv("SURF_CONST_CTAS")) : 2;      // tuning knob
@@ -286,15 +373,25 @@ int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st) {
     timer_mark(0, 0, st);
     // control words + the overflow map in one memset (adjacent in the workspace)
     SURF_CUDA(cudaMemsetAsync(f.ws.cq_ctl, 0, 256 + (size_t)n_launches * prm.n_tiles, st));
+    const int n_streams = std::min(halves, n_launches);
+    if (n_streams > 1) {
+        SURF_CUDA(cudaEventRecord(g_bank.fork[dev], st));
+        for (int k = 0; k + 1 < n_streams; ++k) SURF_CUDA(cudaStreamWaitEvent(g_bank.side[dev][k], g_bank.fork[dev], 0));
+    }
     for (int j = 0; j < n_launches; ++j) {
-        const int first = j * kConstRecs;
-        prm.group0 = first / 2;
-        const int count = std::min(kConstRecs, sv.count - first);
-        prm.n_groups = (count + 1) / 2;
+        const int first = j * per_launch;
+        const int count = std::min(per_launch, sv.count - first);
+        const int n_groups = (count + group_size - 1) / group_size;
+        const int part = j % halves;
+        const int bank0 = part * (kBankGroups / halves);                           // first bank group of this launch
+        cudaStream_t s = part == 0 || n_streams == 1 ? st : g_bank.side[dev][part - 1];
+        prm.group0 = first / group_size - bank0;
         prm.flags = f.ws.cq_flags + (size_t)j * prm.n_tiles;
-        SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, recs + 2 * (size_t)first, (size_t)count * 32, 0, cudaMemcpyDeviceToDevice, st));
-        if (count & 1) SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, pad, 32, (size_t)count * 32, cudaMemcpyDeviceToDevice, st));
-        const int n_groups = prm.n_groups;
+        SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, bank_src + (size_t)first * rec_bytes, (size_t)count * rec_bytes, (size_t)bank0 * 64,
+                                          cudaMemcpyDeviceToDevice, s));
+        if (count % group_size)      // fill the last group with records that never pass
+            SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, (const char*)pad + (filter == 1 ? 32 : 0), (size_t)(group_size - count % group_size) * rec_bytes,
+                                              (size_t)bank0 * 64 + (size_t)count * rec_bytes, cudaMemcpyDeviceToDevice, s));
         const long long units = (long long)prm.n_tiles * n_groups;
         const int grid = (int)std::min<long long>(units, grid_max);
         for (int b = 0; b < grid; ++b) {
@@ -302,25 +399,39 @@ int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st) {
             const int t0 = (int)(lo / n_groups), t1 = (int)((hi - 1) / n_groups);      // first and last tile touched
             const int g0 = (int)(lo - (long long)t0 * n_groups), g1 = (int)(hi - (long long)t1 * n_groups);
             int4* sg = prm.seg + 3 * b;
-            // group ranges end one past the last group and hold an even number of groups: see the loop of k_filter_const
-            auto seg = [](int ta, int tb, int ga, int gb) { return make_int4(ta, tb, ga, gb + 1 + ((gb + 1 - ga) & 1)); };
+            // group ranges count bank groups, end one past the last group and hold an even number of groups: see the
+            // loop of k_filter_const
+            auto seg = [bank0](int ta, int tb, int ga, int gb) { return make_int4(ta, tb, bank0 + ga, bank0 + gb + 1 + ((gb + 1 - ga) & 1)); };
             if (t0 == t1) { sg[0] = seg(t0, t0 + 1, g0, g1); sg[1] = sg[2] = make_int4(0, 0, 0, 0); }
             else { sg[0] = seg(t0, t0 + 1, g0, n_groups); sg[1] = seg(t0 + 1, t1, 0, n_groups); sg[2] = seg(t1, t1 + 1, 0, g1); }
         }
-        k_filter_const<P><<<grid, kThreads, 0, st>>>(prm);
+        if (filter == 1) k_filter_const<P, 1><<<grid, kThreads, 0, s>>>(prm);
+        else k_filter_const<P, 0><<<grid, kThreads, 0, s>>>(prm);
         SURF_LAUNCHED("k_filter_const");
+    }
+    for (int k = 0; k + 1 < n_streams; ++k) {
+        SURF_CUDA(cudaEventRecord(g_bank.join[dev][k], g_bank.side[dev][k]));
+        SURF_CUDA(cudaStreamWaitEvent(st, g_bank.join[dev][k], 0));
     }
     if (ordered) { SURF_CUDA(cudaEventRecord(g_bank.done[dev], st)); g_bank.used[dev] = true; }
     FallbackParams fp;
     NarrowParams& np = fp.np;
     np.sv = sv; np.cam = f.ws.cam; np.recs = recs; np.rays = f.ws.rays; np.zbuf = f.ws.zbuf; np.n_pix = f.n;
-    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = f.ws.cq_capacity;
-    fp.flags = f.ws.cq_flags; fp.n_launches = n_launches; fp.n_tiles = prm.n_tiles;
+    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = f.ws.cq_capacity; np.group_size = group_size; np.spheres = filter == 1 ? f.ws.circ + sv.first : nullptr;
+    fp.flags = f.ws.cq_flags; fp.n_launches = n_launches; fp.n_tiles = prm.n_tiles; fp.recs_per_launch = per_launch;
     k_narrow_queue<P><<<sm_count() * 8, 256, 0, st>>>(np);
     SURF_LAUNCHED("k_narrow_queue");
     k_const_fallback<P><<<sm_count() * 2, kThreads, 0, st>>>(fp);
     SURF_LAUNCHED("k_const_fallback");
     timer_mark(0, 1, st);
+    static const bool debug = getenv("SURF_CONST_DEBUG") != nullptr;        // prints the queue fill; synchronises
+    if (debug && ordered) {
+        int ctl[2] = {0, 0};
+        SURF_CUDA(cudaMemcpyAsync(ctl, f.ws.cq_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+        SURF_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[surf const] filter %d: %d pixels, %d disks, %d launches, %d candidates (capacity %d)\n", filter, f.n, sv.count,
+                n_launches, ctl[0], f.ws.cq_capacity);
+    }
     return SURF_OK;
 }
 

@@ -62,19 +62,19 @@ int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const
     // Disk sets of large single frames go through k_intersect_const (records via the constant bank / uniform registers,
     // surf_isect_const.cu); the staged kernel below then handles the scene's other sets.  math_mode 5 keeps the staged
     // kernel for everything (A/B, and the cross-check of the GPU suite).
-    if (mode == 0 && !ba && (opt->pixels_per_thread == 0 || opt->pixels_per_thread == 8)) {
+    if ((mode == 0 || mode == 6) && !ba && (opt->pixels_per_thread == 0 || opt->pixels_per_thread == 8)) {
         int kept = 0;
         for (int k = 0; k < f.sc.n_sets; ++k) {
             const SetView& sv = f.sc.sets[k];
             if (sv.kind == KIND_DISK && sv.count >= 256 && const_path_fits(f, sv)) {
-                const int rc = run_intersect_const(f, sv, st);
+                const int rc = run_intersect_const(f, sv, mode == 0 ? 1 : 0, st);
                 if (rc) return rc;
             } else prm.sc.sets[kept++] = sv;
         }
         if (kept == 0) return SURF_OK;
         prm.sc.n_sets = kept;
     }
-    if (mode == 5) mode = 0;
+    if (mode == 5 || mode == 6) mode = 0;
     const SceneView& scv = prm.sc;
     prm.cam = f.ws.cam; prm.packed = f.ws.packed; prm.rays = f.ws.rays; prm.zbuf = f.ws.zbuf;
     prm.n_pix = f.n;

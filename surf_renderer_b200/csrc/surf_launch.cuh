@@ -33,7 +33,7 @@ struct Frame {           // everything derived from (scene, camera, options) onc
 // surf_isect_main.cu.  `ba` non-null: strided batch (perspective, plane-filter modes only)
 int run_intersect(const Frame& f, const SurfOptions* opt, cudaStream_t st, const BatchArgs* ba = nullptr);
 // surf_isect_const.cu: one disk set of a perspective frame, records streamed through the constant bank
-int run_intersect_const(const Frame& f, const SetView& sv, cudaStream_t st);
+int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStream_t st);     // filter 0: plane, 1: sphere + plane
 bool const_path_fits(const Frame& f, const SetView& sv);       // the workspace carries a candidate queue for this frame
 // surf_isect_rays.cu
 int run_intersect_screen(const Frame& f, const SurfOptions* opt, cudaStream_t st);                 // math_mode 3

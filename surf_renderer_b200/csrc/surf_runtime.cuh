@@ -122,11 +122,11 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
     if (n_pix > 256 * 256 && !generic_rays) {
-        // 2 candidates per pixel (config E appends about 1.1 per pixel); one flag byte per (2042-disk launch, 2048-pixel tile)
-        ws->cq_capacity = 2 * n_pix;
+        // 10 candidates per pixel (config E appends 1.6 per pixel with the plane filter, 7.7 with the sphere filter); one flag byte per (launch of at least 506 disks, 2048-pixel tile)
+        ws->cq_capacity = 10 * n_pix;
         ws->cq = (uint2*)(p + off); off += align_up((size_t)ws->cq_capacity * sizeof(uint2), 256);
         ws->cq_ctl = (int*)(p + off); off += 256;
-        ws->cq_flag_bytes = align_up((size_t)(total_prims / 2042 + 1) * (size_t)(n_pix / 2048 + 1), 256);
+        ws->cq_flag_bytes = align_up((size_t)(total_prims / 506 + 1) * (size_t)(n_pix / 2048 + 1), 256);
         ws->cq_flags = (unsigned char*)(p + off); off += ws->cq_flag_bytes;
     }
     ws->bytes = off;

@@ -12,8 +12,11 @@ from surf_renderer_b200 import scenes as synth   # noqa: E402
 from surf_renderer_b200._lib import lib           # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'E'
-if which == 'E':
-    sc = scene_io.clone_scene(synth.config_e(), device='cuda')
+if which.startswith('E'):
+    scene = synth.config_e()
+    if len(which) > 1:        # E128: a 1024 x 128 frame, the size of one of eight row bands
+        scene['camera']['viewport'] = [0, 0, 1024, int(which[1:])]
+    sc = scene_io.clone_scene(scene, device='cuda')
 else:
     scene, _, _, _, _ = scene_io.load_case(os.path.join(ROOT, 'tests', 'golden', 'b_bunny_48.npz'))
     scene['camera']['viewport'] = [0, 0, 1024, 1024]
