@@ -45,18 +45,22 @@ namespace surf {
 #include "surf_launch.cuh"
 #include "surf_intersect.cuh"
 
-constexpr int kBankGroups = 1024;                     // the 64 KB constant bank holds 1024 groups of two 32-byte disk records
+// One group of the bank: FILTER 0 - two 32-byte plane-filter records (16 floats); FILTER 1 - four 12-byte sphere records
+// (12 floats).  The 64 KB bank holds 1024 / 1365 groups.
+constexpr int group_floats(int filter) { return filter == 1 ? 12 : 16; }
+constexpr int group_disks(int filter) { return filter == 1 ? 4 : 2; }
+constexpr int bank_groups(int filter) { return 16384 / group_floats(filter); }
 constexpr int kSlackGroups = 3;                       // the filter loop may read (and ignore) this many groups behind a segment's last
-// records per launch: the whole bank, or one half of it - then consecutive launches alternate between the halves and
+// groups per launch: the whole bank, or one half of it - then consecutive launches alternate between the halves and
 // between two streams, so that the copy into one half and the ramp of the next kernel overlap the kernel on the other
-constexpr int const_groups(int halves) { return kBankGroups / halves - kSlackGroups; }
+constexpr int const_groups(int filter, int halves) { return bank_groups(filter) / halves - kSlackGroups; }
 constexpr int kConstGrid = 3 * 160;                   // persistent grid: at most 3 CTAs per SM, 160 SMs
 constexpr int kConstP = 8;                            // pixels per thread
-__constant__ float4 c_recs[4 * kBankGroups];
+__constant__ float c_recs[16384];
 // records that never pass, to fill the last group of a launch.  Plane filter: n = (0, 0, 1), numer = 0, o - c = 0,
-// -(r + slack)^2 = +inf (the margin is +inf or NaN for every ray); then three sphere records: oc = 0, -(|oc|^2 - r^2) = -inf
-__device__ float4 g_pad_record[5] = {{0.f, 0.f, 1.f, 0.f}, {0.f, 0.f, 0.f, __builtin_huge_valf()}, {0.f, 0.f, 0.f, -__builtin_huge_valf()},
-                                     {0.f, 0.f, 0.f, -__builtin_huge_valf()}, {0.f, 0.f, 0.f, -__builtin_huge_valf()}};
+// -(r + slack)^2 = +inf (the margin is +inf or NaN for every ray); sphere filter: three times oc' = 0
+__device__ float g_pad_plane[8] = {0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, __builtin_huge_valf()};
+__device__ float g_pad_sphere[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
 struct ConstParams {
     const float* rays;               // [3, n]
@@ -115,15 +119,15 @@ __device__ __forceinline__ float const_margin_min(const float4 A, const float4 B
     return m;
 }
 
-// FILTER 1 - bounding sphere of the disk (centre c, radius r): the ray passes within r of c iff (oc . d)^2 - (|oc|^2 - r^2) >= 0
-// for a unit d.  Four FMA-pipe lane-instructions per ray-disk test (3 for oc . d, 1 for the square-and-subtract) instead of
-// the plane filter's 10 + a reciprocal; what passes is re-filtered per pixel by the plane filter in k_narrow_queue before
-// the exact test.  S = (oc, -(|oc|^2 - (r + slack)^2)) comes from k_sphere_records, the slack covering every rounding of
-// this evaluation and of the reference-order hit test.  Running maximum over the thread's pixels (NaN-ignoring).
+// FILTER 1 - bounding sphere of the disk (centre c, radius r): a unit ray d passes within r of c iff (oc . d)^2 >= |oc|^2 - r^2,
+// i.e. |oc' . d| >= 1 with oc' = oc / sqrt(|oc|^2 - r^2).  THREE FMA-pipe lane-instructions per ray-disk test (the dot product)
+// and half an FMNMX3 (running maximum of |oc' . d|, NaN-ignoring) instead of the plane filter's 10 + a reciprocal; what
+// passes is re-filtered per pixel by the plane filter in k_narrow_queue before the exact test.  oc' comes from
+// k_sphere_records, with the slack that covers every rounding of this evaluation and of the reference-order hit test.
 template <int P>
-__device__ __forceinline__ float sphere_margin_max(const float4 S, const PixelRegs<P>& r, float m) {
+__device__ __forceinline__ float sphere_margin_max(float sx, float sy, float sz, const PixelRegs<P>& r, float m) {
     constexpr int Q = P / 2;
-    const unsigned long long ox = pack2(S.x, S.x), oy = pack2(S.y, S.y), oz = pack2(S.z, S.z), nc = pack2(S.w, S.w);
+    const unsigned long long ox = pack2(sx, sx), oy = pack2(sy, sy), oz = pack2(sz, sz);
     unsigned long long s2[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) s2[q] = mul2(ox, r.dx[q]);
@@ -132,25 +136,26 @@ __device__ __forceinline__ float sphere_margin_max(const float4 S, const PixelRe
 #pragma unroll
     for (int q = 0; q < Q; ++q) s2[q] = fma2(oz, r.dz[q], s2[q]);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) s2[q] = fma2(s2[q], s2[q], nc);
-#pragma unroll
     for (int q = 0; q < Q; ++q) {
         float e0, e1;
         unpack2(s2[q], e0, e1);
-        m = fmaxf(m, fmaxf(e0, e1));
+        m = fmaxf(m, fmaxf(fabsf(e0), fabsf(e1)));
     }
     return m;
 }
 
-// one group of the bank = 64 bytes: two plane-filter records (FILTER 0) or four sphere records (FILTER 1).  Returns a value
-// that is <= 0 iff some (pixel, disk) pair of the group passed.
+// one group of the bank, g[0 .. group_floats).  Returns a value that is <= 0 iff some (pixel, disk) pair of the group passed.
 template <int P, int FILTER>
-__device__ __forceinline__ float group_margin(const float4 a, const float4 b, const float4 c, const float4 d, const PixelRegs<P>& r) {
-    if (FILTER == 0) return const_margin_min<P>(c, d, r, const_margin_min<P>(a, b, r, INFINITY));
-    float m = sphere_margin_max<P>(a, r, -INFINITY);
-    m = sphere_margin_max<P>(b, r, m);
-    m = sphere_margin_max<P>(c, r, m);
-    return -sphere_margin_max<P>(d, r, m);
+__device__ __forceinline__ float group_margin(const float* g, const PixelRegs<P>& r) {
+    if (FILTER == 0) {
+        const float m = const_margin_min<P>(make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]), r, INFINITY);
+        return const_margin_min<P>(make_float4(g[8], g[9], g[10], g[11]), make_float4(g[12], g[13], g[14], g[15]), r, m);
+    }
+    float m = sphere_margin_max<P>(g[0], g[1], g[2], r, 0.f);
+    m = sphere_margin_max<P>(g[3], g[4], g[5], r, m);
+    m = sphere_margin_max<P>(g[6], g[7], g[8], r, m);
+    m = sphere_margin_max<P>(g[9], g[10], g[11], r, m);
+    return 1.f - m;
 }
 
 template <int P>
@@ -193,15 +198,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_filter_const(const __grid_const
             // filter minimum that finished long ago, so neither the FMNMX3 chain nor the branch resolution sits on the
             // critical path.  The host makes every segment an even number of groups and ends it one group past its last
             // (that group's minimum is never tested): code behind the loop costs the uniform registers, too.
+            constexpr int GF = group_floats(FILTER);
             float m_prev = INFINITY;
-            float4 a0 = c_recs[4 * sg.z], b0 = c_recs[4 * sg.z + 1], a1 = c_recs[4 * sg.z + 2], b1 = c_recs[4 * sg.z + 3];
+            float ga[GF], gc[GF];
+#pragma unroll
+            for (int j = 0; j < GF; ++j) ga[j] = c_recs[GF * sg.z + j];
 #pragma unroll 1
             for (int k = sg.z; k < sg.w; k += 2) {
-                const float4 c0 = c_recs[4 * k + 4], d0 = c_recs[4 * k + 5], c1 = c_recs[4 * k + 6], d1 = c_recs[4 * k + 7];
-                const float m = group_margin<P, FILTER>(a0, b0, a1, b1, r);
+#pragma unroll
+                for (int j = 0; j < GF; ++j) gc[j] = c_recs[GF * (k + 1) + j];
+                const float m = group_margin<P, FILTER>(ga, r);
                 if (m_prev <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k - 1);
-                a0 = c_recs[4 * k + 8]; b0 = c_recs[4 * k + 9]; a1 = c_recs[4 * k + 10]; b1 = c_recs[4 * k + 11];
-                const float m2 = group_margin<P, FILTER>(c0, d0, c1, d1, r);
+#pragma unroll
+                for (int j = 0; j < GF; ++j) ga[j] = c_recs[GF * (k + 2) + j];
+                const float m2 = group_margin<P, FILTER>(gc, r);
                 if (m <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k);
                 m_prev = m2;
             }
@@ -220,7 +230,7 @@ struct NarrowParams {
     const int* ctl;
     int capacity;
     int group_size;                  // disks per queue entry: 2 (plane filter) or 4 (sphere filter)
-    const float4* spheres;           // sphere filter: the set's sphere records (the pairs that passed are found again first)
+    const float* spheres;            // sphere filter: the set's sphere records [count, 3] (the pairs that passed are found again first)
 };
 
 // one thread per candidate: per-pixel filter of the group's disks, exact narrow phase for the pairs that pass
@@ -239,7 +249,8 @@ __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ Na
         const int first = (int)c.y * prm.group_size, last = min(first + prm.group_size, prm.sv.count);
         for (int i = first; i < last; ++i) {
             if (prm.spheres) {
-                if (!(sphere_margin_max<P>(prm.spheres[i], r, -INFINITY) >= 0.f)) continue;
+                const float* sp = prm.spheres + 3 * (size_t)i;
+                if (!(sphere_margin_max<P>(sp[0], sp[1], sp[2], r, 0.f) >= 1.f)) continue;
             }
             const float4 A = prm.recs[2 * i], B = prm.recs[2 * i + 1];
 #pragma unroll
@@ -292,12 +303,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_const_fallback(const __grid_con
     }
 }
 
-// sphere-filter records of a disk set, S_i = (o - c_i, -(|o - c_i|^2 - rs^2) + slack) in global primitive order.  rs is the
-// plane filter's inflated radius (prep_disk: r + 2e-6 * scale bounds what the reference-order fp32 hit test can accept);
-// the distance from c to the ray's line is at most the in-plane distance the hit test measures, so a hit implies
-// |oc|^2 - (oc . d^)^2 <= rs^2.  slack = 16 u |oc|^2 (u = 2^-24) covers the fp32 evaluation: rounding of oc (<= 2 u |oc|^2 on the
-// square of the dot product), of the three-term dot product (<= 6 u |oc|^2), |d|^2 = 1 +- 4 u, and the final rounding up.
-__global__ void __launch_bounds__(256) k_sphere_records(SetView sv, const CamState* __restrict__ cam, float4* __restrict__ out) {
+// sphere-filter records of a disk set: oc'_i = (o - c_i) / sqrt(|o - c_i|^2 - rs^2 - slack), three floats per disk.  rs is the
+// plane filter's inflated radius (prep_disk: r + 2e-6 * scale bounds what the reference-order fp32 hit test can accept); the
+// distance from c to the ray's line is at most the in-plane distance the hit test measures, so a hit implies
+// |oc|^2 - (oc . d^)^2 <= rs^2.  slack = 16 u |oc|^2 (u = 2^-24) covers the fp32 evaluation of |oc' . d| >= 1: rounding of oc'
+// (<= 2 u relative on the square), of the three-term dot product (<= 6 u), |d|^2 = 1 +- 4 u, with a margin.  A disk whose
+// inflated sphere holds the eye (nothing to divide by) gets a record that never passes and goes on the `inside` list, which
+// k_inside_disks tests against every pixel.
+__global__ void __launch_bounds__(256) k_sphere_records(SetView sv, const CamState* __restrict__ cam, float* __restrict__ out,
+                                                        int* __restrict__ n_inside, int* __restrict__ inside) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sv.count) return;
     const float* c = sv.pos + (size_t)i * sv.pos_stride;
@@ -306,8 +320,59 @@ __global__ void __launch_bounds__(256) k_sphere_records(SetView sv, const CamSta
     const double oc2 = x * x + y * y + z * z;
     const double scale = sqrt(ox * ox + oy * oy + oz * oz) + sqrt((double)c[0] * c[0] + (double)c[1] * c[1] + (double)c[2] * c[2]) + sqrt(oc2) + r;
     const double rs = r + 2e-6 * scale;
-    const double w = -(oc2 - rs * rs * (1.0 + 1e-6)) + 16.0 * 5.9604644775390625e-8 * oc2 + 1e-30;
-    out[sv.first + i] = make_float4((float)x, (float)y, (float)z, f_round_up(w));
+    const double den = oc2 - rs * rs * (1.0 + 1e-6) - 16.0 * 5.9604644775390625e-8 * oc2;
+    float* o = out + 3 * (size_t)i;
+    if (!(den > 1e-30 * oc2) || !(den > 0.0)) {          // also NaN / infinite inputs
+        o[0] = o[1] = o[2] = 0.f;
+        inside[atomicAdd(n_inside, 1)] = i;
+        return;
+    }
+    const double inv = 1.0 / sqrt(den);
+    o[0] = (float)(x * inv); o[1] = (float)(y * inv); o[2] = (float)(z * inv);
+}
+
+// disks on the `inside` list (the eye sits inside their bounding sphere) against every pixel: plane filter + exact test
+struct InsideParams {
+    SetView sv;
+    const CamState* cam;
+    const float4* recs;
+    const float* rays;
+    unsigned long long* zbuf;
+    int n_pix, n_tiles;
+    const int* n_inside;
+    const int* inside;
+};
+template <int P>
+__global__ void __launch_bounds__(kThreads, 2) k_inside_disks(const __grid_constant__ InsideParams prm) {
+    const int n = *prm.n_inside;
+    if (n == 0) return;
+    const Vec3 eye = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
+    const float near_clip = prm.cam->near_clip, far_clip = prm.cam->far_clip;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+        PixelRegs<P> r;
+        load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
+#pragma unroll
+        for (int p = 0; p < P; ++p) { r.best_t[p] = INFINITY; r.best_i[p] = -1; }
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const int i = prm.inside[j];
+            const float4 A = prm.recs[2 * i], B = prm.recs[2 * i + 1];
+#pragma unroll
+            for (int q = 0; q < P / 2; ++q) {
+                float e0, e1;
+                unpack2(disk_margin2<P>(A, B, r, q), e0, e1);
+                if (e0 <= 0.f) narrow_one<P>(prm.sv, i, A, eye, near_clip, far_clip, r, 2 * q);
+                if (e1 <= 0.f) narrow_one<P>(prm.sv, i, A, eye, near_clip, far_clip, r, 2 * q + 1);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int pix = tile * (kThreads * P) + p * kThreads + tid;
+            if (r.best_i[p] >= 0 && pix < prm.n_pix)
+                atomicMin(prm.zbuf + pix, ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
+        }
+    }
 }
 
 // The constant bank is one per device: launches that use it are serialised across streams with an event (a stream
@@ -322,8 +387,8 @@ static ConstBankState g_bank;
 
 bool const_path_fits(const Frame& f, const SetView& sv) {
     const int n_tiles = (f.n + kThreads * kConstP - 1) / (kThreads * kConstP);
-    const long long n_launches = (sv.count + 2 * const_groups(4) - 1) / (2 * const_groups(4));
-    return f.ws.cq != nullptr && n_launches * n_tiles <= (long long)f.ws.cq_flag_bytes;
+    const long long n_launches = (sv.count + 2 * const_groups(0, 4) - 1) / (2 * const_groups(0, 4));
+    return f.ws.cq != nullptr && f.ws.cq_inside != nullptr && n_launches * n_tiles <= (long long)f.ws.cq_flag_bytes;
 }
 
 int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStream_t st) {
@@ -338,10 +403,10 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     // kernel -> copy -> kernel bubbles (about 8 us per launch, 8 % of a 1/8-frame launch); large frames: whole-bank launches
     static const int halves_env = getenv("SURF_CONST_HALVES") ? atoi(getenv("SURF_CONST_HALVES")) : 0;      // tuning knob
     const int halves = halves_env == 1 || halves_env == 2 || halves_env == 4 ? halves_env : 2;
-    // filter 0: 32-byte plane records, two per group; filter 1: 16-byte sphere records (computed here), four per group
-    const int group_size = filter == 1 ? 4 : 2;
-    const size_t rec_bytes = 64 / group_size;
-    const int per_launch = const_groups(halves) * group_size;
+    // filter 0: 32-byte plane records, two per group; filter 1: 12-byte sphere records (computed here), four per group
+    const int group_size = group_disks(filter);
+    const size_t rec_bytes = filter == 1 ? 12 : 32, group_bytes = rec_bytes * group_size;
+    const int per_launch = const_groups(filter, halves) * group_size;
     const int n_launches = (sv.count + per_launch - 1) / per_launch;
     int dev = 0;
     SURF_CUDA(cudaGetDevice(&dev));
@@ -362,17 +427,21 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     const float4* recs = f.ws.packed + sv.rec_off;
     const char* bank_src = (const char*)recs;
     if (filter == 1) {
-        k_sphere_records<<<(sv.count + 255) / 256, 256, 0, st>>>(sv, f.ws.cam, f.ws.circ);
-        SURF_LAUNCHED("k_sphere_records");
-        bank_src = (const char*)(f.ws.circ + sv.first);
+        bank_src = (const char*)((float*)f.ws.circ + 3 * (size_t)sv.first);
     }
     void* pad = nullptr;
-    SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_record));
+    if (filter == 1) SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_sphere));
+    else SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_plane));
     static const int per_sm = getenv("SURF_CONST_CTAS") ? atoi(getenv("SURF_CONST_CTAS")) : 2;      // tuning knob
     const int grid_max = std::min(sm_count() * per_sm, kConstGrid);
     timer_mark(0, 0, st);
     // control words + the overflow map in one memset (adjacent in the workspace)
     SURF_CUDA(cudaMemsetAsync(f.ws.cq_ctl, 0, 256 + (size_t)n_launches * prm.n_tiles, st));
+    if (filter == 1) {
+        k_sphere_records<<<(sv.count + 255) / 256, 256, 0, st>>>(sv, f.ws.cam, (float*)f.ws.circ + 3 * (size_t)sv.first, f.ws.cq_ctl + 2,
+                                                                  f.ws.cq_inside);
+        SURF_LAUNCHED("k_sphere_records");
+    }
     const int n_streams = std::min(halves, n_launches);
     if (n_streams > 1) {
         SURF_CUDA(cudaEventRecord(g_bank.fork[dev], st));
@@ -383,15 +452,15 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
         const int count = std::min(per_launch, sv.count - first);
         const int n_groups = (count + group_size - 1) / group_size;
         const int part = j % halves;
-        const int bank0 = part * (kBankGroups / halves);                           // first bank group of this launch
+        const int bank0 = part * (bank_groups(filter) / halves);                   // first bank group of this launch
         cudaStream_t s = part == 0 || n_streams == 1 ? st : g_bank.side[dev][part - 1];
         prm.group0 = first / group_size - bank0;
         prm.flags = f.ws.cq_flags + (size_t)j * prm.n_tiles;
-        SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, bank_src + (size_t)first * rec_bytes, (size_t)count * rec_bytes, (size_t)bank0 * 64,
+        SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, bank_src + (size_t)first * rec_bytes, (size_t)count * rec_bytes, (size_t)bank0 * group_bytes,
                                           cudaMemcpyDeviceToDevice, s));
         if (count % group_size)      // fill the last group with records that never pass
-            SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, (const char*)pad + (filter == 1 ? 32 : 0), (size_t)(group_size - count % group_size) * rec_bytes,
-                                              (size_t)bank0 * 64 + (size_t)count * rec_bytes, cudaMemcpyDeviceToDevice, s));
+            SURF_CUDA(cudaMemcpyToSymbolAsync(c_recs, pad, (size_t)(group_size - count % group_size) * rec_bytes,
+                                              (size_t)bank0 * group_bytes + (size_t)count * rec_bytes, cudaMemcpyDeviceToDevice, s));
         const long long units = (long long)prm.n_tiles * n_groups;
         const int grid = (int)std::min<long long>(units, grid_max);
         for (int b = 0; b < grid; ++b) {
@@ -417,12 +486,19 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     FallbackParams fp;
     NarrowParams& np = fp.np;
     np.sv = sv; np.cam = f.ws.cam; np.recs = recs; np.rays = f.ws.rays; np.zbuf = f.ws.zbuf; np.n_pix = f.n;
-    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = f.ws.cq_capacity; np.group_size = group_size; np.spheres = filter == 1 ? f.ws.circ + sv.first : nullptr;
+    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = f.ws.cq_capacity; np.group_size = group_size; np.spheres = filter == 1 ? (const float*)f.ws.circ + 3 * (size_t)sv.first : nullptr;
     fp.flags = f.ws.cq_flags; fp.n_launches = n_launches; fp.n_tiles = prm.n_tiles; fp.recs_per_launch = per_launch;
     k_narrow_queue<P><<<sm_count() * 8, 256, 0, st>>>(np);
     SURF_LAUNCHED("k_narrow_queue");
     k_const_fallback<P><<<sm_count() * 2, kThreads, 0, st>>>(fp);
     SURF_LAUNCHED("k_const_fallback");
+    if (filter == 1) {
+        InsideParams ip;
+        ip.sv = sv; ip.cam = f.ws.cam; ip.recs = recs; ip.rays = f.ws.rays; ip.zbuf = f.ws.zbuf; ip.n_pix = f.n; ip.n_tiles = prm.n_tiles;
+        ip.n_inside = f.ws.cq_ctl + 2; ip.inside = f.ws.cq_inside;
+        k_inside_disks<P><<<std::min(prm.n_tiles, sm_count() * 2), kThreads, 0, st>>>(ip);
+        SURF_LAUNCHED("k_inside_disks");
+    }
     timer_mark(0, 1, st);
     static const bool debug = getenv("SURF_CONST_DEBUG") != nullptr;        // prints the queue fill; synchronises
     if (debug && ordered) {

@@ -81,6 +81,7 @@ struct Workspace {
     uint2* cq;                   // [cq_capacity] (thread slot, record group) pairs that passed the conservative filter
     int* cq_ctl;                 // [0] entries appended; 256 bytes, followed directly by
     unsigned char* cq_flags;     // [launch][tile] overflow map, cq_flag_bytes
+    int* cq_inside;              // [total_prims] disks whose bounding sphere holds the eye (count in cq_ctl[2])
     int cq_capacity;
     size_t cq_flag_bytes;
     size_t bytes;
@@ -120,7 +121,7 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->zbuf2 = (unsigned long long*)(p + off); off += align_up(n_rays * 8, 256);
     ws->gimg = (float*)(p + off);
     if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
-    ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
+    ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_inside = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
     if (n_pix > 256 * 256 && !generic_rays) {
         // 10 candidates per pixel (config E appends 1.6 per pixel with the plane filter, 7.7 with the sphere filter); one flag byte per (launch of at least 506 disks, 2048-pixel tile)
         ws->cq_capacity = 10 * n_pix;
@@ -128,6 +129,7 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
         ws->cq_ctl = (int*)(p + off); off += 256;
         ws->cq_flag_bytes = align_up((size_t)(total_prims / 506 + 1) * (size_t)(n_pix / 2048 + 1), 256);
         ws->cq_flags = (unsigned char*)(p + off); off += ws->cq_flag_bytes;
+        ws->cq_inside = (int*)(p + off); off += align_up((size_t)total_prims * sizeof(int) + 4, 256);
     }
     ws->bytes = off;
 }
