@@ -40,7 +40,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions)
+FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions) - the plane filter
+FMA_INSTR_SPHERE_TEST = 3         # default path of large disk frames: |oc' . d| >= 1 (k_filter_const<8, 1>), 3 FFMA2/FMUL2 lane-instr
+# math_mode -> (kernel name, FMA-pipe lane-instr per ray-disk test, description)
+INTERSECT_MODES = {
+    0: ('k_filter_const', FMA_INSTR_SPHERE_TEST, 'bounding-sphere filter through the constant bank / uniform registers (3 lane-instr per test), '
+        'plane filter + exact test on the candidates in k_narrow_queue'),
+    6: ('k_filter_const', FMA_INSTR_PER_DISK_TEST, 'plane filter (SURVEY 8(d) formulation, 10 lane-instr per test + 1 MUFU.RCP) through the constant bank / uniform registers'),
+    5: ('k_intersect', FMA_INSTR_PER_DISK_TEST, 'plane filter (10 lane-instr per test), records staged in shared memory by TMA'),
+}
 N_SM, FP32_LANES = 148, 128
 L2_FLUSH_BYTES = 144 * 1024 * 1024     # > the 126 MB L2
 
@@ -56,7 +64,8 @@ def parse_args():
     ap.add_argument('--size', type=int, default=None)
     ap.add_argument('--ppt', type=int, default=0, help='pixels per thread of the intersection kernel (0 = default)')
     ap.add_argument('--chunk', type=int, default=0)
-    ap.add_argument('--math', type=int, default=0, help='intersection kernel: 0 = default ray-plane FFMA2 filter (10 instr/test), 3 = screen-space fast mode')
+    ap.add_argument('--math', type=int, default=0, help='intersection kernel: 0 = default (sphere + plane filter through the constant bank), 6 = plane filter through the constant bank, '
+                    '5 = plane filter staged by TMA (round 1 kernel), 3 = screen-space mode')
     ap.add_argument('--graph', action='store_true', help='replay the step from a CUDA graph')
     ap.add_argument('--torch-adam', action='store_true', help="torch.optim.Adam(fused=True) instead of the library's packed Adam kernel")
     ap.add_argument('--ref-size', type=int, default=0, help='reference arm: viewport edge of the bounded sample (0 = auto)')
@@ -481,15 +490,19 @@ def run_config_e(args, rank, world, local_rank):
     roofline = None
     if isect_ms:
         tests_launch = tests_per_step / world
-        ach_lane = tests_launch * FMA_INSTR_PER_DISK_TEST / (isect_ms * 1e-3)
+        kname, instr_per_test, kdesc = INTERSECT_MODES.get(args.math, ('k_intersect', FMA_INSTR_PER_DISK_TEST, 'math_mode %d' % args.math))
+        ach_lane = tests_launch * instr_per_test / (isect_ms * 1e-3)
         fma_meas = max(lib().surf_fma_peak(0, 8192, None), lib().surf_fma_peak(1, 8192, None))
-        roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
-                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane,
-                    # dram bytes of one k_intersect launch from the ncu --set full capture of THIS build, else null
-                    'traffic': ncu_traffic('k_intersect', 'config_e', world), 'source_hash': source_hash(),
+        roofline = {'bound': 'fp32_fma', 'kernel': kname, 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
+                    'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane, 'formulation': kdesc,
+                    'timed': 'the whole intersection stage of a step on the launching stream (CUDA events inside the library): for '
+                             'k_filter_const that is every launch of the kernel over the constant-bank loads of the frame plus '
+                             'k_sphere_records, k_narrow_queue, k_const_fallback, k_inside_disks',
+                    # dram bytes of the dominant kernel per launch from the ncu --set full capture of THIS build, else null
+                    'traffic': ncu_traffic(kname, 'config_e', world), 'source_hash': source_hash(),
                     'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s MEASURED_PEAKS.json has no fp32 entry)' % peak_src,
                     'peak_measured': fma_meas * 2 / 1e12, 'frac_of_measured': ach_lane / fma_meas if fma_meas > 0 else None,
-                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
+                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per step and rank' % (instr_per_test, tests_launch),
                     'kernel_ms': isect_ms, 'kernel_share_of_step': isect_ms / ms_per_step,
                     'step_minus_kernel_ms': ms_per_step - isect_ms,
                     'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
@@ -507,6 +520,35 @@ def run_config_e(args, rank, world, local_rank):
             'k_backward': {'ms': k_mean[2], 'algorithmic_bytes': bwd_bytes, 'achieved_gbs': bwd_bytes / (k_mean[2] * 1e-3) / 1e9,
                            'frac': bwd_bytes / (k_mean[2] * 1e-3) / 1e9 / hbm, 'traffic': ncu_traffic('k_backward', 'config_e', world)} if k_mean[2] > 0 else None}
     launches_per_step = int(plan.launches) + (0 if args.torch_adam else 2)      # + k_adam_advance, k_adam_packed
+
+    # ---- extra: the same step with the other intersection kernels (identical results): the plane filter of SURVEY 8(d)
+    # through the constant bank (math_mode 6) and staged by TMA (math_mode 5, the round-1 kernel), each with its own
+    # fraction of the FP32-FMA peak at 10 lane-instr per test
+    other_modes = {}
+    if args.math == 0 and not args.no_fast and roofline is not None:
+        for mode in (6, 5):
+            plan_m, step_m = build(dict(params, _math_mode=mode))
+            lib().surf_set_kernel_timing(1)
+            for _ in range(2):
+                step_m()
+            barrier()
+            lib().surf_set_kernel_timing(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_m = 3
+            e0.record()
+            for i in range(n_m):
+                flush.fill_(i & 0xff)
+                step_m()
+            e1.record()
+            barrier()
+            k_ms = lib().surf_mean_kernel_ms(0, None)
+            lib().surf_set_kernel_timing(0)
+            other_modes['math_mode_%d' % mode] = {
+                'kernel': INTERSECT_MODES[mode][0], 'formulation': INTERSECT_MODES[mode][2], 'ms_per_step': e0.elapsed_time(e1) / n_m,
+                'kernel_ms': k_ms, 'frac': (tests_per_step / world) * INTERSECT_MODES[mode][1] / (k_ms * 1e-3) / peak_lane if k_ms > 0 else None,
+                'note': 'per-rank time, not max over ranks'}
+            del plan_m, step_m
+        roofline['other_kernels'] = other_modes
 
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results
     fast = None

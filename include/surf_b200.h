@@ -102,15 +102,22 @@ typedef struct SurfOptions {
                                 rays, shadow visibility), skip recomputing it; 0/1 = recompute               */
     int32_t pixels_per_thread; /* 0 = library default; tuning knob (modes 0-2: 2,4,8; mode 3: 4,8,16)        */
     int32_t chunk_prims;     /* 0 = library default; primitives staged per TMA bulk copy (multiple of 32)   */
-    int32_t math_mode;       /* intersection kernel.  0 = default: ray-plane disk filter, packed FFMA2, grouped
-                                branch - 10 FMA-pipe lane-instr per ray-disk test, the SURVEY 8(d) formulation;
-                                1 = same, scalar FFMA; 2 = same, packed, one branch per primitive;
-                                3 = fast: per-pair screen-space bounding-circle test (2.25 lane-instr per test);
-                                4 = dense: mode 0's filter with 2-D pixel tiles and per-disk minima (the strided
-                                batch kernel on one scene) for frames with splats several pixels wide; mode 0
-                                selects it by itself for frames of at most 256x256 pixels and for scenes with
-                                triangle sets (mode 2 never does).
-                                All modes run the same exact narrow phase and give bit-identical results.      */
+    int32_t math_mode;       /* intersection kernel.  All modes run the same exact narrow phase and give bit-identical
+                                results.
+                                0 = default.  Disk sets of at least 256 primitives in single frames above 256x256
+                                    pixels: filter records streamed through the constant bank into uniform registers
+                                    (k_filter_const) - bounding-sphere test, 3 FMA-pipe lane-instr per ray-disk test;
+                                    the candidates go through the plane filter and the exact test in k_narrow_queue.
+                                    Everything else: ray-plane filter, packed FFMA2, records staged in shared memory
+                                    by TMA (k_intersect / k_intersect_batch), 10 lane-instr per ray-disk test - the
+                                    SURVEY 8(d) formulation; frames of at most 256x256 pixels and scenes with triangle
+                                    sets take the dense body (mode 4).
+                                1 = staged kernel, scalar FFMA; 2 = staged kernel, packed, one branch per primitive;
+                                3 = per-pair screen-space bounding-circle test (2.25 lane-instr per test);
+                                4 = dense: the staged filter with 2-D pixel tiles and per-disk minima (the strided
+                                    batch kernel on one scene) for frames with splats several pixels wide;
+                                5 = the staged kernel for everything (mode 0 without the constant-bank path);
+                                6 = mode 0 with the plane filter (10 lane-instr per test) in k_filter_const.        */
 } SurfOptions;
 
 /* outputs for n = pixel_end - pixel_begin pixels (row-major).  Any pointer may be NULL to skip it. */
@@ -158,7 +165,9 @@ const char* surf_last_error(void);
 size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow);
 /* the exact need of one call: `orthographic` = camera proj 1 (per-pixel ray origins: + 40 B per pixel; shadow frames
  * carry that list anyway), `step` = the workspace also holds d(loss)/d(image) of surf_step_mse (+ 12 B per pixel).
- * surf_workspace_bytes() = the bound for orthographic = 1, step = 0. */
+ * Perspective frames above 256x256 pixels include the candidate queue of the constant-bank intersection path
+ * (80 B per pixel); a workspace without room for it is accepted and renders through the staged kernel.
+ * surf_workspace_bytes() = the larger of orthographic = 0 / 1, step = 0. */
 size_t surf_workspace_bytes_ex(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow,
                                int32_t orthographic, int32_t step);
 

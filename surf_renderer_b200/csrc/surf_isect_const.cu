@@ -55,6 +55,9 @@ constexpr int kSlackGroups = 3;                       // the filter loop may rea
 // between two streams, so that the copy into one half and the ramp of the next kernel overlap the kernel on the other
 constexpr int const_groups(int filter, int halves) { return bank_groups(filter) / halves - kSlackGroups; }
 constexpr int kConstGrid = 3 * 160;                   // persistent grid: at most 3 CTAs per SM, 160 SMs
+#ifndef SURF_CONST_SPHERE_CTAS
+#define SURF_CONST_SPHERE_CTAS 3        // resident CTAs per SM of the sphere-filter kernel (80 registers)
+#endif
 constexpr int kConstP = 8;                            // pixels per thread
 __constant__ float c_recs[16384];
 // records that never pass, to fill the last group of a launch.  Plane filter: n = (0, 0, 1), numer = 0, o - c = 0,
@@ -186,7 +189,7 @@ __device__ __forceinline__ void push_candidate(const ConstParams& prm, int tile,
 }
 
 template <int P, int FILTER>
-__global__ void __launch_bounds__(kThreads, 2) k_filter_const(const __grid_constant__ ConstParams prm) {
+__global__ void __launch_bounds__(kThreads, FILTER == 1 ? SURF_CONST_SPHERE_CTAS : 2) k_filter_const(const __grid_constant__ ConstParams prm) {
     const int tid = threadIdx.x;
     for (int sgi = 0; sgi < 3; ++sgi) {
         const int4 sg = prm.seg[3 * blockIdx.x + sgi];
@@ -399,6 +402,8 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     prm.rays = f.ws.rays; prm.n_pix = f.n;
     prm.n_tiles = (f.n + kThreads * P - 1) / (kThreads * P);
     prm.queue = f.ws.cq; prm.ctl = f.ws.cq_ctl; prm.capacity = f.ws.cq_capacity;
+    if (const char* cap_env = getenv("SURF_CONST_CAPACITY"))      // tests: a tiny queue sends tiles through k_const_fallback
+        prm.capacity = std::max(0, std::min(prm.capacity, atoi(cap_env)));
     // small frames (row bands of a multi-GPU step): half-bank launches alternating between two streams hide the
     // kernel -> copy -> kernel bubbles (about 8 us per launch, 8 % of a 1/8-frame launch); large frames: whole-bank launches
     static const int halves_env = getenv("SURF_CONST_HALVES") ? atoi(getenv("SURF_CONST_HALVES")) : 0;      // tuning knob
@@ -432,7 +437,8 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     void* pad = nullptr;
     if (filter == 1) SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_sphere));
     else SURF_CUDA(cudaGetSymbolAddress(&pad, g_pad_plane));
-    static const int per_sm = getenv("SURF_CONST_CTAS") ? atoi(getenv("SURF_CONST_CTAS")) : 2;      // tuning knob
+    static const int per_sm_env = getenv("SURF_CONST_CTAS") ? atoi(getenv("SURF_CONST_CTAS")) : 0;      // tuning knob
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (filter == 1 ? SURF_CONST_SPHERE_CTAS : 2);
     const int grid_max = std::min(sm_count() * per_sm, kConstGrid);
     timer_mark(0, 0, st);
     // control words + the overflow map in one memset (adjacent in the workspace)
@@ -486,7 +492,7 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     FallbackParams fp;
     NarrowParams& np = fp.np;
     np.sv = sv; np.cam = f.ws.cam; np.recs = recs; np.rays = f.ws.rays; np.zbuf = f.ws.zbuf; np.n_pix = f.n;
-    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = f.ws.cq_capacity; np.group_size = group_size; np.spheres = filter == 1 ? (const float*)f.ws.circ + 3 * (size_t)sv.first : nullptr;
+    np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = prm.capacity; np.group_size = group_size; np.spheres = filter == 1 ? (const float*)f.ws.circ + 3 * (size_t)sv.first : nullptr;
     fp.flags = f.ws.cq_flags; fp.n_launches = n_launches; fp.n_tiles = prm.n_tiles; fp.recs_per_launch = per_launch;
     k_narrow_queue<P><<<sm_count() * 8, 256, 0, st>>>(np);
     SURF_LAUNCHED("k_narrow_queue");

@@ -131,6 +131,8 @@ static int make_frame(const SurfScene* scene, const SurfCamera* camera, const Su
     if (f->sc.n_lights > kMaxShadowLights && f->shadow) return fail(SURF_ERR_UNSUPPORTED, "shadow rays support at most 254 lights");
     if (!workspace) return fail(SURF_ERR_WORKSPACE, "null workspace");
     carve(workspace, f->sc.total, f->n, f->sc.n_lights, f->shadow, &f->ws, camera->proj != 0, step);
+    if (f->ws.bytes > workspace_bytes)       // no room for the candidate queue: the staged intersection kernel needs none
+        carve(workspace, f->sc.total, f->n, f->sc.n_lights, f->shadow, &f->ws, camera->proj != 0, step, false);
     if (f->ws.bytes > workspace_bytes) return fail(SURF_ERR_WORKSPACE, "workspace too small; see surf_workspace_bytes");
     return SURF_OK;
 }
@@ -462,7 +464,8 @@ double surf_mean_kernel_ms(int32_t which, int32_t* launches) {
 }
 
 size_t surf_workspace_bytes(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow) {
-    return surf_workspace_bytes_ex(total_prims, n_pixels, n_lights, shadow, 1, 0);
+    return std::max(surf_workspace_bytes_ex(total_prims, n_pixels, n_lights, shadow, 1, 0),
+                    surf_workspace_bytes_ex(total_prims, n_pixels, n_lights, shadow, 0, 0));
 }
 size_t surf_workspace_bytes_ex(int32_t total_prims, int32_t n_pixels, int32_t n_lights, int32_t shadow,
                                int32_t orthographic, int32_t step) {

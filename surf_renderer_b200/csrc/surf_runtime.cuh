@@ -98,8 +98,10 @@ inline size_t packed_bytes_bound(int total_prims) {
 
 // `generic_rays`: the frame traces rays with per-ray origins (orthographic camera, or shadow rays) and needs the
 // generic-ray list + second key buffer (40 B per ray); `step`: a fused step also holds d(loss)/d(image).
+// `queue`: append the candidate queue of the constant-bank intersection path (perspective frames above 256x256 pixels);
+// it sits at the end, so the layout of everything else does not depend on it.
 inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool shadow, Workspace* ws, bool generic_rays = true,
-                  bool step = false) {
+                  bool step = false, bool queue = true) {
     char* p = (char*)base;
     size_t off = 0;
     ws->cam = (CamState*)(p + off); off += align_up(sizeof(CamState), 256);
@@ -122,7 +124,7 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     ws->gimg = (float*)(p + off);
     if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_inside = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
-    if (n_pix > 256 * 256 && !generic_rays) {
+    if (queue && n_pix > 256 * 256 && !generic_rays) {
         // 10 candidates per pixel (config E appends 1.6 per pixel with the plane filter, 7.7 with the sphere filter); one flag byte per (launch of at least 506 disks, 2048-pixel tile)
         ws->cq_capacity = 10 * n_pix;
         ws->cq = (uint2*)(p + off); off += align_up((size_t)ws->cq_capacity * sizeof(uint2), 256);
