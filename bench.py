@@ -41,6 +41,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FMA_INSTR_PER_DISK_TEST = 10      # n.d 3, t 1, rel 3, |rel|^2 3 (FFMA/FMUL lane-instructions) - the plane filter
+FMA_INSTR_DENSE_TEST = 4          # k_intersect_batch (stacked batches, frames <= 256x256): (oc . d)^2 - c0 >= 0 from the staged plane records
 FMA_INSTR_SPHERE_TEST = 3         # default path of large disk frames: |oc' . d| >= 1 (k_filter_const<8, 1>), 3 FFMA2/FMUL2 lane-instr
 # math_mode -> (kernel name, FMA-pipe lane-instr per ray-disk test, description)
 INTERSECT_MODES = {
@@ -689,12 +690,12 @@ def run_config_d(args, rank, world, local_rank):
     roofline = None
     if k_mean[0] > 0:
         tests_launch = tests_per_step / world
-        ach_lane = tests_launch * FMA_INSTR_PER_DISK_TEST / (k_mean[0] * 1e-3)
+        ach_lane = tests_launch * FMA_INSTR_DENSE_TEST / (k_mean[0] * 1e-3)
         roofline = {'bound': 'fp32_fma', 'kernel': 'k_intersect_batch', 'achieved': ach_lane * 2 / 1e12, 'peak': peak_lane * 2 / 1e12,
                     'unit': 'TFLOP/s', 'frac': ach_lane / peak_lane, 'traffic': ncu_traffic('k_intersect_batch', 'config_d', world),
                     'source_hash': source_hash(),
                     'peak_source': 'theoretical 148 SM x 128 lanes x sm_max_mhz (%s)' % peak_src,
-                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test x %.3g tests per launch' % (FMA_INSTR_PER_DISK_TEST, tests_launch),
+                    'algorithmic': '%d FMA-pipe lane-instr per ray-disk test (bounding-sphere test from the staged plane records; the plane filter runs on what passes) x %.3g tests per launch' % (FMA_INSTR_DENSE_TEST, tests_launch),
                     'kernel_ms': k_mean[0], 'kernel_share_of_step': k_mean[0] / ms_per_step, 'step_minus_kernel_ms': ms_per_step - k_mean[0],
                     'shade_ms': k_mean[1], 'backward_ms': k_mean[2], 'launches_timed': int(n_timed.value)}
     # ---- extra: the opt-in screen-space intersection kernel (math_mode 3), same step, same results

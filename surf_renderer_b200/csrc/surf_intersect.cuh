@@ -243,7 +243,13 @@ __device__ __forceinline__ void chunk_disks(const IsectParams& prm, const SetVie
 // another ptxas schedule of the packed-FMA loop) - hence a separate copy used by the batch kernel only.
 // `nf(local, A, p)` runs the exact test of pixel slot p against disk `local` (A = its record's first float4): the
 // camera-ray narrow phase for k_intersect_batch, the shadow-ray narrow phase for k_intersect_shadow.
-template <int P, class NarrowFn>
+// SPHERE (camera rays only: unit directions): the per-disk minima come from the bounding-sphere test of the disk instead
+// of the plane filter - the ray passes within rs of the centre iff (oc . d)^2 >= |oc|^2 - rs^2, FOUR packed FMAs per pixel
+// pair and no reciprocal instead of ten + two MUFU.RCP; a disk that passes is re-filtered per pixel by the plane filter in
+// the rare path, exactly as before.  c0 = |oc|^2 (1 - 32 u) - rs^2 is formed per disk from the record (rs^2 = -B.w is the
+// plane filter's inflated radius): 3 u for the fp32 sum of squares, 16 u for the evaluation of the test (see
+// k_sphere_records in surf_isect_const.cu), the rest margin; c0 <= 0 (the eye inside the sphere) always passes.
+template <int P, bool SPHERE = false, class NarrowFn>
 __device__ __forceinline__ void chunk_disks_dense(const float4* __restrict__ s, int local0, int count, PixelRegs<P>& r,
                                                   NarrowFn&& nf) {
     int i = 0;
@@ -273,6 +279,30 @@ __device__ __forceinline__ void chunk_disks_dense(const float4* __restrict__ s, 
                 float m[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
+                    if (SPHERE) {
+                        const float oc2 = __fmaf_rn(B[g].z, B[g].z, __fmaf_rn(B[g].y, B[g].y, __fmul_rn(B[g].x, B[g].x)));
+                        const float nc0 = -__fmaf_rn(oc2, 1.f - 1.9073486328125e-6f, B[g].w);        // -(|oc|^2 (1 - 2^-19) - rs^2)
+                        const unsigned long long ox = pack2(B[g].x, B[g].x), oy = pack2(B[g].y, B[g].y), oz = pack2(B[g].z, B[g].z);
+                        const unsigned long long nc = pack2(nc0, nc0);
+                        unsigned long long s2[Q];
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) s2[q] = mul2(ox, r.dx[q]);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) s2[q] = fma2(oy, r.dy[q], s2[q]);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) s2[q] = fma2(oz, r.dz[q], s2[q]);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) s2[q] = fma2(s2[q], s2[q], nc);
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            float e0, e1;
+                            unpack2(s2[q], e0, e1);
+                            mx = fmaxf(mx, fmaxf(e0, e1));          // NaN-ignoring max
+                        }
+                        m[g] = -mx;
+                        continue;
+                    }
                     m[g] = INFINITY;
                     const unsigned long long nx = pack2(A[g].x, A[g].x), ny = pack2(A[g].y, A[g].y), nz = pack2(A[g].z, A[g].z);
                     const unsigned long long nm = pack2(A[g].w, A[g].w);
@@ -779,7 +809,7 @@ __device__ __forceinline__ void intersect_body(const IsectParams& prm0, const Ba
         const float4* s = stage_buf + (size_t)stage * prm0.stage_f4;
         if (sv.kind == KIND_DISK) {
             if (MODE == 0)
-                chunk_disks_dense<P>(s, local0, count, r, [&](int local, const float4& A, int p) {
+                chunk_disks_dense<P, true>(s, local0, count, r, [&](int local, const float4& A, int p) {
                     narrow_one<P>(sv, local, A, eye, near_clip, far_clip, r, p);
                 });
             else chunk_disks<P, MODE>(prm, sv, s, local0, count, eye, near_clip, far_clip, r);

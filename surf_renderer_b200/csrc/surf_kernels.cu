@@ -148,7 +148,10 @@ static int run_common_prologue(const Frame& f, float* ray_out, cudaStream_t st, 
 }
 
 // the MSE loss of an inverse-rendering step, fused into the shading epilogue (surf_step_mse)
-struct StepLoss { const float* target; float* g_image; double* loss_acc; float scale; };
+struct StepLoss {
+    const float* target; float* g_image; double* loss_acc; float scale;
+    cudaEvent_t target_ready = nullptr;      // optional: the target arrives on another stream; the shading kernel waits for it
+};
 
 // k_shade / k_shade_batch with 4 pixels per thread (all-vector global accesses) on large frames, 1 on small ones
 static int launch_shade(ShadeParams& sh, const StepLoss* loss, const BatchArgs* ba, int n_scenes, cudaStream_t st) {
@@ -222,6 +225,7 @@ static int forward_impl(const SurfScene* scene, const SurfCamera* camera, const 
     sh.pix0 = f.pix0; sh.n = f.n; sh.fl = f.fl;
     sh.image = out->image; sh.depth = out->depth; sh.normal = out->normal; sh.pos = out->pos;
     sh.nearest = (long long*)out->nearest;
+    if (loss && loss->target_ready) SURF_CUDA(cudaStreamWaitEvent(st, loss->target_ready, 0));
     return launch_shade(sh, loss, nullptr, 1, st);
 }
 
@@ -430,6 +434,8 @@ namespace surf { struct HostState; }
 struct SurfContext {
     int device;
     cudaStream_t stream;
+    cudaStream_t copy_stream;    // the target image of a step is uploaded here, next to the intersection kernels
+    cudaEvent_t target_ready;
     void* arena; size_t arena_bytes;
     uint64_t h2d, d2h;
     surf::HostState* state;      // the call in flight between surf_step_host_begin and surf_step_host_end
@@ -1259,7 +1265,12 @@ static int host_begin(SurfContext* c, const SurfScene* hs, const SurfCamera* hc,
     // with a target image the loss and d(loss)/d(image) are fused into the shading epilogue (mean over this call's pixels)
     StepLoss sl{pl.d_target, (float*)pl.dgout.image, pl.d_loss, loss_scale > 0.f ? loss_scale : 1.0f / (3.0f * (float)n)};
     if (has_target) {
-        if ((rc = h2d(c, pl.d_target, target, (size_t)n * 12))) return rc;
+        // the target is only read by the shading kernel: upload it on the copy stream, under the intersection stage
+        // (the previous call on this context ended with a stream synchronisation, so d_target is free)
+        SURF_CUDA(cudaMemcpyAsync((void*)pl.d_target, target, (size_t)n * 12, cudaMemcpyHostToDevice, c->copy_stream));
+        SURF_CUDA(cudaEventRecord(c->target_ready, c->copy_stream));
+        c->h2d += (size_t)n * 12;
+        sl.target_ready = c->target_ready;
         SURF_CUDA(cudaMemsetAsync(pl.d_loss, 0, 8, c->stream));
     }
     if ((rc = forward_impl(&pl.dscene, &pl.dcam, opt, pl.workspace, pl.workspace_bytes, &pl.dout, c->stream,
@@ -1355,7 +1366,9 @@ SurfContext* surf_context_create(int32_t device) {
     if (cudaSetDevice(device) != cudaSuccess) { g_error = "cudaSetDevice failed"; return nullptr; }
     SurfContext* c = new SurfContext();
     c->device = device; c->arena = nullptr; c->arena_bytes = 0; c->h2d = c->d2h = 0; c->state = nullptr;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->target_ready, cudaEventDisableTiming) != cudaSuccess) {
         g_error = "cudaStreamCreate failed";
         delete c;
         return nullptr;
@@ -1368,6 +1381,8 @@ void surf_context_destroy(SurfContext* c) {
     cudaSetDevice(c->device);
     if (c->arena) cudaFree(c->arena);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->target_ready);
     delete c->state;
     delete c;
 }

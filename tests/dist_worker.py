@@ -36,7 +36,8 @@ def close(a, b, rtol=1e-4, atol_scale=2e-6):
 
 
 # ---- 1. MSEStep over row bands vs the single-GPU step -------------------------------------------------------------
-scene = synth.config_e(m=6000, width=192, height=160, radius=0.02)
+# bands of more than 256 x 256 pixels: the constant-bank intersection path (two streams) runs next to the NCCL stream
+scene = synth.config_e(m=6000, width=512, height=384, radius=0.02)
 target = surf_renderer_b200.render(scene_io.clone_scene(synth.config_e_target_scene(scene, jitter=0.01), device=dev))['image'].detach()
 
 

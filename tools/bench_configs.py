@@ -1,6 +1,8 @@
 """Every BASELINE.json config on one B200: forward and fwd+bwd time (CUDA events), ray-primitive tests/s, and the
-intersection kernel's share and FP32-FMA fraction (algorithmic lane-instr per test from SURVEY 8d: disk 10, sphere 10,
-triangle 16, plane 4).  A  basic.json 64x64 - B  bunny.splat 256x256 - C  torus_1K.obj 512x512 - D  64 x 5000 splats
+intersection kernel's share and FP32-FMA fraction.  Algorithmic FMA-pipe lane-instr per test of the filter that runs:
+disk 3 (frames above 256x256: bounding-sphere test through the constant bank, k_filter_const) or 4 (dense / batch kernel:
+bounding-sphere test from the staged plane records), sphere 10, triangle 16, plane 4 (the plane filter of a disk,
+math_mode 5 / 6, is 10).  A  basic.json 64x64 - B  bunny.splat 256x256 - C  torus_1K.obj 512x512 - D  64 x 5000 splats
 128x128 (stacked batch) - E  100K splats 1024x1024.  Scenes A-C come from the reference-generated fixtures in
 tests/golden (same primitives, the viewport set to the config's size)."""
 import json, os, sys
@@ -12,7 +14,8 @@ from surf_renderer_b200 import scenes as synth
 from surf_renderer_b200._lib import lib
 from surf_renderer_b200.renderer import _stack_scenes
 
-INSTR = {'disk': 10, 'sphere': 10, 'triangle': 16, 'plane': 4}
+INSTR = {'disk': 4, 'sphere': 10, 'triangle': 16, 'plane': 4}
+INSTR_DISK_CONST = 3
 PEAK = 148 * 128 * 1.965e9          # FP32 lane-instr/s at the measured max clock
 
 
@@ -44,7 +47,8 @@ def measure(name, scene, params, n_scenes=1, reps=20, batched=False):
     H = W = scene['camera']['viewport'][2]
     counts = {k: int((v['face'] if k == 'triangle' else v['pos']).shape[-3 if k == 'triangle' else -2]) for k, v in objs.items()}
     tests = float(sum(counts.values())) * H * W * n_scenes
-    lane_instr = float(sum(INSTR[k] * c for k, c in counts.items())) * H * W * n_scenes
+    const_path = not batched and H * W > 256 * 256 and 'triangle' not in counts and params.get('_math_mode', 0) == 0
+    lane_instr = float(sum((INSTR_DISK_CONST if (k == 'disk' and const_path and c >= 256) else INSTR[k]) * c for k, c in counts.items())) * H * W * n_scenes
     call = (lambda: surf_renderer_b200.render_batch(scene, **params)) if batched else (lambda: surf_renderer_b200.render(scene, **params))
 
     def fwd():
