@@ -611,7 +611,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_intersect_shadow(const __grid_c
             const bool hit = exact_hit(sv, local, nn, numer, o, dir, -INFINITY, INFINITY, &t) && t > 0.f && t < tmax;
             if (hit && t < r.best_t[p]) { r.best_t[p] = t; r.best_i[p] = sv.first + local; }
         };
-        if (sv.kind == KIND_DISK) chunk_disks_dense<P>(s, local0, count, r, nf);
+        // (-L is a unit vector and the filter tests the LINE through the light: the bounding-sphere form applies)
+        if (sv.kind == KIND_DISK) chunk_disks_dense<P, true>(s, local0, count, r, nf);
         else if (sv.kind == KIND_TRIANGLE) chunk_triangles_packed<P, false>(s, local0, count, r, nf);
         else if (sv.kind == KIND_SPHERE) chunk_spheres_fn<P>(s, local0, count, r, nf);
         else chunk_planes_fn<P>(s, local0, count, nf);

@@ -236,40 +236,43 @@ struct NarrowParams {
     const float* spheres;            // sphere filter: the set's sphere records [count, 3] (the pairs that passed are found again first)
 };
 
-// one thread per candidate: per-pixel filter of the group's disks, exact narrow phase for the pairs that pass
+// one thread per (candidate, pixel pair): the two pixels' rays, the sphere test of the group's disks again (sphere filter),
+// the plane filter, and the exact reference-order hit test for what passes.  Consecutive threads share a candidate, so
+// the queue entry and the records are broadcast loads.
 template <int P>
 __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ NarrowParams prm) {
-    const int n = min(prm.ctl[0], prm.capacity);
+    constexpr int Q = P / 2;
+    const long long n = (long long)min(prm.ctl[0], prm.capacity) * Q;
     const Vec3 eye = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
     const float near_clip = prm.cam->near_clip, far_clip = prm.cam->far_clip;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const uint2 c = prm.queue[e];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const uint2 c = prm.queue[t / Q];
+        const int q = (int)(t % Q);
         const int tile = (int)(c.x / kThreads), tid = (int)(c.x % kThreads);
-        PixelRegs<P> r;
-        load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
-#pragma unroll
-        for (int p = 0; p < P; ++p) { r.best_t[p] = INFINITY; r.best_i[p] = -1; }
+        const int pix0 = tile * (kThreads * P) + 2 * q * kThreads + tid, pix1 = pix0 + kThreads;
+        const bool ok0 = pix0 < prm.n_pix, ok1 = pix1 < prm.n_pix;
+        PixelRegs<2> r;
+        r.dx[0] = pack2(ok0 ? prm.rays[pix0] : 0.f, ok1 ? prm.rays[pix1] : 0.f);
+        r.dy[0] = pack2(ok0 ? prm.rays[(size_t)prm.n_pix + pix0] : 0.f, ok1 ? prm.rays[(size_t)prm.n_pix + pix1] : 0.f);
+        r.dz[0] = pack2(ok0 ? prm.rays[2 * (size_t)prm.n_pix + pix0] : 0.f, ok1 ? prm.rays[2 * (size_t)prm.n_pix + pix1] : 0.f);
+        r.best_t[0] = r.best_t[1] = INFINITY;
+        r.best_i[0] = r.best_i[1] = -1;
         const int first = (int)c.y * prm.group_size, last = min(first + prm.group_size, prm.sv.count);
         for (int i = first; i < last; ++i) {
             if (prm.spheres) {
                 const float* sp = prm.spheres + 3 * (size_t)i;
-                if (!(sphere_margin_max<P>(sp[0], sp[1], sp[2], r, 0.f) >= 1.f)) continue;
+                if (!(sphere_margin_max<2>(sp[0], sp[1], sp[2], r, 0.f) >= 1.f)) continue;
             }
             const float4 A = prm.recs[2 * i], B = prm.recs[2 * i + 1];
-#pragma unroll
-            for (int q = 0; q < P / 2; ++q) {
-                float e0, e1;
-                unpack2(disk_margin2<P>(A, B, r, q), e0, e1);
-                if (e0 <= 0.f) narrow_one<P>(prm.sv, i, A, eye, near_clip, far_clip, r, 2 * q);
-                if (e1 <= 0.f) narrow_one<P>(prm.sv, i, A, eye, near_clip, far_clip, r, 2 * q + 1);
-            }
+            float e0, e1;
+            unpack2(disk_margin2<2>(A, B, r, 0), e0, e1);
+            if (e0 <= 0.f) narrow_one<2>(prm.sv, i, A, eye, near_clip, far_clip, r, 0);
+            if (e1 <= 0.f) narrow_one<2>(prm.sv, i, A, eye, near_clip, far_clip, r, 1);
         }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int pix = tile * (kThreads * P) + p * kThreads + tid;
-            if (r.best_i[p] >= 0 && pix < prm.n_pix)
-                atomicMin(prm.zbuf + pix, ((unsigned long long)float_order_key(r.best_t[p]) << 32) | (unsigned)r.best_i[p]);
-        }
+        if (r.best_i[0] >= 0 && ok0)
+            atomicMin(prm.zbuf + pix0, ((unsigned long long)float_order_key(r.best_t[0]) << 32) | (unsigned)r.best_i[0]);
+        if (r.best_i[1] >= 0 && ok1)
+            atomicMin(prm.zbuf + pix1, ((unsigned long long)float_order_key(r.best_t[1]) << 32) | (unsigned)r.best_i[1]);
     }
 }
 
@@ -494,7 +497,7 @@ int run_intersect_const(const Frame& f, const SetView& sv, int filter, cudaStrea
     np.sv = sv; np.cam = f.ws.cam; np.recs = recs; np.rays = f.ws.rays; np.zbuf = f.ws.zbuf; np.n_pix = f.n;
     np.queue = f.ws.cq; np.ctl = f.ws.cq_ctl; np.capacity = prm.capacity; np.group_size = group_size; np.spheres = filter == 1 ? (const float*)f.ws.circ + 3 * (size_t)sv.first : nullptr;
     fp.flags = f.ws.cq_flags; fp.n_launches = n_launches; fp.n_tiles = prm.n_tiles; fp.recs_per_launch = per_launch;
-    k_narrow_queue<P><<<sm_count() * 8, 256, 0, st>>>(np);
+    k_narrow_queue<P><<<sm_count() * 16, 256, 0, st>>>(np);
     SURF_LAUNCHED("k_narrow_queue");
     k_const_fallback<P><<<sm_count() * 2, kThreads, 0, st>>>(fp);
     SURF_LAUNCHED("k_const_fallback");
