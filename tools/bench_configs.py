@@ -59,6 +59,17 @@ def measure(name, scene, params, n_scenes=1, reps=20, batched=False):
         call()['image'].sum().backward()
     t_f = timed(fwd, reps)
     t_fb = timed(fb, reps)
+    # the same fwd + loss + bwd as ONE library call (MSEStep), eager and replayed from a CUDA graph
+    t_step = t_graph = None
+    if not batched:
+        with torch.no_grad():
+            target = torch.rand_like(call()['image'])
+        plan = surf_renderer_b200.MSEStep(scene, target, **params)
+        t_step = timed(plan, reps)
+        graphed = surf_renderer_b200.GraphedStep(plan, warmup=3)
+        t_graph = timed(graphed, reps)
+        for t in plan.leaves:
+            t.grad = None
     L = lib()
     L.surf_set_kernel_timing(1)
     fwd(); fwd(); fwd()
@@ -66,7 +77,7 @@ def measure(name, scene, params, n_scenes=1, reps=20, batched=False):
     k_ms = L.surf_mean_kernel_ms(0, None)
     L.surf_set_kernel_timing(0)
     row = {'config': name, 'primitives': counts, 'scenes': n_scenes, 'size': [H, W], 'tests_per_frame': tests,
-           'forward_ms': t_f, 'fwd_bwd_ms': t_fb, 'forward_tests_per_s': tests / (t_f * 1e-3),
+           'forward_ms': t_f, 'fwd_bwd_ms': t_fb, 'mse_step_ms': t_step, 'mse_step_graph_ms': t_graph, 'forward_tests_per_s': tests / (t_f * 1e-3),
            'fwd_bwd_tests_per_s': tests / (t_fb * 1e-3), 'fwd_bwd_frames_per_s': n_scenes * 1e3 / t_fb,
            'k_intersect_ms': k_ms, 'k_intersect_frac_fp32_peak': lane_instr / (k_ms * 1e-3) / PEAK,
            'k_intersect_share_of_forward': k_ms / t_f}

@@ -23,7 +23,7 @@ def launches(path, out):
     setups = [i for i, (n, _) in enumerate(seq) if 'k_setup' in n]
     # a step = from one k_setup launch to the next; take the last complete one that contains k_backward
     steps = [(a, b) for a, b in zip(setups, setups[1:] + [len(seq)])
-             if any('k_backward(' in n for n, _ in seq[a:b]) and any('k_intersect<' in n for n, _ in seq[a:b])]
+             if any('k_backward(' in n for n, _ in seq[a:b]) and any(('k_intersect<' in n or 'k_filter_const<' in n) for n, _ in seq[a:b])]
     a, b = steps[-2] if len(steps) > 1 else steps[-1]   # a full fwd+bwd step of the main timed loop (default kernel)
     agg = {}
     for n, ms in seq[a:b]:
@@ -46,6 +46,7 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active', 'idc__request_hit_rate.pct',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
