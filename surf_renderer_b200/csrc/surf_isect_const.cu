@@ -56,9 +56,13 @@ constexpr int kSlackGroups = 3;                       // the filter loop may rea
 constexpr int const_groups(int filter, int halves) { return bank_groups(filter) / halves - kSlackGroups; }
 constexpr int kConstGrid = 3 * 160;                   // persistent grid: at most 3 CTAs per SM, 160 SMs
 #ifndef SURF_CONST_SPHERE_CTAS
-#define SURF_CONST_SPHERE_CTAS 3        // resident CTAs per SM of the sphere-filter kernel (80 registers)
+#define SURF_CONST_SPHERE_CTAS 2        // resident CTAs per SM of the sphere-filter kernel (3 fit at 8 pixels per thread: 72 registers)
 #endif
-constexpr int kConstP = 8;                            // pixels per thread
+#ifndef SURF_CONST_P
+#define SURF_CONST_P 16                   // pixels per thread of the constant-bank kernels (tile = 256 x P pixels).  Measured on
+                                         // config E, sphere filter: 8 -> 11.58 ms (3 CTAs per SM), 12 -> 11.36 ms, 16 -> 11.21 ms
+#endif
+constexpr int kConstP = SURF_CONST_P;                            // pixels per thread
 __constant__ float c_recs[16384];
 // records that never pass, to fill the last group of a launch.  Plane filter: n = (0, 0, 1), numer = 0, o - c = 0,
 // -(r + slack)^2 = +inf (the margin is +inf or NaN for every ray); sphere filter: three times oc' = 0
@@ -69,7 +73,7 @@ struct ConstParams {
     const float* rays;               // [3, n]
     int n_pix, n_tiles;
     int group0;                      // set-local group index of bank group 0 (the segments count bank groups)
-    uint2* queue;                    // candidates: x = thread slot (tile * kThreads + tid), y = set-local group index
+    uint2* queue;                    // candidates: x = 2 * thread slot (tile * kThreads + tid) + half of its pixels, y = set-local group index
     int* ctl;                        // [0] entries appended (may exceed capacity), [1] flagged (launch, tile) pairs
     int capacity;
     unsigned char* flags;            // this launch's row of the [launch][tile] overflow map
@@ -82,9 +86,10 @@ struct ConstParams {
     int4 seg[3 * kConstGrid];
 };
 
-// filter minimum of one disk over the P pixels of the thread; A, B are warp-uniform (uniform registers)
+// filter minima of one disk over the lower and the upper half of the thread's P pixels (a queue entry names a half, which
+// halves the pixel pairs k_narrow_queue has to look at again); A, B are warp-uniform (uniform registers)
 template <int P>
-__device__ __forceinline__ float const_margin_min(const float4 A, const float4 B, const PixelRegs<P>& r, float m) {
+__device__ __forceinline__ float2 const_margin_min(const float4 A, const float4 B, const PixelRegs<P>& r, float2 m) {
     constexpr int Q = P / 2;
     const unsigned long long nx = pack2(A.x, A.x), ny = pack2(A.y, A.y), nz = pack2(A.z, A.z), nm = pack2(A.w, A.w);
     const unsigned long long ox = pack2(B.x, B.x), oy = pack2(B.y, B.y), oz = pack2(B.z, B.z), nr = pack2(B.w, B.w);
@@ -117,7 +122,8 @@ __device__ __forceinline__ float const_margin_min(const float4 A, const float4 B
     for (int q = 0; q < Q; ++q) {
         float e0, e1;
         unpack2(e2[q], e0, e1);
-        m = fminf(m, fminf(e0, e1));     // NaN-ignoring min: NaN margins are misses
+        if (q < Q / 2) m.x = fminf(m.x, fminf(e0, e1));     // NaN-ignoring min: NaN margins are misses
+        else m.y = fminf(m.y, fminf(e0, e1));
     }
     return m;
 }
@@ -128,7 +134,7 @@ __device__ __forceinline__ float const_margin_min(const float4 A, const float4 B
 // passes is re-filtered per pixel by the plane filter in k_narrow_queue before the exact test.  oc' comes from
 // k_sphere_records, with the slack that covers every rounding of this evaluation and of the reference-order hit test.
 template <int P>
-__device__ __forceinline__ float sphere_margin_max(float sx, float sy, float sz, const PixelRegs<P>& r, float m) {
+__device__ __forceinline__ float2 sphere_margin_max(float sx, float sy, float sz, const PixelRegs<P>& r, float2 m) {
     constexpr int Q = P / 2;
     const unsigned long long ox = pack2(sx, sx), oy = pack2(sy, sy), oz = pack2(sz, sz);
     unsigned long long s2[Q];
@@ -142,23 +148,25 @@ __device__ __forceinline__ float sphere_margin_max(float sx, float sy, float sz,
     for (int q = 0; q < Q; ++q) {
         float e0, e1;
         unpack2(s2[q], e0, e1);
-        m = fmaxf(m, fmaxf(fabsf(e0), fabsf(e1)));
+        if (q < Q / 2 || Q == 1) m.x = fmaxf(m.x, fmaxf(fabsf(e0), fabsf(e1)));
+        else m.y = fmaxf(m.y, fmaxf(fabsf(e0), fabsf(e1)));
     }
     return m;
 }
 
-// one group of the bank, g[0 .. group_floats).  Returns a value that is <= 0 iff some (pixel, disk) pair of the group passed.
+// one group of the bank, g[0 .. group_floats).  Returns two values, for the lower and the upper half of the thread's pixels:
+// <= 0 iff some (pixel, disk) pair of the group passed in that half.
 template <int P, int FILTER>
-__device__ __forceinline__ float group_margin(const float* g, const PixelRegs<P>& r) {
+__device__ __forceinline__ float2 group_margin(const float* g, const PixelRegs<P>& r) {
     if (FILTER == 0) {
-        const float m = const_margin_min<P>(make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]), r, INFINITY);
+        const float2 m = const_margin_min<P>(make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]), r, make_float2(INFINITY, INFINITY));
         return const_margin_min<P>(make_float4(g[8], g[9], g[10], g[11]), make_float4(g[12], g[13], g[14], g[15]), r, m);
     }
-    float m = sphere_margin_max<P>(g[0], g[1], g[2], r, 0.f);
+    float2 m = sphere_margin_max<P>(g[0], g[1], g[2], r, make_float2(0.f, 0.f));
     m = sphere_margin_max<P>(g[3], g[4], g[5], r, m);
     m = sphere_margin_max<P>(g[6], g[7], g[8], r, m);
     m = sphere_margin_max<P>(g[9], g[10], g[11], r, m);
-    return 1.f - m;
+    return make_float2(1.f - m.x, 1.f - m.y);
 }
 
 template <int P>
@@ -182,10 +190,14 @@ __device__ __forceinline__ void load_tile_rays(const float* __restrict__ rays, i
 
 // append (thread slot, group) to the candidate queue.  (Plain per-thread atomics: a warp-aggregated append - activemask,
 // shuffle - inside the filter loop also made the compiler drop the uniform registers.)
-__device__ __forceinline__ void push_candidate(const ConstParams& prm, int tile, int slot, int group) {
-    const int at = atomicAdd(prm.ctl, 1);
-    if (at < prm.capacity) prm.queue[at] = make_uint2((unsigned)slot, (unsigned)group);
-    else prm.flags[tile] = 1;           // k_const_fallback redoes this tile against this launch's records
+__device__ __forceinline__ void push_candidate(const ConstParams& prm, int tile, int slot, int group, float2 m) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (!((half ? m.y : m.x) <= 0.f)) continue;
+        const int at = atomicAdd(prm.ctl, 1);
+        if (at < prm.capacity) prm.queue[at] = make_uint2((unsigned)(2 * slot + half), (unsigned)group);
+        else prm.flags[tile] = 1;           // k_const_fallback redoes this tile against this launch's records
+    }
 }
 
 template <int P, int FILTER>
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, FILTER == 1 ? SURF_CONST_SPHERE_CTAS
             // critical path.  The host makes every segment an even number of groups and ends it one group past its last
             // (that group's minimum is never tested): code behind the loop costs the uniform registers, too.
             constexpr int GF = group_floats(FILTER);
-            float m_prev = INFINITY;
+            float2 m_prev = make_float2(INFINITY, INFINITY);
             float ga[GF], gc[GF];
 #pragma unroll
             for (int j = 0; j < GF; ++j) ga[j] = c_recs[GF * sg.z + j];
@@ -210,12 +222,12 @@ __global__ void __launch_bounds__(kThreads, FILTER == 1 ? SURF_CONST_SPHERE_CTAS
             for (int k = sg.z; k < sg.w; k += 2) {
 #pragma unroll
                 for (int j = 0; j < GF; ++j) gc[j] = c_recs[GF * (k + 1) + j];
-                const float m = group_margin<P, FILTER>(ga, r);
-                if (m_prev <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k - 1);
+                const float2 m = group_margin<P, FILTER>(ga, r);
+                if (fminf(m_prev.x, m_prev.y) <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k - 1, m_prev);
 #pragma unroll
                 for (int j = 0; j < GF; ++j) ga[j] = c_recs[GF * (k + 2) + j];
-                const float m2 = group_margin<P, FILTER>(gc, r);
-                if (m <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k);
+                const float2 m2 = group_margin<P, FILTER>(gc, r);
+                if (fminf(m.x, m.y) <= 0.f) push_candidate(prm, tile, tile * kThreads + tid, prm.group0 + k, m);
                 m_prev = m2;
             }
         }
@@ -236,19 +248,19 @@ struct NarrowParams {
     const float* spheres;            // sphere filter: the set's sphere records [count, 3] (the pairs that passed are found again first)
 };
 
-// one thread per (candidate, pixel pair): the two pixels' rays, the sphere test of the group's disks again (sphere filter),
+// one thread per (candidate, pixel pair of the candidate's half): the two pixels' rays, the sphere test of the group's disks again (sphere filter),
 // the plane filter, and the exact reference-order hit test for what passes.  Consecutive threads share a candidate, so
 // the queue entry and the records are broadcast loads.
 template <int P>
 __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ NarrowParams prm) {
-    constexpr int Q = P / 2;
-    const long long n = (long long)min(prm.ctl[0], prm.capacity) * Q;
+    constexpr int QH = P / 4;                    // pixel pairs per candidate (one half of a thread's pixels)
+    const long long n = (long long)min(prm.ctl[0], prm.capacity) * QH;
     const Vec3 eye = v3(prm.cam->eye[0], prm.cam->eye[1], prm.cam->eye[2]);
     const float near_clip = prm.cam->near_clip, far_clip = prm.cam->far_clip;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const uint2 c = prm.queue[t / Q];
-        const int q = (int)(t % Q);
-        const int tile = (int)(c.x / kThreads), tid = (int)(c.x % kThreads);
+        const uint2 c = prm.queue[t / QH];
+        const int q = (int)(c.x & 1u) * QH + (int)(t % QH);
+        const int tile = (int)((c.x >> 1) / kThreads), tid = (int)((c.x >> 1) % kThreads);
         const int pix0 = tile * (kThreads * P) + 2 * q * kThreads + tid, pix1 = pix0 + kThreads;
         const bool ok0 = pix0 < prm.n_pix, ok1 = pix1 < prm.n_pix;
         PixelRegs<2> r;
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ Na
         for (int i = first; i < last; ++i) {
             if (prm.spheres) {
                 const float* sp = prm.spheres + 3 * (size_t)i;
-                if (!(sphere_margin_max<2>(sp[0], sp[1], sp[2], r, 0.f) >= 1.f)) continue;
+                if (!(sphere_margin_max<2>(sp[0], sp[1], sp[2], r, make_float2(0.f, 0.f)).x >= 1.f)) continue;
             }
             const float4 A = prm.recs[2 * i], B = prm.recs[2 * i + 1];
             float e0, e1;

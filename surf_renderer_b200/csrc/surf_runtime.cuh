@@ -125,7 +125,7 @@ inline void carve(void* base, int total_prims, int n_pix, int n_lights, bool sha
     if (step) off += align_up((size_t)3 * n_pix * sizeof(float), 256);
     ws->cq = nullptr; ws->cq_ctl = nullptr; ws->cq_flags = nullptr; ws->cq_inside = nullptr; ws->cq_capacity = 0; ws->cq_flag_bytes = 0;
     if (queue && n_pix > 256 * 256 && !generic_rays) {
-        // 10 candidates per pixel (config E appends 1.6 per pixel with the plane filter, 7.7 with the sphere filter); one flag byte per (launch of at least 506 disks, 2048-pixel tile)
+        // 10 candidates per pixel (config E appends 1.6 per pixel with the plane filter, 7.7 with the sphere filter); one flag byte per (launch of at least 506 disks, tile of at least 2048 pixels)
         ws->cq_capacity = 10 * n_pix;
         ws->cq = (uint2*)(p + off); off += align_up((size_t)ws->cq_capacity * sizeof(uint2), 256);
         ws->cq_ctl = (int*)(p + off); off += 256;
