@@ -436,6 +436,7 @@ struct SurfContext {
     cudaStream_t stream;
     cudaStream_t copy_stream;    // the target image of a step is uploaded here, next to the intersection kernels
     cudaEvent_t target_ready;
+    char* stage_up; char* stage_down;     // pinned staging (kStageBytes each): the small arrays of a call travel as ONE copy per direction
     void* arena; size_t arena_bytes;
     uint64_t h2d, d2h;
     surf::HostState* state;      // the call in flight between surf_step_host_begin and surf_step_host_end
@@ -1085,6 +1086,8 @@ double surf_fma_peak(int32_t mode, int32_t iters, void* cuda_stream) {
 namespace surf {
 
 // bump allocator over the context arena
+constexpr size_t kStageBytes = 64 << 10;
+
 struct Bump {
     char* base; size_t off, cap;
     void* take(size_t bytes) {
@@ -1250,17 +1253,31 @@ static int host_begin(SurfContext* c, const SurfScene* hs, const SurfCamera* hc,
         if (s.radius && (rc = h2d(c, d.radius, s.radius, (size_t)s.count * 4))) return rc;
         if ((rc = h2d(c, d.material_idx, s.material_idx, (size_t)s.count * 4))) return rc;
     }
-    if ((rc = h2d(c, pl.dscene.light_pos, hs->light_pos, (size_t)hs->n_lights * hs->light_pos_stride * 4))) return rc;
-    if ((rc = h2d(c, pl.dscene.light_color_idx, hs->light_color_idx, (size_t)hs->n_lights * 4))) return rc;
-    if ((rc = h2d(c, pl.dscene.light_attenuation, hs->light_attenuation, (size_t)hs->n_lights * 12))) return rc;
-    if ((rc = h2d(c, pl.dscene.ambient, hs->ambient, 12))) return rc;
-    if ((rc = h2d(c, pl.dscene.colors, hs->colors, (size_t)hs->n_colors * 12))) return rc;
-    if ((rc = h2d(c, pl.dscene.albedo, hs->albedo, (size_t)hs->n_materials * 12))) return rc;
-    if ((rc = h2d(c, pl.dscene.coeffs, hs->coeffs, (size_t)hs->n_materials * 12))) return rc;
-    if (hs->gamma && (rc = h2d(c, pl.dscene.gamma, hs->gamma, 4))) return rc;
-    if ((rc = h2d(c, pl.dcam.eye, hc->eye, 12))) return rc;
-    if ((rc = h2d(c, pl.dcam.at, hc->at, 12))) return rc;
-    if ((rc = h2d(c, pl.dcam.up, hc->up, 12))) return rc;
+    {   // lights, colours, materials, tonemap, camera vectors: a dozen arrays of a few bytes each.  Their device mirrors are
+        // neighbours in the arena, so they are packed into pinned staging at the same offsets and uploaded as ONE copy
+        // (each separate copy costs 5 - 10 us of DMA latency on the stream).
+        struct Item { const void* dst; const void* src; size_t bytes; };
+        const Item items[] = {
+            {pl.dscene.light_pos, hs->light_pos, (size_t)hs->n_lights * hs->light_pos_stride * 4},
+            {pl.dscene.light_color_idx, hs->light_color_idx, (size_t)hs->n_lights * 4},
+            {pl.dscene.light_attenuation, hs->light_attenuation, (size_t)hs->n_lights * 12},
+            {pl.dscene.ambient, hs->ambient, 12},
+            {pl.dscene.colors, hs->colors, (size_t)hs->n_colors * 12},
+            {pl.dscene.albedo, hs->albedo, (size_t)hs->n_materials * 12},
+            {pl.dscene.coeffs, hs->coeffs, (size_t)hs->n_materials * 12},
+            {pl.dscene.gamma, hs->gamma, hs->gamma ? (size_t)4 : (size_t)0},
+            {pl.dcam.eye, hc->eye, 12}, {pl.dcam.at, hc->at, 12}, {pl.dcam.up, hc->up, 12}};
+        const char* lo = (const char*)pl.dscene.light_pos;
+        const char* hi = (const char*)pl.dcam.up + 12;
+        if ((size_t)(hi - lo) <= kStageBytes) {
+            for (const Item& it : items)
+                if (it.bytes) std::memcpy(c->stage_up + ((const char*)it.dst - lo), it.src, it.bytes);
+            if ((rc = h2d(c, lo, c->stage_up, (size_t)(hi - lo)))) return rc;
+        } else {
+            for (const Item& it : items)
+                if ((rc = h2d(c, it.dst, it.src, it.bytes))) return rc;
+        }
+    }
 
     // with a target image the loss and d(loss)/d(image) are fused into the shading epilogue (mean over this call's pixels)
     StepLoss sl{pl.d_target, (float*)pl.dgout.image, pl.d_loss, loss_scale > 0.f ? loss_scale : 1.0f / (3.0f * (float)n)};
@@ -1331,20 +1348,37 @@ static int host_end(SurfContext* c, const SurfSceneGrads* hgrads, float* loss) {
             if (s.normal && (rc = d2h(c, hgrads->sets[k].normal, pl.dgrads.sets[k].normal, (size_t)s.count * s.normal_stride * 4))) return rc;
             if (s.kind == SURF_SPHERE && (rc = d2h(c, hgrads->sets[k].radius, pl.dgrads.sets[k].radius, (size_t)s.count * 4))) return rc;
         }
-        if ((rc = d2h(c, hgrads->light_pos, pl.dgrads.light_pos, (size_t)hs->n_lights * hs->light_pos_stride * 4))) return rc;
-        if ((rc = d2h(c, hgrads->light_attenuation, pl.dgrads.light_attenuation, (size_t)hs->n_lights * 12))) return rc;
-        if ((rc = d2h(c, hgrads->ambient, pl.dgrads.ambient, 12))) return rc;
-        if ((rc = d2h(c, hgrads->colors, pl.dgrads.colors, (size_t)hs->n_colors * 12))) return rc;
-        if ((rc = d2h(c, hgrads->albedo, pl.dgrads.albedo, (size_t)hs->n_materials * 12))) return rc;
-        if ((rc = d2h(c, hgrads->coeffs, pl.dgrads.coeffs, (size_t)hs->n_materials * 12))) return rc;
-        if (hs->gamma && (rc = d2h(c, hgrads->gamma, pl.dgrads.gamma, 4))) return rc;
     }
+    // the small gradient arrays and the loss: neighbours in the arena, ONE copy into pinned staging, handed out after the wait
+    struct Item { void* dst; const void* src; size_t bytes; };
     float loss_f = 0.f;
-    if (has_target && loss) {
-        SURF_CUDA(cudaMemcpyAsync(&loss_f, pl.d_loss_f, 4, cudaMemcpyDeviceToHost, c->stream));
-        c->d2h += 4;
+    Item items[8];
+    int n_items = 0;
+    if (hsx.want_bwd) {
+        items[n_items++] = {hgrads->light_pos, pl.dgrads.light_pos, (size_t)hs->n_lights * hs->light_pos_stride * 4};
+        items[n_items++] = {hgrads->light_attenuation, pl.dgrads.light_attenuation, (size_t)hs->n_lights * 12};
+        items[n_items++] = {hgrads->ambient, pl.dgrads.ambient, 12};
+        items[n_items++] = {hgrads->colors, pl.dgrads.colors, (size_t)hs->n_colors * 12};
+        items[n_items++] = {hgrads->albedo, pl.dgrads.albedo, (size_t)hs->n_materials * 12};
+        items[n_items++] = {hgrads->coeffs, pl.dgrads.coeffs, (size_t)hs->n_materials * 12};
+        if (hs->gamma) items[n_items++] = {hgrads->gamma, pl.dgrads.gamma, 4};
+        if (has_target && loss) items[n_items++] = {&loss_f, pl.d_loss_f, 4};
+    }
+    const char* lo = hsx.want_bwd ? (const char*)pl.dgrads.light_pos : nullptr;
+    const char* hi = hsx.want_bwd ? (const char*)pl.d_loss_f + 4 : nullptr;
+    const bool staged = hsx.want_bwd && (size_t)(hi - lo) <= kStageBytes;
+    if (staged) {
+        SURF_CUDA(cudaMemcpyAsync(c->stage_down, lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->stream));
+        for (int k = 0; k < n_items; ++k)
+            if (items[k].dst) c->d2h += items[k].bytes;
+    } else {
+        for (int k = 0; k < n_items; ++k)
+            if ((rc = d2h(c, items[k].dst, items[k].src, items[k].bytes))) return rc;
     }
     SURF_CUDA(cudaStreamSynchronize(c->stream));
+    if (staged)
+        for (int k = 0; k < n_items; ++k)
+            if (items[k].dst && items[k].bytes) std::memcpy(items[k].dst, c->stage_down + ((const char*)items[k].src - lo), items[k].bytes);
     if (has_target && loss) *loss = loss_f;
     return SURF_OK;
 }
@@ -1368,7 +1402,9 @@ SurfContext* surf_context_create(int32_t device) {
     c->device = device; c->arena = nullptr; c->arena_bytes = 0; c->h2d = c->d2h = 0; c->state = nullptr;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->target_ready, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->target_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->stage_up, surf::kStageBytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->stage_down, surf::kStageBytes, cudaHostAllocDefault) != cudaSuccess) {
         g_error = "cudaStreamCreate failed";
         delete c;
         return nullptr;
@@ -1383,6 +1419,8 @@ void surf_context_destroy(SurfContext* c) {
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->target_ready);
+    cudaFreeHost(c->stage_up);
+    cudaFreeHost(c->stage_down);
     delete c->state;
     delete c;
 }
