@@ -11,4 +11,4 @@ python tools/run_config.py B 5 > gpurun_out/plain_b.log 2>&1 && ncu --set full -
 python tools/bench_configs.py > gpurun_out/r2_bench_configs.jsonl 2>&1
 python bench.py --workload config_d --steps 20 --warmup 3 > gpurun_out/r2_bench_config_d_n1.json 2> gpurun_out/r2_bench_config_d_n1.err
 python tools/bench_along_ray.py > gpurun_out/r2_bench_along_ray.log 2>&1
-tail -2 gpurun_out/plain.log gpurun_out/plain_d.log
+tail -n 2 gpurun_out/plain.log; tail -n 2 gpurun_out/plain_d.log
