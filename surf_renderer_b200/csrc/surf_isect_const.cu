@@ -1,5 +1,5 @@
-// surf_isect_const.cu - translation unit of libsurf_b200.so: k_intersect_const<P>, the camera-ray x disk intersection +
-// z-buffer kernel whose filter records reach the FMA pipe through the UNIFORM datapath.
+// surf_isect_const.cu - translation unit of libsurf_b200.so: the camera-ray x disk intersection + z-buffer stage whose
+// filter records reach the FMA pipe through the UNIFORM datapath (k_filter_const and the kernels around it).
 //
 // Why: the packed filter of k_intersect (surf_intersect.cuh, chunk_disks) multiplies two pixel-pair registers by a
 // warp-uniform scalar of the disk record.  With the record staged in shared memory that scalar arrives in a vector
@@ -7,22 +7,28 @@
 // instead of two: the staged kernel tops out at 70 % of the FP32-FMA peak (tools/ubench/pipes.cu).  Blackwell's FFMA2
 // also takes the scalar from a uniform register (SASS `FFMA2 R, R.F32x2.HI_LO, UR.F32, R.F32x2.HI_LO`), which costs
 // no vector register-file port - but uniform registers can only be loaded from the constant bank (LDCU).  So the
-// records are streamed through the 64 KB constant bank, 2048 disks at a time, by device-to-device copies between
-// launches: same arithmetic, same filter + exact narrow phase, 114 -> 96 cycles per warp and disk
-// (tools/ubench/uniform.cu: 70.0 % -> 83.7 % of peak).
+// records are streamed through the 64 KB constant bank by device-to-device copies between launches: the same plane
+// filter goes from 114 to 96 cycles per warp and disk (tools/ubench/uniform.cu: 70.0 % -> 83.7 % of peak).
 //
-// The compiler only keeps the records in uniform registers while the kernel is simple: a subroutine call (the slow path
-// of an IEEE division) or a narrow phase of any size inside the filter loop turned all 200 FFMA2 of the kernel back to
-// vector-register scalars (bisected on the SASS).  So the stage is split:
-//   k_filter_const   the conservative filter only: all pixels of the frame x the <= 2048 records resident in the bank.
-//                    The work grid [pixel tile][record group] is cut into equal contiguous ranges over the persistent CTAs
-//                    (nothing is staged, so a range may start and stop at any group).  A (thread, group) whose filter
-//                    minimum passes is appended to a candidate queue in the workspace (warp-aggregated atomic) - about one
-//                    8-byte entry per pixel and frame on config E.
-//   k_narrow_queue   one thread per candidate: per-pixel filter of the group's two disks, the exact reference-order hit
-//                    test for the pairs that pass, 64-bit atomicMin into the z-buffer keys.
+// The compiler only keeps the records in uniform registers while the kernel is very plain: a subroutine call (the slow
+// path of an IEEE division), a narrow phase of any size in or behind the filter loop, a loop bound that is not used
+// exactly as loaded from the parameter block, a hand-written warp-aggregated append - each turned every packed FMA of
+// the kernel back to vector-register scalars (bisected on the SASS; tests/test_const_path.py checks the built library).
+// So the stage is split:
+//   k_sphere_records sphere filter only: the 12-byte records oc / sqrt(|oc|^2 - rs^2 - slack) of the disk set.
+//   k_filter_const   the conservative filter only - FILTER 1: bounding sphere, |oc' . d| >= 1, 3 FMA-pipe lane-instructions
+//                    per ray-disk test; FILTER 0: the plane filter of k_intersect, 10 + a reciprocal - for all pixels of the
+//                    frame x the records resident in one half of the bank.  The work grid [pixel tile][record group] is cut
+//                    into equal contiguous ranges over the persistent CTAs by the host (nothing is staged, so a range may
+//                    start and stop at any group).  A (half thread, group) whose filter passes is appended to a candidate
+//                    queue in the workspace - about six 8-byte entries per pixel and frame on config E.
+//   k_narrow_queue   one thread per candidate and pixel pair: the sphere test again, the plane filter, the exact
+//                    reference-order hit test for the pairs that pass, 64-bit atomicMin into the z-buffer keys.
 //   k_const_fallback tiles whose candidates did not fit the queue (dense close-ups) are flagged per launch and redone
 //                    here with filter + narrow phase inline, records read from global memory; exits at once otherwise.
+//   k_inside_disks   disks whose bounding sphere holds the eye (no sphere record) against every pixel; exits at once otherwise.
+// Consecutive launches alternate between the halves of the bank and between two streams: the copy into one half, the cold
+// constant cache and the tail of one kernel overlap the kernel on the other half.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -74,7 +80,7 @@ struct ConstParams {
     int n_pix, n_tiles;
     int group0;                      // set-local group index of bank group 0 (the segments count bank groups)
     uint2* queue;                    // candidates: x = 2 * thread slot (tile * kThreads + tid) + half of its pixels, y = set-local group index
-    int* ctl;                        // [0] entries appended (may exceed capacity), [1] flagged (launch, tile) pairs
+    int* ctl;                        // [0] entries appended (may exceed capacity), [2] length of the `inside` list
     int capacity;
     unsigned char* flags;            // this launch's row of the [launch][tile] overflow map
     // Work of the CTAs, computed by the host: CTA b runs three segments seg[3 b .. 3 b + 2], each = tiles [x, y) against
@@ -208,11 +214,13 @@ __global__ void __launch_bounds__(kThreads, FILTER == 1 ? SURF_CONST_SPHERE_CTAS
         for (int tile = sg.x; tile < sg.y; ++tile) {
             PixelRegs<P> r;
             load_tile_rays<P>(prm.rays, prm.n_pix, tile, tid, r);
-            // Groups of two (plane filter) or four (sphere filter) disks, two groups per iteration with the records of the next group fetched (LDCU) while the
-            // current one computes - the constant cache is cold at every launch.  The branch taken for group k tests a
-            // filter minimum that finished long ago, so neither the FMNMX3 chain nor the branch resolution sits on the
-            // critical path.  The host makes every segment an even number of groups and ends it one group past its last
-            // (that group's minimum is never tested): code behind the loop costs the uniform registers, too.
+            // Groups of two (plane filter) or four (sphere filter) disks, two groups per iteration with the records of the
+            // next group fetched (LDCU) while the current one computes - the constant cache is cold at every launch.  The
+            // branch taken for group k tests a filter result that finished long ago, so neither the FMNMX3 chain nor the
+            // branch resolution sits on the critical path.  The host makes every segment an even number of groups and ends
+            // it one group past its last (that group's result is never tested): code behind the loop costs the uniform
+            // registers, too.  A segment padded to even length tests one group of the NEXT segment (or stale bank
+            // contents) as well: a duplicate or spurious candidate, which k_narrow_queue filters again - never a miss.
             constexpr int GF = group_floats(FILTER);
             float2 m_prev = make_float2(INFINITY, INFINITY);
             float ga[GF], gc[GF];
@@ -248,8 +256,8 @@ struct NarrowParams {
     const float* spheres;            // sphere filter: the set's sphere records [count, 3] (the pairs that passed are found again first)
 };
 
-// one thread per (candidate, pixel pair of the candidate's half): the two pixels' rays, the sphere test of the group's disks again (sphere filter),
-// the plane filter, and the exact reference-order hit test for what passes.  Consecutive threads share a candidate, so
+// one thread per (candidate, pixel pair of the candidate's half): the two pixels' rays, the sphere test of the group's
+// disks again (sphere filter), the plane filter, and the exact reference-order hit test for what passes.  Consecutive threads share a candidate, so
 // the queue entry and the records are broadcast loads.
 template <int P>
 __global__ void __launch_bounds__(256) k_narrow_queue(const __grid_constant__ NarrowParams prm) {
