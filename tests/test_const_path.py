@@ -146,3 +146,29 @@ def test_gpu_const_path_gradients_match_the_staged_kernel():
         grads[mode] = {k: sc['objects']['disk'][k].grad.clone() for k in ('pos', 'normal')}
     for k in ('pos', 'normal'):
         assert torch.allclose(grads[0][k], grads[5][k], rtol=1e-5, atol=1e-7 * float(grads[5][k].abs().max()))
+
+
+@pytest.mark.gpu
+def test_gpu_const_path_with_shadow_rays_and_double_sided():
+    """the primary rays take the constant-bank path, the shadow pass its own kernels: same frame as with the staged kernel"""
+    scene = synth.config_e(m=1800, width=336, height=288, radius=0.03)
+    out = _render_modes(scene, shadow=True, double_sided=True)
+    assert int((out[5]['depth'] < 1000).sum()) > 1000
+    _same(out[0], out[5])
+    _same(out[6], out[5])
+
+
+@pytest.mark.gpu
+def test_gpu_const_path_pixel_band_equals_the_rows_of_the_full_frame():
+    """row bands (the multi-GPU sharding) through the constant-bank path: bit-identical to the full frame"""
+    import surf_renderer_b200
+    scene = synth.config_e(m=3000, width=512, height=384, radius=0.02)
+    sc = scene_io.clone_scene(scene, device='cuda')
+    with torch.no_grad():
+        full = surf_renderer_b200.render(sc)
+        n = 512 * 384
+        lo, hi = n // 3, n // 3 + 70001            # a ragged band of more than 256 x 256 pixels
+        (image, depth, _, _, nearest, _), _ = surf_renderer_b200.render_flat(sc, pixel_range=(lo, hi))
+    torch.cuda.synchronize()
+    for k, v in (('nearest', nearest), ('depth', depth), ('image', image)):
+        assert torch.equal(v.reshape(hi - lo, -1), full[k].reshape(n, -1)[lo:hi]), k
