@@ -193,3 +193,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text and 'torch_oracle' not in text, f
+
+
+def test_workspace_sizes_cover_the_candidate_queue():
+    """perspective frames above 256 x 256 pixels carry the candidate queue of the constant-bank intersection path (80 B per
+    pixel + flags + the `inside` list); surf_workspace_bytes() bounds every camera; small frames and orthographic ones do
+    not pay for it"""
+    from surf_renderer_b200._lib import lib
+    L = lib()
+    prims, lights = 100000, 3
+    for n in (64 * 64, 256 * 256):
+        assert L.surf_workspace_bytes_ex(prims, n, lights, 0, 0, 0) <= L.surf_workspace_bytes_ex(prims, n, lights, 0, 1, 0)
+    n = 1024 * 1024
+    persp, ortho = L.surf_workspace_bytes_ex(prims, n, lights, 0, 0, 0), L.surf_workspace_bytes_ex(prims, n, lights, 0, 1, 0)
+    w0, w1 = L.surf_workspace_bytes_ex(prims, 64 * 64, lights, 0, 0, 0), L.surf_workspace_bytes_ex(prims, 256 * 256, lights, 0, 0, 0)
+    without_queue = w1 + (w1 - w0) / (256 * 256 - 64 * 64) * (n - 256 * 256)       # linear in the pixel count below the threshold
+    assert 80 * n <= persp - without_queue <= 82 * n            # the queue: 10 entries of 8 bytes per pixel (+ flags, inside list)
+    assert persp - ortho >= 40 * n - (1 << 20)                 # 80 B per pixel of queue against 40 B per pixel of generic rays
+    assert L.surf_workspace_bytes(prims, n, lights, 0) == max(persp, ortho)
+    assert L.surf_workspace_bytes_ex(prims, n, lights, 0, 0, 1) - persp >= 12 * n      # + d(loss)/d(image) of a fused step
